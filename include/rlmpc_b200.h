@@ -1,0 +1,130 @@
+/* rlmpc_b200.h -- C ABI of the B200 batched MPC engine (librlmpc_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  What the reference reaches
+ * through ctypes into the acados-generated shared library (acados_template.AcadosOcpSolver:
+ * set / get / solve / get_cost / constraints_set / cost_set / reset, called from
+ * rlmpc/mpc/common/mpc.py:27-96,177-285) plus the CasADi/SuperLU work of update_nlp
+ * (rlmpc/mpc/nlp.py:1341-1424) is exposed here as batched entry points with plain pointers
+ * and sizes.  No torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - all functions return 0 on success and a negative RLMPC_E* code on failure; they never
+ *     throw.  rlmpc_last_error() gives a message for the calling thread.
+ *   - "_dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *     "_host" pointers are ordinary host memory.  Matrices are row-major [B, dim].
+ *   - one handle = one problem on one device with room for max_batch samples.  The handle
+ *     owns the persistent primal-dual iterate of every sample (the warm start, what acados
+ *     keeps inside its solver object) and the per-stage scratch.  Calls on one handle must be
+ *     serialised by the caller (stream order); the handle is not re-entrant, like an
+ *     AcadosOcpSolver.
+ *   - per-sample status uses acados' codes: 0 ok, 1 NaN, 2 max iter, 3 min step, 4 QP failure
+ *     (what mpc.py:81-82,197-198 turns into RuntimeError).
+ */
+#ifndef RLMPC_B200_H
+#define RLMPC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLMPC_MAXN 128
+#define RLMPC_MAXD 8
+
+/* models (device code emitted per problem, the role of acados' c_generated_code) */
+#define RLMPC_MODEL_CARTPOLE 1 /* rlmpc/mpc/cartpole/acados.py:28-108 */
+
+#define RLMPC_MODE_V 0 /* x_0 fixed            -> V(s), pi(s)   mpc.py:177-202 (update, get_action) */
+#define RLMPC_MODE_Q 1 /* x_0 and u_0 fixed    -> Q(s,a)        mpc.py:52-96   (q_update) */
+
+#define RLMPC_EINVAL (-1)
+#define RLMPC_ECUDA (-2)
+#define RLMPC_ENOMEM (-3)
+#define RLMPC_ENODEV (-4)
+
+typedef struct rlmpc_handle rlmpc_handle;
+
+/* What AcadosOcp carries for one problem (dims, cost scaling, bounds, integrator constants).
+ * Replaces: AcadosOcp + AcadosOcpSolver(ocp, json_file=...) construction
+ * (rlmpc/mpc/cartpole/acados.py:169-203). */
+typedef struct rlmpc_problem_desc {
+  int model;                        /* RLMPC_MODEL_* */
+  int N;                            /* horizon, <= RLMPC_MAXN */
+  double scale[RLMPC_MAXN + 1];     /* cost scaling per stage: dT, gamma^k dT, ... (nlp.py:1038-1134) */
+  double lbu[RLMPC_MAXD], ubu[RLMPC_MAXD]; /* input bounds, all stages (constraints.lbu/ubu) */
+  double lbx[RLMPC_MAXD], ubx[RLMPC_MAXD]; /* state bounds stages 1..N-1 (+-1e30 = none) */
+  double lbx_e[RLMPC_MAXD], ubx_e[RLMPC_MAXD];
+  double model_const[8];            /* cartpole: [0]=RK4 step h, [1]=g */
+} rlmpc_problem_desc;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Replaces AcadosOcpSolver.__init__ (code generation + gcc + dlopen). */
+int rlmpc_create(const rlmpc_problem_desc* desc, int max_batch, int device, rlmpc_handle** out);
+void rlmpc_destroy(rlmpc_handle* h);
+const char* rlmpc_last_error(void);
+/* dims: nx, nu, ntheta (length of the reference's p vector, nlp.py:970-989), iterate doubles per sample */
+int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* iterate_size);
+
+/* ---- parameters / options --------------------------------------------------------------- */
+/* Replaces ocp_solver.set(stage,"p",..) for all stages + cost_set(stage,"W"/"yref",..)
+ * (mpc.py:137-149, 212-257).  theta is the reference's full p vector.  per_sample=0: one theta
+ * shared by the batch; per_sample=1: theta_host is [B, ntheta] (parameter sweeps,
+ * scripts/cartpole_mpc_sensitivities.py:79-98). */
+int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, int B);
+/* Replaces ocp_nlp_cost_model_set(..., "scaling", ...) (mpc.py:259-285). n = N+1. */
+int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n);
+/* Replaces constraints_set(stage, "lbu"/"ubu"/..) for the nominal bounds. field in
+ * {"lbu","ubu","lbx","ubx","lbx_e","ubx_e"}. */
+int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n);
+/* options: "tol" (1e-6), "tau" (1e-8), "mu0" (1.0), "max_ipm" (50), "warm_ipm" (0),
+ * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */
+int rlmpc_set_option(rlmpc_handle* h, const char* name, double value);
+
+/* ---- iterate (warm start) --------------------------------------------------------------- */
+/* Replaces ocp_solver.reset() + set(stage,"x",x0) for all stages (mpc.py:204-210):
+ * x_k = x0, u = 0, multipliers = 0 for samples [0,B). */
+int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream);
+/* Replaces ocp_solver.get/set(stage, field). field in {"x","u","pi","lam","t"}; buf_dev is
+ * [B, dim(field)] row-major; lam/t are in acados order [lbu, ubu] for this problem class. */
+int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, double* buf_dev, void* stream);
+int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, const double* buf_dev, void* stream);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* Replaces ocp_solver.set(0,"lbx"/"ubx",x0) [+ constraints_set(0,"lbu"/"ubu",u0)] + solve()
+ * + get(0,"u") + get_cost() for B samples (mpc.py:27-50, 52-82, 177-202).
+ * max_sqp = 1 is one SQP-RTI step; larger = SQP to convergence (tol).
+ * u0_dev may be NULL in V-mode.  Outputs may be NULL.  cost_out is the cost of the last
+ * linearisation point (for converged solves: of the solution). */
+int rlmpc_solve(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
+                double* u0_out_dev, double* cost_out_dev, int* status_out_dev, void* stream);
+/* Replaces update_nlp() (nlp.py:1341-1563) at the current iterate: cost, KKT residual norms
+ * [stat, eq, ineq, comp], dL/dtheta [B, ntheta] (= dV/dtheta = dQ/dtheta) and
+ * dpi/dtheta [B, nu, ntheta].  Output rows must be zero-initialised by the caller; entries that
+ * are structurally zero are not written. */
+int rlmpc_sens(rlmpc_handle* h, int mode, int B, double* dL_dtheta_dev, double* dpi_dtheta_dev,
+               double* cost_out_dev, double* res_out_dev, int* status_out_dev, void* stream);
+/* One fused launch: solve + sens (one "unit" of BASELINE.json's metric). */
+int rlmpc_solve_sens(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
+                     double* u0_out_dev, double* cost_out_dev, int* status_out_dev, double* dL_dtheta_dev,
+                     double* dpi_dtheta_dev, double* res_out_dev, void* stream);
+/* Host-buffer variant of rlmpc_solve_sens: copies x0/u0 in, runs, copies all outputs back and
+ * synchronises.  This is the end-to-end call the reference-side binding would make. */
+int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_host,
+                          const double* u0_host, double* u0_out_host, double* cost_out_host, int* status_out_host,
+                          double* dL_dtheta_host, double* dpi_dtheta_host, double* res_out_host);
+
+/* ---- TD / policy-gradient accumulator ------------------------------------------------------ */
+/* Replaces  dp = mean_i(LR * td_i * dQ_dp_i)  (examples/linear_system_mpc_qlearning.py:193,203):
+ * acc_out_dev[0..ntheta) = sum_i td_i * dQ_dtheta[i,:], acc[ntheta] = sum_i td_i, acc[ntheta+1] =
+ * number of valid samples (status 0).  The caller all-reduces acc over ranks (NCCL). */
+int rlmpc_td_grad(rlmpc_handle* h, int B, const double* td_dev, const double* dQ_dtheta_dev, const int* status_dev,
+                  double* acc_out_dev, void* stream);
+
+/* number of kernels launched through this handle so far (bench.py's gpu_launches) */
+long long rlmpc_launch_count(const rlmpc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLMPC_B200_H */

@@ -1,0 +1,59 @@
+// Shared definitions of the rlmpc-b200 engine (host/device generic maths).
+// The same templates are instantiated in CUDA kernels (kernels.cu, the product) and, for
+// timing/debugging only, in a host build under oracle/cpu_port (test infrastructure).
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#define MPC_UNROLL _Pragma("unroll")
+#else
+#define MPC_HD inline __attribute__((always_inline))
+#define MPC_UNROLL
+#endif
+
+namespace rlmpc {
+
+constexpr int MAXN = 128;  // max horizon supported by ProblemData
+constexpr int MAXD = 8;    // max nx / nu held in ProblemData bound arrays (thread-per-sample engine)
+
+// acados status codes: 0 ok, 1 NaN, 2 max iter, 3 min step, 4 QP failure
+enum Status : int { ST_OK = 0, ST_NAN = 1, ST_MAXITER = 2, ST_MINSTEP = 3, ST_QPFAIL = 4 };
+
+enum Mode : int { MODE_V = 0, MODE_Q = 1 };
+
+// Everything that is shared by all samples of a batch. Passed to kernels by value
+// (fits the 4 KB kernel-parameter space), so it sits in constant memory.
+struct ProblemData {
+  int N;
+  int mode;             // MODE_V / MODE_Q
+  int max_sqp;          // max SQP iterations (QP solves); 1 == RTI
+  int max_ipm;          // max interior-point iterations per QP
+  int warm_ipm;         // 1: start the IPM from the stored (lam,t)
+  int param_cost;       // 1: gradient wrt cost parameters requested (parameterize_tracking_cost)
+  double tol;           // SQP convergence tolerance on the 4 KKT residual norms
+  double tau;           // complementarity target lam*t = tau (nlp.py:1199)
+  double mu0;           // initial barrier parameter of a cold-started IPM
+  double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
+  double lbu[MAXD], ubu[MAXD];
+  double lbx[MAXD], ubx[MAXD];      // stages 1..N-1
+  double lbx_e[MAXD], ubx_e[MAXD];  // stage N
+  double mc[8];         // model constants (integrator step, gravity, ...)
+};
+
+// One sample's strided view: element i of a logical per-sample vector lives at p[i*bs].
+struct Lane {
+  double* it;        // iterate (persistent primal-dual state, warm start)
+  double* ws;        // per-stage scratch
+  size_t bs;         // batch stride (padded batch size)
+  const double* th;  // parameter vector theta
+  size_t ths;        // stride between theta entries (1: shared theta; bs: per-sample theta)
+};
+
+MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
+MPC_HD double dmin(double a, double b) { return a < b ? a : b; }
+MPC_HD double dabs(double a) { return a < 0 ? -a : a; }
+
+}  // namespace rlmpc

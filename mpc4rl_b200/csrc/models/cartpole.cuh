@@ -1,0 +1,178 @@
+// Cart-pole swing-up model of the reference (rlmpc/mpc/cartpole/acados.py:28-108):
+//   x = [s, s_dot, theta, theta_dot], u = [F], model parameters (M, m, l), g fixed.
+//   x+ = ONE explicit RK4 step of length h = tf/N/sim_method_num_stages (quirk Q1,
+//   cartpole/acados.py:86-92, rlmpc/common/integrator.py:6-33).
+//   cost y = [x;u], y_e = x (acados.py:104-106), NONLINEAR_LS with W_0/W/W_e, yref_*.
+// theta layout (rlmpc/mpc/nlp.py:970-989, CasADi column-major):
+//   [M, m, l | W_0(25) | W(25) | W_e(16) | yref_0(5) | yref(5) | yref_e(4)]  = 83
+//
+// First/second derivatives of the RK4 map are built by hand-written forward/adjoint
+// propagation around sympy-generated leaf code (cartpole_gen.cuh) -- this replaces the
+// CasADi-generated C the reference compiles at construction time.
+#pragma once
+#include "../common.cuh"
+
+namespace rlmpc {
+
+#include "cartpole_gen.cuh"
+
+struct CartpoleModel {
+  static constexpr int NX = 4, NU = 1, NPM = 3, NZ = 8;  // NZ = NX+NU+NPM (derivative columns)
+  static constexpr int NTH = 83;
+  static constexpr int TH_W0 = 3, TH_W = 28, TH_WE = 53, TH_YREF0 = 69, TH_YREF = 74, TH_YREFE = 79;
+
+  // ---- quadratic tracking cost  l = 1/2 (y-yref)' W (y-yref),  y=[x;u] -------------------
+  // kind: 0 initial stage, 1 intermediate, 2 terminal (ny = NX).
+  MPC_HD static int ny(int kind) { return kind == 2 ? NX : NX + NU; }
+  MPC_HD static int w_off(int kind) { return kind == 0 ? TH_W0 : (kind == 1 ? TH_W : TH_WE); }
+  MPC_HD static int yref_off(int kind) { return kind == 0 ? TH_YREF0 : (kind == 1 ? TH_YREF : TH_YREFE); }
+  // symmetrised weight entry (i,j)
+  MPC_HD static double W(int kind, int i, int j, const double* th, size_t ths) {
+    const int n = ny(kind), o = w_off(kind);
+    return 0.5 * (th[(size_t)(o + j * n + i) * ths] + th[(size_t)(o + i * n + j) * ths]);
+  }
+  MPC_HD static double yref(int kind, int i, const double* th, size_t ths) {
+    return th[(size_t)(yref_off(kind) + i) * ths];
+  }
+  MPC_HD static double flin(int, int, const double*, size_t) { return 0.0; }  // no linear term
+  MPC_HD static double c0(int, const double*, size_t) { return 0.0; }         // no constant term
+
+  // ---- dynamics -------------------------------------------------------------------------
+  // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l);
+  // NC = 5 -> columns (x,u) only (SQP linearisation), NC = 8 -> also the parameter columns.
+  template <int NC>
+  MPC_HD static void rk4_fwd(const double* x, double F, double M, double m, double l, double g, double h,
+                             double* xn, double* DF /* 4 x NC row-major */,
+                             double* keep /* optional per-stage data for the adjoint pass, or nullptr */) {
+    double S[4][NC], acc[4][NC], s[4], xa[4];
+    MPC_UNROLL for (int i = 0; i < 4; ++i) {
+      s[i] = x[i];
+      xa[i] = 0.0;
+      MPC_UNROLL for (int c = 0; c < NC; ++c) {
+        S[i][c] = (i == c) ? 1.0 : 0.0;
+        acc[i][c] = 0.0;
+      }
+    }
+    MPC_UNROLL for (int st = 0; st < 4; ++st) {
+      double sn, cs, xdd, thdd, jx[6], jt[6];
+      sincos(s[2], &sn, &cs);
+      cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
+      if (keep) {  // stage point + the S rows the adjoint pass needs
+        double* kp = keep + st * (4 + 2 * NC + 4);
+        kp[0] = sn; kp[1] = cs; kp[2] = s[3];
+        kp[3] = 0.0;
+        MPC_UNROLL for (int c = 0; c < NC; ++c) { kp[4 + c] = S[2][c]; kp[4 + NC + c] = S[3][c]; }
+        kp[4 + 2 * NC + 0] = jx[0]; kp[4 + 2 * NC + 1] = jx[1];
+        kp[4 + 2 * NC + 2] = jt[0]; kp[4 + 2 * NC + 3] = jt[1];
+      }
+      const double k[4] = {s[1], xdd, s[3], thdd};
+      double Dk[4][NC];
+      MPC_UNROLL for (int c = 0; c < NC; ++c) {
+        Dk[0][c] = S[1][c];
+        Dk[2][c] = S[3][c];
+        double a = jx[0] * S[2][c] + jx[1] * S[3][c];
+        double b = jt[0] * S[2][c] + jt[1] * S[3][c];
+        if (c >= 4) { a += jx[2 + (c - 4)]; b += jt[2 + (c - 4)]; }
+        Dk[1][c] = a;
+        Dk[3][c] = b;
+      }
+      const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
+      MPC_UNROLL for (int i = 0; i < 4; ++i) {
+        xa[i] += wgt * k[i];
+        MPC_UNROLL for (int c = 0; c < NC; ++c) acc[i][c] += wgt * Dk[i][c];
+      }
+      if (st < 3) {
+        const double a = (st < 2) ? 0.5 * h : h;
+        MPC_UNROLL for (int i = 0; i < 4; ++i) {
+          s[i] = x[i] + a * k[i];
+          MPC_UNROLL for (int c = 0; c < NC; ++c) S[i][c] = ((i == c) ? 1.0 : 0.0) + a * Dk[i][c];
+        }
+      }
+    }
+    const double h6 = h / 6.0;
+    MPC_UNROLL for (int i = 0; i < 4; ++i) {
+      xn[i] = x[i] + h6 * xa[i];
+      MPC_UNROLL for (int c = 0; c < NC; ++c) DF[i * NC + c] = ((i == c) ? 1.0 : 0.0) + h6 * acc[i][c];
+    }
+  }
+
+  // x+ and its Jacobians wrt x (A, NX x NX row-major) and u (B, NX x NU)
+  MPC_HD static void dyn_lin(const double* x, const double* u, const double* th, size_t ths, const double* mc,
+                             double* xn, double* A, double* B) {
+    double DF[4 * 5];
+    rk4_fwd<5>(x, u[0], th[0], th[ths], th[2 * ths], mc[1], mc[0], xn, DF, nullptr);
+    MPC_UNROLL for (int i = 0; i < 4; ++i) {
+      MPC_UNROLL for (int j = 0; j < 4; ++j) A[i * 4 + j] = DF[i * 5 + j];
+      B[i] = DF[i * 5 + 4];
+    }
+  }
+
+  // Full second-order information at one stage:
+  //   xn, A, B, Fp = dF/dp_model (NX x NPM), and the Hessian of pi' F wrt zeta split into
+  //   Hww ((NX+NU) x (NX+NU), full symmetric storage) and Hwp ((NX+NU) x NPM).
+  MPC_HD static void dyn_sens(const double* x, const double* u, const double* th, size_t ths, const double* mc,
+                              const double* pi, double* xn, double* A, double* B, double* Fp, double* Hww,
+                              double* Hwp) {
+    constexpr int NC = 8, KS = 4 + 2 * NC + 4;
+    const double F = u[0], M = th[0], m = th[ths], l = th[2 * ths], g = mc[1], h = mc[0];
+    double DF[4 * NC], keep[4 * KS];
+    rk4_fwd<NC>(x, F, M, m, l, g, h, xn, DF, keep);
+    MPC_UNROLL for (int i = 0; i < 4; ++i) {
+      MPC_UNROLL for (int j = 0; j < 4; ++j) A[i * 4 + j] = DF[i * NC + j];
+      B[i] = DF[i * NC + 4];
+      MPC_UNROLL for (int j = 0; j < 3; ++j) Fp[i * 3 + j] = DF[i * NC + 5 + j];
+    }
+    // adjoint sweep over the RK stages: mu_i = d(pi'F)/dk_i
+    double Hacc[NC][NC];
+    MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = 0; b < NC; ++b) Hacc[a][b] = 0.0;
+    double mu[4];
+    MPC_UNROLL for (int i = 0; i < 4; ++i) mu[i] = (h / 6.0) * pi[i];
+    MPC_UNROLL for (int st = 3; st >= 0; --st) {
+      const double* kp = keep + st * KS;
+      const double sn = kp[0], cs = kp[1], thd = kp[2];
+      double xdd, thdd, jx[6], jt[6], hs[36];
+      cartpole_f_hess(sn, cs, thd, F, M, m, l, g, mu[1], mu[3], &xdd, &thdd, jx, jt, hs);
+      // symmetric 6x6 Hessian of mu1*xdd + mu3*thdd wrt v = (theta, theta_dot, F, M, m, l)
+      double Hf[6][6];
+      MPC_UNROLL for (int a = 0; a < 6; ++a) MPC_UNROLL for (int b = a; b < 6; ++b) {
+        Hf[a][b] = hs[a * 6 + b];
+        Hf[b][a] = hs[a * 6 + b];
+      }
+      const double* Sr0 = kp + 4;       // d s[2] / d zeta
+      const double* Sr1 = kp + 4 + NC;  // d s[3] / d zeta
+      double T[6][NC];
+      MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+        double v = Hf[p][0] * Sr0[b] + Hf[p][1] * Sr1[b];
+        if (b >= 4) v += Hf[p][b - 2];
+        T[p][b] = v;
+      }
+      MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+        double v = Sr0[a] * T[0][b] + Sr1[a] * T[1][b];
+        if (a >= 4) v += T[a - 2][b];
+        Hacc[a][b] += v;
+      }
+      if (st > 0) {
+        // adjoint of the stage point s_st = x + a*k_{st-1}:  mu_{st-1} = w*h/6*pi + a * (df/ds)' mu_st
+        const double a = (st == 3) ? h : 0.5 * h;
+        const double wgt = (st - 1 == 0) ? 1.0 : 2.0;
+        const double jx0 = kp[4 + 2 * NC + 0], jx1 = kp[4 + 2 * NC + 1];
+        const double jt0 = kp[4 + 2 * NC + 2], jt1 = kp[4 + 2 * NC + 3];
+        const double a0 = 0.0;
+        const double a1 = mu[0];
+        const double a2 = jx0 * mu[1] + jt0 * mu[3];
+        const double a3 = mu[2] + jx1 * mu[1] + jt1 * mu[3];
+        const double c6 = wgt * h / 6.0;
+        mu[0] = c6 * pi[0] + a * a0;
+        mu[1] = c6 * pi[1] + a * a1;
+        mu[2] = c6 * pi[2] + a * a2;
+        mu[3] = c6 * pi[3] + a * a3;
+      }
+    }
+    MPC_UNROLL for (int a = 0; a < 5; ++a) {
+      MPC_UNROLL for (int b = 0; b < 5; ++b) Hww[a * 5 + b] = Hacc[a][b];
+      MPC_UNROLL for (int b = 0; b < 3; ++b) Hwp[a * 3 + b] = Hacc[a][5 + b];
+    }
+  }
+};
+
+}  // namespace rlmpc

@@ -1,0 +1,485 @@
+// librlmpc_b200.so -- CUDA kernels (sm_100a) + the C ABI declared in include/rlmpc_b200.h.
+//
+// Mapping: one CUDA thread per replay-buffer sample (nx <= 4 problems).  The whole
+// primal-dual iterate and the per-stage scratch live in HBM in batch-minor (SoA) arrays, so every
+// load/store a warp issues is a fully coalesced 256-byte access; theta and the problem data
+// are broadcast (constant bank / L1).  See DESIGN.md for the roofline discussion.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/rlmpc_b200.h"
+#include "engine.cuh"
+#include "models/cartpole.cuh"
+
+using namespace rlmpc;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(RLMPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+constexpr int TPB = 128;  // threads per block
+
+struct KArgs {
+  double* it;
+  double* ws;
+  size_t bs;
+  const double* th;
+  int th_per_sample;
+  int B;
+  const double* x0;  // [B, NX] row-major or null
+  const double* u0;  // [B, NU] row-major or null
+  double* u0_out;    // [B, NU]
+  double* cost_out;  // [B]
+  int* status_out;   // [B]
+  double* dL;        // [B, NTH]
+  double* dpi;       // [B, NU, NTH]
+  double* res_out;   // [B, 4]
+  int do_solve, do_sens;
+};
+
+template <class M>
+__global__ void __launch_bounds__(TPB) k_unit(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  Lane L;
+  L.it = a.it + b;
+  L.ws = a.ws + b;
+  L.bs = a.bs;
+  L.th = a.th_per_sample ? a.th + b : a.th;
+  L.ths = a.th_per_sample ? a.bs : 1;
+  int status = ST_OK;
+  double cost = 0.0;
+  if (a.do_solve) {
+    E::set_initial(pd, L, a.x0 + (size_t)b * M::NX, 1, a.u0 ? a.u0 + (size_t)b * M::NU : nullptr, 1);
+    typename E::SolveOut o = E::solve(pd, L);
+    status = o.status;
+    cost = o.res.cost;
+  }
+  if (a.do_sens) {
+    int ok = 1;
+    typename E::Residuals r = E::sens(pd, L, a.dL ? a.dL + (size_t)b * M::NTH : nullptr,
+                                      a.dpi ? a.dpi + (size_t)b * M::NU * M::NTH : nullptr, &ok);
+    cost = r.cost;
+    if (a.res_out) {
+      a.res_out[(size_t)b * 4 + 0] = r.stat;
+      a.res_out[(size_t)b * 4 + 1] = r.eq;
+      a.res_out[(size_t)b * 4 + 2] = r.ineq;
+      a.res_out[(size_t)b * 4 + 3] = r.comp;
+    }
+    const double rmax = dmax(dmax(r.stat, r.eq), dmax(r.ineq, r.comp));
+    if (!(rmax == rmax)) status = ST_NAN;
+    if (!a.do_solve) status = (rmax == rmax) ? (rmax < pd.tol ? ST_OK : ST_MAXITER) : ST_NAN;
+    if (!ok && status == ST_OK) status = ST_QPFAIL;  // reduced Hessian not PD: sensitivities invalid
+  }
+  if (a.u0_out) {
+#pragma unroll
+    for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * L.bs];
+  }
+  if (a.cost_out) a.cost_out[b] = cost;
+  if (a.status_out) a.status_out[b] = status;
+}
+
+// MPC.reset: x_k = x0 for all stages, everything else zero
+template <class M>
+__global__ void k_reset(int N, double* it, size_t bs, int B, const double* x0) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = E::it_size(N);
+  for (int i = 0; i < n; ++i) {
+    double v = 0.0;
+    if (x0 && i < (N + 1) * M::NX) v = x0[(size_t)b * M::NX + (i % M::NX)];
+    it[(size_t)i * bs + b] = v;
+  }
+}
+
+// gather/scatter one field of one stage between the SoA iterate and a row-major [B, dim] buffer
+__global__ void k_copy_field(double* it, size_t bs, int B, int off, int dim, double* buf, int to_iterate) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < dim; ++i) {
+    if (to_iterate)
+      it[(size_t)(off + i) * bs + b] = buf[(size_t)b * dim + i];
+    else
+      buf[(size_t)b * dim + i] = it[(size_t)(off + i) * bs + b];
+  }
+}
+
+// theta [B, nth] row-major -> [nth][bs] batch-minor
+__global__ void k_theta_transpose(const double* in, double* out, int B, int nth, size_t bs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < nth; ++i) out[(size_t)i * bs + b] = in[(size_t)b * nth + i];
+}
+
+// acc[j] += sum_b td_b * dQ[b, j] over valid samples; acc[nth] += sum td; acc[nth+1] += count
+__global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, const int* status, double* acc) {
+  extern __shared__ double sm[];  // [nth + 2]
+  for (int j = threadIdx.x; j < nth + 2; j += blockDim.x) sm[j] = 0.0;
+  __syncthreads();
+  // each warp walks rows; lanes walk theta entries (dQ is row-major [B, nth]: coalesced along j)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    if (status && status[b] != 0) continue;
+    const double t = td[b];
+    for (int j = lane; j < nth; j += 32) atomicAdd(&sm[j], t * dQ[(size_t)b * nth + j]);
+    if (lane == 0) {
+      atomicAdd(&sm[nth], t);
+      atomicAdd(&sm[nth + 1], 1.0);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nth + 2; j += blockDim.x)
+    if (sm[j] != 0.0) atomicAdd(&acc[j], sm[j]);
+}
+
+}  // namespace
+
+struct rlmpc_handle {
+  int model, device, max_batch;
+  size_t bs;
+  int nx, nu, nth, it_size, ws_size;
+  ProblemData pd;
+  double *it = nullptr, *ws = nullptr, *th = nullptr, *th_stage = nullptr;
+  int th_per_sample = 0;
+  long long launches = 0;
+  // staging for the host-buffer entry point
+  double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+  int *h_status = nullptr, *d_status = nullptr;
+  cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+template <class M>
+int launch_unit(rlmpc_handle* h, const KArgs& a, cudaStream_t s) {
+  const int grid = (a.B + TPB - 1) / TPB;
+  k_unit<M><<<grid, TPB, 0, s>>>(h->pd, a);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int check_batch(rlmpc_handle* h, int B) {
+  if (!h) return fail(RLMPC_EINVAL, "null handle");
+  if (B < 0 || B > h->max_batch) return fail(RLMPC_EINVAL, "batch exceeds max_batch");
+  return 0;
+}
+
+int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, const double* u0, double* u0_out,
+             double* cost_out, int* status_out, double* dL, double* dpi, double* res_out, int do_solve, int do_sens,
+             cudaStream_t s) {
+  if (int r = check_batch(h, B)) return r;
+  if (B == 0) return 0;
+  if (mode != RLMPC_MODE_V && mode != RLMPC_MODE_Q) return fail(RLMPC_EINVAL, "bad mode");
+  if (do_solve && !x0) return fail(RLMPC_EINVAL, "x0 is required");
+  if (do_solve && mode == RLMPC_MODE_Q && !u0) return fail(RLMPC_EINVAL, "u0 is required in Q-mode");
+  CUDA_OK(cudaSetDevice(h->device));
+  h->pd.mode = mode;
+  h->pd.max_sqp = max_sqp;
+  KArgs a;
+  a.it = h->it; a.ws = h->ws; a.bs = h->bs; a.th = h->th; a.th_per_sample = h->th_per_sample; a.B = B;
+  a.x0 = x0; a.u0 = (mode == RLMPC_MODE_Q) ? u0 : nullptr;
+  a.u0_out = u0_out; a.cost_out = cost_out; a.status_out = status_out;
+  a.dL = dL; a.dpi = dpi; a.res_out = res_out; a.do_solve = do_solve; a.do_sens = do_sens;
+  switch (h->model) {
+    case RLMPC_MODEL_CARTPOLE: return launch_unit<CartpoleModel>(h, a, s);
+  }
+  return fail(RLMPC_EINVAL, "unknown model");
+}
+
+int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* dim) {
+  const int N = h->pd.N;
+  using E = Engine<CartpoleModel>;  // layouts depend only on (NX, NU); dispatch on model when more are added
+  if (h->model != RLMPC_MODEL_CARTPOLE) return fail(RLMPC_EINVAL, "unknown model");
+  if (!strcmp(field, "x")) {
+    if (stage < 0 || stage > N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_x(N, stage); *dim = E::NX;
+  } else if (!strcmp(field, "u")) {
+    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_u(N, stage); *dim = E::NU;
+  } else if (!strcmp(field, "pi")) {
+    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_pi(N, stage); *dim = E::NX;
+  } else if (!strcmp(field, "lam")) {
+    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_lu(N, stage); *dim = 2 * E::NU;
+  } else if (!strcmp(field, "t")) {
+    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_tu(N, stage); *dim = 2 * E::NU;
+  } else if (!strcmp(field, "rho_x0")) {
+    *off = E::it_rx0(N); *dim = E::NX;
+  } else if (!strcmp(field, "rho_u0")) {
+    *off = E::it_ru0(N); *dim = E::NU;
+  } else {
+    return fail(RLMPC_EINVAL, std::string("unknown field ") + field);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rlmpc_last_error(void) { return g_err.c_str(); }
+
+int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_handle** out) {
+  if (!d || !out || max_batch <= 0) return fail(RLMPC_EINVAL, "bad arguments");
+  if (d->N < 1 || d->N > RLMPC_MAXN) return fail(RLMPC_EINVAL, "N out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(RLMPC_ENODEV, "no CUDA device: rlmpc_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(RLMPC_EINVAL, "bad device index");
+  rlmpc_handle* h = new (std::nothrow) rlmpc_handle();
+  if (!h) return fail(RLMPC_ENOMEM, "out of host memory");
+  h->model = d->model;
+  h->device = device;
+  h->max_batch = max_batch;
+  h->bs = ((size_t)max_batch + 127) / 128 * 128;
+  switch (d->model) {
+    case RLMPC_MODEL_CARTPOLE: {
+      using E = Engine<CartpoleModel>;
+      h->nx = E::NX; h->nu = E::NU; h->nth = CartpoleModel::NTH;
+      h->it_size = E::it_size(d->N); h->ws_size = E::ws_size(d->N);
+      break;
+    }
+    default:
+      delete h;
+      return fail(RLMPC_EINVAL, "unknown model");
+  }
+  ProblemData& pd = h->pd;
+  memset(&pd, 0, sizeof(pd));
+  pd.N = d->N;
+  pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 0; pd.param_cost = 0;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0;
+  memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
+  memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
+  memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
+  memcpy(pd.lbx_e, d->lbx_e, sizeof(pd.lbx_e)); memcpy(pd.ubx_e, d->ubx_e, sizeof(pd.ubx_e));
+  memcpy(pd.mc, d->model_const, sizeof(pd.mc));
+  cudaError_t e = cudaSetDevice(device);
+  const size_t nio_in = (size_t)max_batch * (h->nx + h->nu);
+  const size_t nio_out = (size_t)max_batch * (h->nu + 1 + 4 + (size_t)h->nth * (1 + h->nu));
+  if (e == cudaSuccess) e = cudaMalloc(&h->it, sizeof(double) * h->it_size * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws, sizeof(double) * h->ws_size * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->th, sizeof(double) * h->nth * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->th_stage, sizeof(double) * h->nth * (size_t)max_batch);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int) * max_batch);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, sizeof(double) * nio_in);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(double) * nio_out);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_status, sizeof(int) * max_batch);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemset(h->it, 0, sizeof(double) * h->it_size * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->ws, 0, sizeof(double) * h->ws_size * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->th, 0, sizeof(double) * h->nth * h->bs);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("allocation failed: ") + cudaGetErrorString(e);
+    rlmpc_destroy(h);
+    return fail(e == cudaErrorMemoryAllocation ? RLMPC_ENOMEM : RLMPC_ECUDA, msg);
+  }
+  *out = h;
+  return 0;
+}
+
+void rlmpc_destroy(rlmpc_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->it); cudaFree(h->ws); cudaFree(h->th); cudaFree(h->th_stage);
+  cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_status);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* iterate_size) {
+  if (!h) return fail(RLMPC_EINVAL, "null handle");
+  if (nx) *nx = h->nx;
+  if (nu) *nu = h->nu;
+  if (ntheta) *ntheta = h->nth;
+  if (iterate_size) *iterate_size = h->it_size;
+  return 0;
+}
+
+int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, int B) {
+  if (!h || !theta_host) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (!per_sample) {
+    CUDA_OK(cudaMemcpy(h->th, theta_host, sizeof(double) * h->nth, cudaMemcpyHostToDevice));
+    h->th_per_sample = 0;
+    return 0;
+  }
+  if (int r = check_batch(h, B)) return r;
+  CUDA_OK(cudaMemcpy(h->th_stage, theta_host, sizeof(double) * h->nth * (size_t)B, cudaMemcpyHostToDevice));
+  k_theta_transpose<<<(B + 127) / 128, 128>>>(h->th_stage, h->th, B, h->nth, h->bs);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  h->th_per_sample = 1;
+  return 0;
+}
+
+int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n) {
+  if (!h || !scale || n != h->pd.N + 1) return fail(RLMPC_EINVAL, "scale must have N+1 entries");
+  memcpy(h->pd.scale, scale, sizeof(double) * n);
+  return 0;
+}
+
+int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n) {
+  if (!h || !field || !v || n < 0 || n > RLMPC_MAXD) return fail(RLMPC_EINVAL, "bad arguments");
+  double* dst = nullptr;
+  if (!strcmp(field, "lbu")) dst = h->pd.lbu;
+  else if (!strcmp(field, "ubu")) dst = h->pd.ubu;
+  else if (!strcmp(field, "lbx")) dst = h->pd.lbx;
+  else if (!strcmp(field, "ubx")) dst = h->pd.ubx;
+  else if (!strcmp(field, "lbx_e")) dst = h->pd.lbx_e;
+  else if (!strcmp(field, "ubx_e")) dst = h->pd.ubx_e;
+  else return fail(RLMPC_EINVAL, std::string("unknown bound field ") + field);
+  memcpy(dst, v, sizeof(double) * n);
+  return 0;
+}
+
+int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
+  if (!h || !name) return fail(RLMPC_EINVAL, "bad arguments");
+  if (!strcmp(name, "tol")) h->pd.tol = value;
+  else if (!strcmp(name, "tau")) h->pd.tau = value;
+  else if (!strcmp(name, "mu0")) h->pd.mu0 = value;
+  else if (!strcmp(name, "max_ipm")) h->pd.max_ipm = (int)value;
+  else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
+  else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;
+  else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
+  return 0;
+}
+
+int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream) {
+  if (int r = check_batch(h, B)) return r;
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  switch (h->model) {
+    case RLMPC_MODEL_CARTPOLE:
+      k_reset<CartpoleModel><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, h->bs, B, x0_dev);
+      break;
+    default: return fail(RLMPC_EINVAL, "unknown model");
+  }
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, double* buf_dev, void* stream) {
+  if (int r = check_batch(h, B)) return r;
+  if (!field || !buf_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  int off, dim;
+  if (int r = field_offset(h, field, stage, &off, &dim)) return r;
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->bs, B, off, dim, buf_dev, 0);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, const double* buf_dev, void* stream) {
+  if (int r = check_batch(h, B)) return r;
+  if (!field || !buf_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  int off, dim;
+  if (int r = field_offset(h, field, stage, &off, &dim)) return r;
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->bs, B, off, dim, const_cast<double*>(buf_dev), 1);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_solve(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
+                double* u0_out_dev, double* cost_out_dev, int* status_out_dev, void* stream) {
+  return run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, nullptr, nullptr,
+                  nullptr, 1, 0, (cudaStream_t)stream);
+}
+
+int rlmpc_sens(rlmpc_handle* h, int mode, int B, double* dL_dtheta_dev, double* dpi_dtheta_dev, double* cost_out_dev,
+               double* res_out_dev, int* status_out_dev, void* stream) {
+  return run_unit(h, mode, h ? h->pd.max_sqp : 1, B, nullptr, nullptr, nullptr, cost_out_dev, status_out_dev,
+                  dL_dtheta_dev, dpi_dtheta_dev, res_out_dev, 0, 1, (cudaStream_t)stream);
+}
+
+int rlmpc_solve_sens(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
+                     double* u0_out_dev, double* cost_out_dev, int* status_out_dev, double* dL_dtheta_dev,
+                     double* dpi_dtheta_dev, double* res_out_dev, void* stream) {
+  return run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, dL_dtheta_dev,
+                  dpi_dtheta_dev, res_out_dev, 1, 1, (cudaStream_t)stream);
+}
+
+int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_host, const double* u0_host,
+                          double* u0_out_host, double* cost_out_host, int* status_out_host, double* dL_dtheta_host,
+                          double* dpi_dtheta_host, double* res_out_host) {
+  if (int r = check_batch(h, B)) return r;
+  if (B == 0) return 0;
+  if (!x0_host) return fail(RLMPC_EINVAL, "x0 is required");
+  if (mode == RLMPC_MODE_Q && !u0_host) return fail(RLMPC_EINVAL, "u0 is required in Q-mode");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = h->own_stream;
+  const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->nth;
+  // stage inputs through pinned memory so the copies are real DMA transfers
+  memcpy(h->h_in, x0_host, sizeof(double) * nB * nx);
+  if (u0_host) memcpy(h->h_in + nB * nx, u0_host, sizeof(double) * nB * nu);
+  CUDA_OK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(double) * nB * (nx + (u0_host ? nu : 0)), cudaMemcpyHostToDevice, s));
+  double* d_u0o = h->d_out;
+  double* d_cost = d_u0o + nB * nu;
+  double* d_res = d_cost + nB;
+  double* d_dL = d_res + nB * 4;
+  double* d_dpi = d_dL + nB * nth;
+  const size_t n_out = nB * (nu + 1 + 4 + nth * (1 + nu));
+  CUDA_OK(cudaMemsetAsync(d_dL, 0, sizeof(double) * nB * nth * (1 + nu), s));
+  if (int r = run_unit(h, mode, max_sqp, B, h->d_in, u0_host ? h->d_in + nB * nx : nullptr, d_u0o, d_cost, h->d_status,
+                       d_dL, d_dpi, d_res, 1, 1, s))
+    return r;
+  CUDA_OK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int) * nB, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  const double* o = h->h_out;
+  if (u0_out_host) memcpy(u0_out_host, o, sizeof(double) * nB * nu);
+  if (cost_out_host) memcpy(cost_out_host, o + nB * nu, sizeof(double) * nB);
+  if (res_out_host) memcpy(res_out_host, o + nB * (nu + 1), sizeof(double) * nB * 4);
+  if (dL_dtheta_host) memcpy(dL_dtheta_host, o + nB * (nu + 5), sizeof(double) * nB * nth);
+  if (dpi_dtheta_host) memcpy(dpi_dtheta_host, o + nB * (nu + 5 + nth), sizeof(double) * nB * nth * nu);
+  if (status_out_host) memcpy(status_out_host, h->h_status, sizeof(int) * nB);
+  return 0;
+}
+
+int rlmpc_td_grad(rlmpc_handle* h, int B, const double* td_dev, const double* dQ_dtheta_dev, const int* status_dev,
+                  double* acc_out_dev, void* stream) {
+  if (int r = check_batch(h, B)) return r;
+  if (!td_dev || !dQ_dtheta_dev || !acc_out_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_OK(cudaMemsetAsync(acc_out_dev, 0, sizeof(double) * (h->nth + 2), s));
+  if (B == 0) return 0;
+  const int threads = 256, nwarp = threads / 32;
+  int grid = (B + nwarp - 1) / nwarp;
+  if (grid > 148 * 4) grid = 148 * 4;
+  k_td_grad<<<grid, threads, sizeof(double) * (h->nth + 2), s>>>(B, h->nth, td_dev, dQ_dtheta_dev, status_dev, acc_out_dev);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+long long rlmpc_launch_count(const rlmpc_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

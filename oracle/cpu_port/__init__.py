@@ -1,0 +1,101 @@
+"""ctypes loader of the host build of the engine (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Not an independent checker (shares engine.cuh with the CUDA product): used to debug the
+templates on a box without a GPU and as bench.py's ``cpu_baseline`` of kind "port".
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+MAXN, MAXD = 128, 8
+
+
+class ProblemData(C.Structure):
+    """Mirror of rlmpc::ProblemData (mpc4rl_b200/csrc/common.cuh)."""
+    _fields_ = [
+        ("N", C.c_int), ("mode", C.c_int), ("max_sqp", C.c_int), ("max_ipm", C.c_int),
+        ("warm_ipm", C.c_int), ("param_cost", C.c_int),
+        ("tol", C.c_double), ("tau", C.c_double), ("mu0", C.c_double),
+        ("scale", C.c_double * (MAXN + 1)),
+        ("lbu", C.c_double * MAXD), ("ubu", C.c_double * MAXD),
+        ("lbx", C.c_double * MAXD), ("ubx", C.c_double * MAXD),
+        ("lbx_e", C.c_double * MAXD), ("ubx_e", C.c_double * MAXD),
+        ("mc", C.c_double * 8),
+    ]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_DIR, "libcpu_port.so")
+    if force or not os.path.exists(so):
+        subprocess.run(["make", "-C", _DIR, "-B" if force else "-s"], check=True, capture_output=True)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = build()
+        try:
+            _lib = C.CDLL(so)
+        except OSError:
+            _lib = C.CDLL(build(force=True))
+        assert _lib.cpu_port_sizeof_problem_data() == C.sizeof(ProblemData), "ProblemData layout mismatch"
+    return _lib
+
+
+def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0) -> ProblemData:
+    pd = ProblemData()
+    pd.N = N; pd.max_ipm = max_ipm; pd.warm_ipm = warm_ipm; pd.param_cost = param_cost
+    pd.tol = tol; pd.tau = tau; pd.mu0 = mu0
+    for i, v in enumerate(scale):
+        pd.scale[i] = v
+    for i in range(MAXD):
+        pd.lbx[i] = pd.lbx_e[i] = -1e30
+        pd.ubx[i] = pd.ubx_e[i] = 1e30
+    for i, v in enumerate(lbu):
+        pd.lbu[i] = v
+    for i, v in enumerate(ubu):
+        pd.ubu[i] = v
+    for i, v in enumerate(mc):
+        pd.mc[i] = v
+    return pd
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def unit(model: int, pd: ProblemData, mode: int, max_sqp: int, theta, x0, u0=None, iterate=None, nx=4, nu=1,
+         do_solve=True, do_sens=True, threads=0):
+    """Run solve(+sens) for a batch on the host.  Returns a dict of row-major outputs and the iterate."""
+    L = lib()
+    L.cpu_port_set_threads(int(threads))
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    per_sample = int(theta.ndim == 2)
+    nth = theta.shape[-1]
+    itsz = L.cpu_port_iterate_size(model, pd.N)
+    if iterate is None:  # MPC.reset: all stages = x0
+        iterate = np.zeros((itsz, B))
+        for k in range(pd.N + 1):
+            iterate[k * nx:(k + 1) * nx, :] = x0.T
+    iterate = np.ascontiguousarray(iterate)
+    u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, nu)
+    out = dict(u0=np.zeros((B, nu)), cost=np.zeros(B), status=np.zeros(B, dtype=np.int32), dL=np.zeros((B, nth)),
+               dpi=np.zeros((B, nu, nth)), res=np.zeros((B, 4)), iters=np.zeros((B, 2), dtype=np.int32))
+    r = L.cpu_port_unit(C.c_int(model), C.byref(pd), C.c_int(mode), C.c_int(max_sqp), C.c_int(B), _p(theta),
+                        C.c_int(per_sample), _p(x0), _p(u0a), _p(iterate), C.c_int(int(do_solve)), C.c_int(int(do_sens)),
+                        _p(out["u0"]), _p(out["cost"]), _p(out["status"], C.c_int), _p(out["dL"]), _p(out["dpi"]),
+                        _p(out["res"]), _p(out["iters"], C.c_int))
+    assert r == 0
+    out["iterate"] = iterate
+    return out

@@ -1,0 +1,247 @@
+"""Restated problem definitions (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Each ``Problem`` carries what the reference puts into an ``AcadosOcp``: discrete
+dynamics, stage/terminal cost, bounds, the parameter struct ``p`` (layout of
+``rlmpc/mpc/nlp.py:970-989``: ``model, W_0, W, W_e, yref_0, yref, yref_e`` -- only the
+non-empty ones, matrices flattened column-major), horizon and cost scaling.
+Everything is written with torch float64 ops so that every derivative the oracle
+needs comes from torch.func, independently of the hand-derived CUDA code.
+
+Reference files followed:
+  cartpole       rlmpc/mpc/cartpole/acados.py:28-108, config/cartpole*.yaml,
+                 rlmpc/common/integrator.py:6-33
+  linear system  rlmpc/mpc/linear_system/acados.py:27-131
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+F64 = torch.float64
+
+
+def erk4(f: Callable, x, u, pm, h: float):
+    """One explicit RK4 step (rlmpc/common/integrator.py:6-33)."""
+    k1 = f(x, u, pm)
+    k2 = f(x + h / 2 * k1, u, pm)
+    k3 = f(x + h / 2 * k2, u, pm)
+    k4 = f(x + h * k3, u, pm)
+    return x + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+
+
+@dataclass
+class Problem:
+    name: str
+    N: int
+    nx: int
+    nu: int
+    tf: float
+    p_entries: List[Tuple[str, Tuple[int, ...]]]
+    p_nominal: np.ndarray
+    cost_type: str  # "NLS" | "EXTERNAL"
+    hessian_approx: str  # "GAUSS_NEWTON" | "EXACT"
+    f_disc: Callable  # (x, u, p_model) -> x_next
+    gamma: float = 1.0
+    parameterize_tracking_cost: bool = False
+    # NLS pieces (y = y_fun(x,u), y_e = y_e_fun(x)); constants used when not parameterised
+    y_fun: Optional[Callable] = None
+    y_e_fun: Optional[Callable] = None
+    W_0: Optional[np.ndarray] = None
+    W: Optional[np.ndarray] = None
+    W_e: Optional[np.ndarray] = None
+    yref_0: Optional[np.ndarray] = None
+    yref: Optional[np.ndarray] = None
+    yref_e: Optional[np.ndarray] = None
+    # EXTERNAL pieces
+    ext_cost_0: Optional[Callable] = None  # (x,u,pm)
+    ext_cost: Optional[Callable] = None
+    ext_cost_e: Optional[Callable] = None  # (x,pm)
+    # bounds (acados BGH subset the reference uses)
+    idxbu: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    lbu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    ubu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    idxbx: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    lbx: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    ubx: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    idxbx_e: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    lbx_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    ubx_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    idxsbx: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    zl: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    zu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    idxsbx_e: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
+    zl_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    zu_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
+
+    # ---- parameter struct helpers (nlp.py:970-989; CasADi column-major) ----
+    @property
+    def ntheta(self) -> int:
+        return int(sum(int(np.prod(s)) for _, s in self.p_entries))
+
+    def p_slices(self):
+        out, o = {}, 0
+        for name, shape in self.p_entries:
+            n = int(np.prod(shape))
+            out[name] = (slice(o, o + n), shape)
+            o += n
+        return out
+
+    def p_get(self, p, name):
+        sl, shape = self.p_slices()[name]
+        v = p[sl]
+        if len(shape) == 2 and shape[1] > 1:
+            return v.reshape(shape[1], shape[0]).T  # column-major
+        return v.reshape(shape[0]) if len(shape) >= 1 else v
+
+    def p_model(self, p):
+        sl, _ = self.p_slices()["model"]
+        return p[sl]
+
+    @property
+    def dT(self) -> float:
+        return self.tf / self.N
+
+    # ---- cost exactly as build_nlp assembles it (nlp.py:1038-1134) ----
+    def stage_scale(self, k: int) -> float:
+        """Multiplier of the stage-k cost term."""
+        N, g, dT = self.N, self.gamma, self.dT
+        if self.cost_type == "NLS" and not self.parameterize_tracking_cost:
+            return dT if k < N else 1.0  # nlp.py:1044-1055 (no gamma)
+        # parameterised NLS (1057-1074) and EXTERNAL (1084-1091)
+        if k == 0:
+            return dT
+        if k < N:
+            return g**k * dT
+        return g**N
+
+
+def _nls(y, yref, W):
+    e = y - yref
+    return 0.5 * (e @ (W @ e))
+
+
+def stage_cost_unscaled(pb: Problem, k: int, x, u, p):
+    """l_0 / l / l_e of the reference (unscaled)."""
+    if pb.cost_type == "NLS":
+        if pb.parameterize_tracking_cost:
+            if k == 0:
+                return _nls(pb.y_fun(x, u), pb.p_get(p, "yref_0"), pb.p_get(p, "W_0"))
+            if k < pb.N:
+                return _nls(pb.y_fun(x, u), pb.p_get(p, "yref"), pb.p_get(p, "W"))
+            return _nls(pb.y_e_fun(x), pb.p_get(p, "yref_e"), pb.p_get(p, "W_e"))
+        T = lambda a: torch.as_tensor(a, dtype=F64)
+        if k == 0:
+            return _nls(pb.y_fun(x, u), T(pb.yref_0), T(pb.W_0))
+        if k < pb.N:
+            return _nls(pb.y_fun(x, u), T(pb.yref), T(pb.W))
+        return _nls(pb.y_e_fun(x), T(pb.yref_e), T(pb.W_e))
+    pm = pb.p_model(p)
+    if k == 0:
+        return pb.ext_cost_0(x, u, pm)
+    if k < pb.N:
+        return pb.ext_cost(x, u, pm)
+    return pb.ext_cost_e(x, pm)
+
+
+# --------------------------------------------------------------------------------------
+# cartpole  (rlmpc/mpc/cartpole/acados.py:28-108)
+# --------------------------------------------------------------------------------------
+def cartpole_ode(x, u, pm, g: float = 9.8):
+    M, m, l = pm[0], pm[1], pm[2]
+    s_dot, theta, theta_dot = x[1], x[2], x[3]
+    c, sn = torch.cos(theta), torch.sin(theta)
+    temp = (u[0] + m * theta_dot**2 * sn) / (m + M)
+    theta_ddot = (g * sn - c * temp) / (l * (4.0 / 3.0 - m * c**2 / (m + M)))
+    return torch.stack([s_dot, temp - m * theta_ddot * c / (m + M), theta_dot, theta_ddot])
+
+
+def make_cartpole(variant: str = "original", gamma: float = 1.0) -> Problem:
+    """variant 'original' = config/cartpole_original.yaml (N=40, tf=0.8, |u|<=80, no state
+    bounds); 'default' = config/cartpole.yaml (N=30, tf=3.0, |u|<=30, state bounds)."""
+    if variant == "original":
+        N, tf, umax = 40, 0.8, 80.0
+        W = np.diag([200.0, 0.02, 200.0, 0.02, 0.01])
+        W_e = np.diag([200.0, 0.02, 200.0, 0.02])
+        bx = None
+    elif variant == "default":
+        N, tf, umax = 30, 3.0, 30.0
+        W = np.diag([10.0, 0.1, 10.0, 0.1, 0.01])
+        W_e = np.diag([10.0, 0.1, 10.0, 0.1])
+        bx = np.array([2.4, 10.0, 6.28, 10.0])
+    else:
+        raise ValueError(variant)
+    h = tf / N / 4  # quirk Q1: ONE RK4 step of dT / sim_method_num_stages (cartpole/acados.py:86-92)
+    p_entries = [("model", (3,)), ("W_0", (5, 5)), ("W", (5, 5)), ("W_e", (4, 4)),
+                 ("yref_0", (5,)), ("yref", (5,)), ("yref_e", (4,))]
+    p_nom = np.concatenate([[1.0, 0.1, 0.5], W.T.ravel(), W.T.ravel(), W_e.T.ravel(),
+                            np.zeros(5), np.zeros(5), np.zeros(4)])
+    pb = Problem(
+        name=f"cartpole_{variant}", N=N, nx=4, nu=1, tf=tf, p_entries=p_entries, p_nominal=p_nom,
+        cost_type="NLS", hessian_approx="GAUSS_NEWTON", gamma=gamma,
+        f_disc=lambda x, u, pm: erk4(cartpole_ode, x, u, pm, h),
+        y_fun=lambda x, u: torch.cat([x, u]), y_e_fun=lambda x: x,
+        W_0=W, W=W, W_e=W_e, yref_0=np.zeros(5), yref=np.zeros(5), yref_e=np.zeros(4),
+        idxbu=np.array([0]), lbu=np.array([-umax]), ubu=np.array([umax]),
+    )
+    if bx is not None:
+        pb.idxbx = np.arange(4); pb.lbx = -bx; pb.ubx = bx
+        pb.idxbx_e = np.arange(4); pb.lbx_e = -bx; pb.ubx_e = bx
+    return pb
+
+
+# --------------------------------------------------------------------------------------
+# linear system  (rlmpc/mpc/linear_system/acados.py:27-131)
+# --------------------------------------------------------------------------------------
+def linear_system_param_nominal():
+    """tests/test_linear_example.py:9-17 / examples/linear_system_mpc_qlearning.py:109-117"""
+    return {
+        "A": np.array([[1.0, 0.25], [0.0, 1.0]]), "B": np.array([[0.03125], [0.25]]),
+        "Q": np.identity(2), "R": np.identity(1), "b": np.array([[0.0], [0.0]]),
+        "f": np.array([[0.0], [0.0], [0.0]]), "V_0": np.array([1e-3]),
+    }
+
+
+def make_linear_system(param: Optional[dict] = None, gamma: float = 0.99, N: int = 40,
+                       lbx=(-0.0, -1.0), ubx=(1.0, 1.0)) -> Problem:
+    from scipy.linalg import solve_discrete_are
+
+    param = linear_system_param_nominal() if param is None else param
+    P = solve_discrete_are(param["A"], param["B"], param["Q"], param["R"])  # constant (acados.py:51-57)
+    Pt = torch.as_tensor(P, dtype=F64)
+
+    def unpack(pm):
+        A = pm[0:4].reshape(2, 2).T  # column-major (acados.py:60-70)
+        B = pm[4:6]
+        b = pm[6:8]
+        V0 = pm[8]
+        f = pm[9:12]
+        return A, B, b, V0, f
+
+    def f_disc(x, u, pm):
+        A, B, b, _, _ = unpack(pm)
+        return A @ x + B * u[0] + b
+
+    def ext(x, u, pm):
+        _, _, _, _, f = unpack(pm)
+        y = torch.cat([x, u])
+        return 0.5 * (y @ y) + f @ y
+
+    def ext0(x, u, pm):
+        return unpack(pm)[3] + ext(x, u, pm)
+
+    def exte(x, pm):
+        return 0.5 * (x @ (Pt @ x))
+
+    # ocp.parameter_values = concat(param[key].T.reshape(-1,1)) (acados.py:90)
+    p_nom = np.concatenate([np.asarray(param[k], dtype=float).T.reshape(-1) for k in ["A", "B", "b", "V_0", "f"]])
+    return Problem(
+        name="linear_system", N=N, nx=2, nu=1, tf=float(N), p_entries=[("model", (12,))], p_nominal=p_nom,
+        cost_type="EXTERNAL", hessian_approx="EXACT", gamma=gamma, f_disc=f_disc,
+        ext_cost_0=ext0, ext_cost=ext, ext_cost_e=exte,
+        idxbu=np.array([0]), lbu=np.array([-1.0]), ubu=np.array([1.0]),
+        idxbx=np.array([0, 1]), lbx=np.array(lbx, dtype=float), ubx=np.array(ubx, dtype=float),
+        idxsbx=np.array([0]), zl=np.array([1e2]), zu=np.array([1e2]),
+    )
