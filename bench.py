@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric   MPC solves+sensitivities/sec: one unit = for one sample, one SQP-RTI step of the cartpole
+         NMPC (N=40, nx=4, nu=1, config/cartpole_original.yaml) from the stored warm-start iterate
+         PLUS dL/dtheta and dpi/dtheta at the new iterate (= one `update`/`q_update` + one
+         `update_nlp` of the reference).  SURVEY.md 8(d).
+step     one fused launch over a batch of 65 536 synthetic samples per GPU (weak scaling), followed
+         by the TD-gradient accumulator kernel and, for N>1, its NCCL all-reduce.
+value    whole-job units/s with inputs resident in HBM, CUDA-event timed, max over ranks.
+e2e      same metric through the C ABI host entry point (rlmpc_solve_sens_host): pinned host buffers,
+         H2D of the states and D2H of every result inside the timed region (wall clock, max over ranks).
+
+`--impl reference` times the CPU path instead: acados/CasADi are not installable here, so this is the
+oracle's host port of the same structure-exploiting algorithm (oracle/cpu_port, all host threads) --
+"restated, not acados" (BASELINE.md section 3).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MPC solves+sensitivities/sec (cartpole N=40, batch 65k)"
+UNIT = "units/s"
+BATCH = 65536
+B_ALG = 8492  # algorithmic bytes per unit, SURVEY.md 8(d): 8*(2*524 + 4+1 + 1+1+3+3) + 4
+
+
+def synth_states(B, seed):
+    """s~U(-1,1), s_dot~U(-2,2), theta~U(-pi,pi), theta_dot~U(-4,4)."""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    return lo + (-2.0 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)
+
+
+def config_dict(B, n_gpus):
+    return {"workload": "cartpole_original N=40 nx=4 nu=1 ntheta=83 (3 with gradient), V-mode SQP-RTI (K=1) + "
+                        "dL/dtheta + dpi/dtheta, warm-started from the converged iterate, states perturbed every step",
+            "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, replicated theta)",
+            "l2": "working set (iterate 0.29 GB + stage scratch 1.5 GB per GPU) is larger than L2, no flush needed",
+            "seed": 1234}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(n_samples, steps, warmup, threads=0, seed=1234):
+    """RTI + sensitivities on the host (oracle/cpu_port): returns (units/s, threads, seconds per step)."""
+    from oracle import cpu_port as cp
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+
+    spec = cartpole_spec(cartpole_original_config())
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-6)
+    x0 = synth_states(n_samples, seed).numpy()
+    o = cp.unit(1, pd, 0, 30, spec.p_nominal, x0, threads=threads)  # converge (untimed)
+    it = o["iterate"]
+    rng = np.random.default_rng(seed)
+    ts = []
+    for s in range(warmup + steps):
+        x1 = x0 + 1e-3 * rng.standard_normal(x0.shape)
+        t0 = time.perf_counter()
+        o = cp.unit(1, pd, 0, 1, spec.p_nominal, x1, iterate=it, threads=threads)
+        dt = time.perf_counter() - t0
+        it = o["iterate"]
+        if s >= warmup:
+            ts.append(dt)
+    nthreads = cp.lib().cpu_port_get_threads() if threads == 0 else threads
+    return n_samples * len(ts) / sum(ts), nthreads, sum(ts) / len(ts)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = 16384
+    val, cores, sec = cpu_port_run(n, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(BATCH, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} samples of the same workload per step (bounded sample of the 65536 batch); "
+                                       "restated structure-exploiting SQP-RTI + adjoint sensitivities in C++, NOT acados"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    spec = cartpole_spec(cartpole_original_config())
+    mpc = BatchedMPC(spec, max_batch=B, device=local_rank)
+    x0 = synth_states(B, 1234 + rank).to(dev)
+    # untimed setup: converge the batch once (cold start like MPC.reset), this is the warm-start state
+    mpc.set_option("tol", 1e-6)
+    mpc.reset(x0)
+    _, _, st = mpc.solve(x0, max_sqp=60)
+    torch.cuda.synchronize()
+    conv_frac = float((st == 0).double().mean().item())
+    n_steps = args.warmup + args.steps
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    # every step sees fresh states: the converged ones moved by a small "environment step"
+    xs = [(x0 + 1e-3 * torch.randn(B, 4, generator=g, dtype=torch.float64).to(dev)) for _ in range(n_steps)]
+    td = torch.randn(B, generator=g, dtype=torch.float64).to(dev)
+    out = mpc.alloc_outputs(B)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        mpc.solve_sens(xs[i], max_sqp=1, out=out)
+        acc = mpc.td_grad(td, out["dL"], out["status"])
+        if dist is not None:
+            dist.all_reduce(acc)
+        return acc
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    l0 = mpc.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clk:
+        ev[0].record(stream)
+        for i in range(args.steps):
+            kev[i][0].record(stream)
+            mpc.solve_sens(xs[args.warmup + i], max_sqp=1, out=out)
+            kev[i][1].record(stream)
+            acc = mpc.td_grad(td, out["dL"], out["status"])
+            if dist is not None:
+                dist.all_reduce(acc)
+            ev[i + 1].record(stream)
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        time.sleep(0.25)
+    launches = mpc.launch_count - l0
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ok_frac = float((out["status"] == 0).double().mean().item())
+    res_max = float(out["res"].max().item())
+
+    # ---- e2e: host buffers through the C ABI, every step ----
+    xs_host = [x.cpu().numpy() for x in xs]
+    mpc.reset(x0)
+    mpc.solve(x0, max_sqp=60)
+    for i in range(args.warmup):
+        mpc.solve_sens_host(xs_host[i], max_sqp=1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o = mpc.solve_sens_host(xs_host[args.warmup + i], max_sqp=1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = B * 4 * 8
+    d2h = B * ((1 + 1 + 4 + 3 + 3) * 8 + 4)
+
+    tt = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kernel_ms = (float(v) for v in tt.tolist())
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        units = B * world * args.steps
+        value = units / (total_ms * 1e-3)
+        achieved = B * B_ALG / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(B, world),
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_unit<CartpoleModel>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_unit": B_ALG,
+                         "note": "path is FP64 CUDA-core/latency bound, not HBM bound (SURVEY.md 8(d)); "
+                                 "fraction reported as defined, bytes not padded"},
+            "quality": {"status0_frac_after_setup": conv_frac, "status0_frac_last_step": ok_frac, "kkt_res_max_last_step": res_max},
+        }
+        if world == 1 and not args.no_cpu:
+            cval, cores, csec = cpu_port_run(args.cpu_samples, 3, 1)
+            line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_samples} samples of the same workload x 3 steps ({csec:.2f} s per step); "
+                                              "restated structure-exploiting C++ port (oracle/cpu_port), NOT acados"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
+    ap.add_argument("--cpu-samples", type=int, default=16384)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,8 +63,9 @@ typedef struct rlmpc_problem_desc {
 int rlmpc_create(const rlmpc_problem_desc* desc, int max_batch, int device, rlmpc_handle** out);
 void rlmpc_destroy(rlmpc_handle* h);
 const char* rlmpc_last_error(void);
-/* dims: nx, nu, ntheta (length of the reference's p vector, nlp.py:970-989), iterate doubles per sample */
-int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* iterate_size);
+/* dims: nx, nu, ntheta (length of the reference's p vector, nlp.py:970-989), ngrad (width of the
+ * gradient rows, see rlmpc_sens), iterate doubles per sample */
+int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* ngrad, int* iterate_size);
 
 /* ---- parameters / options --------------------------------------------------------------- */
 /* Replaces ocp_solver.set(stage,"p",..) for all stages + cost_set(stage,"W"/"yref",..)
@@ -99,9 +100,11 @@ int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, cons
 int rlmpc_solve(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
                 double* u0_out_dev, double* cost_out_dev, int* status_out_dev, void* stream);
 /* Replaces update_nlp() (nlp.py:1341-1563) at the current iterate: cost, KKT residual norms
- * [stat, eq, ineq, comp], dL/dtheta [B, ntheta] (= dV/dtheta = dQ/dtheta) and
- * dpi/dtheta [B, nu, ntheta].  Output rows must be zero-initialised by the caller; entries that
- * are structurally zero are not written. */
+ * [stat, eq, ineq, comp], dL/dtheta [B, ngrad] (= dV/dtheta = dQ/dtheta) and
+ * dpi/dtheta [B, nu, ngrad].  ngrad = number of model parameters when option "param_cost" is 0
+ * (build_nlp(parameterize_tracking_cost=False): every other entry of p has zero gradient, quirk
+ * Q8 -- the rows are the non-zero prefix of the reference's [1, ntheta] arrays), = ntheta when it
+ * is 1 (rows must then be zero-initialised by the caller). */
 int rlmpc_sens(rlmpc_handle* h, int mode, int B, double* dL_dtheta_dev, double* dpi_dtheta_dev,
                double* cost_out_dev, double* res_out_dev, int* status_out_dev, void* stream);
 /* One fused launch: solve + sens (one "unit" of BASELINE.json's metric). */
@@ -116,10 +119,11 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
 
 /* ---- TD / policy-gradient accumulator ------------------------------------------------------ */
 /* Replaces  dp = mean_i(LR * td_i * dQ_dp_i)  (examples/linear_system_mpc_qlearning.py:193,203):
- * acc_out_dev[0..ntheta) = sum_i td_i * dQ_dtheta[i,:], acc[ntheta] = sum_i td_i, acc[ntheta+1] =
- * number of valid samples (status 0).  The caller all-reduces acc over ranks (NCCL). */
-int rlmpc_td_grad(rlmpc_handle* h, int B, const double* td_dev, const double* dQ_dtheta_dev, const int* status_dev,
-                  double* acc_out_dev, void* stream);
+ * dQ_dtheta_dev is [B, ncols]; acc_out_dev[0..ncols) = sum_i td_i * dQ_dtheta[i,:], acc[ncols] =
+ * sum_i td_i, acc[ncols+1] = number of valid samples (status 0; status_dev may be NULL).  The
+ * caller all-reduces acc over ranks (NCCL) and divides. */
+int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const double* dQ_dtheta_dev,
+                  const int* status_dev, double* acc_out_dev, void* stream);
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);

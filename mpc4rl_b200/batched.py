@@ -1,0 +1,193 @@
+"""Batched MPC engine: torch CUDA tensors in, torch CUDA tensors out, stream-ordered, FP64.
+
+This is the *new* API of SURVEY.md 8(b): one call evaluates a whole replay-buffer minibatch
+(what the reference does with a Python loop over samples, e.g.
+rlmpc/examples/linear_system_mpc_qlearning.py:178-190, rlmpc/td3/policies.py:197).
+torch is used for device memory and streams only; all arithmetic happens in the CUDA library
+behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .problems import ProblemSpec
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedMPC:
+    def __init__(self, spec: ProblemSpec, max_batch: int, device: int | torch.device = 0):
+        self.spec = spec
+        self.lib = _cabi.load()
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise RuntimeError("BatchedMPC runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device visible: mpc4rl_b200 has no CPU fallback")
+        self.device = dev
+        self.max_batch = int(max_batch)
+        self._h = C.c_void_p()
+        desc = spec.to_desc()
+        _cabi.check(self.lib.rlmpc_create(C.byref(desc), self.max_batch, dev.index or 0, C.byref(self._h)))
+        self.nx, self.nu, self.ntheta = spec.nx, spec.nu, spec.ntheta
+        self.theta = np.array(spec.p_nominal, dtype=np.float64)
+        self.set_theta(self.theta)
+        self.param_cost = bool(spec.parameterize_tracking_cost)
+        self.set_option("param_cost", 1.0 if self.param_cost else 0.0)
+
+    @property
+    def ngrad(self) -> int:
+        """Width of the gradient rows: the model parameters (the only entries of the reference's p
+        with non-zero gradient when parameterize_tracking_cost=False, quirk Q8) or all of p."""
+        return self.ntheta if self.param_cost else self.spec.np_model
+
+    def full_grad(self, g: torch.Tensor) -> torch.Tensor:
+        """Pad [..., ngrad] gradient rows to the reference's [..., ntheta] layout."""
+        if g.shape[-1] == self.ntheta:
+            return g
+        return torch.nn.functional.pad(g, (0, self.ntheta - g.shape[-1]))
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.rlmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk_in(self, t: torch.Tensor, cols: int, name: str) -> torch.Tensor:
+        if not (t.is_cuda and t.dtype == torch.float64):
+            raise TypeError(f"{name} must be a float64 CUDA tensor")
+        if t.dim() != 2 or t.shape[1] != cols:
+            raise ValueError(f"{name} must have shape [B, {cols}], got {tuple(t.shape)}")
+        return t.contiguous()
+
+    # ---- parameters ----
+    def set_theta(self, theta) -> None:
+        """theta: [ntheta] shared by the batch, or [B, ntheta] per sample."""
+        th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
+        if th.shape[-1] != self.ntheta:
+            raise ValueError(f"theta must have {self.ntheta} entries per sample")
+        per = int(th.ndim == 2)
+        _cabi.check(self.lib.rlmpc_set_theta(self._h, th.ctypes.data_as(C.c_void_p), per, th.shape[0] if per else 0))
+        self.theta = th
+
+    def set_option(self, name: str, value: float) -> None:
+        _cabi.check(self.lib.rlmpc_set_option(self._h, name.encode(), float(value)))
+        if name == "param_cost":
+            self.param_cost = bool(value)
+
+    def set_cost_scaling(self, scale) -> None:
+        s = np.ascontiguousarray(np.asarray(scale, dtype=np.float64))
+        _cabi.check(self.lib.rlmpc_set_cost_scaling(self._h, s.ctypes.data_as(C.c_void_p), len(s)))
+
+    def set_bounds(self, field: str, v) -> None:
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+        _cabi.check(self.lib.rlmpc_set_bounds(self._h, field.encode(), a.ctypes.data_as(C.c_void_p), len(a)))
+
+    # ---- iterate ----
+    def reset(self, x0: Optional[torch.Tensor] = None, B: Optional[int] = None) -> None:
+        if x0 is not None:
+            x0 = self._chk_in(x0, self.nx, "x0")
+            B = x0.shape[0]
+        _cabi.check(self.lib.rlmpc_reset(self._h, int(B), _ptr(x0), self._stream()))
+
+    def get(self, field: str, stage: int, B: int) -> torch.Tensor:
+        dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": 2 * self.nu, "t": 2 * self.nu,
+               "rho_x0": self.nx, "rho_u0": self.nu}[field]
+        out = torch.empty(B, dim, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.rlmpc_get_iterate(self._h, field.encode(), int(stage), int(B), _ptr(out), self._stream()))
+        return out
+
+    def put(self, field: str, stage: int, value: torch.Tensor) -> None:
+        value = value.contiguous()
+        _cabi.check(self.lib.rlmpc_put_iterate(self._h, field.encode(), int(stage), value.shape[0], _ptr(value), self._stream()))
+
+    # ---- hot path ----
+    def solve(self, x0: torch.Tensor, u0: Optional[torch.Tensor] = None, max_sqp: int = 1):
+        """V-mode if u0 is None else Q-mode.  Returns (u0 [B,nu], cost [B], status [B] int32)."""
+        x0 = self._chk_in(x0, self.nx, "x0")
+        B = x0.shape[0]
+        mode = _cabi.MODE_V if u0 is None else _cabi.MODE_Q
+        if u0 is not None:
+            u0 = self._chk_in(u0, self.nu, "u0")
+        uo = torch.empty(B, self.nu, dtype=torch.float64, device=self.device)
+        cost = torch.empty(B, dtype=torch.float64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.rlmpc_solve(self._h, mode, int(max_sqp), B, _ptr(x0), _ptr(u0), _ptr(uo), _ptr(cost),
+                                         _ptr(status), self._stream()))
+        return uo, cost, status
+
+    def sens(self, B: int, qmode: bool = False):
+        """update_nlp at the current iterate: (dL_dtheta [B,ngrad], dpi_dtheta [B,nu,ngrad], cost, res [B,4], status)."""
+        dL = torch.zeros(B, self.ngrad, dtype=torch.float64, device=self.device)
+        dpi = torch.zeros(B, self.nu, self.ngrad, dtype=torch.float64, device=self.device)
+        cost = torch.empty(B, dtype=torch.float64, device=self.device)
+        res = torch.empty(B, 4, dtype=torch.float64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        _cabi.check(self.lib.rlmpc_sens(self._h, _cabi.MODE_Q if qmode else _cabi.MODE_V, int(B), _ptr(dL), _ptr(dpi),
+                                        _ptr(cost), _ptr(res), _ptr(status), self._stream()))
+        return dL, dpi, cost, res, status
+
+    def solve_sens(self, x0: torch.Tensor, u0: Optional[torch.Tensor] = None, max_sqp: int = 1, out: dict | None = None):
+        """One fused launch = one unit of the headline metric per sample."""
+        x0 = self._chk_in(x0, self.nx, "x0")
+        B = x0.shape[0]
+        mode = _cabi.MODE_V if u0 is None else _cabi.MODE_Q
+        if u0 is not None:
+            u0 = self._chk_in(u0, self.nu, "u0")
+        if out is None:
+            out = self.alloc_outputs(B)
+        elif self.param_cost:
+            out["dL"].zero_(); out["dpi"].zero_()
+        _cabi.check(self.lib.rlmpc_solve_sens(self._h, mode, int(max_sqp), B, _ptr(x0), _ptr(u0), _ptr(out["u0"]),
+                                              _ptr(out["cost"]), _ptr(out["status"]), _ptr(out["dL"]), _ptr(out["dpi"]),
+                                              _ptr(out["res"]), self._stream()))
+        return out
+
+    def alloc_outputs(self, B: int) -> dict:
+        f64 = dict(dtype=torch.float64, device=self.device)
+        return dict(u0=torch.empty(B, self.nu, **f64), cost=torch.empty(B, **f64),
+                    status=torch.empty(B, dtype=torch.int32, device=self.device),
+                    dL=torch.zeros(B, self.ngrad, **f64), dpi=torch.zeros(B, self.nu, self.ngrad, **f64),
+                    res=torch.empty(B, 4, **f64))
+
+    def solve_sens_host(self, x0: np.ndarray, u0: Optional[np.ndarray] = None, max_sqp: int = 1) -> dict:
+        """Host buffers in/out through the C ABI (H2D + kernels + D2H + sync inside the call)."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        mode = _cabi.MODE_V if u0 is None else _cabi.MODE_Q
+        u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, self.nu)
+        out = dict(u0=np.empty((B, self.nu)), cost=np.empty(B), status=np.empty(B, dtype=np.int32),
+                   dL=np.empty((B, self.ngrad)), dpi=np.empty((B, self.nu, self.ngrad)), res=np.empty((B, 4)))
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        _cabi.check(self.lib.rlmpc_solve_sens_host(self._h, mode, int(max_sqp), B, p(x0), p(u0a), p(out["u0"]),
+                                                   p(out["cost"]), p(out["status"]), p(out["dL"]), p(out["dpi"]),
+                                                   p(out["res"])))
+        return out
+
+    def td_grad(self, td: torch.Tensor, dQ: torch.Tensor, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[sum_i td_i dQ_i/dtheta (ncols), sum_i td_i, n_valid] over samples with status 0."""
+        B, ncols = td.shape[0], dQ.shape[1]
+        acc = torch.empty(ncols + 2, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.rlmpc_td_grad(self._h, B, ncols, _ptr(td.contiguous()), _ptr(dQ.contiguous()),
+                                           _ptr(status), _ptr(acc), self._stream()))
+        return acc
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rlmpc_launch_count(self._h))

@@ -368,7 +368,7 @@ struct Engine {
             const double cl = lu[i] * itl, cu = lu[NU + i] * itu;
             Hm[(NX + i) * NW + NX + i] += cl + cu;
             // J'(target/t + lam + C*hbar), hbar_l = lb - u, hbar_u = u - ub
-            gr[i] += -(target * itl + lu[i] + cl * (pd.lbu[i] - u[i])) + (target * itu + lu[NU + i] + cu * (u[i] - pd.ubu[i]));
+            gr[i] += -(target * itl + lu[i] - cl * (u[i] - pd.lbu[i])) + (target * itu + lu[NU + i] - cu * (pd.ubu[i] - u[i]));
           }
           if (!riccati_step(P, p, A, B, bb, Hm, gq, gr, K, kff, nullptr)) failed = true;
         } else {
@@ -400,8 +400,10 @@ struct Engine {
           ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
           ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
           MPC_UNROLL for (int i = 0; i < NU; ++i) {
-            th[i] = u[i] + du[i] - pd.lbu[i];
-            th[NU + i] = pd.ubu[i] - u[i] - du[i];
+            // (u - lb) + du, NOT (u + du) - lb: the slack must use the same rounded distance to the
+            // bound as the condensed gradient above, or lam_hat picks up c*ulp(u) ~ 1e-8 of noise
+            th[i] = (u[i] - pd.lbu[i]) + du[i];
+            th[NU + i] = (pd.ubu[i] - u[i]) - du[i];
           }
           MPC_UNROLL for (int i = 0; i < 2 * NU; ++i) {
             const double it_ = 1.0 / tu[i];
@@ -430,7 +432,7 @@ struct Engine {
       if (failed || !(amax == amax)) break;
       alpha = (amax >= 1.0 / 0.995) ? 1.0 : 0.995 * amax;
       const double mu_new = (s0 + alpha * s1 + alpha * alpha * s2) / m_rows;
-      if (target <= pd.tau && alpha == 1.0 && cmax <= 0.05 * pd.tau) converged = true;
+      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
       // centring heuristic: aggressive after long steps, conservative after short ones
       const double r = 1.0 - alpha;
       sigma = dmin(0.8, dmax(0.05, r * r * 4.0 + 0.05));
@@ -577,8 +579,12 @@ struct Engine {
   //   * dL/dtheta (model part; cost part when pd.param_cost)           nlp.py:1211-1212,1401
   //   * dpi/dtheta via ONE exact-Hessian Riccati factorisation and NU adjoint solves, instead of
   //     the reference's dense (nz x nz) sparse LU with ntheta right-hand sides  nlp.py:1413-1424
-  // dLdth / dpidth point at this sample's rows of row-major [B, NTH] / [B, NU, NTH] outputs.
+  // dLdth / dpidth point at this sample's rows of row-major [B, ng] / [B, NU, ng] outputs.
   // ---------------------------------------------------------------------------------------
+  // Gradient rows have width ng = grad_width(pd): the model parameters only (the structurally
+  // non-zero prefix of the reference's p, quirk Q8) or the whole p when pd.param_cost is set.
+  MPC_HD static int grad_width(const ProblemData& pd) { return pd.param_cost ? M::NTH : NPM; }
+
   MPC_HD static Residuals sens(const ProblemData& pd, const Lane& L, double* dLdth, double* dpidth, int* ok_out) {
     const int N = pd.N;
     const size_t bs = L.bs;
@@ -757,7 +763,7 @@ struct Engine {
           }
         }
       }
-      MPC_UNROLL for (int r = 0; r < NU; ++r) MPC_UNROLL for (int j = 0; j < NPM; ++j) dpidth[(size_t)r * M::NTH + j] = acc[r * NPM + j];
+      MPC_UNROLL for (int r = 0; r < NU; ++r) MPC_UNROLL for (int j = 0; j < NPM; ++j) dpidth[(size_t)r * grad_width(pd) + j] = acc[r * NPM + j];
     }
     *ok_out = ok ? 1 : 0;
     return R;

@@ -44,8 +44,8 @@ struct KArgs {
   double* u0_out;    // [B, NU]
   double* cost_out;  // [B]
   int* status_out;   // [B]
-  double* dL;        // [B, NTH]
-  double* dpi;       // [B, NU, NTH]
+  double* dL;        // [B, ng]
+  double* dpi;       // [B, NU, ng]
   double* res_out;   // [B, 4]
   int do_solve, do_sens;
 };
@@ -71,8 +71,9 @@ __global__ void __launch_bounds__(TPB) k_unit(const __grid_constant__ ProblemDat
   }
   if (a.do_sens) {
     int ok = 1;
-    typename E::Residuals r = E::sens(pd, L, a.dL ? a.dL + (size_t)b * M::NTH : nullptr,
-                                      a.dpi ? a.dpi + (size_t)b * M::NU * M::NTH : nullptr, &ok);
+    const int ng = E::grad_width(pd);
+    typename E::Residuals r = E::sens(pd, L, a.dL ? a.dL + (size_t)b * ng : nullptr,
+                                      a.dpi ? a.dpi + (size_t)b * M::NU * ng : nullptr, &ok);
     cost = r.cost;
     if (a.res_out) {
       a.res_out[(size_t)b * 4 + 0] = r.stat;
@@ -152,7 +153,8 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 struct rlmpc_handle {
   int model, device, max_batch;
   size_t bs;
-  int nx, nu, nth, it_size, ws_size;
+  int nx, nu, nth, npm, it_size, ws_size;
+  int ng() const { return pd.param_cost ? nth : npm; }
   ProblemData pd;
   double *it = nullptr, *ws = nullptr, *th = nullptr, *th_stage = nullptr;
   int th_per_sample = 0;
@@ -253,7 +255,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   switch (d->model) {
     case RLMPC_MODEL_CARTPOLE: {
       using E = Engine<CartpoleModel>;
-      h->nx = E::NX; h->nu = E::NU; h->nth = CartpoleModel::NTH;
+      h->nx = E::NX; h->nu = E::NU; h->nth = CartpoleModel::NTH; h->npm = E::NPM;
       h->it_size = E::it_size(d->N); h->ws_size = E::ws_size(d->N);
       break;
     }
@@ -307,11 +309,12 @@ void rlmpc_destroy(rlmpc_handle* h) {
   delete h;
 }
 
-int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* iterate_size) {
+int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* ngrad, int* iterate_size) {
   if (!h) return fail(RLMPC_EINVAL, "null handle");
   if (nx) *nx = h->nx;
   if (nu) *nu = h->nu;
   if (ntheta) *ntheta = h->nth;
+  if (ngrad) *ngrad = h->ng();
   if (iterate_size) *iterate_size = h->it_size;
   return 0;
 }
@@ -435,7 +438,7 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   if (mode == RLMPC_MODE_Q && !u0_host) return fail(RLMPC_EINVAL, "u0 is required in Q-mode");
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = h->own_stream;
-  const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->nth;
+  const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->ng();
   // stage inputs through pinned memory so the copies are real DMA transfers
   memcpy(h->h_in, x0_host, sizeof(double) * nB * nx);
   if (u0_host) memcpy(h->h_in + nB * nx, u0_host, sizeof(double) * nB * nu);
@@ -463,18 +466,18 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   return 0;
 }
 
-int rlmpc_td_grad(rlmpc_handle* h, int B, const double* td_dev, const double* dQ_dtheta_dev, const int* status_dev,
-                  double* acc_out_dev, void* stream) {
+int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const double* dQ_dtheta_dev,
+                  const int* status_dev, double* acc_out_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
-  if (!td_dev || !dQ_dtheta_dev || !acc_out_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  if (!td_dev || !dQ_dtheta_dev || !acc_out_dev || ncols < 1 || ncols > 4096) return fail(RLMPC_EINVAL, "bad arguments");
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  CUDA_OK(cudaMemsetAsync(acc_out_dev, 0, sizeof(double) * (h->nth + 2), s));
+  CUDA_OK(cudaMemsetAsync(acc_out_dev, 0, sizeof(double) * (ncols + 2), s));
   if (B == 0) return 0;
   const int threads = 256, nwarp = threads / 32;
   int grid = (B + nwarp - 1) / nwarp;
   if (grid > 148 * 4) grid = 148 * 4;
-  k_td_grad<<<grid, threads, sizeof(double) * (h->nth + 2), s>>>(B, h->nth, td_dev, dQ_dtheta_dev, status_dev, acc_out_dev);
+  k_td_grad<<<grid, threads, sizeof(double) * (ncols + 2), s>>>(B, ncols, td_dev, dQ_dtheta_dev, status_dev, acc_out_dev);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,0 +1,148 @@
+"""Host-side problem descriptions: what the reference packs into an ``AcadosOcp`` before it
+hands it to ``AcadosOcpSolver`` -- dims, cost scaling, bounds, integrator constants and the
+parameter vector ``p`` (layout of rlmpc/mpc/nlp.py:970-989).  They are turned into the
+``rlmpc_problem_desc`` of the C ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import _cabi
+
+INF = 1e30
+
+
+@dataclass
+class ProblemSpec:
+    name: str
+    model: int
+    N: int
+    nx: int
+    nu: int
+    tf: float
+    p_entries: List[Tuple[str, Tuple[int, ...]]]  # name, shape -- column-major flattening
+    p_nominal: np.ndarray
+    lbu: np.ndarray
+    ubu: np.ndarray
+    lbx: np.ndarray
+    ubx: np.ndarray
+    lbx_e: np.ndarray
+    ubx_e: np.ndarray
+    model_const: np.ndarray
+    gamma: float = 1.0
+    cost_type: str = "NONLINEAR_LS"
+    parameterize_tracking_cost: bool = False
+    state_labels: List[str] = field(default_factory=list)
+    input_labels: List[str] = field(default_factory=list)
+    parameter_labels: List[str] = field(default_factory=list)  # labels of p["model"]
+
+    @property
+    def ntheta(self) -> int:
+        return int(sum(int(np.prod(s)) for _, s in self.p_entries))
+
+    @property
+    def np_model(self) -> int:
+        return int(np.prod(dict(self.p_entries).get("model", (0,))))
+
+    def p_slices(self) -> Dict[str, Tuple[slice, Tuple[int, ...]]]:
+        out, o = {}, 0
+        for name, shape in self.p_entries:
+            n = int(np.prod(shape))
+            out[name] = (slice(o, o + n), shape)
+            o += n
+        return out
+
+    def cost_scaling(self, gamma: float | None = None) -> np.ndarray:
+        """s_k of the reference's NLP cost (nlp.py:1038-1134, quirk Q3)."""
+        g = self.gamma if gamma is None else gamma
+        N, dT = self.N, self.tf / self.N
+        s = np.empty(N + 1)
+        if self.cost_type in ("NONLINEAR_LS", "LINEAR_LS") and not self.parameterize_tracking_cost:
+            s[:N] = dT; s[N] = 1.0  # nlp.py:1044-1055: no gamma
+        else:
+            s[0] = dT
+            for k in range(1, N):
+                s[k] = g**k * dT
+            s[N] = g**N
+        return s
+
+    def to_desc(self) -> _cabi.ProblemDesc:
+        d = _cabi.ProblemDesc()
+        d.model, d.N = self.model, self.N
+        for i, v in enumerate(self.cost_scaling()):
+            d.scale[i] = v
+        for i in range(_cabi.MAXD):
+            d.lbu[i] = d.lbx[i] = d.lbx_e[i] = -INF
+            d.ubu[i] = d.ubx[i] = d.ubx_e[i] = INF
+        for name in ("lbu", "ubu", "lbx", "ubx", "lbx_e", "ubx_e"):
+            arr = getattr(d, name)
+            for i, v in enumerate(np.asarray(getattr(self, name), dtype=float).ravel()):
+                arr[i] = v
+        for i, v in enumerate(self.model_const):
+            d.model_const[i] = v
+        return d
+
+
+def cartpole_spec(config: dict, gamma: float = 1.0) -> ProblemSpec:
+    """From the reference's YAML ``config["mpc"]`` (config/cartpole*.yaml), following
+    rlmpc/mpc/cartpole/acados.py:28-203 and cartpole/common.py:349-360."""
+    N = int(config["dimensions"]["N"])
+    tf = float(config["ocp_options"]["tf"])
+    nstg = int(config["ocp_options"].get("sim_method_num_stages", 4))
+    params = config["model"]["params"]
+    free = [k for k in ("M", "m", "l", "g") if not params[k]["fixed"]]
+    if free != ["M", "m", "l"]:
+        raise NotImplementedError(f"cartpole device model is generated for free parameters (M, m, l); got {free}")
+    cost = config["cost"]
+    W_0, W, W_e = (np.array(cost[k], dtype=float) for k in ("W_0", "W", "W_e"))
+    yref_0, yref, yref_e = (np.array(cost[k], dtype=float) for k in ("yref_0", "yref", "yref_e"))
+    cons = config["constraints"]
+    nx, nu = 4, 1
+    full = lambda lo, idx, val: _scatter(lo, idx, val, nx)
+    lbx = full(-INF, cons.get("idxbx", []), cons.get("lbx", []))
+    ubx = full(INF, cons.get("idxbx", []), cons.get("ubx", []))
+    lbx_e = full(-INF, cons.get("idxbx_e", []), cons.get("lbx_e", []))
+    ubx_e = full(INF, cons.get("idxbx_e", []), cons.get("ubx_e", []))
+    p_entries = [("model", (3,)), ("W_0", W_0.shape), ("W", W.shape), ("W_e", W_e.shape),
+                 ("yref_0", yref_0.shape), ("yref", yref.shape), ("yref_e", yref_e.shape)]
+    p_nom = np.concatenate([[params[k]["value"] for k in free], W_0.T.ravel(), W.T.ravel(), W_e.T.ravel(),
+                            yref_0, yref, yref_e]).astype(float)
+    return ProblemSpec(
+        name=config["model"].get("name", "cartpole"), model=_cabi.MODEL_CARTPOLE, N=N, nx=nx, nu=nu, tf=tf,
+        p_entries=p_entries, p_nominal=p_nom,
+        lbu=np.array(cons["lbu"], dtype=float), ubu=np.array(cons["ubu"], dtype=float),
+        lbx=lbx, ubx=ubx, lbx_e=lbx_e, ubx_e=ubx_e,
+        model_const=np.array([tf / N / nstg, float(params["g"]["value"])]),  # quirk Q1: one RK4 step of dT/4
+        gamma=gamma, cost_type=cost.get("cost_type", "NONLINEAR_LS"),
+        state_labels=["x", "x_dot", "theta", "theta_dot"], input_labels=["F"], parameter_labels=free,
+    )
+
+
+def _scatter(fill, idx, val, n):
+    out = np.full(n, fill, dtype=float)
+    for i, v in zip(idx, val):
+        out[int(i)] = float(v)
+    return out
+
+
+def cartpole_original_config() -> dict:
+    """config/cartpole_original.yaml of the reference as a dict (``config["mpc"]``): N=40, tf=0.8,
+    |u| <= 80, no state bounds -- BASELINE.json configs[1]."""
+    W = np.diag([200.0, 0.02, 200.0, 0.02, 0.01]).tolist()
+    W_e = np.diag([200.0, 0.02, 200.0, 0.02]).tolist()
+    return {
+        "id": "cartpole",
+        "meta": {"json_file": "config/cartpole_ocp.json", "code_export_dir": "c_generated_code/acados_mpc"},
+        "ocp_options": {"tf": 0.8, "qp_solver": "PARTIAL_CONDENSING_HPIPM", "hessian_approx": "GAUSS_NEWTON",
+                        "integrator_type": "DISCRETE", "sim_method_num_stages": 4, "nlp_solver_type": "SQP",
+                        "nlp_solver_max_iter": 500, "qp_solver_iter_max": 200},
+        "dimensions": {"nx": 4, "nu": 1, "N": 40},
+        "cost": {"cost_type_0": "NONLINEAR_LS", "cost_type": "NONLINEAR_LS", "cost_type_e": "NONLINEAR_LS",
+                 "W_0": W, "W": W, "W_e": W_e, "yref_0": [0.0] * 5, "yref": [0.0] * 5, "yref_e": [0.0] * 4},
+        "model": {"name": "cartpole", "params": {"M": {"value": 1.0, "fixed": False}, "m": {"value": 0.1, "fixed": False},
+                                                 "l": {"value": 0.5, "fixed": False}, "g": {"value": 9.8, "fixed": True}}},
+        "constraints": {"constr_type": "BGH", "x0": [0.0, 0.0, 3.14, 0.0], "idxbu": [0], "lbu": [-80.0], "ubu": [80.0]},
+    }

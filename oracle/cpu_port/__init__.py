@@ -31,8 +31,11 @@ class ProblemData(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_DIR, "libcpu_port.so")
-    if force or not os.path.exists(so):
-        subprocess.run(["make", "-C", _DIR, "-B" if force else "-s"], check=True, capture_output=True)
+    # make tracks staleness against engine.cuh / the model headers; on a box without the sources'
+    # toolchain the prebuilt .so is used as is
+    r = subprocess.run(["make", "-C", _DIR, "-s"] + (["-B"] if force else []), capture_output=True, text=True)
+    if r.returncode != 0 and not os.path.exists(so):
+        raise RuntimeError("building oracle/cpu_port failed:\n" + r.stdout + r.stderr)
     return so
 
 
@@ -90,8 +93,9 @@ def unit(model: int, pd: ProblemData, mode: int, max_sqp: int, theta, x0, u0=Non
             iterate[k * nx:(k + 1) * nx, :] = x0.T
     iterate = np.ascontiguousarray(iterate)
     u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, nu)
-    out = dict(u0=np.zeros((B, nu)), cost=np.zeros(B), status=np.zeros(B, dtype=np.int32), dL=np.zeros((B, nth)),
-               dpi=np.zeros((B, nu, nth)), res=np.zeros((B, 4)), iters=np.zeros((B, 2), dtype=np.int32))
+    ng = L.cpu_port_grad_width(C.c_int(model), C.byref(pd))  # model parameters only unless pd.param_cost
+    out = dict(u0=np.zeros((B, nu)), cost=np.zeros(B), status=np.zeros(B, dtype=np.int32), dL=np.zeros((B, ng)),
+               dpi=np.zeros((B, nu, ng)), res=np.zeros((B, 4)), iters=np.zeros((B, 2), dtype=np.int32))
     r = L.cpu_port_unit(C.c_int(model), C.byref(pd), C.c_int(mode), C.c_int(max_sqp), C.c_int(B), _p(theta),
                         C.c_int(per_sample), _p(x0), _p(u0a), _p(iterate), C.c_int(int(do_solve)), C.c_int(int(do_sens)),
                         _p(out["u0"]), _p(out["cost"]), _p(out["status"], C.c_int), _p(out["dL"]), _p(out["dpi"]),

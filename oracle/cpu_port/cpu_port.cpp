@@ -52,8 +52,9 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     }
     if (do_sens) {
       int ok = 1;
-      typename E::Residuals r = E::sens(pd, L, dL ? dL + (size_t)b * M::NTH : nullptr,
-                                        dpi ? dpi + (size_t)b * M::NU * M::NTH : nullptr, &ok);
+      const int ng = E::grad_width(pd);
+      typename E::Residuals r = E::sens(pd, L, dL ? dL + (size_t)b * ng : nullptr,
+                                        dpi ? dpi + (size_t)b * M::NU * ng : nullptr, &ok);
       cost = r.cost;
       if (res_out) {
         res_out[4 * b] = r.stat; res_out[4 * b + 1] = r.eq; res_out[4 * b + 2] = r.ineq; res_out[4 * b + 3] = r.comp;
@@ -99,6 +100,11 @@ int cpu_port_sizeof_problem_data() { return (int)sizeof(ProblemData); }
 
 int cpu_port_iterate_size(int model, int N) {
   if (model == 1) return Engine<CartpoleModel>::it_size(N);
+  return -1;
+}
+
+int cpu_port_grad_width(int model, const ProblemData* pd) {
+  if (model == 1) return Engine<CartpoleModel>::grad_width(*pd);
   return -1;
 }
 

@@ -1,0 +1,58 @@
+"""Generate the golden fixtures under tests/golden/ with the dense oracle (TEST INFRASTRUCTURE).
+
+NOT reference outputs: the reference cannot run here (no acados/CasADi) and ships
+no golden vectors; these are outputs of the float64 restatement in oracle/ (cold-started dense
+SQP+IPM, then restated update_nlp with dense dR/dz + SuperLU).  "Parity unpinned" applies.
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz (about 3 minutes)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from .problems import make_cartpole
+from .solver import DenseSolver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sample_states(n, seed):
+    """SURVEY.md 8(d) config 2 distribution."""
+    rng = np.random.default_rng(seed)
+    lo = np.array([-1.0, -2.0, -np.pi, -4.0]); hi = -lo
+    x = rng.uniform(lo, hi, size=(n, 4))
+    a = rng.uniform(-80.0, 80.0, size=(n, 1))
+    return x, a
+
+
+def cartpole_golden(variant="original", n=20, seed=1234):
+    pb = make_cartpole(variant)
+    s = DenseSolver(pb)
+    x0s, acts = sample_states(n, seed)
+    # the reference's own test point (scripts/cartpole_mpc_sensitivities.py:80-81)
+    x0s[0] = [0.0, 0.0, np.pi / 2, 0.0]; acts[0] = [-30.0]
+    out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "U", "X", "pi", "lam", "t", "UQ", "XQ", "status")}
+    for i in range(n):
+        sol, upd = s.unit(x0s[i], tol=1e-10)
+        solq, updq = s.unit(x0s[i], u0=acts[i], tol=1e-10)
+        print(f"[{variant} {i}] V={sol.cost:.6f} u0={sol.U[0]} it={sol.sqp_iter} kkt={sol.kkt:.1e} | Q={solq.cost:.6f} it={solq.sqp_iter}",
+              flush=True)
+        out["status"].append([sol.status, solq.status])
+        out["V"].append(sol.cost); out["u0"].append(sol.U[0]); out["dV"].append(upd["dL_dp"][0]); out["dpi"].append(upd["dpi_dp"])
+        out["Q"].append(solq.cost); out["dQ"].append(updq["dL_dp"][0])
+        out["U"].append(sol.U); out["X"].append(sol.X); out["pi"].append(sol.pi); out["lam"].append(sol.lam); out["t"].append(sol.t)
+        out["UQ"].append(solq.U); out["XQ"].append(solq.X)
+    out = {k: np.array(v) for k, v in out.items()}
+    out["x0"] = x0s; out["a"] = acts; out["theta"] = pb.p_nominal
+    path = os.path.join(ROOT, "tests", "golden", f"cartpole_{variant}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["original"]
+    for v in which:
+        cartpole_golden(v)

@@ -1,0 +1,201 @@
+"""GPU parity tests for the cartpole hot path (BASELINE.json configs[1]) -- all calls go through
+the C ABI (librlmpc_b200.so).  Oracle = oracle/ (dense restatement); golden fixtures were produced
+by oracle/make_golden.py.  Tolerances: |u0| 1e-6 abs (north-star: 1e-5),
+V/Q 1e-9 rel, dQ/dtheta 1e-6 rel, dpi/dtheta 1e-5 rel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "cartpole_original.npz"))
+
+
+@pytest.fixture(scope="module")
+def spec():
+    from mpc4rl_b200 import cartpole_original_config, cartpole_spec
+
+    return cartpole_spec(cartpole_original_config())
+
+
+def _mpc(spec, B):
+    from mpc4rl_b200 import BatchedMPC
+
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-9)
+    return m
+
+
+def _dev(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda:0")
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def test_v_mode_matches_golden(spec, golden):
+    x0 = _dev(golden["x0"])
+    m = _mpc(spec, x0.shape[0])
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=200)
+    ok = golden["status"][:, 0] == 0
+    # full-step SQP (acados default) 2-cycles on two samples of this seed -- in the oracle too
+    assert np.array_equal(out["status"].cpu().numpy() == 0, ok)
+    golden = {k: golden[k][ok] for k in ("u0", "V", "dV", "dpi", "X", "U", "pi")}
+    out = {k: v[torch.tensor(ok, device=v.device)] for k, v in out.items()}
+    assert np.abs(out["u0"].cpu().numpy() - golden["u0"]).max() < 1e-6
+    assert _rel(out["cost"].cpu().numpy(), golden["V"]) < 1e-9
+    # the reference's p has 83 entries of which only (M, m, l) carry gradient (quirk Q8): the
+    # engine returns that non-zero prefix, full_grad() pads to the reference layout
+    assert out["dL"].shape[1] == 3 and np.count_nonzero(golden["dV"][:, 3:]) == 0
+    assert np.count_nonzero(golden["dpi"][:, :, 3:]) == 0
+    assert _rel(m.full_grad(out["dL"]).cpu().numpy(), golden["dV"]) < 1e-6
+    assert _rel(m.full_grad(out["dpi"]).cpu().numpy(), golden["dpi"]) < 1e-5
+    # full primal-dual solution
+    N = spec.N
+    X = np.stack([m.get("x", k, x0.shape[0]).cpu().numpy() for k in range(N + 1)], axis=1)[ok]
+    U = np.stack([m.get("u", k, x0.shape[0]).cpu().numpy() for k in range(N)], axis=1)[ok]
+    PI = np.stack([m.get("pi", k, x0.shape[0]).cpu().numpy() for k in range(N)], axis=1)[ok]
+    assert np.abs(X - golden["X"]).max() < 1e-6
+    assert np.abs(U - golden["U"]).max() < 1e-6
+    assert np.abs(PI.reshape(len(PI), -1) - golden["pi"]).max() < 1e-5 * max(1.0, np.abs(golden["pi"]).max())
+
+
+def test_q_mode_matches_golden(spec, golden):
+    x0, a = _dev(golden["x0"]), _dev(golden["a"])
+    m = _mpc(spec, x0.shape[0])
+    m.reset(x0)
+    out = m.solve_sens(x0, a, max_sqp=200)
+    ok = golden["status"][:, 1] == 0
+    assert np.array_equal(out["status"].cpu().numpy() == 0, ok)
+    assert np.abs(out["u0"].cpu().numpy() - golden["a"]).max() == 0.0  # u0 is clamped to a
+    assert _rel(out["cost"].cpu().numpy()[ok], golden["Q"][ok]) < 1e-9
+    assert _rel(m.full_grad(out["dL"]).cpu().numpy()[ok], golden["dQ"][ok]) < 1e-6
+    assert torch.count_nonzero(out["dpi"]) == 0  # dpi/dtheta == 0 in Q-mode by construction (quirk Q7)
+
+
+def test_host_entry_point_equals_device_path(spec, golden):
+    x0 = golden["x0"]
+    m = _mpc(spec, x0.shape[0])
+    m.reset(_dev(x0))
+    o_dev = m.solve_sens(_dev(x0), max_sqp=100)
+    m.reset(_dev(x0))
+    o_host = m.solve_sens_host(x0, max_sqp=100)
+    for k in ("u0", "cost", "dL", "dpi", "res"):
+        assert np.array_equal(o_dev[k].cpu().numpy(), o_host[k]), k
+    assert np.array_equal(o_dev["status"].cpu().numpy(), o_host["status"])
+
+
+def test_live_oracle_kkt_and_sensitivities(spec):
+    """The reference's own test method (nlp.py:1445-1537): the NLP mirror must accept the solver's
+    primal-dual point as a KKT point, and the dense dR/dz solve must give the same dpi/dtheta."""
+    from oracle.problems import make_cartpole
+    from oracle.solver import DenseSolver
+
+    rng = np.random.default_rng(7)
+    x0 = rng.uniform([-1, -2, -np.pi, -4], [1, 2, np.pi, 4], size=(3, 4))
+    m = _mpc(spec, 3)
+    m.set_option("tol", 1e-10)
+    m.reset(_dev(x0))
+    out = m.solve_sens(_dev(x0), max_sqp=200)
+    assert (out["status"].cpu().numpy() == 0).all()
+    s = DenseSolver(make_cartpole("original"))
+    N = spec.N
+    for i in range(3):
+        X = np.stack([m.get("x", k, 3)[i].cpu().numpy() for k in range(N + 1)])
+        U = np.stack([m.get("u", k, 3)[i].cpu().numpy() for k in range(N)])
+        sol, upd = s.unit(x0[i], init=(U, X), tol=1e-10)
+        assert sol.sqp_iter <= 2  # the GPU point already is the oracle's KKT point
+        assert np.abs(sol.U - U).max() < 1e-7 and np.abs(sol.X - X).max() < 1e-7
+        assert abs(sol.cost - out["cost"][i].item()) < 1e-9 * abs(sol.cost)
+        assert _rel(m.full_grad(out["dL"][i]).cpu().numpy(), upd["dL_dp"][0]) < 1e-6
+        assert _rel(m.full_grad(out["dpi"][i]).cpu().numpy(), upd["dpi_dp"]) < 1e-5
+
+
+def test_rti_step_tracks_converged_solution(spec, golden):
+    """K=1 (SQP-RTI) from a converged iterate at a nearby state lands close to the converged answer."""
+    x0 = golden["x0"]
+    B = x0.shape[0]
+    m = _mpc(spec, B)
+    m.reset(_dev(x0))
+    m.solve(_dev(x0), max_sqp=100)
+    x1 = x0 + 1e-3 * np.random.default_rng(0).standard_normal(x0.shape)
+    rti = m.solve_sens(_dev(x1), max_sqp=1)
+    u_rti = rti["u0"].cpu().numpy()
+    conv = m.solve_sens(_dev(x1), max_sqp=100)
+    ok = golden["status"][:, 0] == 0
+    assert (conv["status"].cpu().numpy()[ok] == 0).all()
+    assert np.abs(u_rti - conv["u0"].cpu().numpy())[ok].max() < 1e-3
+    assert rti["res"].cpu().numpy()[ok].max() < 1e-2
+
+
+def test_full_batch_properties(spec):
+    """BASELINE size (65 536): every sample converges, KKT residuals tiny, replicated inputs give
+    bit-identical outputs wherever they sit in the batch, dV/dtheta agrees with central differences
+    of V over per-sample theta (the reference's FD check, scripts/linear_system_mpc_nlp.py:43-49)."""
+    B = 65536
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    x0[B // 2:] = x0[: B // 2]  # replicate
+    m = _mpc(spec, B)
+    m.set_option("tol", 1e-8)
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=200)
+    st = out["status"].cpu().numpy()
+    assert (st == 0).mean() > 0.9, np.bincount(st)  # full-step SQP (acados default) 2-cycles on a few % of random states
+    okm = out["status"] == 0
+    assert out["res"][okm].max().item() < 1e-8
+    for k in ("u0", "cost", "dL", "dpi"):
+        assert torch.equal(out[k][: B // 2], out[k][B // 2:]), k
+    # FD check of dV/dtheta through per-sample theta
+    n = 64
+    xs = x0[:n]
+    d = 1e-6
+    th = np.tile(spec.p_nominal, (6 * n, 1))
+    for j in range(3):
+        th[(2 * j) * n:(2 * j + 1) * n, j] += d
+        th[(2 * j + 1) * n:(2 * j + 2) * n, j] -= d
+    m2 = _mpc(spec, 6 * n)
+    m2.set_option("tol", 1e-11)
+    m2.set_theta(th)
+    xx = xs.repeat(6, 1)
+    m2.reset(xx)
+    o2 = m2.solve_sens(xx, max_sqp=300)
+    V = o2["cost"].cpu().numpy().reshape(6, n)
+    fd = np.stack([(V[2 * j] - V[2 * j + 1]) / (2 * d) for j in range(3)], axis=1)
+    an = out["dL"][:n, :3].cpu().numpy()
+    assert np.abs(fd - an).max() < 1e-4 * max(1.0, np.abs(an).max())
+
+
+def test_td_grad_reduction(spec):
+    B = 1000
+    m = _mpc(spec, B)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    td = torch.randn(B, generator=g, dtype=torch.float64).cuda()
+    dQ = torch.randn(B, spec.ntheta, generator=g, dtype=torch.float64).cuda()
+    status = (torch.rand(B, generator=g) < 0.1).to(torch.int32).cuda() * 2
+    acc = m.td_grad(td, dQ, status)
+    ok = status == 0
+    ref = torch.cat([(td[ok, None] * dQ[ok]).sum(0), td[ok].sum()[None], ok.sum()[None].double()])
+    assert torch.allclose(acc, ref, rtol=1e-12, atol=1e-10)
+
+
+def test_errors_are_reported(spec):
+    from mpc4rl_b200 import BatchedMPC
+
+    m = BatchedMPC(spec, max_batch=4, device=0)
+    with pytest.raises(RuntimeError):
+        m.solve(torch.zeros(8, 4, dtype=torch.float64, device="cuda:0"))  # batch > max_batch
+    with pytest.raises(TypeError):
+        m.solve(torch.zeros(2, 4, dtype=torch.float32, device="cuda:0"))
+    with pytest.raises(RuntimeError):
+        m.set_option("no_such_option", 1.0)

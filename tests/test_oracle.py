@@ -1,0 +1,135 @@
+"""Pins of the oracle itself (CPU).  The reference ships no golden vectors and cannot run here
+(SURVEY.md 8(c)); what it does have are relational checks, reproduced here on the restatement:
+  * update_nlp's assertions (rlmpc/mpc/nlp.py:1445-1537): KKT self-consistency at the solution
+  * finite-difference agreement of dV/dp (scripts/linear_system_mpc_nlp.py:43-49), here at 1e-5
+    instead of the reference's atol=1e-1
+plus consistency of the committed golden fixtures and of the host port of the engine."""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cartpole():
+    from oracle.problems import make_cartpole
+    from oracle.solver import DenseSolver
+
+    return DenseSolver(make_cartpole("original"))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "cartpole_original.npz"))
+
+
+def test_layout_matches_reference_counts(cartpole):
+    nlp = cartpole.nlp
+    # cartpole_original N=40: nw=204, npi=160, nlam=88, nz=540, ntheta=83
+    assert (nlp.nw, nlp.npi, nlp.nlam, nlp.nz, cartpole.pb.ntheta) == (204, 160, 88, 540, 83)
+    kinds = [r.kind for r in nlp.rows if r.stage == 0]
+    assert kinds == ["lbu"] + ["lbx"] * 4 + ["ubu"] + ["ubx"] * 4  # acados order, stage 0
+    assert [r.kind for r in nlp.rows if r.stage == 5] == ["lbu", "ubu"]
+
+
+def test_update_nlp_assertions_hold_at_golden_solution(cartpole, golden):
+    """nlp.py:1445-1537 on a stored solution: g~0, h<=0, complementarity, stationarity, R~0."""
+    from oracle.nlp import Bounds
+
+    pb, nlp = cartpole.pb, cartpole.nlp
+    for i in (0, 2):
+        N = pb.N
+        b = Bounds(lbu=np.tile(pb.lbu, (N, 1)), ubu=np.tile(pb.ubu, (N, 1)), lbx0=golden["x0"][i], ubx0=golden["x0"][i],
+                   slbx=np.zeros((N + 1, 0)), subx=np.zeros((N + 1, 0)))
+        upd = nlp.update(golden["U"][i], golden["X"][i], golden["pi"][i], golden["lam"][i], golden["t"][i], pb.p_nominal, b)
+        assert abs(upd["cost"] - golden["V"][i]) < 1e-9 * abs(golden["V"][i])
+        assert np.abs(upd["g"]).max() <= 1e-4 and np.abs(upd["g"]).max() < 1e-10
+        assert (upd["h"] < 1e-6).all()
+        assert np.abs(golden["lam"][i] * upd["h"]).max() <= 1e-5
+        nu = pb.nu * N
+        assert np.abs(upd["dL_dw"][:nu]).max() < 1e-3 and np.abs(upd["dL_dw"][:nu]).max() < 1e-8  # dL/du
+        assert np.abs(upd["dL_dw"][nu + pb.nx:]).max() < 1e-8  # dL/dx (x_0 rows hold the equality multipliers)
+        assert np.abs(upd["R"]).max() < 1e-6  # nlp.assert_kkt_residual (nlp.py:1295-1299)
+        assert np.allclose(upd["dL_dp"][0], golden["dV"][i], rtol=1e-9, atol=1e-12)
+        assert np.allclose(upd["dpi_dp"], golden["dpi"][i], rtol=1e-7, atol=1e-9)
+
+
+def test_value_gradient_matches_finite_differences(cartpole, golden):
+    """dV/dp = dL/dp (envelope theorem) against central differences of the re-solved V."""
+    pb = cartpole.pb
+    i = 1
+    x0 = golden["x0"][i]
+    init = (golden["U"][i], golden["X"][i])
+    d = 1e-5
+    for j in range(3):
+        p = pb.p_nominal.copy(); p[j] += d
+        vp = cartpole.solve(x0, p=p, init=init, tol=1e-11)
+        p[j] -= 2 * d
+        vm = cartpole.solve(x0, p=p, init=init, tol=1e-11)
+        fd = (vp.cost - vm.cost) / (2 * d)
+        assert abs(fd - golden["dV"][i][j]) < 1e-5 * max(1.0, abs(fd))
+        fdu = (vp.U[0, 0] - vm.U[0, 0]) / (2 * d)
+        assert abs(fdu - golden["dpi"][i][0, j]) < 1e-4 * max(1.0, abs(fdu))
+
+
+def test_scipy_cross_check_of_the_minimiser(cartpole, golden):
+    """Independent NLP solve (scipy SLSQP on the restated cost/constraints) reaches the same optimum."""
+    import torch
+    from scipy.optimize import minimize
+    from torch.func import grad, jacrev
+
+    from oracle.nlp import Bounds
+    from oracle.problems import F64
+
+    pb, nlp = cartpole.pb, cartpole.nlp
+    i = 4
+    x0 = golden["x0"][i]
+    N = pb.N
+    b = Bounds(lbu=np.tile(pb.lbu, (N, 1)), ubu=np.tile(pb.ubu, (N, 1)), lbx0=x0, ubx0=x0, slbx=np.zeros((N + 1, 0)),
+               subx=np.zeros((N + 1, 0)))
+    p = torch.as_tensor(pb.p_nominal, dtype=F64)
+    T = lambda w: torch.as_tensor(w, dtype=F64)
+    f = lambda w: float(nlp.cost(T(w), p, b))
+    df = lambda w: grad(lambda w_: nlp.cost(w_, p, b))(T(w)).numpy()
+    nu = N * pb.nu
+    geq = lambda w: np.concatenate([nlp.g(T(w), p).numpy(), w[nu:nu + pb.nx] - x0])
+    E0 = np.zeros((pb.nx, nlp.nw)); E0[:, nu:nu + pb.nx] = np.eye(pb.nx)
+    dgeq = lambda w: np.vstack([jacrev(lambda w_: nlp.g(w_, p))(T(w)).numpy(), E0])
+    w0 = nlp.pack_w(golden["U"][i] * 0.9, golden["X"][i]).numpy()
+    bounds = [(-80.0, 80.0)] * nu + [(None, None)] * (nlp.nw - nu)
+    r = minimize(f, w0, jac=df, bounds=bounds, constraints=[{"type": "eq", "fun": geq, "jac": dgeq}], method="SLSQP",
+                 options={"maxiter": 300, "ftol": 1e-14})
+    assert abs(r.fun - golden["V"][i]) < 1e-6 * abs(golden["V"][i])
+    assert abs(r.x[0] - golden["u0"][i][0]) < 1e-3
+
+
+def test_q_mode_fixes_first_input(golden):
+    assert np.array_equal(golden["UQ"][:, 0, :], golden["a"])
+    ok = (golden["status"] == 0).all(axis=1)
+    assert (golden["Q"][ok] >= golden["V"][ok] - 1e-9).all()  # Q(s,a) >= V(s) = min_a Q(s,a)
+    # full-step SQP (acados' default, no globalisation) 2-cycles on samples 3 and 18 of this seed
+    assert ok.sum() == 18 and not ok[3] and not ok[18]
+
+
+def test_host_port_of_engine_matches_oracle(golden):
+    """The Riccati/IPM/adjoint engine (host build of the CUDA templates) against the dense oracle."""
+    from oracle import cpu_port as cp
+    from oracle.problems import make_cartpole
+
+    pb = make_cartpole("original")
+    pd = cp.make_pd(pb.N, [pb.stage_scale(k) for k in range(pb.N + 1)], pb.lbu, pb.ubu, [pb.tf / pb.N / 4, 9.8], tol=1e-10)
+    o = cp.unit(1, pd, 0, 200, pb.p_nominal, golden["x0"])
+    ok = golden["status"][:, 0] == 0
+    assert np.array_equal(o["status"] == 0, ok)  # the same samples 2-cycle in both implementations
+    assert np.abs(o["u0"] - golden["u0"])[ok].max() < 1e-6
+    assert np.abs(o["cost"] - golden["V"])[ok].max() < 1e-9 * np.abs(golden["V"]).max()
+    assert np.abs(o["dL"][:, :3] - golden["dV"][:, :3])[ok].max() < 1e-6 * np.abs(golden["dV"]).max()
+    assert np.abs(o["dpi"][:, :, :3] - golden["dpi"][:, :, :3])[ok].max() < 1e-5 * np.abs(golden["dpi"]).max()
+    q = cp.unit(1, pd, 1, 200, pb.p_nominal, golden["x0"], u0=golden["a"])
+    okq = golden["status"][:, 1] == 0
+    assert np.array_equal(q["status"] == 0, okq)
+    assert np.abs(q["cost"] - golden["Q"])[okq].max() < 1e-9 * np.abs(golden["Q"]).max()
+    assert np.abs(q["dL"][:, :3] - golden["dQ"][:, :3])[okq].max() < 1e-6 * np.abs(golden["dQ"]).max()
+    assert np.count_nonzero(q["dpi"]) == 0
