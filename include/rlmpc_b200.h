@@ -78,7 +78,8 @@ int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n);
 /* Replaces constraints_set(stage, "lbu"/"ubu"/..) for the nominal bounds. field in
  * {"lbu","ubu","lbx","ubx","lbx_e","ubx_e"}. */
 int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n);
-/* options: "tol" (1e-6), "tau" (1e-8), "mu0" (1.0), "max_ipm" (50), "warm_ipm" (0),
+/* options: "tol" (1e-6), "tau" (1e-8), "mu0" (1.0), "max_ipm" (50), "warm_ipm" (1: start every QP's
+ * interior-point iteration from the multipliers of the previous QP, with a cold restart if jammed),
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */
 int rlmpc_set_option(rlmpc_handle* h, const char* name, double value);
 

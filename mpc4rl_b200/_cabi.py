@@ -13,7 +13,7 @@ MODEL_CARTPOLE = 1
 MODE_V, MODE_Q = 0, 1
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librlmpc_b200.so")
+LIB_PATH = os.environ.get("RLMPC_B200_LIB", os.path.join(_PKG, "librlmpc_b200.so"))  # env override: tuning variants
 
 # every symbol include/rlmpc_b200.h declares
 SYMBOLS = [

@@ -37,7 +37,9 @@ struct Engine {
   // gradient of the rest of the Lagrangian wrt x_0 / u_0; written by sens()
   MPC_HD static int it_rx0(int N) { return (N + 1) * NX + N * NU + N * NX + 4 * N * NU; }
   MPC_HD static int it_ru0(int N) { return it_rx0(N) + NX; }
-  MPC_HD static int it_size(int N) { return it_rx0(N) + NX + NU; }
+  // meta[0] = 1.0 once (lam,t) hold the result of a QP solve (valid IPM warm start)
+  MPC_HD static int it_meta(int N) { return it_ru0(N) + NU; }
+  MPC_HD static int it_size(int N) { return it_meta(N) + 1; }
 
   // ---------------- workspace record per stage ----------------
   static constexpr int W_A = 0;
@@ -285,30 +287,29 @@ struct Engine {
   // State of the method is (lam,t) only (absolute-step form); the primal step dx,du of the last
   // iteration is left in the workspace.  Returns the number of IPM iterations, <0 on failure.
   // ---------------------------------------------------------------------------------------
-  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
+  static constexpr int WARM_LIMIT = 6;  // IPM iterations granted to a warm start before a cold restart
+
+  // returns sum(lam*t)
+  MPC_HD static double ipm_init(const ProblemData& pd, const Lane& L, int k_first, bool warm) {
     const int N = pd.N;
     const size_t bs = L.bs;
-    const bool qmode = pd.mode == MODE_Q;
-    const int k_first = qmode ? 1 : 0;  // first stage with a free input
-    const double m_rows = 2.0 * NU * (N - k_first);
-    // ---- initialise (lam,t) ----
     double mu = 0.0;
     for (int k = k_first; k < N; ++k) {
       double u[NU], lu[2 * NU], tu[2 * NU];
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-      if (pd.warm_ipm) {
+      if (warm) {
         ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
         ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
       }
       MPC_UNROLL for (int i = 0; i < NU; ++i) {
         const double range = pd.ubu[i] - pd.lbu[i];
-        const double tmin = 1e-2 * range;
-        if (pd.warm_ipm) {
+        if (warm) {
           tu[i] = dmax(tu[i], 1e-10 * range);
           tu[NU + i] = dmax(tu[NU + i], 1e-10 * range);
           lu[i] = dmax(lu[i], 1e-14);
           lu[NU + i] = dmax(lu[NU + i], 1e-14);
         } else {
+          const double tmin = 1e-2 * range;
           tu[i] = dmax(u[i] - pd.lbu[i], tmin);
           tu[NU + i] = dmax(pd.ubu[i] - u[i], tmin);
           lu[i] = pd.mu0 / tu[i];
@@ -319,14 +320,34 @@ struct Engine {
       st<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
       st<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
     }
-    mu /= m_rows;
+    return mu;
+  }
+
+  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
+    const int N = pd.N;
+    const size_t bs = L.bs;
+    const bool qmode = pd.mode == MODE_Q;
+    const int k_first = qmode ? 1 : 0;  // first stage with a free input
+    const double m_rows = 2.0 * NU * (N - k_first);
+    // ---- initialise (lam,t): warm = keep the multipliers of the previous QP (clipped away from
+    // zero), cold = slacks from the current inputs, lam = mu0 / t ----
+    bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
+    double mu = ipm_init(pd, L, k_first, warm) / m_rows;
 
     double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
-    double sigma = 0.3;
-    int iters = 0;
+    double sigma = warm ? 0.05 : 0.3;
+    int iters = 0, warm_iters = 0;
     bool converged = false, failed = false;
     for (int j = 0; j < pd.max_ipm && !converged; ++j) {
       ++iters;
+      if (warm && (warm_iters >= WARM_LIMIT || (warm_iters > 0 && alpha < 0.05))) {
+        // the warm start is jammed (active set changed too much): restart from a cold point
+        warm = false;
+        mu = ipm_init(pd, L, k_first, false) / m_rows;
+        alpha = 0.0;
+        sigma = 0.3;
+      }
+      if (warm) ++warm_iters;
       const double target = dmax(sigma * mu, pd.tau);
       // ---------------- backward sweep ----------------
       double P[NX * NX], p[NX];
@@ -561,6 +582,7 @@ struct Engine {
         break;
       }
       apply_step(pd, L, alpha);
+      L.it[(size_t)it_meta(pd.N) * L.bs] = 1.0;
       o.sqp_iter = itn + 1;
       if (r < 0) {  // IPM hit its iteration limit
         o.status = ST_QPFAIL;

@@ -30,7 +30,13 @@ int fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess) return fail(RLMPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr int TPB = 128;  // threads per block
+#ifndef RLMPC_TPB
+#define RLMPC_TPB 128
+#endif
+#ifndef RLMPC_MINB
+#define RLMPC_MINB 1
+#endif
+constexpr int TPB = RLMPC_TPB;  // threads per block
 
 struct KArgs {
   double* it;
@@ -51,7 +57,7 @@ struct KArgs {
 };
 
 template <class M>
-__global__ void __launch_bounds__(TPB) k_unit(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(TPB, RLMPC_MINB) k_unit(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
@@ -266,7 +272,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   ProblemData& pd = h->pd;
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
-  pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 0; pd.param_cost = 0;
+  pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
   pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));

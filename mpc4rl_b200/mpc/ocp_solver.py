@@ -1,0 +1,224 @@
+"""``AcadosOcpSolver`` look-alike backed by the B200 engine (batch of one sample).
+
+Covers the subset of acados_template.AcadosOcpSolver that the reference uses (census in
+SURVEY.md section 1 / 8(b)): set, get, solve, solve_for_x0, get_cost, get_residuals, cost_set,
+constraints_set, reset, store_iterate, load_iterate, status, acados_ocp.  One instance owns one
+mutable iterate and is not re-entrant, like the original.
+"""
+from __future__ import annotations
+
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from ..batched import BatchedMPC
+from ..problems import INF, ProblemSpec
+
+
+def _finite_idx(lo, hi):
+    return np.array([i for i in range(len(lo)) if lo[i] > -INF / 2 or hi[i] < INF / 2], dtype=int)
+
+
+def make_ocp_view(spec: ProblemSpec) -> SimpleNamespace:
+    """The attributes of ``ocp_solver.acados_ocp`` that the reference reads."""
+    idxbx, idxbx_e = _finite_idx(spec.lbx, spec.ubx), _finite_idx(spec.lbx_e, spec.ubx_e)
+    sl = spec.p_slices()
+    pv = lambda k: (spec.p_nominal[sl[k][0]].reshape(sl[k][1][::-1]).T.copy() if len(sl[k][1]) == 2
+                    else spec.p_nominal[sl[k][0]].copy()) if k in sl else np.array([])
+    cons = SimpleNamespace(
+        idxbu=np.arange(spec.nu), lbu=spec.lbu.copy(), ubu=spec.ubu.copy(),
+        idxbx=idxbx, lbx=spec.lbx[idxbx].copy(), ubx=spec.ubx[idxbx].copy(),
+        idxbx_e=idxbx_e, lbx_e=spec.lbx_e[idxbx_e].copy(), ubx_e=spec.ubx_e[idxbx_e].copy(),
+        idxbx_0=np.arange(spec.nx), lbx_0=np.zeros(spec.nx), ubx_0=np.zeros(spec.nx),
+        idxsbx=np.array([], dtype=int), idxsbu=np.array([], dtype=int), idxsh=np.array([], dtype=int),
+        idxsbx_e=np.array([], dtype=int), idxsh_e=np.array([], dtype=int),
+        lh=np.array([]), uh=np.array([]), lh_e=np.array([]), uh_e=np.array([]),
+    )
+    dims = SimpleNamespace(N=spec.N, nx=spec.nx, nu=spec.nu, np=spec.np_model, nbu=spec.nu, nbx=len(idxbx),
+                           nbx_0=spec.nx, nbx_e=len(idxbx_e), nh=0, nh_e=0, nsbx=0, nsbu=0, nsh=0, nsbx_e=0, nsh_e=0,
+                           ny_0=spec.nx + spec.nu, ny=spec.nx + spec.nu, ny_e=spec.nx)
+    cost = SimpleNamespace(cost_type_0=spec.cost_type, cost_type=spec.cost_type, cost_type_e=spec.cost_type,
+                           W_0=pv("W_0"), W=pv("W"), W_e=pv("W_e"), yref_0=pv("yref_0"), yref=pv("yref"), yref_e=pv("yref_e"),
+                           zl=np.array([]), zu=np.array([]), zl_e=np.array([]), zu_e=np.array([]))
+    model = SimpleNamespace(name=spec.name, x_labels=list(spec.state_labels), u_labels=list(spec.input_labels),
+                            p_labels=list(spec.parameter_labels))
+    return SimpleNamespace(dims=dims, constraints=cons, cost=cost, model=model,
+                           parameter_values=spec.p_nominal[sl["model"][0]].copy() if "model" in sl else np.array([]),
+                           solver_options=SimpleNamespace(tf=spec.tf, nlp_solver_max_iter=100, tol=1e-6))
+
+
+class OcpSolverShim:
+    def __init__(self, spec: ProblemSpec, device: int = 0, max_iter: int = 100, tol: float = 1e-6):
+        self.spec = spec
+        self.engine = BatchedMPC(spec, max_batch=1, device=device)
+        self.acados_ocp = make_ocp_view(spec)
+        self.acados_ocp.solver_options.nlp_solver_max_iter = int(max_iter)
+        self.acados_ocp.solver_options.tol = float(tol)
+        self.engine.set_option("tol", tol)
+        self.status = 0
+        self.N = spec.N
+        self._theta = np.array(spec.p_nominal, dtype=np.float64)
+        self._lbx0 = np.zeros(spec.nx)
+        self._ubx0 = np.zeros(spec.nx)
+        self._lbu0 = spec.lbu.copy()
+        self._ubu0 = spec.ubu.copy()
+        self._cost = float("nan")
+        self._res = np.full(4, np.nan)
+        self._dev = self.engine.device
+
+    # ---- helpers ----
+    def _t(self, v, n):
+        a = np.asarray(v, dtype=np.float64).reshape(-1)
+        if a.shape[0] != n:
+            raise ValueError(f"expected {n} values, got {a.shape[0]}")
+        return torch.tensor(a.reshape(1, n), dtype=torch.float64, device=self._dev)
+
+    @property
+    def qmode(self) -> bool:
+        """u_0 is clamped (q_update: constraints_set(0,'lbu'/'ubu',u0), mpc.py:71-73)."""
+        return bool(np.all(self._lbu0 == self._ubu0))
+
+    def _push_theta(self):
+        self.engine.set_theta(self._theta)
+
+    # ---- acados API subset ----
+    def set(self, stage: int, field: str, value) -> None:
+        if field in ("lbx", "ubx"):
+            if stage != 0:
+                raise NotImplementedError("only the stage-0 state bounds (x0 fixing) can be changed at run time")
+            setattr(self, "_lbx0" if field == "lbx" else "_ubx0", np.asarray(value, dtype=np.float64).reshape(-1).copy())
+            getattr(self.acados_ocp.constraints, field + "_0")[:] = np.asarray(value, dtype=np.float64).reshape(-1)
+        elif field in ("x", "u", "pi"):
+            dim = {"x": self.spec.nx, "u": self.spec.nu, "pi": self.spec.nx}[field]
+            self.engine.put(field, stage, self._t(value, dim))
+        elif field == "p":
+            sl = self.spec.p_slices()["model"][0]
+            self._theta[sl] = np.asarray(value, dtype=np.float64).reshape(-1)
+            self.acados_ocp.parameter_values = self._theta[sl].copy()
+            self._push_theta()
+        else:
+            raise NotImplementedError(f"set(stage, {field!r}, ...) is not part of the reference's usage")
+
+    def constraints_set(self, stage: int, field: str, value) -> None:
+        v = np.asarray(value, dtype=np.float64).reshape(-1)
+        if field in ("lbu", "ubu"):
+            if stage == 0:
+                setattr(self, "_lbu0" if field == "lbu" else "_ubu0", v.copy())
+            else:
+                raise NotImplementedError("input bounds of stages > 0 are fixed at construction")
+        elif field in ("lbx", "ubx"):
+            self.set(stage, field, v)
+        else:
+            raise NotImplementedError(field)
+
+    def cost_set(self, stage: int, field: str, value, api: str = "warn") -> None:
+        key = {"W": "W", "yref": "yref"}.get(field)
+        if key is None:
+            raise NotImplementedError(field)
+        name = key + ("_0" if stage == 0 else "_e" if stage == self.N else "")
+        sl, shape = self.spec.p_slices()[name]
+        v = np.asarray(value, dtype=np.float64)
+        self._theta[sl] = v.T.reshape(-1) if v.ndim == 2 else v.reshape(-1)  # column-major like CasADi
+        setattr(self.acados_ocp.cost, name, v.copy())
+        self._push_theta()
+
+    def set_theta(self, theta) -> None:
+        """Whole parameter vector p at once (what MPC.set_p / set_parameter need)."""
+        self._theta = np.array(theta, dtype=np.float64).reshape(-1)
+        sl = self.spec.p_slices()
+        if "model" in sl:
+            self.acados_ocp.parameter_values = self._theta[sl["model"][0]].copy()
+        self._push_theta()
+
+    def get_theta(self) -> np.ndarray:
+        return self._theta.copy()
+
+    def reset(self) -> None:
+        self.engine.reset(B=1)
+
+    def solve(self) -> int:
+        if not np.array_equal(self._lbx0, self._ubx0):
+            raise NotImplementedError("the engine fixes x_0: set(0,'lbx',x0) and set(0,'ubx',x0) must agree")
+        x0 = self._t(self._lbx0, self.spec.nx)
+        u0 = None
+        if self.qmode:
+            u0 = self._t(self._lbu0, self.spec.nu)
+        elif not (np.array_equal(self._lbu0, self.spec.lbu) and np.array_equal(self._ubu0, self.spec.ubu)):
+            raise NotImplementedError("stage-0 input bounds must be nominal (V) or equal (Q)")
+        _, cost, status = self.engine.solve(x0, u0, max_sqp=self.acados_ocp.solver_options.nlp_solver_max_iter)
+        self._cost = float(cost.item())
+        self.status = int(status.item())
+        return self.status
+
+    def solve_for_x0(self, x0_bar, fail_on_nonzero_status: bool = True, print_stats_on_failure: bool = True):
+        self.set(0, "lbx", x0_bar)
+        self.set(0, "ubx", x0_bar)
+        status = self.solve()
+        if status != 0 and fail_on_nonzero_status:
+            raise Exception(f"acados acados_ocp_solver returned status {status}")
+        return self.get(0, "u")
+
+    def evaluate(self):
+        """update_nlp work at the current iterate: returns (dL_dtheta [ntheta], dpi_dtheta [nu, ntheta])."""
+        dL, dpi, cost, res, status = self.engine.sens(1, qmode=self.qmode)
+        self._cost = float(cost.item())
+        self._res = res[0].cpu().numpy()
+        return (self.engine.full_grad(dL)[0].cpu().numpy(), self.engine.full_grad(dpi)[0].cpu().numpy(), int(status.item()))
+
+    def get_cost(self) -> float:
+        return self._cost
+
+    def get_residuals(self):
+        """[stat, eq, ineq, comp] of the last evaluation (acados: get_residuals())."""
+        _, _, cost, res, _ = self.engine.sens(1, qmode=self.qmode)
+        self._res = res[0].cpu().numpy()
+        return self._res.copy()
+
+    def get(self, stage: int, field: str) -> np.ndarray:
+        nx, nu, N = self.spec.nx, self.spec.nu, self.N
+        if field in ("x", "u", "pi"):
+            return self.engine.get(field, stage, 1)[0].cpu().numpy()
+        if field in ("sl", "su"):
+            return np.zeros(0)
+        if field in ("lam", "t"):
+            # acados order within a stage: [lbu, lbx, ubu, ubx] (rlmpc/common/utils.py:4-25)
+            if stage == N:
+                return np.zeros(0)  # no terminal bounds in this problem class
+            v = self.engine.get(field, stage, 1)[0].cpu().numpy()
+            lo_u, up_u = v[:nu], v[nu:]
+            if stage > 0:
+                return np.concatenate([lo_u, up_u])
+            # stage 0 carries the x_0 (and, in Q-mode, u_0) equalities as two opposing bounds
+            rho_x = self.engine.get("rho_x0", 0, 1)[0].cpu().numpy()
+            if self.qmode:
+                rho_u = self.engine.get("rho_u0", 0, 1)[0].cpu().numpy()
+                lo_u, up_u = (np.maximum(rho_u, 0.0), np.maximum(-rho_u, 0.0)) if field == "lam" else (np.zeros(nu), np.zeros(nu))
+            lo_x, up_x = (np.maximum(rho_x, 0.0), np.maximum(-rho_x, 0.0)) if field == "lam" else (np.zeros(nx), np.zeros(nx))
+            return np.concatenate([lo_u, lo_x, up_u, up_x])
+        raise NotImplementedError(field)
+
+    # ---- iterate hand-off (examples/chain_mass.py:119-120) ----
+    def store_iterate(self, filename: str = "iterate.json", overwrite: bool = False, verbose: bool = True) -> None:
+        if os.path.exists(filename) and not overwrite:
+            raise FileExistsError(filename)
+        d = {}
+        for k in range(self.N + 1):
+            d[f"x_{k}"] = self.get(k, "x").tolist()
+            if k < self.N:
+                d[f"u_{k}"] = self.get(k, "u").tolist()
+                d[f"pi_{k}"] = self.get(k, "pi").tolist()
+                for f in ("lam", "t"):
+                    d[f"{f}_{k}"] = self.engine.get(f, k, 1)[0].cpu().numpy().tolist()
+        with open(filename, "w") as fh:
+            json.dump(d, fh, indent=1)
+
+    def load_iterate(self, filename: str, verbose: bool = True) -> None:
+        with open(filename) as fh:
+            d = json.load(fh)
+        for key, val in d.items():
+            f, k = key.rsplit("_", 1)
+            dim = len(val)
+            self.engine.put(f, int(k), torch.tensor([val], dtype=torch.float64, device=self._dev))
