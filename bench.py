@@ -5,8 +5,10 @@ metric   MPC solves+sensitivities/sec: one unit = for one sample, one SQP-RTI st
          NMPC (N=40, nx=4, nu=1, config/cartpole_original.yaml) from the stored warm-start iterate
          PLUS dL/dtheta and dpi/dtheta at the new iterate (= one `update`/`q_update` + one
          `update_nlp` of the reference).  SURVEY.md 8(d).
-step     one fused launch over a batch of 65 536 synthetic samples per GPU (weak scaling), followed
-         by the TD-gradient accumulator kernel and, for N>1, its NCCL all-reduce.
+step     one rlmpc_solve_sens call over a batch of 65 536 synthetic samples per GPU (weak scaling): five
+         kernels (linearise | convergence test + fast QP | full interior point on the queued samples |
+         exact-Hessian stage evaluation | factorisation + adjoint sweeps), followed by the TD-gradient
+         accumulator kernel and, for N>1, its NCCL all-reduce.
 value    whole-job units/s with inputs resident in HBM, CUDA-event timed, max over ranks.
 e2e      same metric through the C ABI host entry point (rlmpc_solve_sens_host): pinned host buffers,
          H2D of the states and D2H of every result inside the timed region (wall clock, max over ranks).
@@ -169,6 +171,7 @@ def run_gpu(args, rank, world, local_rank):
     x0 = synth_states(B, 1234 + rank).to(dev)
     # untimed setup: converge the batch once (cold start like MPC.reset), this is the warm-start state
     mpc.set_option("tol", 1e-6)
+    mpc.set_option("timing", 1)
     mpc.reset(x0)
     _, _, st = mpc.solve(x0, max_sqp=60)
     torch.cuda.synchronize()
@@ -199,6 +202,7 @@ def run_gpu(args, rank, world, local_rank):
     l0 = mpc.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    phase_ms = {k: 0.0 for k in mpc.PHASES}
     with ClockSampler(local_rank) as clk:
         ev[0].record(stream)
         for i in range(args.steps):
@@ -213,6 +217,13 @@ def run_gpu(args, rank, world, local_rank):
         total_ms = ev[0].elapsed_time(ev[-1])
         time.sleep(0.25)
     launches = mpc.launch_count - l0
+    # per-kernel device times (CUDA events recorded by the library on the launching stream between
+    # the kernels of a call); separate pass because reading them waits for the call
+    n_ph = 3
+    for i in range(n_ph):
+        mpc.solve_sens(xs[args.warmup + (i % args.steps)], max_sqp=1, out=out)
+        for k, v in mpc.timings().items():
+            phase_ms[k] += v / n_ph
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     ok_frac = float((out["status"] == 0).double().mean().item())
     res_max = float(out["res"].max().item())
@@ -250,7 +261,9 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_unit<CartpoleModel>", "kernel_ms": kernel_ms,
+                         "kernel": "rlmpc_solve_sens = k_lin + k_qp1 + k_qp2 + k_sens_stage + k_sens_sweep "
+                                   f"(dominant: {max(phase_ms, key=phase_ms.get)})",
+                         "kernel_ms": kernel_ms, "kernels_ms": {k: round(v, 4) for k, v in phase_ms.items()},
                          "algorithmic_bytes_per_unit": B_ALG,
                          "note": "path is FP64 CUDA-core/latency bound, not HBM bound (SURVEY.md 8(d)); "
                                  "fraction reported as defined, bytes not padded"},

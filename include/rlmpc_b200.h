@@ -66,6 +66,9 @@ const char* rlmpc_last_error(void);
 /* dims: nx, nu, ntheta (length of the reference's p vector, nlp.py:970-989), ngrad (width of the
  * gradient rows, see rlmpc_sens), iterate doubles per sample */
 int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* ngrad, int* iterate_size);
+/* inequality rows per stage held in "lam"/"t": 2*(nu + nbx), acados order [lbu, lbx, ubu, ubx]
+ * (rlmpc/common/utils.py:4-25); nbx = 0 unless the problem was created with finite state bounds */
+int rlmpc_nrows(const rlmpc_handle* h);
 
 /* ---- parameters / options --------------------------------------------------------------- */
 /* Replaces ocp_solver.set(stage,"p",..) for all stages + cost_set(stage,"W"/"yref",..)
@@ -80,6 +83,8 @@ int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n);
 int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n);
 /* options: "tol" (1e-6), "tau" (1e-8), "mu0" (1.0), "max_ipm" (50), "warm_ipm" (1: start every QP's
  * interior-point iteration from the multipliers of the previous QP, with a cold restart if jammed),
+ * "sync_every" (4: SQP rounds between host checks "has every sample converged" when max_sqp > 1),
+ * "timing" (0; 1 = record per-phase CUDA events, see rlmpc_get_timings),
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */
 int rlmpc_set_option(rlmpc_handle* h, const char* name, double value);
 
@@ -128,6 +133,12 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);
+/* With option "timing" = 1 the library records CUDA events on the caller's stream between the phases
+ * of a solve / sens call.  ms_out[0..5) = device time of the last call's
+ * [linearise | convergence test + fast QP | full interior point | sens stage evaluation | sens sweeps]
+ * kernels (of the last SQP round when max_sqp > 1); waits for the call to finish.  The reference's
+ * analogue is the nlp_timing dict of update_nlp (nlp.py:1397-1422). */
+int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n);
 
 #ifdef __cplusplus
 }

@@ -17,10 +17,10 @@ LIB_PATH = os.environ.get("RLMPC_B200_LIB", os.path.join(_PKG, "librlmpc_b200.so
 
 # every symbol include/rlmpc_b200.h declares
 SYMBOLS = [
-    "rlmpc_create", "rlmpc_destroy", "rlmpc_last_error", "rlmpc_dims", "rlmpc_set_theta",
+    "rlmpc_create", "rlmpc_destroy", "rlmpc_last_error", "rlmpc_dims", "rlmpc_nrows", "rlmpc_set_theta",
     "rlmpc_set_cost_scaling", "rlmpc_set_bounds", "rlmpc_set_option", "rlmpc_reset", "rlmpc_get_iterate",
     "rlmpc_put_iterate", "rlmpc_solve", "rlmpc_sens", "rlmpc_solve_sens", "rlmpc_solve_sens_host",
-    "rlmpc_td_grad", "rlmpc_launch_count",
+    "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings",
 ]
 
 
@@ -55,6 +55,7 @@ def load():
     lib.rlmpc_destroy.argtypes = [H]; lib.rlmpc_destroy.restype = None
     lib.rlmpc_last_error.restype = C.c_char_p
     lib.rlmpc_dims.argtypes = [H, ip, ip, ip, ip, ip]
+    lib.rlmpc_nrows.argtypes = [H]
     lib.rlmpc_set_theta.argtypes = [H, vp, C.c_int, C.c_int]
     lib.rlmpc_set_cost_scaling.argtypes = [H, vp, C.c_int]
     lib.rlmpc_set_bounds.argtypes = [H, cp, vp, C.c_int]
@@ -67,6 +68,7 @@ def load():
     lib.rlmpc_solve_sens.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rlmpc_solve_sens_host.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rlmpc_td_grad.argtypes = [H, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.rlmpc_get_timings.argtypes = [H, vp, C.c_int]
     lib.rlmpc_launch_count.argtypes = [H]; lib.rlmpc_launch_count.restype = C.c_longlong
     for name in SYMBOLS:
         f = getattr(lib, name)

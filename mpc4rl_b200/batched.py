@@ -37,6 +37,8 @@ class BatchedMPC:
         desc = spec.to_desc()
         _cabi.check(self.lib.rlmpc_create(C.byref(desc), self.max_batch, dev.index or 0, C.byref(self._h)))
         self.nx, self.nu, self.ntheta = spec.nx, spec.nu, spec.ntheta
+        self.nrows = int(self.lib.rlmpc_nrows(self._h))  # 2*(nu+nbx) inequality rows per stage [lbu lbx ubu ubx]
+        self.nbx = self.nrows // 2 - self.nu
         self.theta = np.array(spec.p_nominal, dtype=np.float64)
         self.set_theta(self.theta)
         self.param_cost = bool(spec.parameterize_tracking_cost)
@@ -107,7 +109,7 @@ class BatchedMPC:
         _cabi.check(self.lib.rlmpc_reset(self._h, int(B), _ptr(x0), self._stream()))
 
     def get(self, field: str, stage: int, B: int) -> torch.Tensor:
-        dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": 2 * self.nu, "t": 2 * self.nu,
+        dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": self.nrows, "t": self.nrows,
                "rho_x0": self.nx, "rho_u0": self.nu}[field]
         out = torch.empty(B, dim, dtype=torch.float64, device=self.device)
         _cabi.check(self.lib.rlmpc_get_iterate(self._h, field.encode(), int(stage), int(B), _ptr(out), self._stream()))
@@ -187,6 +189,14 @@ class BatchedMPC:
         _cabi.check(self.lib.rlmpc_td_grad(self._h, B, ncols, _ptr(td.contiguous()), _ptr(dQ.contiguous()),
                                            _ptr(status), _ptr(acc), self._stream()))
         return acc
+
+    PHASES = ("linearize", "qp_fast", "qp_full", "sens_stage", "sens_sweep")
+
+    def timings(self) -> dict:
+        """Device milliseconds of the phases of the last call (needs set_option("timing", 1))."""
+        ms = np.zeros(5)
+        _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 5))
+        return dict(zip(self.PHASES, ms.tolist()))
 
     @property
     def launch_count(self) -> int:

@@ -1,5 +1,5 @@
 // Shared definitions of the rlmpc-b200 engine (host/device generic maths).
-// The same templates are instantiated in CUDA kernels (kernels.cu, the product) and, for
+// The same templates are instantiated in CUDA kernels (rlmpc_b200.cu, the product) and, for
 // timing/debugging only, in a host build under oracle/cpu_port (test infrastructure).
 #pragma once
 #include <cmath>
@@ -18,11 +18,19 @@ namespace rlmpc {
 
 constexpr int MAXN = 128;  // max horizon supported by ProblemData
 constexpr int MAXD = 8;    // max nx / nu held in ProblemData bound arrays (thread-per-sample engine)
+constexpr double BIG = 1e29;  // |bound| >= BIG means "no bound"
 
 // acados status codes: 0 ok, 1 NaN, 2 max iter, 3 min step, 4 QP failure
 enum Status : int { ST_OK = 0, ST_NAN = 1, ST_MAXITER = 2, ST_MINSTEP = 3, ST_QPFAIL = 4 };
 
 enum Mode : int { MODE_V = 0, MODE_Q = 1 };
+
+// per-sample pipeline state between the kernels of one solve call
+enum Work : int {
+  WK_ACTIVE = 0,   // needs (another) SQP iteration
+  WK_HARD = 1,     // linearised, fast QP path declined: queued for the full interior-point solve
+  WK_DONE = 2,     // finished (status holds the result)
+};
 
 // Everything that is shared by all samples of a batch. Passed to kernels by value
 // (fits the 4 KB kernel-parameter space), so it sits in constant memory.
@@ -38,7 +46,7 @@ struct ProblemData {
   double mu0;           // initial barrier parameter of a cold-started IPM
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
-  double lbx[MAXD], ubx[MAXD];      // stages 1..N-1
+  double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component
   double lbx_e[MAXD], ubx_e[MAXD];  // stage N
   double mc[8];         // model constants (integrator step, gravity, ...)
 };
@@ -50,6 +58,8 @@ struct Lane {
   size_t bs;         // batch stride (padded batch size)
   const double* th;  // parameter vector theta
   size_t ths;        // stride between theta entries (1: shared theta; bs: per-sample theta)
+  const double* ct;  // quadratic cost table derived from theta (Engine::CT_*)
+  size_t cts;        // stride between cost-table entries (1 shared / bs per-sample)
 };
 
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }

@@ -1,10 +1,10 @@
-// rlmpc-b200 engine: per-sample SQP (Gauss-Newton / exact) with a Riccati-structured
-// primal-dual interior-point QP solve, followed by the exact-Hessian adjoint KKT solve that
-// yields dpi/dtheta and the stage sweep that yields dL/dtheta (= dV/dtheta = dQ/dtheta).
+// rlmpc-b200 engine: per-sample SQP (Gauss-Newton Hessian) with a Riccati-structured primal-dual
+// interior-point QP solve, followed by the exact-Hessian adjoint KKT solve that yields
+// dpi/dtheta and the stage sweep that yields dL/dtheta (= dV/dtheta = dQ/dtheta).
 //
 // What this replaces in the reference:
-//   a4  AcadosOcpSolver.solve()  (acados SQP + HPIPM Riccati IPM)   -> Engine::solve
-//   a5  update_nlp()  rlmpc/mpc/nlp.py:1341-1563 (dense dR/dz + SuperLU, dL/dp) -> Engine::sens
+//   a4  AcadosOcpSolver.solve()  (acados SQP + HPIPM Riccati IPM)   -> lin_stage + qp_fast/qp_full
+//   a5  update_nlp()  rlmpc/mpc/nlp.py:1341-1563 (dense dR/dz + SuperLU, dL/dp) -> sens_stage + sens_sweep
 // The maths is specified by rlmpc/mpc/nlp.py:884-1275:
 //   L = cost + lam'h + pi'g,  g_k = F(x_k,u_k;theta) - x_{k+1},  h <= 0 (bounds),
 //   R = [dL/dw ; g ; h + t ; lam*t - tau] = 0,  tau = 1e-8,
@@ -12,10 +12,15 @@
 // Equal bounds of stage 0 (x_0 = s always; u_0 = a in Q-mode) are imposed by elimination
 // (the tau -> 0 limit of the reference, quirk Q7).
 //
-// One "lane" = one sample.  All per-sample vectors live in batch-minor (SoA) arrays: element
-// i of sample b is at base[i*bs + b], so a warp touching element i reads 32 consecutive
-// doubles (one 256-byte line pair).  The code is host/device generic: kernels.cu runs one
-// lane per CUDA thread; the host build exists only for debugging and the CPU baseline.
+// Work decomposition.  The functions below come in two shapes:
+//   *_stage(pd, L, k)  one (sample, stage) pair: function/derivative evaluation, no dependence
+//                      between stages -> launched over B x (N+1) threads, compute bound;
+//   qp_* / sens_sweep  one sample: the Riccati recursions, sequential in the stage index ->
+//                      launched over B threads, streaming the per-stage records from HBM.
+// All per-sample vectors live in batch-minor (SoA) arrays: element i of sample b is at
+// base[i*bs + b], so a warp touching element i reads 32 consecutive doubles (256 bytes).
+// The code is host/device generic: rlmpc_b200.cu runs it in CUDA kernels; a host build of the
+// same templates exists only as test infrastructure (debugging, CPU baseline).
 #pragma once
 #include "common.cuh"
 
@@ -23,43 +28,65 @@ namespace rlmpc {
 
 template <class M>
 struct Engine {
-  static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NPM = M::NPM;
+  static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NPM = M::NPM, NBX = M::NBX;
+  static constexpr int NV = NU + NBX;   // box-constrained variables of a stage: [u ; x[bx]]
+  static constexpr int NR = 2 * NV;     // inequality rows per stage, acados order [lbu lbx ubu ubx]
   static constexpr int NPS = NX * (NX + 1) / 2;
+  static constexpr int NWS = NW * (NW + 1) / 2;
 
   // ---------------- iterate layout (per sample, persistent) ----------------
-  //   x[(N+1)NX] | u[N NU] | pi[N NX] | lam_u[N 2NU] | t_u[N 2NU]      (lower rows first)
+  //   x[(N+1)NX] | u[N NU] | pi[N NX] | lam[(N+1) NR] | t[(N+1) NR] | rho_x0 | rho_u0 | meta
   MPC_HD static int it_x(int N, int k) { (void)N; return k * NX; }
   MPC_HD static int it_u(int N, int k) { return (N + 1) * NX + k * NU; }
   MPC_HD static int it_pi(int N, int k) { return (N + 1) * NX + N * NU + k * NX; }
-  MPC_HD static int it_lu(int N, int k) { return (N + 1) * NX + N * NU + N * NX + k * 2 * NU; }
-  MPC_HD static int it_tu(int N, int k) { return (N + 1) * NX + N * NU + N * NX + N * 2 * NU + k * 2 * NU; }
+  MPC_HD static int it_lam(int N, int k) { return (N + 1) * NX + N * NU + N * NX + k * NR; }
+  MPC_HD static int it_t(int N, int k) { return it_lam(N, 0) + (N + 1) * NR + k * NR; }
   // multipliers of the eliminated equal bounds of stage 0 (x_0 = s; u_0 = a in Q-mode), i.e. the
-  // gradient of the rest of the Lagrangian wrt x_0 / u_0; written by sens()
-  MPC_HD static int it_rx0(int N) { return (N + 1) * NX + N * NU + N * NX + 4 * N * NU; }
+  // gradient of the rest of the Lagrangian wrt x_0 / u_0; written by sens_sweep()
+  MPC_HD static int it_rx0(int N) { return it_t(N, 0) + (N + 1) * NR; }
   MPC_HD static int it_ru0(int N) { return it_rx0(N) + NX; }
   // meta[0] = 1.0 once (lam,t) hold the result of a QP solve (valid IPM warm start)
   MPC_HD static int it_meta(int N) { return it_ru0(N) + NU; }
   MPC_HD static int it_size(int N) { return it_meta(N) + 1; }
 
+  // ---------------- quadratic cost table (derived from theta by M::cost_table) ----------------
+  //   l_kind(y) = c0 + flin'y + 1/2 (y - yref)' W (y - yref),  y = [x;u]  (terminal: u part zero)
+  static constexpr int CT_W = 0;                 // NWS, packed upper triangle, row-major
+  static constexpr int CT_Y = CT_W + NWS;        // yref (NW)
+  static constexpr int CT_F = CT_Y + NW;         // flin (NW)
+  static constexpr int CT_C = CT_F + NW;         // c0
+  static constexpr int CT_REC = CT_C + 1;
+  static constexpr int CT_SIZE = 3 * CT_REC;     // kinds: 0 initial, 1 intermediate, 2 terminal
+  MPC_HD static constexpr int pidx(int i, int j) { return i * NW - i * (i - 1) / 2 + (j - i); }  // i <= j
+
   // ---------------- workspace record per stage ----------------
+  // solve phase
   static constexpr int W_A = 0;
   static constexpr int W_B = W_A + NX * NX;
   static constexpr int W_b = W_B + NX * NU;
-  static constexpr int W_q = W_b + NX;
-  static constexpr int W_r = W_q + NX;
+  static constexpr int W_q = W_b + NX;          // scaled cost gradient wrt x
+  static constexpr int W_r = W_q + NX;          // ... wrt u
   static constexpr int W_K = W_r + NU;
   static constexpr int W_k = W_K + NU * NX;
   static constexpr int W_dx = W_k + NU;
   static constexpr int W_du = W_dx + NX;
-  static constexpr int W_lh = W_du + NU;       // lam_hat (2NU)
-  static constexpr int W_th = W_lh + 2 * NU;   // t_hat   (2NU)
-  static constexpr int W_SOLVE_END = W_th + 2 * NU;
-  // sensitivity pass re-uses the record: A, B, K stay where they are, the rest is overlaid
-  static constexpr int W_P = W_K + NU * NX;            // P_{k+1} packed symmetric (NPS)
-  static constexpr int W_Hwp = W_P + NPS;              // d(grad_w L)/d p_model  (NW x NPM)
-  static constexpr int W_Fp = W_Hwp + NW * NPM;        // dF/d p_model (NX x NPM)
-  static constexpr int W_Gi = W_Fp + NX * NPM;         // stage 0 only: inv(G_0) (NU x NU)
-  static constexpr int W_SENS_END = W_Gi + NU * NU;
+  static constexpr int W_lh = W_du + NU;        // lam_hat (NR)
+  static constexpr int W_th = W_lh + NR;        // t_hat   (NR)
+  static constexpr int W_c = W_th + NR;         // scaled stage cost
+  static constexpr int W_e = W_c + 1;           // |F(x_k,u_k) - x_{k+1}|_inf
+  static constexpr int W_SOLVE_END = W_e + 1;
+  // sensitivity phase (overlays the solve record; A, B stay where they are)
+  static constexpr int S_g = W_b;                      // scaled cost gradient [x;u] (NW)
+  static constexpr int S_H = S_g + NW;                 // Hessian of pi'F wrt w, packed upper (NWS)
+  static constexpr int S_Hwp = S_H + NWS;              // d(grad_w pi'F)/d p_model  (NW x NPM)
+  static constexpr int S_Fp = S_Hwp + NW * NPM;        // dF/d p_model (NX x NPM)
+  static constexpr int S_gp = S_Fp + NX * NPM;         // pi_k' dF/dp (NPM)
+  static constexpr int S_c = S_gp + NPM;               // scaled stage cost
+  static constexpr int S_e = S_c + 1;                  // dynamics defect norm
+  static constexpr int S_K = S_e + 1;                  // feedback gain of the exact-Hessian factorisation
+  static constexpr int S_P = S_K + NU * NX;            // P_{k+1} packed symmetric (NPS)
+  static constexpr int S_Gi = S_P + NPS;               // stage 0 only: inv(G_0) (NU x NU)
+  static constexpr int W_SENS_END = S_Gi + NU * NU;
   static constexpr int W_REC = W_SOLVE_END > W_SENS_END ? W_SOLVE_END : W_SENS_END;
   MPC_HD static int ws_size(int N) { return (N + 1) * W_REC; }
 
@@ -73,7 +100,7 @@ struct Engine {
     MPC_UNROLL for (int i = 0; i < n; ++i) p[(size_t)i * bs] = in[i];
   }
 
-  // in-place Cholesky-based solve of a small SPD system G X = R (G: n x n, R: n x m); returns false if not PD
+  // in-place LDL'-based solve of a small SPD system G X = R (G: n x n, R: n x m); returns false if not PD
   template <int n, int m>
   MPC_HD static bool spd_solve(double* G, double* R) {
     if (n == 1) {
@@ -82,7 +109,6 @@ struct Engine {
       MPC_UNROLL for (int j = 0; j < m; ++j) R[j] *= inv;
       return true;
     }
-    // LDL^T without pivoting
     bool ok = true;
     MPC_UNROLL for (int j = 0; j < n; ++j) {
       double d = G[j * n + j];
@@ -112,11 +138,164 @@ struct Engine {
     return ok;
   }
 
-  // Cost weight blocks of stage kind (0 initial / 1 intermediate / 2 terminal), scaled by s
-  MPC_HD static void load_W(int kind, double s, const Lane& L, double* Wm /* NW x NW (or NX x NX top-left) */) {
-    const int n = (kind == 2) ? NX : NW;
-    MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = 0; j < NW; ++j) {
-      Wm[i * NW + j] = (i < n && j < n) ? s * M::W(kind, i, j, L.th, L.ths) : 0.0;
+  // ---------------- quadratic stage cost ----------------
+  struct CostK {
+    double W[NW * NW];  // full symmetric, unscaled
+    double yref[NW], flin[NW], c0;
+  };
+  MPC_HD static void load_cost(int kind, const Lane& L, CostK& c) {
+    const double* p = L.ct + (size_t)(kind * CT_REC) * L.cts;
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      MPC_UNROLL for (int j = i; j < NW; ++j) {
+        const double v = p[(size_t)(CT_W + pidx(i, j)) * L.cts];
+        c.W[i * NW + j] = v;
+        c.W[j * NW + i] = v;
+      }
+      c.yref[i] = p[(size_t)(CT_Y + i) * L.cts];
+      c.flin[i] = p[(size_t)(CT_F + i) * L.cts];
+    }
+    c.c0 = p[(size_t)CT_C * L.cts];
+  }
+  // scaled Hessian block only (what the Riccati sweeps need)
+  MPC_HD static void load_W(int kind, double s, const Lane& L, double* Wm) {
+    const double* p = L.ct + (size_t)(kind * CT_REC + CT_W) * L.cts;
+    MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) {
+      const double v = s * p[(size_t)pidx(i, j) * L.cts];
+      Wm[i * NW + j] = v;
+      Wm[j * NW + i] = v;
+    }
+  }
+  // gradient g = s (W (y - yref) + flin) and value s l(y) of one stage, y = [x;u] (n = NW or NX)
+  MPC_HD static double cost_grad(const CostK& c, double s, int n, const double* y, double* g) {
+    double e[NW], val = c.c0;
+    MPC_UNROLL for (int i = 0; i < NW; ++i) e[i] = (i < n) ? y[i] - c.yref[i] : 0.0;
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      double a = 0.0;
+      MPC_UNROLL for (int j = 0; j < NW; ++j) a += c.W[i * NW + j] * e[j];
+      g[i] = (i < n) ? s * (a + c.flin[i]) : 0.0;
+      if (i < n) val += 0.5 * a * e[i] + c.flin[i] * y[i];
+    }
+    return s * val;
+  }
+
+  // ---------------- box rows of one stage ----------------
+  // Variables v = [u ; x[bx]]; row r < NV is the lower bound of v_r, row NV + r its upper bound
+  // (acados order [lbu, lbx, ubu, ubx], rlmpc/common/utils.py:4-25).  A row that does not exist at
+  // this stage (u at stage N or clamped in Q-mode, x at stage 0, infinite bound) gets lb = -inf /
+  // ub = +inf and is skipped everywhere.
+  MPC_HD static int vidx(int r) { return r < NU ? NX + r : M::bx(r - NU); }  // index into w = [x;u]
+  MPC_HD static void stage_bounds(const ProblemData& pd, int k, double* lb, double* ub) {
+    const bool uact = (k < pd.N) && !(k == 0 && pd.mode == MODE_Q);
+    MPC_UNROLL for (int i = 0; i < NU; ++i) {
+      lb[i] = uact ? pd.lbu[i] : -1e300;
+      ub[i] = uact ? pd.ubu[i] : 1e300;
+    }
+    MPC_UNROLL for (int j = 0; j < NBX; ++j) {
+      const int ix = M::bx(j);
+      lb[NU + j] = (k == 0) ? -1e300 : (k == pd.N ? pd.lbx_e[ix] : pd.lbx[ix]);
+      ub[NU + j] = (k == 0) ? 1e300 : (k == pd.N ? pd.ubx_e[ix] : pd.ubx[ix]);
+    }
+  }
+  MPC_HD static int count_rows(const ProblemData& pd) {
+    int m = 0;
+    for (int k = 0; k <= pd.N; ++k) {
+      double lb[NV], ub[NV];
+      stage_bounds(pd, k, lb, ub);
+      MPC_UNROLL for (int r = 0; r < NV; ++r) m += (lb[r] > -BIG) + (ub[r] < BIG);
+    }
+    return m;
+  }
+  MPC_HD static void stage_vars(const double* x, const double* u, double* v) {
+    MPC_UNROLL for (int i = 0; i < NU; ++i) v[i] = u[i];
+    MPC_UNROLL for (int j = 0; j < NBX; ++j) v[NU + j] = x[M::bx(j)];
+  }
+  // warm-start safeguard: keep (lam,t) strictly inside the cone
+  MPC_HD static void clip_rows(const double* lb, const double* ub, double* lam, double* t) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
+      t[r] = dmax(t[r], 1e-10 * range);
+      t[NV + r] = dmax(t[NV + r], 1e-10 * range);
+      lam[r] = dmax(lam[r], 1e-14);
+      lam[NV + r] = dmax(lam[NV + r], 1e-14);
+    }
+  }
+  // condensed barrier terms: Hm += J' diag(lam/t) J,  g += J'(target/t + lam + (lam/t) hbar),
+  // hbar_l = lb - v, hbar_u = v - ub  (g = [gq ; gr] of the stage)
+  MPC_HD static void barrier_add(const double* lb, const double* ub, const double* v, const double* lam, const double* t,
+                                 double target, double* Hm, double* g) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      const int ix = vidx(r);
+      if (lb[r] > -BIG) {
+        const double itl = 1.0 / t[r], cl = lam[r] * itl;
+        Hm[ix * NW + ix] += cl;
+        g[ix] -= target * itl + lam[r] - cl * (v[r] - lb[r]);
+      }
+      if (ub[r] < BIG) {
+        const double itu = 1.0 / t[NV + r], cu = lam[NV + r] * itu;
+        Hm[ix * NW + ix] += cu;
+        g[ix] += target * itu + lam[NV + r] - cu * (ub[r] - v[r]);
+      }
+    }
+  }
+  // Hessian part only (sensitivity factorisation)
+  MPC_HD static void barrier_hess(const double* lb, const double* ub, const double* lam, const double* t, double* Hm) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      const int ix = vidx(r);
+      if (lb[r] > -BIG) Hm[ix * NW + ix] += lam[r] / t[r];
+      if (ub[r] < BIG) Hm[ix * NW + ix] += lam[NV + r] / t[NV + r];
+    }
+  }
+  struct StepStats {
+    double amax, s0, s1, s2, cmax;
+  };
+  // new slacks/multipliers of the rows for the primal step dv (dw = [dx;du]); step-length statistics
+  MPC_HD static void rows_forward(const double* lb, const double* ub, const double* v, const double* dw,
+                                  const double* lam, const double* t, double target, double* lh, double* th,
+                                  StepStats& S) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      const double dv = dw[vidx(r)];
+      MPC_UNROLL for (int side = 0; side < 2; ++side) {
+        const int q = side * NV + r;
+        const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
+        if (!act) {
+          lh[q] = 0.0;
+          th[q] = 0.0;
+          continue;
+        }
+        // (v - lb) + dv, NOT (v + dv) - lb: the slack must use the same rounded distance to the
+        // bound as the condensed gradient, or lam_hat picks up c*ulp(v) ~ 1e-8 of noise
+        th[q] = side ? (ub[r] - v[r]) - dv : (v[r] - lb[r]) + dv;
+        const double it_ = 1.0 / t[q];
+        lh[q] = target * it_ + lam[q] - lam[q] * it_ * th[q];
+        const double dt = th[q] - t[q], dl = lh[q] - lam[q];
+        if (dt < 0.0) S.amax = dmin(S.amax, -t[q] / dt);
+        if (dl < 0.0) S.amax = dmin(S.amax, -lam[q] / dl);
+        S.s0 += lam[q] * t[q];
+        S.s1 += lam[q] * dt + t[q] * dl;
+        S.s2 += dl * dt;
+        S.cmax = dmax(S.cmax, dabs(dl * dt));
+      }
+    }
+  }
+
+  struct Residuals {
+    double stat, eq, ineq, comp, cost;
+  };
+  // comp / ineq residuals of the rows of one stage and their contribution J'lam to stationarity
+  MPC_HD static void rows_residual(const ProblemData& pd, const double* lb, const double* ub, const double* v,
+                                   const double* lam, const double* t, Residuals& R, double* jl /* NW, += */) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      const int ix = vidx(r);
+      if (lb[r] > -BIG) {
+        jl[ix] -= lam[r];
+        R.comp = dmax(R.comp, dabs(lam[r] * t[r] - pd.tau));
+        R.ineq = dmax(R.ineq, dabs(lb[r] - v[r] + t[r]));
+      }
+      if (ub[r] < BIG) {
+        jl[ix] += lam[NV + r];
+        R.comp = dmax(R.comp, dabs(lam[NV + r] * t[NV + r] - pd.tau));
+        R.ineq = dmax(R.ineq, dabs(v[r] - ub[r] + t[NV + r]));
+      }
     }
   }
 
@@ -124,8 +303,10 @@ struct Engine {
   // Returns false if the reduced Hessian block G is not positive definite.
   MPC_HD static bool riccati_step(double* P, double* p, const double* A, const double* B, const double* b,
                                   const double* Hm /* NW x NW: [Q S'; S R] incl. barrier */,
-                                  const double* gq /* NX */, const double* gr /* NU */, double* K, double* kff,
+                                  const double* g /* NW: [gq ; gr] */, double* K, double* kff,
                                   double* Ginv /* optional NU x NU or nullptr */) {
+    const double* gq = g;
+    const double* gr = g + NX;
     double v[NX], PA[NX * NX], PB[NX * NU];
     MPC_UNROLL for (int i = 0; i < NX; ++i) {
       double a = p[i];
@@ -193,146 +374,291 @@ struct Engine {
     return ok;
   }
 
-  struct Residuals {
-    double stat, eq, ineq, comp, cost;
-  };
-
-  // ---------------------------------------------------------------------------------------
-  // Linearise all stages at the current iterate: store A,B,b,q,r per stage, return the cost
-  // and the four KKT residual norms (acados' convergence test).
-  // ---------------------------------------------------------------------------------------
-  MPC_HD static Residuals linearize(const ProblemData& pd, const Lane& L) {
+  // =======================================================================================
+  // (sample, stage) function: linearise stage k at the current iterate.
+  // k < N: A, B, b = F(x_k,u_k) - x_{k+1}, scaled cost gradient q, r, stage cost, defect norm.
+  // k = N: terminal cost gradient and value.
+  // =======================================================================================
+  MPC_HD static void lin_stage(const ProblemData& pd, const Lane& L, int k) {
     const int N = pd.N;
     const size_t bs = L.bs;
-    Residuals R = {0, 0, 0, 0, 0};
-    double pim[NX];  // pi_{k-1}
-    MPC_UNROLL for (int i = 0; i < NX; ++i) pim[i] = 0.0;
-    for (int k = 0; k < N; ++k) {
-      double x[NX], u[NU], xn[NX], xnext[NX], A[NX * NX], B[NX * NU], bb[NX];
-      ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
-      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+    double* w = L.ws + (size_t)k * W_REC * bs;
+    CostK ck;
+    double y[NW], g[NW];
+    if (k < N) {
+      double xn[NX], xnext[NX], A[NX * NX], B[NX * NU], bb[NX];
+      ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, y);
+      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, y + NX);
       ld<NX>(L.it + (size_t)it_x(N, k + 1) * bs, bs, xnext);
-      M::dyn_lin(x, u, L.th, L.ths, pd.mc, xn, A, B);
+      M::dyn_lin(y, y + NX, L.th, L.ths, pd.mc, xn, A, B);
+      double eq = 0.0;
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
         bb[i] = xn[i] - xnext[i];
-        R.eq = dmax(R.eq, dabs(bb[i]));
+        eq = dmax(eq, dabs(bb[i]));
+        if (!(bb[i] == bb[i])) eq = bb[i];  // propagate NaN
       }
-      double* w = L.ws + (size_t)k * W_REC * bs;
       st<NX * NX>(w + (size_t)W_A * bs, bs, A);
       st<NX * NU>(w + (size_t)W_B * bs, bs, B);
       st<NX>(w + (size_t)W_b * bs, bs, bb);
-      // cost gradient
-      const int kind = (k == 0) ? 0 : 1;
-      const double s = pd.scale[k];
-      double e[NW], gr[NW];
-      MPC_UNROLL for (int i = 0; i < NW; ++i) e[i] = ((i < NX) ? x[i] : u[i - NX]) - M::yref(kind, i, L.th, L.ths);
-      double c = M::c0(kind, L.th, L.ths);
-      MPC_UNROLL for (int i = 0; i < NW; ++i) {
-        double a = 0.0;
-        MPC_UNROLL for (int j = 0; j < NW; ++j) a += M::W(kind, i, j, L.th, L.ths) * e[j];
-        const double fl = M::flin(kind, i, L.th, L.ths);
-        gr[i] = s * (a + fl);
-        c += 0.5 * a * e[i] + fl * ((i < NX) ? x[i] : u[i - NX]);
+      load_cost(k == 0 ? 0 : 1, L, ck);
+      const double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      st<NW>(w + (size_t)W_q * bs, bs, g);
+      w[(size_t)W_c * bs] = c;
+      w[(size_t)W_e * bs] = eq;
+    } else {
+      ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, y);
+      MPC_UNROLL for (int i = 0; i < NU; ++i) y[NX + i] = 0.0;
+      load_cost(2, L, ck);
+      const double c = cost_grad(ck, pd.scale[N], NX, y, g);
+      st<NX>(w + (size_t)W_q * bs, bs, g);
+      w[(size_t)W_c * bs] = c;
+      w[(size_t)W_e * bs] = 0.0;
+    }
+  }
+
+  // =======================================================================================
+  // Sample function, fast path of one SQP iteration.  One backward sweep evaluates acados'
+  // convergence test (the four KKT residual norms) and, fused with it, the Riccati factorisation
+  // of ONE interior-point Newton iteration started at the stored (lam,t) with target tau; a
+  // forward sweep computes the step.  If that iteration is a full step that lands on the
+  // tau-central point (the usual case when the active set did not change) the step is applied.
+  // Otherwise nothing is modified and the sample is handed to qp_full().
+  // =======================================================================================
+  enum Fast : int { FAST_CONVERGED = 0, FAST_STEPPED = 1, FAST_HARD = 2, FAST_NAN = 3 };
+
+  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R) {
+    const int N = pd.N;
+    const size_t bs = L.bs;
+    const bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
+    const double target = pd.tau;
+    R.stat = R.eq = R.ineq = R.comp = R.cost = 0.0;
+    bool failed = false;
+    double P[NX * NX], p[NX];
+    double carry[NX];  // x-stationarity of stage k+1 without the -pi_k term
+    {                  // terminal stage
+      const double* w = L.ws + (size_t)N * W_REC * bs;
+      double g[NW], Hm[NW * NW];
+      ld<NX>(w + (size_t)W_q * bs, bs, g);
+      MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
+      R.cost += w[(size_t)W_c * bs];
+      MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] = g[i];
+      load_W(2, pd.scale[N], L, Hm);
+      if (NBX > 0) {
+        double lb[NV], ub[NV], x[NX], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
+        stage_bounds(pd, N, lb, ub);
+        ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
+        MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+        stage_vars(x, u0, v);
+        ld<NR>(L.it + (size_t)it_lam(N, N) * bs, bs, lam);
+        ld<NR>(L.it + (size_t)it_t(N, N) * bs, bs, t);
+        MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
+        rows_residual(pd, lb, ub, v, lam, t, R, jl);
+        MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] += jl[i];
+        if (warm) {
+          clip_rows(lb, ub, lam, t);
+          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+        }
       }
-      R.cost += s * c;
-      st<NX>(w + (size_t)W_q * bs, bs, gr);
-      st<NU>(w + (size_t)W_r * bs, bs, gr + NX);
-      // stationarity / complementarity residuals with the current multipliers
-      double pik[NX], lu[2 * NU], tu[2 * NU];
+      MPC_UNROLL for (int i = 0; i < NX; ++i) {
+        p[i] = g[i];
+        MPC_UNROLL for (int j = 0; j < NX; ++j) P[i * NX + j] = Hm[i * NW + j];
+      }
+    }
+    for (int k = N - 1; k >= 0; --k) {
+      double* w = L.ws + (size_t)k * W_REC * bs;
+      double A[NX * NX], B[NX * NU], bb[NX], g[NW], x[NX], u[NU], pik[NX], lam[NR], t[NR], lb[NV], ub[NV], v[NV];
+      ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
+      ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
+      ld<NX>(w + (size_t)W_b * bs, bs, bb);
+      ld<NW>(w + (size_t)W_q * bs, bs, g);
+      R.cost += w[(size_t)W_c * bs];
+      {
+        const double e = w[(size_t)W_e * bs];
+        R.eq = (e == e) ? dmax(R.eq, e) : e;
+      }
+      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
-      ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-      ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
+      ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+      stage_bounds(pd, k, lb, ub);
+      stage_vars(x, u, v);
+      // ---- residuals at the current iterate (raw multipliers) ----
+      MPC_UNROLL for (int i = 0; i < NX; ++i) R.stat = dmax(R.stat, dabs(carry[i] - pik[i]));
+      double jl[NW];
+      MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
+      rows_residual(pd, lb, ub, v, lam, t, R, jl);
       const bool ufixed = (k == 0 && pd.mode == MODE_Q);
       if (!ufixed) {
         MPC_UNROLL for (int i = 0; i < NU; ++i) {
-          double a = gr[NX + i] - lu[i] + lu[NU + i];
+          double a = g[NX + i] + jl[NX + i];
           MPC_UNROLL for (int l = 0; l < NX; ++l) a += B[l * NU + i] * pik[l];
           R.stat = dmax(R.stat, dabs(a));
-          R.comp = dmax(R.comp, dmax(dabs(lu[i] * tu[i] - pd.tau), dabs(lu[NU + i] * tu[NU + i] - pd.tau)));
-          R.ineq = dmax(R.ineq, dmax(dabs(pd.lbu[i] - u[i] + tu[i]), dabs(u[i] - pd.ubu[i] + tu[NU + i])));
         }
       }
-      if (k > 0) {
-        MPC_UNROLL for (int i = 0; i < NX; ++i) {
-          double a = gr[i] - pim[i];
-          MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[l * NX + i] * pik[l];
-          R.stat = dmax(R.stat, dabs(a));
-        }
-      }
-      MPC_UNROLL for (int i = 0; i < NX; ++i) pim[i] = pik[i];
-    }
-    {  // terminal stage
-      double x[NX], gr[NX];
-      ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
-      const double s = pd.scale[N];
-      double e[NX];
-      MPC_UNROLL for (int i = 0; i < NX; ++i) e[i] = x[i] - M::yref(2, i, L.th, L.ths);
-      double c = M::c0(2, L.th, L.ths);
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
-        double a = 0.0;
-        MPC_UNROLL for (int j = 0; j < NX; ++j) a += M::W(2, i, j, L.th, L.ths) * e[j];
-        const double fl = M::flin(2, i, L.th, L.ths);
-        gr[i] = s * (a + fl);
-        c += 0.5 * a * e[i] + fl * x[i];
-        R.stat = dmax(R.stat, dabs(gr[i] - pim[i]));
+        double a = g[i] + jl[i];
+        MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[l * NX + i] * pik[l];
+        carry[i] = a;
       }
-      R.cost += s * c;
-      st<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, gr);
+      // ---- Riccati step of the Newton iteration ----
+      if (warm) {
+        double Hm[NW * NW], K[NU * NX], kff[NU];
+        load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
+        clip_rows(lb, ub, lam, t);
+        barrier_add(lb, ub, v, lam, t, target, Hm, g);
+        if (!ufixed) {
+          if (!riccati_step(P, p, A, B, bb, Hm, g, K, kff, nullptr)) failed = true;
+        } else {
+          MPC_UNROLL for (int i = 0; i < NU * NX; ++i) K[i] = 0.0;
+          MPC_UNROLL for (int i = 0; i < NU; ++i) kff[i] = 0.0;
+        }
+        st<NU * NX>(w + (size_t)W_K * bs, bs, K);
+        st<NU>(w + (size_t)W_k * bs, bs, kff);
+      }
     }
-    return R;
+    const double rmax = dmax(dmax(R.stat, R.eq), dmax(R.ineq, R.comp));
+    if (!(rmax == rmax) || !(R.cost == R.cost)) return FAST_NAN;
+    if (rmax < pd.tol) return FAST_CONVERGED;
+    if (!warm || failed) return FAST_HARD;
+    StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
+    forward_sweep(pd, L, target, /*clip=*/true, S);
+    if (!(S.amax == S.amax)) return FAST_HARD;
+    if (S.amax >= 1.0 / 0.995 && S.cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) {
+      apply_step(pd, L, 1.0, /*clip=*/true);
+      return FAST_STEPPED;
+    }
+    return FAST_HARD;
+  }
+
+  // Forward sweep of one interior-point iteration: dx, du from the feedback law, new slacks and
+  // multipliers (lam_hat, t_hat) of every row, fraction-to-boundary statistics.
+  MPC_HD static void forward_sweep(const ProblemData& pd, const Lane& L, double target, bool clip, StepStats& S) {
+    const int N = pd.N;
+    const size_t bs = L.bs;
+    double dw[NW];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) dw[i] = 0.0;
+    for (int k = 0; k <= N; ++k) {
+      double* w = L.ws + (size_t)k * W_REC * bs;
+      double A[NX * NX], B[NX * NU], bb[NX];
+      if (k < N) {
+        double K[NU * NX];
+        ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
+        ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
+        ld<NX>(w + (size_t)W_b * bs, bs, bb);
+        ld<NU * NX>(w + (size_t)W_K * bs, bs, K);
+        ld<NU>(w + (size_t)W_k * bs, bs, dw + NX);
+        MPC_UNROLL for (int i = 0; i < NU; ++i) MPC_UNROLL for (int l = 0; l < NX; ++l) dw[NX + i] += K[i * NX + l] * dw[l];
+        st<NU>(w + (size_t)W_du * bs, bs, dw + NX);
+      } else {
+        MPC_UNROLL for (int i = 0; i < NU; ++i) dw[NX + i] = 0.0;
+      }
+      st<NX>(w + (size_t)W_dx * bs, bs, dw);
+      if (k < N || NBX > 0) {
+        double lb[NV], ub[NV], x[NX], u[NU], v[NV], lam[NR], t[NR], lh[NR], th[NR];
+        stage_bounds(pd, k, lb, ub);
+        if (k < N) {
+          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+        } else {
+          MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
+        }
+        if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+        stage_vars(x, u, v);
+        ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+        ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+        if (clip) clip_rows(lb, ub, lam, t);
+        rows_forward(lb, ub, v, dw, lam, t, target, lh, th, S);
+        st<NR>(w + (size_t)W_lh * bs, bs, lh);
+        st<NR>(w + (size_t)W_th * bs, bs, th);
+      }
+      if (k < N) {
+        double dxn[NX];
+        MPC_UNROLL for (int i = 0; i < NX; ++i) {
+          double a = bb[i];
+          MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[i * NX + l] * dw[l];
+          MPC_UNROLL for (int l = 0; l < NU; ++l) a += B[i * NU + l] * dw[NX + l];
+          dxn[i] = a;
+        }
+        MPC_UNROLL for (int i = 0; i < NX; ++i) dw[i] = dxn[i];
+      }
+    }
   }
 
   // ---------------------------------------------------------------------------------------
-  // Interior-point solve of the stage QP (Riccati factorisation per iteration).
+  // Full interior-point solve of the stage QP (Riccati factorisation per iteration).
   // State of the method is (lam,t) only (absolute-step form); the primal step dx,du of the last
   // iteration is left in the workspace.  Returns the number of IPM iterations, <0 on failure.
   // ---------------------------------------------------------------------------------------
   static constexpr int WARM_LIMIT = 6;  // IPM iterations granted to a warm start before a cold restart
 
   // returns sum(lam*t)
-  MPC_HD static double ipm_init(const ProblemData& pd, const Lane& L, int k_first, bool warm) {
+  MPC_HD static double ipm_init(const ProblemData& pd, const Lane& L, bool warm) {
     const int N = pd.N;
     const size_t bs = L.bs;
     double mu = 0.0;
-    for (int k = k_first; k < N; ++k) {
-      double u[NU], lu[2 * NU], tu[2 * NU];
-      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+    for (int k = 0; k <= N; ++k) {
+      if (k == N && NBX == 0) break;
+      double x[NX], u[NU], v[NV], lam[NR], t[NR], lb[NV], ub[NV];
+      stage_bounds(pd, k, lb, ub);
+      if (k < N) {
+        ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+      } else {
+        MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
+      }
+      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      stage_vars(x, u, v);
       if (warm) {
-        ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-        ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-      }
-      MPC_UNROLL for (int i = 0; i < NU; ++i) {
-        const double range = pd.ubu[i] - pd.lbu[i];
-        if (warm) {
-          tu[i] = dmax(tu[i], 1e-10 * range);
-          tu[NU + i] = dmax(tu[NU + i], 1e-10 * range);
-          lu[i] = dmax(lu[i], 1e-14);
-          lu[NU + i] = dmax(lu[NU + i], 1e-14);
-        } else {
+        ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+        ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+        clip_rows(lb, ub, lam, t);
+      } else {
+        MPC_UNROLL for (int r = 0; r < NV; ++r) {
+          const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
           const double tmin = 1e-2 * range;
-          tu[i] = dmax(u[i] - pd.lbu[i], tmin);
-          tu[NU + i] = dmax(pd.ubu[i] - u[i], tmin);
-          lu[i] = pd.mu0 / tu[i];
-          lu[NU + i] = pd.mu0 / tu[NU + i];
+          t[r] = dmax(v[r] - lb[r], tmin);
+          t[NV + r] = dmax(ub[r] - v[r], tmin);
+          lam[r] = pd.mu0 / t[r];
+          lam[NV + r] = pd.mu0 / t[NV + r];
         }
-        mu += lu[i] * tu[i] + lu[NU + i] * tu[NU + i];
       }
-      st<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-      st<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
+      MPC_UNROLL for (int r = 0; r < NV; ++r) {
+        if (lb[r] > -BIG) mu += lam[r] * t[r]; else { lam[r] = 0.0; t[r] = 0.0; }
+        if (ub[r] < BIG) mu += lam[NV + r] * t[NV + r]; else { lam[NV + r] = 0.0; t[NV + r] = 0.0; }
+      }
+      st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
     }
     return mu;
+  }
+
+  // pending damped update (lam,t) += alpha ((lam_hat,t_hat) - (lam,t)) of the rows of stage k; returns them
+  MPC_HD static void rows_update(const Lane& L, int N, int k, double alpha, double* lam, double* t) {
+    const size_t bs = L.bs;
+    const double* w = L.ws + (size_t)k * W_REC * bs;
+    ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+    ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+    if (alpha > 0.0) {
+      double lh[NR], th[NR];
+      ld<NR>(w + (size_t)W_lh * bs, bs, lh);
+      ld<NR>(w + (size_t)W_th * bs, bs, th);
+      MPC_UNROLL for (int i = 0; i < NR; ++i) {
+        lam[i] += alpha * (lh[i] - lam[i]);
+        t[i] += alpha * (th[i] - t[i]);
+      }
+      st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+    }
   }
 
   MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
     const int N = pd.N;
     const size_t bs = L.bs;
     const bool qmode = pd.mode == MODE_Q;
-    const int k_first = qmode ? 1 : 0;  // first stage with a free input
-    const double m_rows = 2.0 * NU * (N - k_first);
+    const double m_rows = (double)count_rows(pd);
     // ---- initialise (lam,t): warm = keep the multipliers of the previous QP (clipped away from
-    // zero), cold = slacks from the current inputs, lam = mu0 / t ----
+    // zero), cold = slacks from the current point, lam = mu0 / t ----
     bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
-    double mu = ipm_init(pd, L, k_first, warm) / m_rows;
+    double mu = ipm_init(pd, L, warm) / m_rows;
 
     double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
     double sigma = warm ? 0.05 : 0.3;
@@ -343,7 +669,7 @@ struct Engine {
       if (warm && (warm_iters >= WARM_LIMIT || (warm_iters > 0 && alpha < 0.05))) {
         // the warm start is jammed (active set changed too much): restart from a cold point
         warm = false;
-        mu = ipm_init(pd, L, k_first, false) / m_rows;
+        mu = ipm_init(pd, L, false) / m_rows;
         alpha = 0.0;
         sigma = 0.3;
       }
@@ -352,46 +678,45 @@ struct Engine {
       // ---------------- backward sweep ----------------
       double P[NX * NX], p[NX];
       {
-        double Wm[NW * NW];
-        load_W(2, pd.scale[N], L, Wm);
-        MPC_UNROLL for (int i = 0; i < NX; ++i) MPC_UNROLL for (int jj = 0; jj < NX; ++jj) P[i * NX + jj] = Wm[i * NW + jj];
-        ld<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, p);
+        double Hm[NW * NW], g[NW];
+        load_W(2, pd.scale[N], L, Hm);
+        ld<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, g);
+        MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
+        if (NBX > 0) {
+          double lb[NV], ub[NV], x[NX], u0[NU], v[NV], lam[NR], t[NR];
+          stage_bounds(pd, N, lb, ub);
+          ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
+          MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+          stage_vars(x, u0, v);
+          rows_update(L, N, N, alpha, lam, t);
+          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+        }
+        MPC_UNROLL for (int i = 0; i < NX; ++i) {
+          p[i] = g[i];
+          MPC_UNROLL for (int jj = 0; jj < NX; ++jj) P[i * NX + jj] = Hm[i * NW + jj];
+        }
       }
       for (int k = N - 1; k >= 0; --k) {
         double* w = L.ws + (size_t)k * W_REC * bs;
-        double A[NX * NX], B[NX * NU], bb[NX], gq[NX], gr[NU], K[NU * NX], kff[NU];
+        double A[NX * NX], B[NX * NU], bb[NX], g[NW], K[NU * NX], kff[NU];
         ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
         ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
         ld<NX>(w + (size_t)W_b * bs, bs, bb);
-        ld<NX>(w + (size_t)W_q * bs, bs, gq);
-        ld<NU>(w + (size_t)W_r * bs, bs, gr);
+        ld<NW>(w + (size_t)W_q * bs, bs, g);
         double Hm[NW * NW];
         load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
+        {
+          double lb[NV], ub[NV], x[NX], u[NU], v[NV], lam[NR], t[NR];
+          stage_bounds(pd, k, lb, ub);
+          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+          if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+          stage_vars(x, u, v);
+          rows_update(L, N, k, alpha, lam, t);
+          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+        }
         const bool ufixed = (k == 0 && qmode);
         if (!ufixed) {
-          double u[NU], lu[2 * NU], tu[2 * NU];
-          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-          ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-          ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-          if (alpha > 0.0) {  // apply the pending damped update lam += alpha (lam_hat - lam)
-            double lh[2 * NU], th[2 * NU];
-            ld<2 * NU>(w + (size_t)W_lh * bs, bs, lh);
-            ld<2 * NU>(w + (size_t)W_th * bs, bs, th);
-            MPC_UNROLL for (int i = 0; i < 2 * NU; ++i) {
-              lu[i] += alpha * (lh[i] - lu[i]);
-              tu[i] += alpha * (th[i] - tu[i]);
-            }
-            st<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-            st<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-          }
-          MPC_UNROLL for (int i = 0; i < NU; ++i) {
-            const double itl = 1.0 / tu[i], itu = 1.0 / tu[NU + i];
-            const double cl = lu[i] * itl, cu = lu[NU + i] * itu;
-            Hm[(NX + i) * NW + NX + i] += cl + cu;
-            // J'(target/t + lam + C*hbar), hbar_l = lb - u, hbar_u = u - ub
-            gr[i] += -(target * itl + lu[i] - cl * (u[i] - pd.lbu[i])) + (target * itu + lu[NU + i] - cu * (pd.ubu[i] - u[i]));
-          }
-          if (!riccati_step(P, p, A, B, bb, Hm, gq, gr, K, kff, nullptr)) failed = true;
+          if (!riccati_step(P, p, A, B, bb, Hm, g, K, kff, nullptr)) failed = true;
         } else {
           // u_0 fixed (Q-mode): no feedback; x_0 is fixed as well so P_0, p_0 are not needed
           MPC_UNROLL for (int i = 0; i < NU * NX; ++i) K[i] = 0.0;
@@ -401,59 +726,12 @@ struct Engine {
         st<NU>(w + (size_t)W_k * bs, bs, kff);
       }
       // ---------------- forward sweep ----------------
-      double dx[NX];
-      MPC_UNROLL for (int i = 0; i < NX; ++i) dx[i] = 0.0;
-      double amax = 1e300, s0 = 0.0, s1 = 0.0, s2 = 0.0, cmax = 0.0;
-      for (int k = 0; k < N; ++k) {
-        double* w = L.ws + (size_t)k * W_REC * bs;
-        double A[NX * NX], B[NX * NU], bb[NX], K[NU * NX], du[NU];
-        ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
-        ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
-        ld<NX>(w + (size_t)W_b * bs, bs, bb);
-        ld<NU * NX>(w + (size_t)W_K * bs, bs, K);
-        ld<NU>(w + (size_t)W_k * bs, bs, du);
-        MPC_UNROLL for (int i = 0; i < NU; ++i) MPC_UNROLL for (int l = 0; l < NX; ++l) du[i] += K[i * NX + l] * dx[l];
-        st<NX>(w + (size_t)W_dx * bs, bs, dx);
-        st<NU>(w + (size_t)W_du * bs, bs, du);
-        if (!(k == 0 && qmode)) {
-          double u[NU], lu[2 * NU], tu[2 * NU], lh[2 * NU], th[2 * NU];
-          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-          ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-          ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-          MPC_UNROLL for (int i = 0; i < NU; ++i) {
-            // (u - lb) + du, NOT (u + du) - lb: the slack must use the same rounded distance to the
-            // bound as the condensed gradient above, or lam_hat picks up c*ulp(u) ~ 1e-8 of noise
-            th[i] = (u[i] - pd.lbu[i]) + du[i];
-            th[NU + i] = (pd.ubu[i] - u[i]) - du[i];
-          }
-          MPC_UNROLL for (int i = 0; i < 2 * NU; ++i) {
-            const double it_ = 1.0 / tu[i];
-            lh[i] = target * it_ + lu[i] - lu[i] * it_ * th[i];
-            const double dt = th[i] - tu[i], dl = lh[i] - lu[i];
-            if (dt < 0.0) amax = dmin(amax, -tu[i] / dt);
-            if (dl < 0.0) amax = dmin(amax, -lu[i] / dl);
-            s0 += lu[i] * tu[i];
-            s1 += lu[i] * dt + tu[i] * dl;
-            s2 += dl * dt;
-            cmax = dmax(cmax, dabs(dl * dt));
-          }
-          st<2 * NU>(w + (size_t)W_lh * bs, bs, lh);
-          st<2 * NU>(w + (size_t)W_th * bs, bs, th);
-        }
-        double dxn[NX];
-        MPC_UNROLL for (int i = 0; i < NX; ++i) {
-          double a = bb[i];
-          MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[i * NX + l] * dx[l];
-          MPC_UNROLL for (int l = 0; l < NU; ++l) a += B[i * NU + l] * du[l];
-          dxn[i] = a;
-        }
-        MPC_UNROLL for (int i = 0; i < NX; ++i) dx[i] = dxn[i];
-      }
-      st<NX>(L.ws + ((size_t)N * W_REC + W_dx) * bs, bs, dx);
-      if (failed || !(amax == amax)) break;
-      alpha = (amax >= 1.0 / 0.995) ? 1.0 : 0.995 * amax;
-      const double mu_new = (s0 + alpha * s1 + alpha * alpha * s2) / m_rows;
-      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
+      StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
+      forward_sweep(pd, L, target, /*clip=*/false, S);
+      if (failed || !(S.amax == S.amax)) break;
+      alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
+      const double mu_new = (S.s0 + alpha * S.s1 + alpha * alpha * S.s2) / m_rows;
+      if (target <= pd.tau && alpha == 1.0 && S.cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
       // centring heuristic: aggressive after long steps, conservative after short ones
       const double r = 1.0 - alpha;
       sigma = dmin(0.8, dmax(0.05, r * r * 4.0 + 0.05));
@@ -468,79 +746,87 @@ struct Engine {
   // Apply the QP step: w += dw, (lam,t) <- last IPM update, pi <- QP multipliers (backward
   // recursion of the x-stationarity rows).
   // ---------------------------------------------------------------------------------------
-  MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha) {
+  MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha, bool clip) {
     const int N = pd.N;
     const size_t bs = L.bs;
-    const bool qmode = pd.mode == MODE_Q;
     double pik[NX];  // pi_k (multiplier of x_{k+1} = F(x_k,u_k))
-    {
-      double dx[NX], q[NX], x[NX], Wm[NW * NW];
-      ld<NX>(L.ws + ((size_t)N * W_REC + W_dx) * bs, bs, dx);
-      ld<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, q);
-      load_W(2, pd.scale[N], L, Wm);
-      MPC_UNROLL for (int i = 0; i < NX; ++i) {
-        double a = q[i];
-        MPC_UNROLL for (int j = 0; j < NX; ++j) a += Wm[i * NW + j] * dx[j];
-        pik[i] = a;
-      }
-      ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
-      MPC_UNROLL for (int i = 0; i < NX; ++i) x[i] += dx[i];
-      st<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
-    }
-    for (int k = N - 1; k >= 0; --k) {
+    for (int k = N; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
-      st<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
-      double dx[NX], du[NU], x[NX], u[NU];
-      ld<NX>(w + (size_t)W_dx * bs, bs, dx);
-      ld<NU>(w + (size_t)W_du * bs, bs, du);
-      if (!(k == 0 && qmode)) {
-        double lu[2 * NU], tu[2 * NU], lh[2 * NU], th[2 * NU];
-        ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-        ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-        ld<2 * NU>(w + (size_t)W_lh * bs, bs, lh);
-        ld<2 * NU>(w + (size_t)W_th * bs, bs, th);
-        MPC_UNROLL for (int i = 0; i < 2 * NU; ++i) {
-          lu[i] += alpha * (lh[i] - lu[i]);
-          tu[i] += alpha * (th[i] - tu[i]);
-        }
-        st<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-        st<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
+      double dw[NW], g[NW], Wm[NW * NW], lam[NR], lb[NV], ub[NV];
+      ld<NX>(w + (size_t)W_dx * bs, bs, dw);
+      if (k < N) {
+        ld<NU>(w + (size_t)W_du * bs, bs, dw + NX);
+        ld<NW>(w + (size_t)W_q * bs, bs, g);
+      } else {
+        MPC_UNROLL for (int i = 0; i < NU; ++i) dw[NX + i] = 0.0;
+        ld<NX>(w + (size_t)W_q * bs, bs, g);
+        MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
       }
+      stage_bounds(pd, k, lb, ub);
+      MPC_UNROLL for (int i = 0; i < NR; ++i) lam[i] = 0.0;
+      if (k < N || NBX > 0) {
+        double t[NR], lh[NR], th[NR];
+        ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+        ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+        if (clip) clip_rows(lb, ub, lam, t);
+        ld<NR>(w + (size_t)W_lh * bs, bs, lh);
+        ld<NR>(w + (size_t)W_th * bs, bs, th);
+        MPC_UNROLL for (int r = 0; r < NV; ++r) {
+          MPC_UNROLL for (int side = 0; side < 2; ++side) {
+            const int q = side * NV + r;
+            const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
+            lam[q] = act ? lam[q] + alpha * (lh[q] - lam[q]) : 0.0;
+            t[q] = act ? t[q] + alpha * (th[q] - t[q]) : 0.0;
+          }
+        }
+        st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+        st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+      }
+      if (k < N) st<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);  // pi_k was completed at stage k+1
       if (k > 0) {
-        double A[NX * NX], q[NX], Wm[NW * NW], pin[NX];
-        ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
-        ld<NX>(w + (size_t)W_q * bs, bs, q);
-        load_W(1, pd.scale[k], L, Wm);
+        // x-stationarity of the QP at stage k gives pi_{k-1}
+        double pin[NX];
+        load_W(k == N ? 2 : 1, pd.scale[k], L, Wm);
         MPC_UNROLL for (int i = 0; i < NX; ++i) {
-          double a = q[i];
-          MPC_UNROLL for (int j = 0; j < NX; ++j) a += Wm[i * NW + j] * dx[j];
-          MPC_UNROLL for (int j = 0; j < NU; ++j) a += Wm[i * NW + NX + j] * du[j];
-          MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[l * NX + i] * pik[l];
+          double a = g[i];
+          MPC_UNROLL for (int j = 0; j < NW; ++j) a += Wm[i * NW + j] * dw[j];
           pin[i] = a;
         }
+        if (k < N) {
+          double A[NX * NX];
+          ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
+          MPC_UNROLL for (int i = 0; i < NX; ++i) MPC_UNROLL for (int l = 0; l < NX; ++l) pin[i] += A[l * NX + i] * pik[l];
+        }
+        MPC_UNROLL for (int j = 0; j < NBX; ++j) {
+          const int ix = M::bx(j);
+          pin[ix] += -lam[NU + j] + lam[NV + NU + j];
+        }
         MPC_UNROLL for (int i = 0; i < NX; ++i) pik[i] = pin[i];
+        double x[NX];
         ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
-        MPC_UNROLL for (int i = 0; i < NX; ++i) x[i] += dx[i];
+        MPC_UNROLL for (int i = 0; i < NX; ++i) x[i] += dw[i];
         st<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       }
-      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-      MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] += du[i];
-      st<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+      if (k < N) {
+        double u[NU];
+        ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+        MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] += dw[NX + i];
+        st<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+      }
     }
+    L.it[(size_t)it_meta(N) * bs] = 1.0;
   }
 
-  // ---------------------------------------------------------------------------------------
-  // SQP driver (acados semantics: linearise -> convergence test -> QP -> full step).
-  // Outputs the residuals/cost of the last linearisation; `fresh` tells whether they belong to
-  // the final iterate (true when converged) or to the iterate before the last step (RTI).
-  // ---------------------------------------------------------------------------------------
-  struct SolveOut {
-    Residuals res;
-    int status;
-    int sqp_iter;
-    int ipm_iter;
-    bool fresh;
-  };
+  // Sample function, slow path of one SQP iteration (after qp_fast returned FAST_HARD): the full
+  // interior-point loop and the step.  Returns the status so far (ST_OK or ST_QPFAIL).
+  MPC_HD static int qp_full(const ProblemData& pd, const Lane& L, int* ipm_iters) {
+    double alpha = 0.0;
+    const int r = qp_ipm(pd, L, &alpha);
+    if (ipm_iters) *ipm_iters += (r > 0) ? r : ((r == -1) ? 0 : -(r + 1000));
+    if (r == -1) return ST_QPFAIL;  // reduced Hessian not positive definite: iterate left untouched
+    apply_step(pd, L, alpha, /*clip=*/false);
+    return (r < 0) ? ST_QPFAIL : ST_OK;  // r < 0: iteration limit, step applied anyway (like acados)
+  }
 
   MPC_HD static void set_initial(const ProblemData& pd, const Lane& L, const double* x0, size_t x0s, const double* u0,
                                  size_t u0s) {
@@ -551,63 +837,71 @@ struct Engine {
     }
   }
 
-  MPC_HD static SolveOut solve(const ProblemData& pd, const Lane& L) {
-    SolveOut o;
-    o.status = ST_MAXITER;
-    o.sqp_iter = 0;
-    o.ipm_iter = 0;
-    o.fresh = false;
-    for (int itn = 0;; ++itn) {
-      o.res = linearize(pd, L);
-      const double rmax = dmax(dmax(o.res.stat, o.res.eq), dmax(o.res.ineq, o.res.comp));
-      if (!(rmax == rmax) || !(o.res.cost == o.res.cost)) {
-        o.status = ST_NAN;
-        o.fresh = true;
-        break;
-      }
-      if (rmax < pd.tol) {
-        o.status = ST_OK;
-        o.fresh = true;
-        break;
-      }
-      if (itn >= pd.max_sqp) {
-        o.fresh = true;
-        break;
-      }
-      double alpha = 0.0;
-      const int r = qp_ipm(pd, L, &alpha);
-      o.ipm_iter += (r > 0) ? r : ((r == -1) ? 0 : -(r + 1000));
-      if (r == -1) {
-        o.status = ST_QPFAIL;
-        break;
-      }
-      apply_step(pd, L, alpha);
-      L.it[(size_t)it_meta(pd.N) * L.bs] = 1.0;
-      o.sqp_iter = itn + 1;
-      if (r < 0) {  // IPM hit its iteration limit
-        o.status = ST_QPFAIL;
-      }
-      if (pd.max_sqp == 1) {  // RTI: one QP, no further linearisation here (sens() re-evaluates)
-        if (o.status != ST_QPFAIL) o.status = ST_OK;
-        break;
-      }
-    }
-    return o;
-  }
-
-  // ---------------------------------------------------------------------------------------
-  // Evaluation + sensitivities at the current iterate.
+  // =======================================================================================
+  // Evaluation + sensitivities at the current iterate (update_nlp, nlp.py:1341-1563):
   //   * cost and KKT residuals (what update_nlp asserts, nlp.py:1445-1537)
   //   * dL/dtheta (model part; cost part when pd.param_cost)           nlp.py:1211-1212,1401
   //   * dpi/dtheta via ONE exact-Hessian Riccati factorisation and NU adjoint solves, instead of
   //     the reference's dense (nz x nz) sparse LU with ntheta right-hand sides  nlp.py:1413-1424
-  // dLdth / dpidth point at this sample's rows of row-major [B, ng] / [B, NU, ng] outputs.
-  // ---------------------------------------------------------------------------------------
   // Gradient rows have width ng = grad_width(pd): the model parameters only (the structurally
   // non-zero prefix of the reference's p, quirk Q8) or the whole p when pd.param_cost is set.
+  // =======================================================================================
   MPC_HD static int grad_width(const ProblemData& pd) { return pd.param_cost ? M::NTH : NPM; }
 
-  MPC_HD static Residuals sens(const ProblemData& pd, const Lane& L, double* dLdth, double* dpidth, int* ok_out) {
+  // (sample, stage) function: exact second-order information of stage k at (x_k, u_k, pi_k).
+  MPC_HD static void sens_stage(const ProblemData& pd, const Lane& L, int k) {
+    const int N = pd.N;
+    const size_t bs = L.bs;
+    double* w = L.ws + (size_t)k * W_REC * bs;
+    CostK ck;
+    double y[NW], g[NW];
+    if (k < N) {
+      double pik[NX], xk1[NX], xn[NX], A[NX * NX], B[NX * NU], Fp[NX * NPM], Hww[NW * NW], Hwp[NW * NPM];
+      ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, y);
+      ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, y + NX);
+      ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
+      ld<NX>(L.it + (size_t)it_x(N, k + 1) * bs, bs, xk1);
+      M::dyn_sens(y, y + NX, L.th, L.ths, pd.mc, pik, xn, A, B, Fp, Hww, Hwp);
+      double eq = 0.0;
+      MPC_UNROLL for (int i = 0; i < NX; ++i) {
+        const double d = xn[i] - xk1[i];
+        eq = dmax(eq, dabs(d));
+        if (!(d == d)) eq = d;
+      }
+      st<NX * NX>(w + (size_t)W_A * bs, bs, A);
+      st<NX * NU>(w + (size_t)W_B * bs, bs, B);
+      double Hp[NWS];
+      MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) Hp[pidx(i, j)] = Hww[i * NW + j];
+      st<NWS>(w + (size_t)S_H * bs, bs, Hp);
+      st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+      st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
+      double gp[NPM];
+      MPC_UNROLL for (int j = 0; j < NPM; ++j) {
+        double a = 0.0;
+        MPC_UNROLL for (int i = 0; i < NX; ++i) a += pik[i] * Fp[i * NPM + j];
+        gp[j] = a;
+      }
+      st<NPM>(w + (size_t)S_gp * bs, bs, gp);
+      load_cost(k == 0 ? 0 : 1, L, ck);
+      const double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      st<NW>(w + (size_t)S_g * bs, bs, g);
+      w[(size_t)S_c * bs] = c;
+      w[(size_t)S_e * bs] = eq;
+    } else {
+      ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, y);
+      MPC_UNROLL for (int i = 0; i < NU; ++i) y[NX + i] = 0.0;
+      load_cost(2, L, ck);
+      const double c = cost_grad(ck, pd.scale[N], NX, y, g);
+      st<NW>(w + (size_t)S_g * bs, bs, g);
+      w[(size_t)S_c * bs] = c;
+      w[(size_t)S_e * bs] = 0.0;
+    }
+  }
+
+  // Sample function: residuals, dL/dtheta, exact-Hessian factorisation (backward) and the NU
+  // adjoint solves (forward).  dLdth / dpidth point at this sample's rows of row-major
+  // [B, ng] / [B, NU, ng] outputs (nullptr: skip).
+  MPC_HD static Residuals sens_sweep(const ProblemData& pd, const Lane& L, double* dLdth, double* dpidth, int* ok_out) {
     const int N = pd.N;
     const size_t bs = L.bs;
     const bool qmode = pd.mode == MODE_Q;
@@ -615,119 +909,109 @@ struct Engine {
     bool ok = true;
     double gp[NPM];
     MPC_UNROLL for (int i = 0; i < NPM; ++i) gp[i] = 0.0;
-
-    // ---- backward pass: exact Hessian blocks, Riccati factorisation ----
-    double P[NX * NX], pdummy[NX];
-    double xk1[NX];  // x_{k+1}
-    double grn[NX];  // cost gradient at x_{k+1} (for the stationarity residual of stage k+1)
-    double An_pik[NX];  // A_{k+1}' pi_{k+1}
-    {
-      double Wm[NW * NW], e[NX];
-      ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, xk1);
-      load_W(2, pd.scale[N], L, Wm);
-      MPC_UNROLL for (int i = 0; i < NX; ++i) e[i] = xk1[i] - M::yref(2, i, L.th, L.ths);
-      double c = pd.scale[N] * M::c0(2, L.th, L.ths);
-      MPC_UNROLL for (int i = 0; i < NX; ++i) {
-        double a = 0.0;
-        MPC_UNROLL for (int j = 0; j < NX; ++j) a += Wm[i * NW + j] * e[j];
-        const double fl = pd.scale[N] * M::flin(2, i, L.th, L.ths);
-        grn[i] = a + fl;
-        c += 0.5 * a * e[i] + fl * xk1[i];
-        An_pik[i] = 0.0;
-        pdummy[i] = 0.0;
-        MPC_UNROLL for (int j = 0; j < NX; ++j) P[i * NX + j] = Wm[i * NW + j];
+    double P[NX * NX], pdummy[NX], carry[NX];
+    {  // terminal stage
+      const double* w = L.ws + (size_t)N * W_REC * bs;
+      double g[NW], Hm[NW * NW];
+      ld<NW>(w + (size_t)S_g * bs, bs, g);
+      R.cost += w[(size_t)S_c * bs];
+      MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] = g[i];
+      load_W(2, pd.scale[N], L, Hm);
+      if (NBX > 0 || (pd.param_cost && dLdth)) {
+        double x[NX];
+        ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
+        if (pd.param_cost && dLdth) M::cost_param_grad(2, pd.scale[N], L.th, L.ths, x, nullptr, dLdth);
+        if (NBX > 0) {
+          double lb[NV], ub[NV], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
+          stage_bounds(pd, N, lb, ub);
+          MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+          stage_vars(x, u0, v);
+          ld<NR>(L.it + (size_t)it_lam(N, N) * bs, bs, lam);
+          ld<NR>(L.it + (size_t)it_t(N, N) * bs, bs, t);
+          MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
+          rows_residual(pd, lb, ub, v, lam, t, R, jl);
+          MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] += jl[i];
+          barrier_hess(lb, ub, lam, t, Hm);
+        }
       }
-      R.cost += c;
-      if (pd.param_cost && dLdth) cost_param_grad(2, pd.scale[N], L, xk1, nullptr, dLdth);
+      MPC_UNROLL for (int i = 0; i < NX; ++i) {
+        pdummy[i] = 0.0;
+        MPC_UNROLL for (int j = 0; j < NX; ++j) P[i * NX + j] = Hm[i * NW + j];
+      }
     }
     for (int k = N - 1; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
-      double x[NX], u[NU], pik[NX], xn[NX], A[NX * NX], B[NX * NU], Fp[NX * NPM], Hww[NW * NW], Hwp[NW * NPM];
-      ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      double A[NX * NX], B[NX * NU], g[NW], Hp[NWS], gpk[NPM], x[NX], u[NU], pik[NX], lam[NR], t[NR], lb[NV], ub[NV], v[NV];
+      ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
+      ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
+      ld<NW>(w + (size_t)S_g * bs, bs, g);
+      ld<NWS>(w + (size_t)S_H * bs, bs, Hp);
+      ld<NPM>(w + (size_t)S_gp * bs, bs, gpk);
+      R.cost += w[(size_t)S_c * bs];
+      {
+        const double e = w[(size_t)S_e * bs];
+        R.eq = (e == e) ? dmax(R.eq, e) : e;
+      }
+      MPC_UNROLL for (int j = 0; j < NPM; ++j) gp[j] += gpk[j];
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
+      if (NBX > 0 || (pd.param_cost && dLdth)) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
-      M::dyn_sens(x, u, L.th, L.ths, pd.mc, pik, xn, A, B, Fp, Hww, Hwp);
-      // stationarity residual wrt x_{k+1}:  grad l_{k+1} + A_{k+1}' pi_{k+1} - pi_k
-      MPC_UNROLL for (int i = 0; i < NX; ++i) {
-        R.eq = dmax(R.eq, dabs(xn[i] - xk1[i]));
-        R.stat = dmax(R.stat, dabs(grn[i] + An_pik[i] - pik[i]));
-      }
-      // dL/dp_model += pi_k' dF/dp
-      MPC_UNROLL for (int j = 0; j < NPM; ++j) MPC_UNROLL for (int i = 0; i < NX; ++i) gp[j] += pik[i] * Fp[i * NPM + j];
-      // cost at stage k
-      const int kind = (k == 0) ? 0 : 1;
-      const double s = pd.scale[k];
-      double Wm[NW * NW], e[NW], gr[NW];
-      load_W(kind, s, L, Wm);
-      MPC_UNROLL for (int i = 0; i < NW; ++i) e[i] = ((i < NX) ? x[i] : u[i - NX]) - M::yref(kind, i, L.th, L.ths);
-      double c = s * M::c0(kind, L.th, L.ths);
-      MPC_UNROLL for (int i = 0; i < NW; ++i) {
-        double a = 0.0;
-        MPC_UNROLL for (int j = 0; j < NW; ++j) a += Wm[i * NW + j] * e[j];
-        const double fl = s * M::flin(kind, i, L.th, L.ths);
-        gr[i] = a + fl;
-        c += 0.5 * a * e[i] + fl * ((i < NX) ? x[i] : u[i - NX]);
-      }
-      R.cost += c;
-      if (pd.param_cost && dLdth) cost_param_grad(kind, s, L, x, u, dLdth);
-      // exact Lagrangian Hessian block + barrier terms
-      double Hm[NW * NW];
-      MPC_UNROLL for (int i = 0; i < NW * NW; ++i) Hm[i] = Wm[i] + Hww[i];
+      ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+      if (pd.param_cost && dLdth) M::cost_param_grad(k == 0 ? 0 : 1, pd.scale[k], L.th, L.ths, x, u, dLdth);
+      stage_bounds(pd, k, lb, ub);
+      stage_vars(x, u, v);
+      // ---- residuals ----
+      MPC_UNROLL for (int i = 0; i < NX; ++i) R.stat = dmax(R.stat, dabs(carry[i] - pik[i]));
+      double jl[NW];
+      MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
+      rows_residual(pd, lb, ub, v, lam, t, R, jl);
       const bool ufixed = (k == 0 && qmode);
-      double lu[2 * NU], tu[2 * NU];
-      ld<2 * NU>(L.it + (size_t)it_lu(N, k) * bs, bs, lu);
-      ld<2 * NU>(L.it + (size_t)it_tu(N, k) * bs, bs, tu);
-      if (!ufixed) {
-        MPC_UNROLL for (int i = 0; i < NU; ++i) {
-          Hm[(NX + i) * NW + NX + i] += lu[i] / tu[i] + lu[NU + i] / tu[NU + i];
-          double a = gr[NX + i] - lu[i] + lu[NU + i];
-          MPC_UNROLL for (int l = 0; l < NX; ++l) a += B[l * NU + i] * pik[l];
-          R.stat = dmax(R.stat, dabs(a));
-          R.comp = dmax(R.comp, dmax(dabs(lu[i] * tu[i] - pd.tau), dabs(lu[NU + i] * tu[NU + i] - pd.tau)));
-          R.ineq = dmax(R.ineq, dmax(dabs(pd.lbu[i] - u[i] + tu[i]), dabs(u[i] - pd.ubu[i] + tu[NU + i])));
-        }
+      double su[NU];  // u-stationarity remainder (multiplier of the clamped u_0 in Q-mode)
+      MPC_UNROLL for (int i = 0; i < NU; ++i) {
+        double a = g[NX + i] + jl[NX + i];
+        MPC_UNROLL for (int l = 0; l < NX; ++l) a += B[l * NU + i] * pik[l];
+        su[i] = a;
+        if (!ufixed) R.stat = dmax(R.stat, dabs(a));
       }
-      // record for the forward (adjoint) pass
+      MPC_UNROLL for (int i = 0; i < NX; ++i) {
+        double a = g[i] + jl[i];
+        MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[l * NX + i] * pik[l];
+        carry[i] = a;
+      }
+      if (k == 0) {  // multipliers of the eliminated stage-0 equalities
+        MPC_UNROLL for (int i = 0; i < NX; ++i) L.it[(size_t)(it_rx0(N) + i) * bs] = carry[i];
+        MPC_UNROLL for (int i = 0; i < NU; ++i) L.it[(size_t)(it_ru0(N) + i) * bs] = su[i];
+      }
+      // ---- exact-Hessian Riccati factorisation ----
       if (dpidth) {
-        st<NX * NX>(w + (size_t)W_A * bs, bs, A);
-        st<NX * NU>(w + (size_t)W_B * bs, bs, B);
+        double Hm[NW * NW];
+        load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
+        MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) {
+          Hm[i * NW + j] += Hp[pidx(i, j)];
+          if (j != i) Hm[j * NW + i] = Hm[i * NW + j];
+        }
+        barrier_hess(lb, ub, lam, t, Hm);
         double Pp[NPS];
         {
           int c_ = 0;
           MPC_UNROLL for (int i = 0; i < NX; ++i) MPC_UNROLL for (int j = i; j < NX; ++j) Pp[c_++] = P[i * NX + j];
         }
-        st<NPS>(w + (size_t)W_P * bs, bs, Pp);
-        st<NW * NPM>(w + (size_t)W_Hwp * bs, bs, Hwp);
-        st<NX * NPM>(w + (size_t)W_Fp * bs, bs, Fp);
-        double K[NU * NX], kff[NU], Ginv[NU * NU], zq[NX], zr[NU], zb[NX];
-        MPC_UNROLL for (int i = 0; i < NX; ++i) { zq[i] = 0.0; zb[i] = 0.0; }
-        MPC_UNROLL for (int i = 0; i < NU; ++i) zr[i] = 0.0;
+        st<NPS>(w + (size_t)S_P * bs, bs, Pp);
+        double K[NU * NX], kff[NU], Ginv[NU * NU], zg[NW], zb[NX];
+        MPC_UNROLL for (int i = 0; i < NW; ++i) zg[i] = 0.0;
+        MPC_UNROLL for (int i = 0; i < NX; ++i) zb[i] = 0.0;
         if (!ufixed) {
-          if (!riccati_step(P, pdummy, A, B, zb, Hm, zq, zr, K, kff, Ginv)) ok = false;
+          if (!riccati_step(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
         } else {
           MPC_UNROLL for (int i = 0; i < NU * NX; ++i) K[i] = 0.0;
           MPC_UNROLL for (int i = 0; i < NU * NU; ++i) Ginv[i] = 0.0;
         }
-        st<NU * NX>(w + (size_t)W_K * bs, bs, K);
-        if (k == 0) st<NU * NU>(w + (size_t)W_Gi * bs, bs, Ginv);
-      }
-      // carry to stage k-1
-      MPC_UNROLL for (int i = 0; i < NX; ++i) {
-        double a = 0.0;
-        MPC_UNROLL for (int l = 0; l < NX; ++l) a += A[l * NX + i] * pik[l];
-        An_pik[i] = a;
-        grn[i] = gr[i];
-        xk1[i] = x[i];
-      }
-      if (k == 0) {  // multipliers of the eliminated stage-0 equalities
-        MPC_UNROLL for (int i = 0; i < NX; ++i) L.it[(size_t)(it_rx0(N) + i) * bs] = gr[i] + An_pik[i];
-        MPC_UNROLL for (int i = 0; i < NU; ++i) {
-          double a = gr[NX + i];
-          MPC_UNROLL for (int l = 0; l < NX; ++l) a += B[l * NU + i] * pik[l];
-          L.it[(size_t)(it_ru0(N) + i) * bs] = a;
-        }
+        st<NU * NX>(w + (size_t)S_K * bs, bs, K);
+        if (k == 0) st<NU * NU>(w + (size_t)S_Gi * bs, bs, Ginv);
       }
     }
+    MPC_UNROLL for (int i = 0; i < NX; ++i) (void)pdummy[i];
     if (dLdth) {
       MPC_UNROLL for (int j = 0; j < NPM; ++j) dLdth[j] = gp[j];
     }
@@ -743,10 +1027,10 @@ struct Engine {
           double A[NX * NX], B[NX * NU], K[NU * NX], Pp[NPS], Hwp[NW * NPM], Fp[NX * NPM];
           ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
           ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
-          ld<NU * NX>(w + (size_t)W_K * bs, bs, K);
-          ld<NPS>(w + (size_t)W_P * bs, bs, Pp);
-          ld<NW * NPM>(w + (size_t)W_Hwp * bs, bs, Hwp);
-          ld<NX * NPM>(w + (size_t)W_Fp * bs, bs, Fp);
+          ld<NU * NX>(w + (size_t)S_K * bs, bs, K);
+          ld<NPS>(w + (size_t)S_P * bs, bs, Pp);
+          ld<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+          ld<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
           double Pf[NX * NX];
           {
             int c_ = 0;
@@ -756,7 +1040,7 @@ struct Engine {
             }
           }
           double Gi[NU * NU];
-          if (k == 0) ld<NU * NU>(w + (size_t)W_Gi * bs, bs, Gi);
+          if (k == 0) ld<NU * NU>(w + (size_t)S_Gi * bs, bs, Gi);
           MPC_UNROLL for (int r = 0; r < NU; ++r) {
             double yu[NU], yxn[NX], ypi[NX];
             MPC_UNROLL for (int i = 0; i < NU; ++i) {
@@ -789,28 +1073,6 @@ struct Engine {
     }
     *ok_out = ok ? 1 : 0;
     return R;
-  }
-
-  // d(s * l)/d(W, yref) accumulated into the [NTH] row (parameterize_tracking_cost=True semantics,
-  // nlp.py:1057-1074): dl/dW_ij = 1/2 e_i e_j, dl/dyref = -W_sym e.
-  MPC_HD static void cost_param_grad(int kind, double s, const Lane& L, const double* x, const double* u, double* dLdth) {
-    const int n = M::ny(kind);
-    double e[NW];
-    MPC_UNROLL for (int i = 0; i < NW; ++i) {
-      e[i] = 0.0;
-      if (i < n) e[i] = ((i < NX) ? x[i] : u[i - NX]) - M::yref(kind, i, L.th, L.ths);
-    }
-    const int wo = M::w_off(kind), yo = M::yref_off(kind);
-    MPC_UNROLL for (int i = 0; i < NW; ++i) {
-      if (i >= n) continue;
-      double a = 0.0;
-      MPC_UNROLL for (int j = 0; j < NW; ++j) {
-        if (j >= n) continue;
-        a += M::W(kind, i, j, L.th, L.ths) * e[j];
-        dLdth[wo + j * n + i] += 0.5 * s * e[i] * e[j];
-      }
-      dLdth[yo + i] -= s * a;
-    }
   }
 };
 

@@ -16,17 +16,23 @@ namespace rlmpc {
 
 #include "cartpole_gen.cuh"
 
-struct CartpoleModel {
+// NBX_ = number of box-constrained states on stages 1..N (0: config/cartpole_original.yaml,
+// 4: config/cartpole.yaml with idxbx = [0,1,2,3]).
+template <int NBX_>
+struct CartpoleModelT {
   static constexpr int NX = 4, NU = 1, NPM = 3, NZ = 8;  // NZ = NX+NU+NPM (derivative columns)
+  static constexpr int NW = NX + NU;
+  static constexpr int NBX = NBX_;
   static constexpr int NTH = 83;
   static constexpr int TH_W0 = 3, TH_W = 28, TH_WE = 53, TH_YREF0 = 69, TH_YREF = 74, TH_YREFE = 79;
+  MPC_HD static int bx(int j) { return j; }  // idxbx (all states, in order)
 
   // ---- quadratic tracking cost  l = 1/2 (y-yref)' W (y-yref),  y=[x;u] -------------------
   // kind: 0 initial stage, 1 intermediate, 2 terminal (ny = NX).
   MPC_HD static int ny(int kind) { return kind == 2 ? NX : NX + NU; }
   MPC_HD static int w_off(int kind) { return kind == 0 ? TH_W0 : (kind == 1 ? TH_W : TH_WE); }
   MPC_HD static int yref_off(int kind) { return kind == 0 ? TH_YREF0 : (kind == 1 ? TH_YREF : TH_YREFE); }
-  // symmetrised weight entry (i,j)
+  // symmetrised weight entry (i,j): the Hessian of 1/2 e'We is (W+W')/2
   MPC_HD static double W(int kind, int i, int j, const double* th, size_t ths) {
     const int n = ny(kind), o = w_off(kind);
     return 0.5 * (th[(size_t)(o + j * n + i) * ths] + th[(size_t)(o + i * n + j) * ths]);
@@ -34,8 +40,43 @@ struct CartpoleModel {
   MPC_HD static double yref(int kind, int i, const double* th, size_t ths) {
     return th[(size_t)(yref_off(kind) + i) * ths];
   }
-  MPC_HD static double flin(int, int, const double*, size_t) { return 0.0; }  // no linear term
-  MPC_HD static double c0(int, const double*, size_t) { return 0.0; }         // no constant term
+  // theta -> the engine's quadratic cost table (Engine::CT_*): per kind
+  //   [W packed upper (15) | yref (5) | flin (5) | c0]
+  MPC_HD static void cost_table(const double* th, size_t ths, double* ct, size_t cts) {
+    constexpr int NWS = NW * (NW + 1) / 2, REC = NWS + 2 * NW + 1;
+    for (int kind = 0; kind < 3; ++kind) {
+      double* c = ct + (size_t)(kind * REC) * cts;
+      const int n = ny(kind);
+      int q = 0;
+      for (int i = 0; i < NW; ++i)
+        for (int j = i; j < NW; ++j) c[(size_t)(q++) * cts] = (i < n && j < n) ? W(kind, i, j, th, ths) : 0.0;
+      for (int i = 0; i < NW; ++i) c[(size_t)(NWS + i) * cts] = (i < n) ? yref(kind, i, th, ths) : 0.0;
+      for (int i = 0; i < NW; ++i) c[(size_t)(NWS + NW + i) * cts] = 0.0;  // no linear term
+      c[(size_t)(NWS + 2 * NW) * cts] = 0.0;                              // no constant term
+    }
+  }
+  // d(s * l)/d(W, yref) accumulated into the [NTH] row (parameterize_tracking_cost=True semantics,
+  // nlp.py:1057-1074): dl/dW_ij = 1/2 e_i e_j, dl/dyref = -W_sym e.
+  MPC_HD static void cost_param_grad(int kind, double s, const double* th, size_t ths, const double* x, const double* u,
+                                     double* dLdth) {
+    const int n = ny(kind);
+    double e[NW];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      e[i] = 0.0;
+      if (i < n) e[i] = ((i < NX) ? x[i] : u[i - NX]) - yref(kind, i, th, ths);
+    }
+    const int wo = w_off(kind), yo = yref_off(kind);
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      if (i >= n) continue;
+      double a = 0.0;
+      MPC_UNROLL for (int j = 0; j < NW; ++j) {
+        if (j >= n) continue;
+        a += W(kind, i, j, th, ths) * e[j];
+        dLdth[wo + j * n + i] += 0.5 * s * e[i] * e[j];
+      }
+      dLdth[yo + i] -= s * a;
+    }
+  }
 
   // ---- dynamics -------------------------------------------------------------------------
   // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l);
@@ -174,5 +215,8 @@ struct CartpoleModel {
     }
   }
 };
+
+using CartpoleModel = CartpoleModelT<0>;    // input bounds only (config/cartpole_original.yaml)
+using CartpoleModelBX = CartpoleModelT<4>;  // + box bounds on all states (config/cartpole.yaml)
 
 }  // namespace rlmpc

@@ -31,20 +31,26 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 #ifndef RLMPC_TPB
-#define RLMPC_TPB 128
+#define RLMPC_TPB 64
 #endif
-#ifndef RLMPC_MINB
-#define RLMPC_MINB 1
-#endif
-constexpr int TPB = RLMPC_TPB;  // threads per block
+constexpr int TPB = RLMPC_TPB;  // threads per block of the sample-parallel kernels
 
+// Per-call state shared by the kernels of one pipeline (device pointers into the handle).
 struct KArgs {
   double* it;
   double* ws;
   size_t bs;
+  double* it2;  // compact copies used by the full interior-point pass (one slot per queued sample)
+  double* ws2;
   const double* th;
+  const double* ct;
   int th_per_sample;
   int B;
+  int* work;    // Work state per sample
+  int* status;  // acados status per sample
+  double* cost; // cost of the last linearisation
+  int* hard;    // queue of samples for the full interior-point pass
+  int* counters;  // [0] queue length, [1] samples still active
   const double* x0;  // [B, NX] row-major or null
   const double* u0;  // [B, NU] row-major or null
   double* u0_out;    // [B, NU]
@@ -53,51 +59,171 @@ struct KArgs {
   double* dL;        // [B, ng]
   double* dpi;       // [B, NU, ng]
   double* res_out;   // [B, 4]
-  int do_solve, do_sens;
+  int last_round;    // this SQP round only evaluates the convergence test
+  int have_solve;    // sens: a solve preceded in this call (keep its status)
 };
 
 template <class M>
-__global__ void __launch_bounds__(TPB, RLMPC_MINB) k_unit(const __grid_constant__ ProblemData pd, const KArgs a) {
-  using E = Engine<M>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+__device__ __forceinline__ Lane make_lane(const KArgs& a, int b) {
   Lane L;
   L.it = a.it + b;
   L.ws = a.ws + b;
   L.bs = a.bs;
   L.th = a.th_per_sample ? a.th + b : a.th;
   L.ths = a.th_per_sample ? a.bs : 1;
-  int status = ST_OK;
-  double cost = 0.0;
-  if (a.do_solve) {
-    E::set_initial(pd, L, a.x0 + (size_t)b * M::NX, 1, a.u0 ? a.u0 + (size_t)b * M::NU : nullptr, 1);
-    typename E::SolveOut o = E::solve(pd, L);
-    status = o.status;
-    cost = o.res.cost;
-  }
-  if (a.do_sens) {
-    int ok = 1;
-    const int ng = E::grad_width(pd);
-    typename E::Residuals r = E::sens(pd, L, a.dL ? a.dL + (size_t)b * ng : nullptr,
-                                      a.dpi ? a.dpi + (size_t)b * M::NU * ng : nullptr, &ok);
-    cost = r.cost;
-    if (a.res_out) {
-      a.res_out[(size_t)b * 4 + 0] = r.stat;
-      a.res_out[(size_t)b * 4 + 1] = r.eq;
-      a.res_out[(size_t)b * 4 + 2] = r.ineq;
-      a.res_out[(size_t)b * 4 + 3] = r.comp;
+  L.ct = a.th_per_sample ? a.ct + b : a.ct;
+  L.cts = a.th_per_sample ? a.bs : 1;
+  return L;
+}
+
+// start of a solve call: x_0 (and u_0 in Q-mode) into the iterate, pipeline state reset
+template <class M>
+__global__ void k_begin(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const Lane L = make_lane<M>(a, b);
+  E::set_initial(pd, L, a.x0 + (size_t)b * M::NX, 1, a.u0 ? a.u0 + (size_t)b * M::NU : nullptr, 1);
+  a.work[b] = WK_ACTIVE;
+  a.status[b] = ST_MAXITER;
+}
+
+// (sample, stage) kernel: linearisation.  grid = (ceil(B / blockDim), N + 1)
+template <class M>
+__global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ProblemData pd, const KArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B || a.work[b] != WK_ACTIVE) return;
+  Engine<M>::lin_stage(pd, make_lane<M>(a, b), blockIdx.y);
+}
+
+// sample kernel: convergence test + one warm interior-point Newton iteration (fast path)
+template <class M>
+__global__ void __launch_bounds__(TPB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B || a.work[b] != WK_ACTIVE) return;
+  const Lane L = make_lane<M>(a, b);
+  typename E::Residuals R;
+  const int code = E::qp_fast(pd, L, R);
+  a.cost[b] = R.cost;
+  if (code == E::FAST_NAN) {
+    a.status[b] = ST_NAN;
+    a.work[b] = WK_DONE;
+  } else if (code == E::FAST_CONVERGED) {
+    a.status[b] = ST_OK;
+    a.work[b] = WK_DONE;
+  } else if (a.last_round) {
+    a.work[b] = WK_DONE;  // status stays ST_MAXITER
+  } else if (code == E::FAST_STEPPED) {
+    if (pd.max_sqp == 1) {  // RTI: one QP, no further linearisation here
+      a.status[b] = ST_OK;
+      a.work[b] = WK_DONE;
     }
-    const double rmax = dmax(dmax(r.stat, r.eq), dmax(r.ineq, r.comp));
-    if (!(rmax == rmax)) status = ST_NAN;
-    if (!a.do_solve) status = (rmax == rmax) ? (rmax < pd.tol ? ST_OK : ST_MAXITER) : ST_NAN;
-    if (!ok && status == ST_OK) status = ST_QPFAIL;  // reduced Hessian not PD: sensitivities invalid
+  } else {
+    a.work[b] = WK_HARD;
+    a.hard[atomicAdd(&a.counters[0], 1)] = b;
   }
+}
+
+// sample kernel over the queue: full interior-point solve on a compact (coalesced) copy of the
+// sample's stage data and iterate; only the iterate is copied back.
+template <class M>
+__global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.counters[0]) return;
+  const int b = a.hard[j];
+  const Lane Ls = make_lane<M>(a, b);
+  Lane L = Ls;
+  L.it = a.it2 + j;
+  L.ws = a.ws2 + j;
+  const int N = pd.N, nit = E::it_size(N);
+  for (int i = 0; i < nit; ++i) L.it[(size_t)i * L.bs] = Ls.it[(size_t)i * L.bs];
+  for (int k = 0; k <= N; ++k) {
+    const size_t o = (size_t)k * E::W_REC;
+#pragma unroll 4
+    for (int i = E::W_A; i < E::W_K; ++i) L.ws[(o + i) * L.bs] = Ls.ws[(o + i) * L.bs];
+  }
+  const int st = E::qp_full(pd, L, nullptr);
+  for (int i = 0; i < nit; ++i) Ls.it[(size_t)i * L.bs] = L.it[(size_t)i * L.bs];
+  if (pd.max_sqp == 1 || st == ST_QPFAIL) {
+    // RTI: done after one QP.  Otherwise a failed QP (not PD / iteration limit) ends the solve
+    a.status[b] = st;
+    a.work[b] = WK_DONE;
+  } else {
+    a.work[b] = WK_ACTIVE;
+  }
+}
+
+template <class M>
+__global__ void k_count_active(const KArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = b < a.B && a.work[b] != WK_DONE;
+  const unsigned m = __ballot_sync(0xffffffffu, act);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&a.counters[1], __popc(m));
+}
+
+// outputs of a solve-only call
+template <class M>
+__global__ void k_out(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  if (a.u0_out) {
+#pragma unroll
+    for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = a.it[(size_t)(E::it_u(pd.N, 0) + i) * a.bs + b];
+  }
+  if (a.cost_out) a.cost_out[b] = a.cost[b];
+  if (a.status_out) a.status_out[b] = a.status[b];
+}
+
+// (sample, stage) kernel: exact second-order stage information.  grid = (ceil(B / blockDim), N + 1)
+template <class M>
+__global__ void __launch_bounds__(128) k_sens_stage(const __grid_constant__ ProblemData pd, const KArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  Engine<M>::sens_stage(pd, make_lane<M>(a, b), blockIdx.y);
+}
+
+// sample kernel: residuals, dL/dtheta, exact-Hessian factorisation, adjoint solves, outputs
+template <class M>
+__global__ void __launch_bounds__(TPB) k_sens_sweep(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const Lane L = make_lane<M>(a, b);
+  int ok = 1;
+  const int ng = E::grad_width(pd);
+  const typename E::Residuals r = E::sens_sweep(pd, L, a.dL ? a.dL + (size_t)b * ng : nullptr,
+                                                a.dpi ? a.dpi + (size_t)b * M::NU * ng : nullptr, &ok);
+  if (a.res_out) {
+    a.res_out[(size_t)b * 4 + 0] = r.stat;
+    a.res_out[(size_t)b * 4 + 1] = r.eq;
+    a.res_out[(size_t)b * 4 + 2] = r.ineq;
+    a.res_out[(size_t)b * 4 + 3] = r.comp;
+  }
+  const double rmax = dmax(dmax(r.stat, r.eq), dmax(r.ineq, r.comp));
+  int status = a.have_solve ? a.status[b] : ST_OK;
+  if (!(rmax == rmax)) status = ST_NAN;
+  if (!a.have_solve) status = (rmax == rmax) ? (rmax < pd.tol ? ST_OK : ST_MAXITER) : ST_NAN;
+  if (!ok && status == ST_OK) status = ST_QPFAIL;  // reduced Hessian not PD: sensitivities invalid
   if (a.u0_out) {
 #pragma unroll
     for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * L.bs];
   }
-  if (a.cost_out) a.cost_out[b] = cost;
+  if (a.cost_out) a.cost_out[b] = r.cost;
   if (a.status_out) a.status_out[b] = status;
+}
+
+// theta -> quadratic cost table (shared: one thread; per sample: one thread per sample)
+template <class M>
+__global__ void k_cost_table(const double* th, double* ct, int per_sample, int B, size_t bs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (per_sample) {
+    if (b < B) M::cost_table(th + b, bs, ct + b, bs);
+  } else if (b == 0) {
+    M::cost_table(th, 1, ct, 1);
+  }
 }
 
 // MPC.reset: x_k = x0 for all stages, everything else zero
@@ -156,14 +282,23 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 
 }  // namespace
 
+enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1 };
+
 struct rlmpc_handle {
-  int model, device, max_batch;
+  int model, variant, device, max_batch;
   size_t bs;
-  int nx, nu, nth, npm, it_size, ws_size;
+  int nx, nu, nth, npm, nr, it_size, ws_size, ct_size;
   int ng() const { return pd.param_cost ? nth : npm; }
   ProblemData pd;
-  double *it = nullptr, *ws = nullptr, *th = nullptr, *th_stage = nullptr;
+  double *it = nullptr, *ws = nullptr, *it2 = nullptr, *ws2 = nullptr, *th = nullptr, *ct = nullptr, *th_stage = nullptr;
+  double* cost = nullptr;
+  int *work = nullptr, *status = nullptr, *hard = nullptr, *counters = nullptr;
+  int* h_counters = nullptr;  // pinned
   int th_per_sample = 0;
+  int sync_every = 4;  // SQP rounds between host checks of the active-sample counter (max_sqp > 1)
+  int timing = 0;      // 1: record CUDA events between the phases of a call (rlmpc_get_timings)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_set[6] = {false, false, false, false, false, false};
   long long launches = 0;
   // staging for the host-buffer entry point
   double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
@@ -173,18 +308,100 @@ struct rlmpc_handle {
 
 namespace {
 
-template <class M>
-int launch_unit(rlmpc_handle* h, const KArgs& a, cudaStream_t s) {
-  const int grid = (a.B + TPB - 1) / TPB;
-  k_unit<M><<<grid, TPB, 0, s>>>(h->pd, a);
-  h->launches++;
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
+// run `expr` with M bound to the model type of the handle
+#define DISPATCH_MODEL(h, expr)                                        \
+  switch ((h)->variant) {                                              \
+    case VAR_CARTPOLE: { using M = CartpoleModel; expr; } break;       \
+    case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; expr; } break;  \
+  }
 
 int check_batch(rlmpc_handle* h, int B) {
   if (!h) return fail(RLMPC_EINVAL, "null handle");
   if (B < 0 || B > h->max_batch) return fail(RLMPC_EINVAL, "batch exceeds max_batch");
+  return 0;
+}
+
+// phase boundaries: 0 start | 1 after k_lin | 2 after k_qp1 | 3 after k_qp2 | 4 after k_sens_stage | 5 after k_sens_sweep
+void mark(rlmpc_handle* h, int i, cudaStream_t s) {
+  if (!h->timing) return;
+  cudaEventRecord(h->ev[i], s);
+  h->ev_set[i] = true;
+}
+
+KArgs base_args(rlmpc_handle* h, int B) {
+  KArgs a;
+  memset(&a, 0, sizeof(a));
+  a.it = h->it; a.ws = h->ws; a.it2 = h->it2; a.ws2 = h->ws2; a.bs = h->bs;
+  a.th = h->th; a.ct = h->ct; a.th_per_sample = h->th_per_sample; a.B = B;
+  a.work = h->work; a.status = h->status; a.cost = h->cost; a.hard = h->hard; a.counters = h->counters;
+  return a;
+}
+
+// SQP: K rounds of (linearise | convergence test + fast QP | full interior point on the queue),
+// then one test-only round.  RTI (K = 1) is a single round without the final test.
+template <class M>
+int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s) {
+  const int B = a.B, N = h->pd.N, K = h->pd.max_sqp;
+  const int gs = (B + TPB - 1) / TPB;
+  const dim3 gstage((B + 127) / 128, N + 1);
+  k_begin<M><<<(B + 127) / 128, 128, 0, s>>>(h->pd, a);
+  h->launches++;
+  for (int i = 0; i < 6; ++i) h->ev_set[i] = false;
+  const int rounds = (K == 1) ? 1 : K + 1;
+  for (int r = 0; r < rounds; ++r) {
+    a.last_round = (K > 1 && r == K) ? 1 : 0;
+    CUDA_OK(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int), s));
+    mark(h, 0, s);
+    k_lin<M><<<gstage, 128, 0, s>>>(h->pd, a);
+    mark(h, 1, s);
+    k_qp1<M><<<gs, TPB, 0, s>>>(h->pd, a);
+    mark(h, 2, s);
+    h->launches += 2;
+    if (!a.last_round) {
+      k_qp2<M><<<(B + 31) / 32, 32, 0, s>>>(h->pd, a);
+      mark(h, 3, s);
+      h->launches++;
+    }
+    if (K > 1 && !a.last_round && (r % h->sync_every) == h->sync_every - 1) {
+      // all samples converged?  (the only host synchronisation of the library; RTI never gets here)
+      k_count_active<M><<<(B + 127) / 128, 128, 0, s>>>(a);
+      h->launches++;
+      CUDA_OK(cudaMemcpyAsync(h->h_counters, h->counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      if (h->h_counters[1] == 0) break;
+    }
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <class M>
+int pipeline_sens(rlmpc_handle* h, const KArgs& a, cudaStream_t s) {
+  const int B = a.B, N = h->pd.N;
+  const dim3 gstage((B + 127) / 128, N + 1);
+  if (!a.have_solve) {
+    for (int i = 0; i < 6; ++i) h->ev_set[i] = false;
+    mark(h, 3, s);
+  }
+  k_sens_stage<M><<<gstage, 128, 0, s>>>(h->pd, a);
+  mark(h, 4, s);
+  k_sens_sweep<M><<<(B + TPB - 1) / TPB, TPB, 0, s>>>(h->pd, a);
+  mark(h, 5, s);
+  h->launches += 2;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <class M>
+int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s) {
+  if (do_solve) {
+    if (int r = pipeline_solve<M>(h, a, s)) return r;
+  }
+  a.have_solve = do_solve;
+  if (do_sens) return pipeline_sens<M>(h, a, s);
+  k_out<M><<<(a.B + 127) / 128, 128, 0, s>>>(h->pd, a);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -196,24 +413,25 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
   if (mode != RLMPC_MODE_V && mode != RLMPC_MODE_Q) return fail(RLMPC_EINVAL, "bad mode");
   if (do_solve && !x0) return fail(RLMPC_EINVAL, "x0 is required");
   if (do_solve && mode == RLMPC_MODE_Q && !u0) return fail(RLMPC_EINVAL, "u0 is required in Q-mode");
+  if (do_solve && max_sqp < 1) return fail(RLMPC_EINVAL, "max_sqp must be >= 1");
   CUDA_OK(cudaSetDevice(h->device));
   h->pd.mode = mode;
   h->pd.max_sqp = max_sqp;
-  KArgs a;
-  a.it = h->it; a.ws = h->ws; a.bs = h->bs; a.th = h->th; a.th_per_sample = h->th_per_sample; a.B = B;
+  KArgs a = base_args(h, B);
   a.x0 = x0; a.u0 = (mode == RLMPC_MODE_Q) ? u0 : nullptr;
   a.u0_out = u0_out; a.cost_out = cost_out; a.status_out = status_out;
-  a.dL = dL; a.dpi = dpi; a.res_out = res_out; a.do_solve = do_solve; a.do_sens = do_sens;
-  switch (h->model) {
-    case RLMPC_MODEL_CARTPOLE: return launch_unit<CartpoleModel>(h, a, s);
-  }
-  return fail(RLMPC_EINVAL, "unknown model");
+  a.dL = dL; a.dpi = dpi; a.res_out = res_out;
+  int rc = fail(RLMPC_EINVAL, "unknown model");
+  DISPATCH_MODEL(h, rc = pipeline<M>(h, a, do_solve, do_sens, s));
+  return rc;
 }
 
-int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* dim) {
+struct Field { int off, dim; };
+
+template <class M>
+int field_offset_t(rlmpc_handle* h, const char* field, int stage, int* off, int* dim) {
+  using E = Engine<M>;
   const int N = h->pd.N;
-  using E = Engine<CartpoleModel>;  // layouts depend only on (NX, NU); dispatch on model when more are added
-  if (h->model != RLMPC_MODEL_CARTPOLE) return fail(RLMPC_EINVAL, "unknown model");
   if (!strcmp(field, "x")) {
     if (stage < 0 || stage > N) return fail(RLMPC_EINVAL, "stage out of range");
     *off = E::it_x(N, stage); *dim = E::NX;
@@ -224,11 +442,11 @@ int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* d
     if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
     *off = E::it_pi(N, stage); *dim = E::NX;
   } else if (!strcmp(field, "lam")) {
-    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
-    *off = E::it_lu(N, stage); *dim = 2 * E::NU;
+    if (stage < 0 || stage > N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_lam(N, stage); *dim = E::NR;
   } else if (!strcmp(field, "t")) {
-    if (stage < 0 || stage >= N) return fail(RLMPC_EINVAL, "stage out of range");
-    *off = E::it_tu(N, stage); *dim = 2 * E::NU;
+    if (stage < 0 || stage > N) return fail(RLMPC_EINVAL, "stage out of range");
+    *off = E::it_t(N, stage); *dim = E::NR;
   } else if (!strcmp(field, "rho_x0")) {
     *off = E::it_rx0(N); *dim = E::NX;
   } else if (!strcmp(field, "rho_u0")) {
@@ -236,6 +454,21 @@ int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* d
   } else {
     return fail(RLMPC_EINVAL, std::string("unknown field ") + field);
   }
+  return 0;
+}
+
+int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* dim) {
+  int rc = fail(RLMPC_EINVAL, "unknown model");
+  DISPATCH_MODEL(h, rc = field_offset_t<M>(h, field, stage, off, dim));
+  return rc;
+}
+
+int refresh_cost_table(rlmpc_handle* h, int B) {
+  DISPATCH_MODEL(h, (k_cost_table<M><<<h->th_per_sample ? (B + 127) / 128 : 1, h->th_per_sample ? 128 : 32>>>(
+                        h->th, h->ct, h->th_per_sample, B, h->bs)));
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -260,15 +493,22 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   h->bs = ((size_t)max_batch + 127) / 128 * 128;
   switch (d->model) {
     case RLMPC_MODEL_CARTPOLE: {
-      using E = Engine<CartpoleModel>;
-      h->nx = E::NX; h->nu = E::NU; h->nth = CartpoleModel::NTH; h->npm = E::NPM;
-      h->it_size = E::it_size(d->N); h->ws_size = E::ws_size(d->N);
+      // state bounds present?  -> the instantiation that carries the 2*nx extra rows per stage
+      bool bx = false;
+      for (int i = 0; i < 4; ++i)
+        bx = bx || d->lbx[i] > -BIG || d->ubx[i] < BIG || d->lbx_e[i] > -BIG || d->ubx_e[i] < BIG;
+      h->variant = bx ? VAR_CARTPOLE_BX : VAR_CARTPOLE;
       break;
     }
     default:
       delete h;
       return fail(RLMPC_EINVAL, "unknown model");
   }
+  DISPATCH_MODEL(h, {
+    using E = Engine<M>;
+    h->nx = E::NX; h->nu = E::NU; h->nth = M::NTH; h->npm = E::NPM; h->nr = E::NR;
+    h->it_size = E::it_size(d->N); h->ws_size = E::ws_size(d->N); h->ct_size = E::CT_SIZE;
+  });
   ProblemData& pd = h->pd;
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
@@ -282,20 +522,36 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   cudaError_t e = cudaSetDevice(device);
   const size_t nio_in = (size_t)max_batch * (h->nx + h->nu);
   const size_t nio_out = (size_t)max_batch * (h->nu + 1 + 4 + (size_t)h->nth * (1 + h->nu));
-  if (e == cudaSuccess) e = cudaMalloc(&h->it, sizeof(double) * h->it_size * h->bs);
-  if (e == cudaSuccess) e = cudaMalloc(&h->ws, sizeof(double) * h->ws_size * h->bs);
+  const size_t n_it = sizeof(double) * h->it_size * h->bs, n_ws = sizeof(double) * h->ws_size * h->bs;
+  if (e == cudaSuccess) e = cudaMalloc(&h->it, n_it);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws, n_ws);
+  if (e == cudaSuccess) e = cudaMalloc(&h->it2, n_it);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ws2, n_ws);
   if (e == cudaSuccess) e = cudaMalloc(&h->th, sizeof(double) * h->nth * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ct, sizeof(double) * h->ct_size * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->th_stage, sizeof(double) * h->nth * (size_t)max_batch);
+  if (e == cudaSuccess) e = cudaMalloc(&h->cost, sizeof(double) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->work, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->status, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->hard, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int) * max_batch);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, sizeof(double) * nio_in);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(double) * nio_out);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_status, sizeof(int) * max_batch);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, sizeof(int) * 4);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMemset(h->it, 0, sizeof(double) * h->it_size * h->bs);
-  if (e == cudaSuccess) e = cudaMemset(h->ws, 0, sizeof(double) * h->ws_size * h->bs);
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  if (e == cudaSuccess) e = cudaMemset(h->it, 0, n_it);
+  if (e == cudaSuccess) e = cudaMemset(h->ws, 0, n_ws);
+  if (e == cudaSuccess) e = cudaMemset(h->it2, 0, n_it);
+  if (e == cudaSuccess) e = cudaMemset(h->ws2, 0, n_ws);
   if (e == cudaSuccess) e = cudaMemset(h->th, 0, sizeof(double) * h->nth * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->ct, 0, sizeof(double) * h->ct_size * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->status, 0, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->cost, 0, sizeof(double) * h->bs);
   if (e != cudaSuccess) {
     std::string msg = std::string("allocation failed: ") + cudaGetErrorString(e);
     rlmpc_destroy(h);
@@ -308,10 +564,14 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
 void rlmpc_destroy(rlmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->it); cudaFree(h->ws); cudaFree(h->th); cudaFree(h->th_stage);
+  cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->th); cudaFree(h->ct);
+  cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
+  cudaFree(h->counters);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_status);
-  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status); cudaFreeHost(h->h_counters);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int i = 0; i < 6; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -325,22 +585,23 @@ int rlmpc_dims(const rlmpc_handle* h, int* nx, int* nu, int* ntheta, int* ngrad,
   return 0;
 }
 
+int rlmpc_nrows(const rlmpc_handle* h) { return h ? h->nr : RLMPC_EINVAL; }
+
 int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, int B) {
   if (!h || !theta_host) return fail(RLMPC_EINVAL, "bad arguments");
   CUDA_OK(cudaSetDevice(h->device));
   if (!per_sample) {
     CUDA_OK(cudaMemcpy(h->th, theta_host, sizeof(double) * h->nth, cudaMemcpyHostToDevice));
     h->th_per_sample = 0;
-    return 0;
+    return refresh_cost_table(h, 0);
   }
   if (int r = check_batch(h, B)) return r;
   CUDA_OK(cudaMemcpy(h->th_stage, theta_host, sizeof(double) * h->nth * (size_t)B, cudaMemcpyHostToDevice));
   k_theta_transpose<<<(B + 127) / 128, 128>>>(h->th_stage, h->th, B, h->nth, h->bs);
   h->launches++;
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaDeviceSynchronize());
   h->th_per_sample = 1;
-  return 0;
+  return refresh_cost_table(h, B);
 }
 
 int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n) {
@@ -352,6 +613,7 @@ int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n) {
 int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n) {
   if (!h || !field || !v || n < 0 || n > RLMPC_MAXD) return fail(RLMPC_EINVAL, "bad arguments");
   double* dst = nullptr;
+  const bool is_x = field[0] && field[1] == 'b' && field[2] == 'x';
   if (!strcmp(field, "lbu")) dst = h->pd.lbu;
   else if (!strcmp(field, "ubu")) dst = h->pd.ubu;
   else if (!strcmp(field, "lbx")) dst = h->pd.lbx;
@@ -359,6 +621,11 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
   else if (!strcmp(field, "lbx_e")) dst = h->pd.lbx_e;
   else if (!strcmp(field, "ubx_e")) dst = h->pd.ubx_e;
   else return fail(RLMPC_EINVAL, std::string("unknown bound field ") + field);
+  if (is_x && h->variant == VAR_CARTPOLE) {
+    for (int i = 0; i < n; ++i)
+      if (v[i] > -BIG && v[i] < BIG)
+        return fail(RLMPC_EINVAL, "this handle was created without state bounds; create it with finite lbx/ubx");
+  }
   memcpy(dst, v, sizeof(double) * n);
   return 0;
 }
@@ -371,6 +638,8 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "max_ipm")) h->pd.max_ipm = (int)value;
   else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
   else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;
+  else if (!strcmp(name, "sync_every")) h->sync_every = value < 1 ? 1 : (int)value;
+  else if (!strcmp(name, "timing")) h->timing = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }
@@ -379,12 +648,7 @@ int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
-  switch (h->model) {
-    case RLMPC_MODEL_CARTPOLE:
-      k_reset<CartpoleModel><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, h->bs, B, x0_dev);
-      break;
-    default: return fail(RLMPC_EINVAL, "unknown model");
-  }
+  DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, h->bs, B, x0_dev)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -490,5 +754,21 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 }
 
 long long rlmpc_launch_count(const rlmpc_handle* h) { return h ? h->launches : 0; }
+
+int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
+  if (!h || !ms_out || n < 5) return fail(RLMPC_EINVAL, "bad arguments");
+  if (!h->timing) return fail(RLMPC_EINVAL, "option \"timing\" is off");
+  CUDA_OK(cudaSetDevice(h->device));
+  for (int i = 0; i < 5; ++i) {
+    ms_out[i] = 0.0;
+    if (h->ev_set[i] && h->ev_set[i + 1]) {
+      CUDA_OK(cudaEventSynchronize(h->ev[i + 1]));
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+      ms_out[i] = ms;
+    }
+  }
+  return 0;
+}
 
 }  // extern "C"

@@ -54,7 +54,8 @@ def lib():
     return _lib
 
 
-def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0) -> ProblemData:
+def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0,
+            lbx=(), ubx=(), lbx_e=(), ubx_e=()) -> ProblemData:
     pd = ProblemData()
     pd.N = N; pd.max_ipm = max_ipm; pd.warm_ipm = warm_ipm; pd.param_cost = param_cost
     pd.tol = tol; pd.tau = tau; pd.mu0 = mu0
@@ -67,6 +68,9 @@ def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, war
         pd.lbu[i] = v
     for i, v in enumerate(ubu):
         pd.ubu[i] = v
+    for name, vals in (("lbx", lbx), ("ubx", ubx), ("lbx_e", lbx_e), ("ubx_e", ubx_e)):
+        for i, v in enumerate(vals):
+            getattr(pd, name)[i] = v
     for i, v in enumerate(mc):
         pd.mc[i] = v
     return pd
@@ -95,7 +99,7 @@ def unit(model: int, pd: ProblemData, mode: int, max_sqp: int, theta, x0, u0=Non
     u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, nu)
     ng = L.cpu_port_grad_width(C.c_int(model), C.byref(pd))  # model parameters only unless pd.param_cost
     out = dict(u0=np.zeros((B, nu)), cost=np.zeros(B), status=np.zeros(B, dtype=np.int32), dL=np.zeros((B, ng)),
-               dpi=np.zeros((B, nu, ng)), res=np.zeros((B, 4)), iters=np.zeros((B, 2), dtype=np.int32))
+               dpi=np.zeros((B, nu, ng)), res=np.zeros((B, 4)), iters=np.zeros((B, 3), dtype=np.int32))
     r = L.cpu_port_unit(C.c_int(model), C.byref(pd), C.c_int(mode), C.c_int(max_sqp), C.c_int(B), _p(theta),
                         C.c_int(per_sample), _p(x0), _p(u0a), _p(iterate), C.c_int(int(do_solve)), C.c_int(int(do_sens)),
                         _p(out["u0"]), _p(out["cost"]), _p(out["status"], C.c_int), _p(out["dL"]), _p(out["dpi"]),

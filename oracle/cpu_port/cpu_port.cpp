@@ -15,6 +15,8 @@ using namespace rlmpc;
 
 static int g_threads = 0;  // 0 = all hardware threads
 
+// Same pipeline as rlmpc_b200.cu, one sample at a time: K rounds of (linearise all stages |
+// convergence test + fast QP | full interior point), one test-only round, then the sensitivities.
 template <class M>
 static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const double* theta, int per_sample,
                 const double* x0, const double* u0, double* iterate, int do_solve, int do_sens, double* u0_out,
@@ -25,11 +27,15 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
   pd.max_sqp = max_sqp;
   const size_t bs = (size_t)B;
   std::vector<double> ws((size_t)E::ws_size(pd.N) * bs, 0.0);
-  std::vector<double> th;
+  std::vector<double> th, ct((size_t)E::CT_SIZE * (per_sample ? bs : 1), 0.0);
   if (per_sample) {
     th.resize((size_t)M::NTH * bs);
-    for (int b = 0; b < B; ++b)
+    for (int b = 0; b < B; ++b) {
       for (int i = 0; i < M::NTH; ++i) th[(size_t)i * bs + b] = theta[(size_t)b * M::NTH + i];
+      M::cost_table(th.data() + b, bs, ct.data() + b, bs);
+    }
+  } else {
+    M::cost_table(theta, 1, ct.data(), 1);
   }
   auto body = [&](int b) {
     Lane L;
@@ -38,23 +44,45 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     L.bs = bs;
     L.th = per_sample ? th.data() + b : theta;
     L.ths = per_sample ? bs : 1;
-    int status = 0;
+    L.ct = per_sample ? ct.data() + b : ct.data();
+    L.cts = per_sample ? bs : 1;
+    int status = ST_OK;
     double cost = 0.0;
+    int sqp_iter = 0, ipm_iter = 0, fast_steps = 0;
     if (do_solve) {
       E::set_initial(pd, L, x0 + (size_t)b * M::NX, 1, u0 ? u0 + (size_t)b * M::NU : nullptr, 1);
-      typename E::SolveOut o = E::solve(pd, L);
-      status = o.status;
-      cost = o.res.cost;
+      status = ST_MAXITER;
+      const int K = pd.max_sqp, rounds = (K == 1) ? 1 : K + 1;
+      for (int r = 0; r < rounds; ++r) {
+        const bool last = (K > 1 && r == K);
+        for (int k = 0; k <= pd.N; ++k) E::lin_stage(pd, L, k);
+        typename E::Residuals R;
+        const int code = E::qp_fast(pd, L, R);
+        cost = R.cost;
+        if (code == E::FAST_NAN) { status = ST_NAN; break; }
+        if (code == E::FAST_CONVERGED) { status = ST_OK; break; }
+        if (last) break;
+        if (code == E::FAST_STEPPED) {
+          ++sqp_iter; ++ipm_iter; ++fast_steps;
+          if (K == 1) { status = ST_OK; break; }
+          continue;
+        }
+        const int st = E::qp_full(pd, L, &ipm_iter);
+        ++sqp_iter;
+        if (K == 1 || st == ST_QPFAIL) { status = st; break; }
+      }
       if (iters_out) {
-        iters_out[2 * b] = o.sqp_iter;
-        iters_out[2 * b + 1] = o.ipm_iter;
+        iters_out[3 * b] = sqp_iter;
+        iters_out[3 * b + 1] = ipm_iter;
+        iters_out[3 * b + 2] = fast_steps;
       }
     }
     if (do_sens) {
       int ok = 1;
       const int ng = E::grad_width(pd);
-      typename E::Residuals r = E::sens(pd, L, dL ? dL + (size_t)b * ng : nullptr,
-                                        dpi ? dpi + (size_t)b * M::NU * ng : nullptr, &ok);
+      for (int k = 0; k <= pd.N; ++k) E::sens_stage(pd, L, k);
+      typename E::Residuals r = E::sens_sweep(pd, L, dL ? dL + (size_t)b * ng : nullptr,
+                                              dpi ? dpi + (size_t)b * M::NU * ng : nullptr, &ok);
       cost = r.cost;
       if (res_out) {
         res_out[4 * b] = r.stat; res_out[4 * b + 1] = r.eq; res_out[4 * b + 2] = r.ineq; res_out[4 * b + 3] = r.comp;
@@ -91,6 +119,14 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
   }
 }
 
+// model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds
+#define PORT_DISPATCH(model, expr)                         \
+  switch (model) {                                         \
+    case 1: { using M = CartpoleModel; expr; } break;      \
+    case 2: { using M = CartpoleModelBX; expr; } break;    \
+    default: return -1;                                    \
+  }
+
 extern "C" {
 
 void cpu_port_set_threads(int n) { g_threads = n; }
@@ -99,24 +135,26 @@ int cpu_port_get_threads() { return g_threads > 0 ? g_threads : (int)std::thread
 int cpu_port_sizeof_problem_data() { return (int)sizeof(ProblemData); }
 
 int cpu_port_iterate_size(int model, int N) {
-  if (model == 1) return Engine<CartpoleModel>::it_size(N);
+  PORT_DISPATCH(model, return Engine<M>::it_size(N));
+  return -1;
+}
+
+int cpu_port_nrows(int model) {
+  PORT_DISPATCH(model, return Engine<M>::NR);
   return -1;
 }
 
 int cpu_port_grad_width(int model, const ProblemData* pd) {
-  if (model == 1) return Engine<CartpoleModel>::grad_width(*pd);
+  PORT_DISPATCH(model, return Engine<M>::grad_width(*pd));
   return -1;
 }
 
-// iterate: [it_size][B] batch-minor, in/out (zero it + set x rows for a cold start)
+// iterate: [it_size][B] batch-minor, in/out (zero it + set x rows for a cold start); iters_out: [B,3]
 int cpu_port_unit(int model, const ProblemData* pd, int mode, int max_sqp, int B, const double* theta, int per_sample,
                   const double* x0, const double* u0, double* iterate, int do_solve, int do_sens, double* u0_out,
                   double* cost_out, int* status_out, double* dL, double* dpi, double* res_out, int* iters_out) {
-  if (model == 1) {
-    run<CartpoleModel>(*pd, mode, max_sqp, B, theta, per_sample, x0, u0, iterate, do_solve, do_sens, u0_out, cost_out,
-                       status_out, dL, dpi, res_out, iters_out);
-    return 0;
-  }
-  return -1;
+  PORT_DISPATCH(model, run<M>(*pd, mode, max_sqp, B, theta, per_sample, x0, u0, iterate, do_solve, do_sens, u0_out,
+                              cost_out, status_out, dL, dpi, res_out, iters_out));
+  return 0;
 }
 }
