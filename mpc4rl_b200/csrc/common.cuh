@@ -19,6 +19,11 @@ namespace rlmpc {
 constexpr int MAXN = 128;  // max horizon supported by ProblemData
 constexpr int MAXD = 8;    // max nx / nu held in ProblemData bound arrays (thread-per-sample engine)
 constexpr double BIG = 1e29;  // |bound| >= BIG means "no bound"
+// Samples are stored in tiles of TILE (one warp): element i of the sample in lane l of tile T lives
+// at base[(T * size + i) * TILE + l].  A warp access to element i is one contiguous 256-byte run
+// (fully coalesced) and, because TILE is a compile-time constant, every element offset inside a
+// thread is an immediate of the load/store instruction -- no per-access index arithmetic.
+constexpr int TILE = 32;
 
 // acados status codes: 0 ok, 1 NaN, 2 max iter, 3 min step, 4 QP failure
 enum Status : int { ST_OK = 0, ST_NAN = 1, ST_MAXITER = 2, ST_MINSTEP = 3, ST_QPFAIL = 4 };
@@ -44,6 +49,9 @@ struct ProblemData {
   double tol;           // SQP convergence tolerance on the 4 KKT residual norms
   double tau;           // complementarity target lam*t = tau (nlp.py:1199)
   double mu0;           // initial barrier parameter of a cold-started IPM
+  double sigma_min;     // smallest centring parameter (barrier reduction per full step)
+  double sigma0;        // centring parameter of the first iteration of a cold start
+  double repair;        // > 0: on a jammed warm start, re-centre only the blocking rows at this product
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component
@@ -51,16 +59,15 @@ struct ProblemData {
   double mc[8];         // model constants (integrator step, gravity, ...)
 };
 
-// One sample's strided view: element i of a logical per-sample vector lives at p[i*bs].
+// One sample's strided view: element i of a logical per-sample vector lives at p[i*TILE].
 struct Lane {
   double* it;        // iterate (persistent primal-dual state, warm start)
   double* ws;        // per-stage scratch
-  size_t bs;         // batch stride (padded batch size)
-  const double* th;  // parameter vector theta
-  size_t ths;        // stride between theta entries (1: shared theta; bs: per-sample theta)
+  const double* th;  // parameter vector theta (a shared theta is stored as one replicated tile)
   const double* ct;  // quadratic cost table derived from theta (Engine::CT_*)
-  size_t cts;        // stride between cost-table entries (1 shared / bs per-sample)
 };
+// offset of element i of sample b in a tiled array whose per-sample size is n
+MPC_HD size_t tile_off(size_t b, size_t n) { return (b / TILE) * n * TILE + (b % TILE); }
 
 MPC_HD double dmax(double a, double b) { return a > b ? a : b; }
 MPC_HD double dmin(double a, double b) { return a < b ? a : b; }

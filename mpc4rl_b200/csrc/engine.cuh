@@ -17,8 +17,8 @@
 //                      between stages -> launched over B x (N+1) threads, compute bound;
 //   qp_* / sens_sweep  one sample: the Riccati recursions, sequential in the stage index ->
 //                      launched over B threads, streaming the per-stage records from HBM.
-// All per-sample vectors live in batch-minor (SoA) arrays: element i of sample b is at
-// base[i*bs + b], so a warp touching element i reads 32 consecutive doubles (256 bytes).
+// All per-sample vectors live in tiled batch-minor (AoSoA) arrays, see TILE in common.cuh: a warp
+// touching element i reads 32 consecutive doubles (256 bytes) at an immediate offset.
 // The code is host/device generic: rlmpc_b200.cu runs it in CUDA kernels; a host build of the
 // same templates exists only as test infrastructure (debugging, CPU baseline).
 #pragma once
@@ -144,23 +144,23 @@ struct Engine {
     double yref[NW], flin[NW], c0;
   };
   MPC_HD static void load_cost(int kind, const Lane& L, CostK& c) {
-    const double* p = L.ct + (size_t)(kind * CT_REC) * L.cts;
+    const double* p = L.ct + (size_t)(kind * CT_REC) * (size_t)TILE;
     MPC_UNROLL for (int i = 0; i < NW; ++i) {
       MPC_UNROLL for (int j = i; j < NW; ++j) {
-        const double v = p[(size_t)(CT_W + pidx(i, j)) * L.cts];
+        const double v = p[(size_t)(CT_W + pidx(i, j)) * (size_t)TILE];
         c.W[i * NW + j] = v;
         c.W[j * NW + i] = v;
       }
-      c.yref[i] = p[(size_t)(CT_Y + i) * L.cts];
-      c.flin[i] = p[(size_t)(CT_F + i) * L.cts];
+      c.yref[i] = p[(size_t)(CT_Y + i) * (size_t)TILE];
+      c.flin[i] = p[(size_t)(CT_F + i) * (size_t)TILE];
     }
-    c.c0 = p[(size_t)CT_C * L.cts];
+    c.c0 = p[(size_t)CT_C * (size_t)TILE];
   }
   // scaled Hessian block only (what the Riccati sweeps need)
   MPC_HD static void load_W(int kind, double s, const Lane& L, double* Wm) {
-    const double* p = L.ct + (size_t)(kind * CT_REC + CT_W) * L.cts;
+    const double* p = L.ct + (size_t)(kind * CT_REC + CT_W) * (size_t)TILE;
     MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) {
-      const double v = s * p[(size_t)pidx(i, j) * L.cts];
+      const double v = s * p[(size_t)pidx(i, j) * (size_t)TILE];
       Wm[i * NW + j] = v;
       Wm[j * NW + i] = v;
     }
@@ -381,7 +381,7 @@ struct Engine {
   // =======================================================================================
   MPC_HD static void lin_stage(const ProblemData& pd, const Lane& L, int k) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     double* w = L.ws + (size_t)k * W_REC * bs;
     CostK ck;
     double y[NW], g[NW];
@@ -390,7 +390,7 @@ struct Engine {
       ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, y);
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, y + NX);
       ld<NX>(L.it + (size_t)it_x(N, k + 1) * bs, bs, xnext);
-      M::dyn_lin(y, y + NX, L.th, L.ths, pd.mc, xn, A, B);
+      M::dyn_lin(y, y + NX, L.th, (size_t)TILE, pd.mc, xn, A, B);
       double eq = 0.0;
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
         bb[i] = xn[i] - xnext[i];
@@ -428,7 +428,7 @@ struct Engine {
 
   MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     const bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
     const double target = pd.tau;
     R.stat = R.eq = R.ineq = R.comp = R.cost = 0.0;
@@ -535,7 +535,7 @@ struct Engine {
   // multipliers (lam_hat, t_hat) of every row, fraction-to-boundary statistics.
   MPC_HD static void forward_sweep(const ProblemData& pd, const Lane& L, double target, bool clip, StepStats& S) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     double dw[NW];
     MPC_UNROLL for (int i = 0; i < NW; ++i) dw[i] = 0.0;
     for (int k = 0; k <= N; ++k) {
@@ -594,7 +594,7 @@ struct Engine {
   // returns sum(lam*t)
   MPC_HD static double ipm_init(const ProblemData& pd, const Lane& L, bool warm) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     double mu = 0.0;
     for (int k = 0; k <= N; ++k) {
       if (k == N && NBX == 0) break;
@@ -631,9 +631,50 @@ struct Engine {
     return mu;
   }
 
+  // Jammed warm start: the last Newton step (lam_hat, t_hat in the workspace) wanted slacks to
+  // cross zero (rows entering the active set) or multipliers to change sign (rows leaving it).
+  // Give exactly those rows room -- product pd.repair -- and keep every other row where it is.
+  // Returns sum(lam*t).
+  MPC_HD static double ipm_repair(const ProblemData& pd, const Lane& L) {
+    const int N = pd.N;
+    constexpr size_t bs = TILE;
+    double mu = 0.0;
+    for (int k = 0; k <= N; ++k) {
+      if (k == N && NBX == 0) break;
+      const double* w = L.ws + (size_t)k * W_REC * bs;
+      double lam[NR], t[NR], lh[NR], th[NR], lb[NV], ub[NV];
+      stage_bounds(pd, k, lb, ub);
+      ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+      ld<NR>(w + (size_t)W_lh * bs, bs, lh);
+      ld<NR>(w + (size_t)W_th * bs, bs, th);
+      MPC_UNROLL for (int r = 0; r < NV; ++r) {
+        const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
+        const double eps_t = 1e-3 * range;
+        MPC_UNROLL for (int side = 0; side < 2; ++side) {
+          const int q = side * NV + r;
+          const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
+          if (!act) continue;
+          if (th[q] < 0.5 * t[q] && th[q] < eps_t) {         // slack collapses: row becomes active
+            t[q] = dmax(t[q] < eps_t ? t[q] : eps_t, 1e-10 * range);
+            t[q] = eps_t;
+            lam[q] = dmax(dmax(lam[q], lh[q]), pd.repair / eps_t);
+          } else if (lh[q] < 0.5 * lam[q] && lam[q] * t[q] < pd.repair) {  // multiplier collapses: row is released
+            t[q] = dmax(dmax(t[q], th[q]), eps_t);
+            lam[q] = pd.repair / t[q];
+          }
+          mu += lam[q] * t[q];
+        }
+      }
+      st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+    }
+    return mu;
+  }
+
   // pending damped update (lam,t) += alpha ((lam_hat,t_hat) - (lam,t)) of the rows of stage k; returns them
   MPC_HD static void rows_update(const Lane& L, int N, int k, double alpha, double* lam, double* t) {
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     const double* w = L.ws + (size_t)k * W_REC * bs;
     ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
     ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
@@ -652,7 +693,7 @@ struct Engine {
 
   MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     const bool qmode = pd.mode == MODE_Q;
     const double m_rows = (double)count_rows(pd);
     // ---- initialise (lam,t): warm = keep the multipliers of the previous QP (clipped away from
@@ -661,17 +702,25 @@ struct Engine {
     double mu = ipm_init(pd, L, warm) / m_rows;
 
     double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
-    double sigma = warm ? 0.05 : 0.3;
+    double sigma = warm ? pd.sigma_min : pd.sigma0;
     int iters = 0, warm_iters = 0;
-    bool converged = false, failed = false;
+    bool converged = false, failed = false, repaired = false;
     for (int j = 0; j < pd.max_ipm && !converged; ++j) {
       ++iters;
       if (warm && (warm_iters >= WARM_LIMIT || (warm_iters > 0 && alpha < 0.05))) {
-        // the warm start is jammed (active set changed too much): restart from a cold point
-        warm = false;
-        mu = ipm_init(pd, L, false) / m_rows;
-        alpha = 0.0;
-        sigma = 0.3;
+        if (pd.repair > 0.0 && !repaired && warm_iters < WARM_LIMIT) {
+          // the Newton step predicts an active-set change: re-centre only the rows that block it
+          repaired = true;
+          mu = ipm_repair(pd, L) / m_rows;
+          alpha = 0.0;
+          sigma = pd.sigma_min;
+        } else {
+          // the warm start is jammed (active set changed too much): restart from a cold point
+          warm = false;
+          mu = ipm_init(pd, L, false) / m_rows;
+          alpha = 0.0;
+          sigma = pd.sigma0;
+        }
       }
       if (warm) ++warm_iters;
       const double target = dmax(sigma * mu, pd.tau);
@@ -731,10 +780,14 @@ struct Engine {
       if (failed || !(S.amax == S.amax)) break;
       alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
       const double mu_new = (S.s0 + alpha * S.s1 + alpha * alpha * S.s2) / m_rows;
+#ifdef IPM_TRACE
+      printf("  ipm it %2d warm %d sigma %.3f mu %.3e target %.3e amax %.4g alpha %.4g cmax %.3e mu_new %.3e\n", iters, (int)warm,
+             sigma, mu, target, S.amax, alpha, S.cmax, mu_new);
+#endif
       if (target <= pd.tau && alpha == 1.0 && S.cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
       // centring heuristic: aggressive after long steps, conservative after short ones
       const double r = 1.0 - alpha;
-      sigma = dmin(0.8, dmax(0.05, r * r * 4.0 + 0.05));
+      sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
       mu = mu_new;
     }
     *alpha_out = alpha;
@@ -748,7 +801,7 @@ struct Engine {
   // ---------------------------------------------------------------------------------------
   MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha, bool clip) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     double pik[NX];  // pi_k (multiplier of x_{k+1} = F(x_k,u_k))
     for (int k = N; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
@@ -831,9 +884,9 @@ struct Engine {
   MPC_HD static void set_initial(const ProblemData& pd, const Lane& L, const double* x0, size_t x0s, const double* u0,
                                  size_t u0s) {
     const int N = pd.N;
-    MPC_UNROLL for (int i = 0; i < NX; ++i) L.it[(size_t)(it_x(N, 0) + i) * L.bs] = x0[(size_t)i * x0s];
+    MPC_UNROLL for (int i = 0; i < NX; ++i) L.it[(size_t)(it_x(N, 0) + i) * TILE] = x0[(size_t)i * x0s];
     if (pd.mode == MODE_Q) {
-      MPC_UNROLL for (int i = 0; i < NU; ++i) L.it[(size_t)(it_u(N, 0) + i) * L.bs] = u0[(size_t)i * u0s];
+      MPC_UNROLL for (int i = 0; i < NU; ++i) L.it[(size_t)(it_u(N, 0) + i) * TILE] = u0[(size_t)i * u0s];
     }
   }
 
@@ -851,7 +904,7 @@ struct Engine {
   // (sample, stage) function: exact second-order information of stage k at (x_k, u_k, pi_k).
   MPC_HD static void sens_stage(const ProblemData& pd, const Lane& L, int k) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     double* w = L.ws + (size_t)k * W_REC * bs;
     CostK ck;
     double y[NW], g[NW];
@@ -861,7 +914,7 @@ struct Engine {
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, y + NX);
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NX>(L.it + (size_t)it_x(N, k + 1) * bs, bs, xk1);
-      M::dyn_sens(y, y + NX, L.th, L.ths, pd.mc, pik, xn, A, B, Fp, Hww, Hwp);
+      M::dyn_sens(y, y + NX, L.th, (size_t)TILE, pd.mc, pik, xn, A, B, Fp, Hww, Hwp);
       double eq = 0.0;
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
         const double d = xn[i] - xk1[i];
@@ -903,7 +956,7 @@ struct Engine {
   // [B, ng] / [B, NU, ng] outputs (nullptr: skip).
   MPC_HD static Residuals sens_sweep(const ProblemData& pd, const Lane& L, double* dLdth, double* dpidth, int* ok_out) {
     const int N = pd.N;
-    const size_t bs = L.bs;
+    constexpr size_t bs = TILE;
     const bool qmode = pd.mode == MODE_Q;
     Residuals R = {0, 0, 0, 0, 0};
     bool ok = true;
@@ -920,7 +973,7 @@ struct Engine {
       if (NBX > 0 || (pd.param_cost && dLdth)) {
         double x[NX];
         ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
-        if (pd.param_cost && dLdth) M::cost_param_grad(2, pd.scale[N], L.th, L.ths, x, nullptr, dLdth);
+        if (pd.param_cost && dLdth) M::cost_param_grad(2, pd.scale[N], L.th, (size_t)TILE, x, nullptr, dLdth);
         if (NBX > 0) {
           double lb[NV], ub[NV], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
           stage_bounds(pd, N, lb, ub);
@@ -958,7 +1011,7 @@ struct Engine {
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-      if (pd.param_cost && dLdth) M::cost_param_grad(k == 0 ? 0 : 1, pd.scale[k], L.th, L.ths, x, u, dLdth);
+      if (pd.param_cost && dLdth) M::cost_param_grad(k == 0 ? 0 : 1, pd.scale[k], L.th, (size_t)TILE, x, u, dLdth);
       stage_bounds(pd, k, lb, ub);
       stage_vars(x, u, v);
       // ---- residuals ----

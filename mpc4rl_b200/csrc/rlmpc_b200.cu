@@ -1,9 +1,9 @@
 // librlmpc_b200.so -- CUDA kernels (sm_100a) + the C ABI declared in include/rlmpc_b200.h.
 //
-// Mapping: one CUDA thread per replay-buffer sample (nx <= 4 problems).  The whole
-// primal-dual iterate and the per-stage scratch live in HBM in batch-minor (SoA) arrays, so every
-// load/store a warp issues is a fully coalesced 256-byte access; theta and the problem data
-// are broadcast (constant bank / L1).  See DESIGN.md for the roofline discussion.
+// Mapping (nx <= 4 problems): function/derivative evaluation runs one CUDA thread per (sample,
+// stage) pair, the Riccati recursions one thread per sample.  The primal-dual iterate and the
+// per-stage records live in HBM in tiles of 32 samples (AoSoA), so every load/store a warp issues
+// is a fully coalesced 256-byte access at an immediate offset.  See DESIGN.md.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -39,7 +39,7 @@ constexpr int TPB = RLMPC_TPB;  // threads per block of the sample-parallel kern
 struct KArgs {
   double* it;
   double* ws;
-  size_t bs;
+  int it_size, ws_size, th_size, ct_size;  // doubles per sample of each tiled array
   double* it2;  // compact copies used by the full interior-point pass (one slot per queued sample)
   double* ws2;
   const double* th;
@@ -66,13 +66,11 @@ struct KArgs {
 template <class M>
 __device__ __forceinline__ Lane make_lane(const KArgs& a, int b) {
   Lane L;
-  L.it = a.it + b;
-  L.ws = a.ws + b;
-  L.bs = a.bs;
-  L.th = a.th_per_sample ? a.th + b : a.th;
-  L.ths = a.th_per_sample ? a.bs : 1;
-  L.ct = a.th_per_sample ? a.ct + b : a.ct;
-  L.cts = a.th_per_sample ? a.bs : 1;
+  L.it = a.it + tile_off(b, a.it_size);
+  L.ws = a.ws + tile_off(b, a.ws_size);
+  // a shared theta is one tile with 32 identical lanes (tile 0)
+  L.th = a.th + (a.th_per_sample ? tile_off(b, a.th_size) : (size_t)(b % TILE));
+  L.ct = a.ct + (a.th_per_sample ? tile_off(b, a.ct_size) : (size_t)(b % TILE));
   return L;
 }
 
@@ -135,17 +133,19 @@ __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData 
   const int b = a.hard[j];
   const Lane Ls = make_lane<M>(a, b);
   Lane L = Ls;
-  L.it = a.it2 + j;
-  L.ws = a.ws2 + j;
+  L.it = a.it2 + tile_off(j, a.it_size);
+  L.ws = a.ws2 + tile_off(j, a.ws_size);
   const int N = pd.N, nit = E::it_size(N);
-  for (int i = 0; i < nit; ++i) L.it[(size_t)i * L.bs] = Ls.it[(size_t)i * L.bs];
+#pragma unroll 8
+  for (int i = 0; i < nit; ++i) L.it[(size_t)i * TILE] = Ls.it[(size_t)i * TILE];
   for (int k = 0; k <= N; ++k) {
     const size_t o = (size_t)k * E::W_REC;
-#pragma unroll 4
-    for (int i = E::W_A; i < E::W_K; ++i) L.ws[(o + i) * L.bs] = Ls.ws[(o + i) * L.bs];
+#pragma unroll
+    for (int i = E::W_A; i < E::W_K; ++i) L.ws[(o + i) * TILE] = Ls.ws[(o + i) * TILE];
   }
   const int st = E::qp_full(pd, L, nullptr);
-  for (int i = 0; i < nit; ++i) Ls.it[(size_t)i * L.bs] = L.it[(size_t)i * L.bs];
+#pragma unroll 8
+  for (int i = 0; i < nit; ++i) Ls.it[(size_t)i * TILE] = L.it[(size_t)i * TILE];
   if (pd.max_sqp == 1 || st == ST_QPFAIL) {
     // RTI: done after one QP.  Otherwise a failed QP (not PD / iteration limit) ends the solve
     a.status[b] = st;
@@ -171,7 +171,8 @@ __global__ void k_out(const __grid_constant__ ProblemData pd, const KArgs a) {
   if (b >= a.B) return;
   if (a.u0_out) {
 #pragma unroll
-    for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = a.it[(size_t)(E::it_u(pd.N, 0) + i) * a.bs + b];
+    for (int i = 0; i < M::NU; ++i)
+      a.u0_out[(size_t)b * M::NU + i] = a.it[tile_off(b, a.it_size) + (size_t)(E::it_u(pd.N, 0) + i) * TILE];
   }
   if (a.cost_out) a.cost_out[b] = a.cost[b];
   if (a.status_out) a.status_out[b] = a.status[b];
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(TPB) k_sens_sweep(const __grid_constant__ Prob
   if (!ok && status == ST_OK) status = ST_QPFAIL;  // reduced Hessian not PD: sensitivities invalid
   if (a.u0_out) {
 #pragma unroll
-    for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * L.bs];
+    for (int i = 0; i < M::NU; ++i) a.u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * TILE];
   }
   if (a.cost_out) a.cost_out[b] = r.cost;
   if (a.status_out) a.status_out[b] = status;
@@ -217,46 +218,47 @@ __global__ void __launch_bounds__(TPB) k_sens_sweep(const __grid_constant__ Prob
 
 // theta -> quadratic cost table (shared: one thread; per sample: one thread per sample)
 template <class M>
-__global__ void k_cost_table(const double* th, double* ct, int per_sample, int B, size_t bs) {
+__global__ void k_cost_table(const double* th, double* ct, int per_sample, int B) {
+  using E = Engine<M>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (per_sample) {
-    if (b < B) M::cost_table(th + b, bs, ct + b, bs);
-  } else if (b == 0) {
-    M::cost_table(th, 1, ct, 1);
-  }
+  if (b >= (per_sample ? B : TILE)) return;  // shared theta: the 32 lanes of tile 0
+  M::cost_table(th + tile_off(b, M::NTH), TILE, ct + tile_off(b, E::CT_SIZE), TILE);
 }
 
 // MPC.reset: x_k = x0 for all stages, everything else zero
 template <class M>
-__global__ void k_reset(int N, double* it, size_t bs, int B, const double* x0) {
+__global__ void k_reset(int N, double* it, int B, const double* x0) {
   using E = Engine<M>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int n = E::it_size(N);
+  double* p = it + tile_off(b, n);
   for (int i = 0; i < n; ++i) {
     double v = 0.0;
     if (x0 && i < (N + 1) * M::NX) v = x0[(size_t)b * M::NX + (i % M::NX)];
-    it[(size_t)i * bs + b] = v;
+    p[(size_t)i * TILE] = v;
   }
 }
 
 // gather/scatter one field of one stage between the SoA iterate and a row-major [B, dim] buffer
-__global__ void k_copy_field(double* it, size_t bs, int B, int off, int dim, double* buf, int to_iterate) {
+__global__ void k_copy_field(double* it, int it_size, int B, int off, int dim, double* buf, int to_iterate) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  double* p = it + tile_off(b, it_size);
   for (int i = 0; i < dim; ++i) {
     if (to_iterate)
-      it[(size_t)(off + i) * bs + b] = buf[(size_t)b * dim + i];
+      p[(size_t)(off + i) * TILE] = buf[(size_t)b * dim + i];
     else
-      buf[(size_t)b * dim + i] = it[(size_t)(off + i) * bs + b];
+      buf[(size_t)b * dim + i] = p[(size_t)(off + i) * TILE];
   }
 }
 
-// theta [B, nth] row-major -> [nth][bs] batch-minor
-__global__ void k_theta_transpose(const double* in, double* out, int B, int nth, size_t bs) {
+// theta [B, nth] row-major -> tiled; shared = 1: the single theta `in` replicated into the lanes of tile 0
+__global__ void k_theta_transpose(const double* in, double* out, int B, int nth, int shared) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  for (int i = 0; i < nth; ++i) out[(size_t)i * bs + b] = in[(size_t)b * nth + i];
+  if (b >= (shared ? TILE : B)) return;
+  double* p = out + tile_off(b, nth);
+  for (int i = 0; i < nth; ++i) p[(size_t)i * TILE] = in[shared ? (size_t)i : (size_t)b * nth + i];
 }
 
 // acc[j] += sum_b td_b * dQ[b, j] over valid samples; acc[nth] += sum td; acc[nth+1] += count
@@ -331,7 +333,8 @@ void mark(rlmpc_handle* h, int i, cudaStream_t s) {
 KArgs base_args(rlmpc_handle* h, int B) {
   KArgs a;
   memset(&a, 0, sizeof(a));
-  a.it = h->it; a.ws = h->ws; a.it2 = h->it2; a.ws2 = h->ws2; a.bs = h->bs;
+  a.it = h->it; a.ws = h->ws; a.it2 = h->it2; a.ws2 = h->ws2;
+  a.it_size = h->it_size; a.ws_size = h->ws_size; a.th_size = h->nth; a.ct_size = h->ct_size;
   a.th = h->th; a.ct = h->ct; a.th_per_sample = h->th_per_sample; a.B = B;
   a.work = h->work; a.status = h->status; a.cost = h->cost; a.hard = h->hard; a.counters = h->counters;
   return a;
@@ -465,7 +468,7 @@ int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* d
 
 int refresh_cost_table(rlmpc_handle* h, int B) {
   DISPATCH_MODEL(h, (k_cost_table<M><<<h->th_per_sample ? (B + 127) / 128 : 1, h->th_per_sample ? 128 : 32>>>(
-                        h->th, h->ct, h->th_per_sample, B, h->bs)));
+                        h->th, h->ct, h->th_per_sample, B)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
@@ -513,7 +516,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.repair = 0.0;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -591,13 +594,16 @@ int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, i
   if (!h || !theta_host) return fail(RLMPC_EINVAL, "bad arguments");
   CUDA_OK(cudaSetDevice(h->device));
   if (!per_sample) {
-    CUDA_OK(cudaMemcpy(h->th, theta_host, sizeof(double) * h->nth, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->th_stage, theta_host, sizeof(double) * h->nth, cudaMemcpyHostToDevice));
+    k_theta_transpose<<<1, TILE>>>(h->th_stage, h->th, TILE, h->nth, 1);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
     h->th_per_sample = 0;
     return refresh_cost_table(h, 0);
   }
   if (int r = check_batch(h, B)) return r;
   CUDA_OK(cudaMemcpy(h->th_stage, theta_host, sizeof(double) * h->nth * (size_t)B, cudaMemcpyHostToDevice));
-  k_theta_transpose<<<(B + 127) / 128, 128>>>(h->th_stage, h->th, B, h->nth, h->bs);
+  k_theta_transpose<<<(B + 127) / 128, 128>>>(h->th_stage, h->th, B, h->nth, 0);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   h->th_per_sample = 1;
@@ -635,6 +641,9 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   if (!strcmp(name, "tol")) h->pd.tol = value;
   else if (!strcmp(name, "tau")) h->pd.tau = value;
   else if (!strcmp(name, "mu0")) h->pd.mu0 = value;
+  else if (!strcmp(name, "sigma_min")) h->pd.sigma_min = value;
+  else if (!strcmp(name, "sigma0")) h->pd.sigma0 = value;
+  else if (!strcmp(name, "repair")) h->pd.repair = value;
   else if (!strcmp(name, "max_ipm")) h->pd.max_ipm = (int)value;
   else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
   else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;
@@ -648,7 +657,7 @@ int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
-  DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, h->bs, B, x0_dev)));
+  DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, B, x0_dev)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -661,7 +670,7 @@ int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, doub
   if (int r = field_offset(h, field, stage, &off, &dim)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
-  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->bs, B, off, dim, buf_dev, 0);
+  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->it_size, B, off, dim, buf_dev, 0);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -674,7 +683,7 @@ int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, cons
   if (int r = field_offset(h, field, stage, &off, &dim)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
-  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->bs, B, off, dim, const_cast<double*>(buf_dev), 1);
+  k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->it_size, B, off, dim, const_cast<double*>(buf_dev), 1);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -25,27 +25,24 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
   ProblemData pd = pd0;
   pd.mode = mode;
   pd.max_sqp = max_sqp;
-  const size_t bs = (size_t)B;
-  std::vector<double> ws((size_t)E::ws_size(pd.N) * bs, 0.0);
-  std::vector<double> th, ct((size_t)E::CT_SIZE * (per_sample ? bs : 1), 0.0);
-  if (per_sample) {
-    th.resize((size_t)M::NTH * bs);
-    for (int b = 0; b < B; ++b) {
-      for (int i = 0; i < M::NTH; ++i) th[(size_t)i * bs + b] = theta[(size_t)b * M::NTH + i];
-      M::cost_table(th.data() + b, bs, ct.data() + b, bs);
-    }
-  } else {
-    M::cost_table(theta, 1, ct.data(), 1);
+  // tiled (AoSoA) storage like the device: element i of sample b at tile_off(b, n) + i*TILE
+  const size_t bs = ((size_t)B + TILE - 1) / TILE * TILE;
+  const int itn_ = E::it_size(pd.N);
+  std::vector<double> ws((size_t)E::ws_size(pd.N) * bs, 0.0), itt((size_t)itn_ * bs, 0.0);
+  std::vector<double> th((size_t)M::NTH * (per_sample ? bs : TILE)), ct((size_t)E::CT_SIZE * (per_sample ? bs : TILE), 0.0);
+  for (int b = 0; b < (per_sample ? B : TILE); ++b) {
+    for (int i = 0; i < M::NTH; ++i)
+      th[tile_off(b, M::NTH) + (size_t)i * TILE] = per_sample ? theta[(size_t)b * M::NTH + i] : theta[i];
+    M::cost_table(th.data() + tile_off(b, M::NTH), TILE, ct.data() + tile_off(b, E::CT_SIZE), TILE);
   }
+  for (int b = 0; b < B; ++b)  // caller's iterate is [it_size][B] batch-minor
+    for (int i = 0; i < itn_; ++i) itt[tile_off(b, itn_) + (size_t)i * TILE] = iterate[(size_t)i * B + b];
   auto body = [&](int b) {
     Lane L;
-    L.it = iterate + b;
-    L.ws = ws.data() + b;
-    L.bs = bs;
-    L.th = per_sample ? th.data() + b : theta;
-    L.ths = per_sample ? bs : 1;
-    L.ct = per_sample ? ct.data() + b : ct.data();
-    L.cts = per_sample ? bs : 1;
+    L.it = itt.data() + tile_off(b, itn_);
+    L.ws = ws.data() + tile_off(b, E::ws_size(pd.N));
+    L.th = th.data() + (per_sample ? tile_off(b, M::NTH) : (size_t)(b % TILE));
+    L.ct = ct.data() + (per_sample ? tile_off(b, E::CT_SIZE) : (size_t)(b % TILE));
     int status = ST_OK;
     double cost = 0.0;
     int sqp_iter = 0, ipm_iter = 0, fast_steps = 0;
@@ -93,7 +90,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
       if (!ok && status == ST_OK) status = ST_QPFAIL;
     }
     if (u0_out)
-      for (int i = 0; i < M::NU; ++i) u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * bs];
+      for (int i = 0; i < M::NU; ++i) u0_out[(size_t)b * M::NU + i] = L.it[(size_t)(E::it_u(pd.N, 0) + i) * TILE];
     if (cost_out) cost_out[b] = cost;
     if (status_out) status_out[b] = status;
   };
@@ -117,6 +114,8 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     for (int i = 0; i < nt; ++i) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
   }
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < itn_; ++i) iterate[(size_t)i * B + b] = itt[tile_off(b, itn_) + (size_t)i * TILE];
 }
 
 // model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds
