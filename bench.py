@@ -172,6 +172,9 @@ def run_gpu(args, rank, world, local_rank):
     # untimed setup: converge the batch once (cold start like MPC.reset), this is the warm-start state
     mpc.set_option("tol", 1e-6)
     mpc.set_option("timing", 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        mpc.set_option(k, float(v))
     mpc.reset(x0)
     _, _, st = mpc.solve(x0, max_sqp=60)
     torch.cuda.synchronize()
@@ -288,6 +291,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
     ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

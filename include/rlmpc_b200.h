@@ -33,7 +33,8 @@ extern "C" {
 #define RLMPC_MAXD 8
 
 /* models (device code emitted per problem, the role of acados' c_generated_code) */
-#define RLMPC_MODEL_CARTPOLE 1 /* rlmpc/mpc/cartpole/acados.py:28-108 */
+#define RLMPC_MODEL_CARTPOLE 1      /* rlmpc/mpc/cartpole/acados.py:28-108 (config/cartpole*.yaml) */
+#define RLMPC_MODEL_LINEAR_SYSTEM 2 /* rlmpc/mpc/linear_system/acados.py:27-131 */
 
 #define RLMPC_MODE_V 0 /* x_0 fixed            -> V(s), pi(s)   mpc.py:177-202 (update, get_action) */
 #define RLMPC_MODE_Q 1 /* x_0 and u_0 fixed    -> Q(s,a)        mpc.py:52-96   (q_update) */
@@ -55,7 +56,9 @@ typedef struct rlmpc_problem_desc {
   double lbu[RLMPC_MAXD], ubu[RLMPC_MAXD]; /* input bounds, all stages (constraints.lbu/ubu) */
   double lbx[RLMPC_MAXD], ubx[RLMPC_MAXD]; /* state bounds stages 1..N-1 (+-1e30 = none) */
   double lbx_e[RLMPC_MAXD], ubx_e[RLMPC_MAXD];
-  double model_const[8];            /* cartpole: [0]=RK4 step h, [1]=g */
+  double model_const[8];            /* cartpole: [0]=RK4 step h, [1]=g; linear system: [0..2] = P11,P12,P22 of
+                                       the constant terminal cost (linear_system/acados.py:51-57) */
+  double zl[RLMPC_MAXD], zu[RLMPC_MAXD]; /* linear penalties of the soft state bounds (cost.zl/zu), per idxsbx row */
 } rlmpc_problem_desc;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -79,12 +82,13 @@ int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, i
 /* Replaces ocp_nlp_cost_model_set(..., "scaling", ...) (mpc.py:259-285). n = N+1. */
 int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n);
 /* Replaces constraints_set(stage, "lbu"/"ubu"/..) for the nominal bounds. field in
- * {"lbu","ubu","lbx","ubx","lbx_e","ubx_e"}. */
+ * {"lbu","ubu","lbx","ubx","lbx_e","ubx_e","zl","zu"}. */
 int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n);
 /* options: "tol" (1e-6), "tau" (1e-8), "mu0" (1.0), "max_ipm" (50), "warm_ipm" (1: start every QP's
  * interior-point iteration from the multipliers of the previous QP, with a cold restart if jammed),
  * "sync_every" (4: SQP rounds between host checks "has every sample converged" when max_sqp > 1),
- * "timing" (0; 1 = record per-phase CUDA events, see rlmpc_get_timings),
+ * "timing" (0; 1 = record per-phase CUDA events, see rlmpc_get_timings), "overlap" (0),
+ * "sigma_min" (0.05), "sigma0" (0.3): centring parameters of the interior-point iteration,
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */
 int rlmpc_set_option(rlmpc_handle* h, const char* name, double value);
 
@@ -134,9 +138,11 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);
 /* With option "timing" = 1 the library records CUDA events on the caller's stream between the phases
- * of a solve / sens call.  ms_out[0..5) = device time of the last call's
- * [linearise | convergence test + fast QP | full interior point | sens stage evaluation | sens sweeps]
- * kernels (of the last SQP round when max_sqp > 1); waits for the call to finish.  The reference's
+ * of a solve / sens call.  ms_out[0..6) = device time of the last call's
+ * [linearise | convergence test + fast QP | full interior point of the queued samples | sens stage
+ * evaluation | sens sweeps | tail = sens kernels of the queued samples] (of the last SQP round when
+ * max_sqp > 1); waits for the call to finish.  n >= 6.  With option "overlap" = 1 (default 0) an RTI
+ * solve_sens call runs the third phase on a side stream concurrently with the fourth and fifth.  The reference's
  * analogue is the nlp_timing dict of update_nlp (nlp.py:1397-1422). */
 int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n);
 

@@ -7,14 +7,16 @@ Layout
   problems.py host-side problem descriptions (the AcadosOcp role)
   mpc/        mirror of the reference's rlmpc.mpc package (MPC, AcadosMPC classes)
 """
-__all__ = ["BatchedMPC", "cartpole_spec", "cartpole_original_config"]
+__all__ = ["BatchedMPC", "cartpole_spec", "cartpole_original_config", "cartpole_config", "linear_system_spec",
+           "linear_system_param_nominal"]
 
 
 def __getattr__(name):
     if name == "BatchedMPC":
         from .batched import BatchedMPC
         return BatchedMPC
-    if name in ("cartpole_spec", "cartpole_original_config", "ProblemSpec"):
+    if name in ("cartpole_spec", "cartpole_original_config", "cartpole_config", "ProblemSpec", "linear_system_spec",
+                "linear_system_param_nominal"):
         from . import problems
         return getattr(problems, name)
     raise AttributeError(name)

@@ -10,6 +10,7 @@ import os
 
 MAXN, MAXD = 128, 8
 MODEL_CARTPOLE = 1
+MODEL_LINEAR_SYSTEM = 2
 MODE_V, MODE_Q = 0, 1
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -33,6 +34,7 @@ class ProblemDesc(C.Structure):
         ("lbx", C.c_double * MAXD), ("ubx", C.c_double * MAXD),
         ("lbx_e", C.c_double * MAXD), ("ubx_e", C.c_double * MAXD),
         ("model_const", C.c_double * 8),
+        ("zl", C.c_double * MAXD), ("zu", C.c_double * MAXD),
     ]
 
 

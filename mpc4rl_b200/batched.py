@@ -190,12 +190,12 @@ class BatchedMPC:
                                            _ptr(status), _ptr(acc), self._stream()))
         return acc
 
-    PHASES = ("linearize", "qp_fast", "qp_full", "sens_stage", "sens_sweep")
+    PHASES = ("linearize", "qp_fast", "qp_full", "sens_stage", "sens_sweep", "sens_tail")
 
     def timings(self) -> dict:
         """Device milliseconds of the phases of the last call (needs set_option("timing", 1))."""
-        ms = np.zeros(5)
-        _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 5))
+        ms = np.zeros(6)
+        _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 6))
         return dict(zip(self.PHASES, ms.tolist()))
 
     @property

@@ -51,11 +51,11 @@ struct ProblemData {
   double mu0;           // initial barrier parameter of a cold-started IPM
   double sigma_min;     // smallest centring parameter (barrier reduction per full step)
   double sigma0;        // centring parameter of the first iteration of a cold start
-  double repair;        // > 0: on a jammed warm start, re-centre only the blocking rows at this product
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component
   double lbx_e[MAXD], ubx_e[MAXD];  // stage N
+  double zl[MAXD], zu[MAXD];        // linear penalties of the soft state bounds (cost.zl / cost.zu), per soft row
   double mc[8];         // model constants (integrator step, gravity, ...)
 };
 

@@ -30,7 +30,11 @@ template <class M>
 struct Engine {
   static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NPM = M::NPM, NBX = M::NBX;
   static constexpr int NV = NU + NBX;   // box-constrained variables of a stage: [u ; x[bx]]
-  static constexpr int NR = 2 * NV;     // inequality rows per stage, acados order [lbu lbx ubu ubx]
+  static constexpr int NSX = M::NSX;    // soft state bounds (subset of bx, stages 1..N-1): slack rows
+  static constexpr int NSXA = NSX > 0 ? NSX : 1;
+  // inequality rows per stage, acados order [lbu lbx ubu ubx lsbx usbx] (rlmpc/common/utils.py:4-25)
+  static constexpr int NR = 2 * NV + 2 * NSX;
+  static constexpr int R_LS = 2 * NV, R_US = 2 * NV + NSX;  // first lower / upper slack row
   static constexpr int NPS = NX * (NX + 1) / 2;
   static constexpr int NWS = NW * (NW + 1) / 2;
 
@@ -183,25 +187,48 @@ struct Engine {
   // (acados order [lbu, lbx, ubu, ubx], rlmpc/common/utils.py:4-25).  A row that does not exist at
   // this stage (u at stage N or clamped in Q-mode, x at stage 0, infinite bound) gets lb = -inf /
   // ub = +inf and is skipped everywhere.
+  // Soft state bounds (constraints.idxsbx, linear penalty zl/zu, nlp.py:1099-1134): the bound row
+  // reads lb - x - sl <= 0 with the extra row -sl <= 0 (multiplier/slack pair R_LS + j); the slack
+  // value is the slack of that extra row, sl = t[R_LS + j].  Stationarity in sl, z = lam_b + lam_s,
+  // is eliminated inside the interior-point iteration (soft_coeffs).
+  struct Bnd {
+    double lb[NV], ub[NV];
+    double zl[NSXA], zu[NSXA];  // scaled penalties s_k * z of the soft pairs, < 0: pair not present at this stage
+  };
   MPC_HD static int vidx(int r) { return r < NU ? NX + r : M::bx(r - NU); }  // index into w = [x;u]
-  MPC_HD static void stage_bounds(const ProblemData& pd, int k, double* lb, double* ub) {
+  MPC_HD static int soft_row(int j) { return NU + M::sx(j); }               // variable index (in v) of soft pair j
+  MPC_HD static void stage_bounds(const ProblemData& pd, int k, Bnd& bd) {
     const bool uact = (k < pd.N) && !(k == 0 && pd.mode == MODE_Q);
     MPC_UNROLL for (int i = 0; i < NU; ++i) {
-      lb[i] = uact ? pd.lbu[i] : -1e300;
-      ub[i] = uact ? pd.ubu[i] : 1e300;
+      bd.lb[i] = uact ? pd.lbu[i] : -1e300;
+      bd.ub[i] = uact ? pd.ubu[i] : 1e300;
     }
     MPC_UNROLL for (int j = 0; j < NBX; ++j) {
       const int ix = M::bx(j);
-      lb[NU + j] = (k == 0) ? -1e300 : (k == pd.N ? pd.lbx_e[ix] : pd.lbx[ix]);
-      ub[NU + j] = (k == 0) ? 1e300 : (k == pd.N ? pd.ubx_e[ix] : pd.ubx[ix]);
+      bd.lb[NU + j] = (k == 0) ? -1e300 : (k == pd.N ? pd.lbx_e[ix] : pd.lbx[ix]);
+      bd.ub[NU + j] = (k == 0) ? 1e300 : (k == pd.N ? pd.ubx_e[ix] : pd.ubx[ix]);
     }
+    MPC_UNROLL for (int j = 0; j < NSXA; ++j) {
+      const bool sact = NSX > 0 && k >= 1 && k < pd.N;
+      bd.zl[j] = (sact && bd.lb[NSX > 0 ? soft_row(j) : 0] > -BIG) ? pd.scale[k] * pd.zl[j] : -1.0;
+      bd.zu[j] = (sact && bd.ub[NSX > 0 ? soft_row(j) : 0] < BIG) ? pd.scale[k] * pd.zu[j] : -1.0;
+    }
+  }
+  // is bound row q (< 2 NV) softened at this stage?  returns the slack row or -1
+  MPC_HD static int slack_of(const Bnd& bd, int r, int side) {
+    int q = -1;
+    MPC_UNROLL for (int j = 0; j < NSX; ++j) {
+      if (soft_row(j) == r && (side ? bd.zu[j] : bd.zl[j]) >= 0.0) q = (side ? R_US : R_LS) + j;
+    }
+    return q;
   }
   MPC_HD static int count_rows(const ProblemData& pd) {
     int m = 0;
     for (int k = 0; k <= pd.N; ++k) {
-      double lb[NV], ub[NV];
-      stage_bounds(pd, k, lb, ub);
-      MPC_UNROLL for (int r = 0; r < NV; ++r) m += (lb[r] > -BIG) + (ub[r] < BIG);
+      Bnd bd;
+      stage_bounds(pd, k, bd);
+      MPC_UNROLL for (int r = 0; r < NV; ++r) m += (bd.lb[r] > -BIG) + (bd.ub[r] < BIG);
+      MPC_UNROLL for (int j = 0; j < NSX; ++j) m += (bd.zl[j] >= 0.0) + (bd.zu[j] >= 0.0);
     }
     return m;
   }
@@ -209,54 +236,105 @@ struct Engine {
     MPC_UNROLL for (int i = 0; i < NU; ++i) v[i] = u[i];
     MPC_UNROLL for (int j = 0; j < NBX; ++j) v[NU + j] = x[M::bx(j)];
   }
+  MPC_HD static double row_range(const Bnd& bd, int r) {
+    return (bd.lb[r] > -BIG && bd.ub[r] < BIG) ? bd.ub[r] - bd.lb[r] : 1.0;
+  }
   // warm-start safeguard: keep (lam,t) strictly inside the cone
-  MPC_HD static void clip_rows(const double* lb, const double* ub, double* lam, double* t) {
+  MPC_HD static void clip_rows(const Bnd& bd, double* lam, double* t) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
-      const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
+      const double range = row_range(bd, r);
       t[r] = dmax(t[r], 1e-10 * range);
       t[NV + r] = dmax(t[NV + r], 1e-10 * range);
       lam[r] = dmax(lam[r], 1e-14);
       lam[NV + r] = dmax(lam[NV + r], 1e-14);
     }
+    MPC_UNROLL for (int j = 0; j < NSX; ++j) {
+      const double range = row_range(bd, soft_row(j));
+      t[R_LS + j] = dmax(t[R_LS + j], 1e-10 * range);
+      t[R_US + j] = dmax(t[R_US + j], 1e-10 * range);
+      lam[R_LS + j] = dmax(lam[R_LS + j], 1e-14);
+      lam[R_US + j] = dmax(lam[R_US + j], 1e-14);
+    }
   }
-  // condensed barrier terms: Hm += J' diag(lam/t) J,  g += J'(target/t + lam + (lam/t) hbar),
-  // hbar_l = lb - v, hbar_u = v - ub  (g = [gq ; gr] of the stage)
-  MPC_HD static void barrier_add(const double* lb, const double* ub, const double* v, const double* lam, const double* t,
+  // One bound row in "lam_hat = a - c * d" form, d = distance to the bound after the step WITHOUT
+  // the slack.  Hard row: c = lam/t, a = target/t + lam.  Soft row (slack row qs, scaled penalty z):
+  // eliminating the new slack s_hat from  z = lam_hat_b + lam_hat_s  gives
+  //   s_hat = (a_b + a_s - z - c_b d) / (c_b + c_s),  c = c_b c_s/(c_b + c_s),  a = (a_b c_s - c_b (a_s - z))/(c_b + c_s).
+  struct RowC {
+    double c, a;            // condensed
+    double cb, ab, cs, as_, z;  // raw pieces (soft rows)
+  };
+  MPC_HD static RowC row_coeffs(const double* lam, const double* t, int q, int qs, double z, double target) {
+    RowC rc;
+    const double itb = 1.0 / t[q];
+    rc.cb = lam[q] * itb;
+    rc.ab = target * itb + lam[q];
+    rc.c = rc.cb;
+    rc.a = rc.ab;
+    rc.cs = 0.0; rc.as_ = 0.0; rc.z = z;
+    if (NSX > 0 && qs >= 0) {
+      const double its = 1.0 / t[qs];
+      rc.cs = lam[qs] * its;
+      rc.as_ = target * its + lam[qs];
+      const double den = 1.0 / (rc.cb + rc.cs);
+      rc.c = rc.cb * rc.cs * den;
+      rc.a = (rc.ab * rc.cs - rc.cb * (rc.as_ - z)) * den;
+    }
+    return rc;
+  }
+  // condensed barrier terms: Hm += J' diag(c) J,  g += J'(+-)(a - c d0),  d0 = v - lb / ub - v
+  // (g = [gq ; gr] of the stage)
+  MPC_HD static void barrier_add(const Bnd& bd, const double* v, const double* lam, const double* t,
                                  double target, double* Hm, double* g) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
       const int ix = vidx(r);
-      if (lb[r] > -BIG) {
-        const double itl = 1.0 / t[r], cl = lam[r] * itl;
-        Hm[ix * NW + ix] += cl;
-        g[ix] -= target * itl + lam[r] - cl * (v[r] - lb[r]);
+      if (bd.lb[r] > -BIG) {
+        const int qs = slack_of(bd, r, 0);
+        const RowC rc = row_coeffs(lam, t, r, qs, qs >= 0 ? bd.zl[qs - R_LS] : 0.0, target);
+        Hm[ix * NW + ix] += rc.c;
+        g[ix] -= rc.a - rc.c * (v[r] - bd.lb[r]);
       }
-      if (ub[r] < BIG) {
-        const double itu = 1.0 / t[NV + r], cu = lam[NV + r] * itu;
-        Hm[ix * NW + ix] += cu;
-        g[ix] += target * itu + lam[NV + r] - cu * (ub[r] - v[r]);
+      if (bd.ub[r] < BIG) {
+        const int qs = slack_of(bd, r, 1);
+        const RowC rc = row_coeffs(lam, t, NV + r, qs, qs >= 0 ? bd.zu[qs - R_US] : 0.0, target);
+        Hm[ix * NW + ix] += rc.c;
+        g[ix] += rc.a - rc.c * (bd.ub[r] - v[r]);
       }
     }
   }
-  // Hessian part only (sensitivity factorisation)
-  MPC_HD static void barrier_hess(const double* lb, const double* ub, const double* lam, const double* t, double* Hm) {
+  // Hessian part only (sensitivity factorisation).  Slack values are constants there, like in the
+  // reference (quirk Q4: slacks are not part of z), so a softened row counts with its own lam/t.
+  MPC_HD static void barrier_hess(const Bnd& bd, const double* lam, const double* t, double* Hm) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
       const int ix = vidx(r);
-      if (lb[r] > -BIG) Hm[ix * NW + ix] += lam[r] / t[r];
-      if (ub[r] < BIG) Hm[ix * NW + ix] += lam[NV + r] / t[NV + r];
+      if (bd.lb[r] > -BIG) Hm[ix * NW + ix] += lam[r] / t[r];
+      if (bd.ub[r] < BIG) Hm[ix * NW + ix] += lam[NV + r] / t[NV + r];
     }
   }
   struct StepStats {
     double amax, s0, s1, s2, cmax;
   };
-  // new slacks/multipliers of the rows for the primal step dv (dw = [dx;du]); step-length statistics
-  MPC_HD static void rows_forward(const double* lb, const double* ub, const double* v, const double* dw,
-                                  const double* lam, const double* t, double target, double* lh, double* th,
-                                  StepStats& S) {
+  MPC_HD static void step_stats(double lam, double t, double lh, double th, StepStats& S) {
+    const double dt = th - t, dl = lh - lam;
+    if (dt < 0.0) S.amax = dmin(S.amax, -t / dt);
+    if (dl < 0.0) S.amax = dmin(S.amax, -lam / dl);
+    S.s0 += lam * t;
+    S.s1 += lam * dt + t * dl;
+    S.s2 += dl * dt;
+    S.cmax = dmax(S.cmax, dabs(dl * dt));
+  }
+  // new slacks/multipliers of the rows for the primal step dw = [dx;du]; step-length statistics
+  MPC_HD static void rows_forward(const Bnd& bd, const double* v, const double* dw, const double* lam,
+                                  const double* t, double target, double* lh, double* th, StepStats& S) {
+    MPC_UNROLL for (int q = 2 * NV; q < NR; ++q) {
+      lh[q] = 0.0;
+      th[q] = 0.0;
+    }
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
       const double dv = dw[vidx(r)];
       MPC_UNROLL for (int side = 0; side < 2; ++side) {
         const int q = side * NV + r;
-        const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
+        const bool act = side ? (bd.ub[r] < BIG) : (bd.lb[r] > -BIG);
         if (!act) {
           lh[q] = 0.0;
           th[q] = 0.0;
@@ -264,16 +342,30 @@ struct Engine {
         }
         // (v - lb) + dv, NOT (v + dv) - lb: the slack must use the same rounded distance to the
         // bound as the condensed gradient, or lam_hat picks up c*ulp(v) ~ 1e-8 of noise
-        th[q] = side ? (ub[r] - v[r]) - dv : (v[r] - lb[r]) + dv;
-        const double it_ = 1.0 / t[q];
-        lh[q] = target * it_ + lam[q] - lam[q] * it_ * th[q];
-        const double dt = th[q] - t[q], dl = lh[q] - lam[q];
-        if (dt < 0.0) S.amax = dmin(S.amax, -t[q] / dt);
-        if (dl < 0.0) S.amax = dmin(S.amax, -lam[q] / dl);
-        S.s0 += lam[q] * t[q];
-        S.s1 += lam[q] * dt + t[q] * dl;
-        S.s2 += dl * dt;
-        S.cmax = dmax(S.cmax, dabs(dl * dt));
+        const double d = side ? (bd.ub[r] - v[r]) - dv : (v[r] - bd.lb[r]) + dv;
+        const int qs = slack_of(bd, r, side);
+        const RowC rc = row_coeffs(lam, t, q, qs, qs >= 0 ? (side ? bd.zu[qs - R_US] : bd.zl[qs - R_LS]) : 0.0, target);
+        if (NSX > 0 && qs >= 0) {
+          // Soft pair.  Evaluate in the order that avoids cancellation amplified by a huge lam/t:
+          if (rc.cb > rc.cs) {
+            // bound row (nearly) active, slack free: lam_hat_b from the condensed form, the rest from it
+            lh[q] = rc.a - rc.c * d;
+            th[q] = (rc.ab - lh[q]) / rc.cb;
+            th[qs] = th[q] - d;
+            lh[qs] = rc.z - lh[q];
+          } else {
+            // slack (nearly) pinned at zero: s_hat first
+            th[qs] = (rc.ab + rc.as_ - rc.z - rc.cb * d) / (rc.cb + rc.cs);
+            lh[qs] = rc.as_ - rc.cs * th[qs];
+            th[q] = d + th[qs];
+            lh[q] = rc.ab - rc.cb * th[q];
+          }
+          step_stats(lam[qs], t[qs], lh[qs], th[qs], S);
+        } else {
+          th[q] = d;
+          lh[q] = rc.ab - rc.cb * d;
+        }
+        step_stats(lam[q], t[q], lh[q], th[q], S);
       }
     }
   }
@@ -281,22 +373,39 @@ struct Engine {
   struct Residuals {
     double stat, eq, ineq, comp, cost;
   };
-  // comp / ineq residuals of the rows of one stage and their contribution J'lam to stationarity
-  MPC_HD static void rows_residual(const ProblemData& pd, const double* lb, const double* ub, const double* v,
-                                   const double* lam, const double* t, Residuals& R, double* jl /* NW, += */) {
+  // comp / ineq residuals of the rows of one stage and their contribution J'lam to stationarity;
+  // soft pairs add the stationarity residual in the slack, z - lam_b - lam_s
+  MPC_HD static void rows_residual(const ProblemData& pd, const Bnd& bd, const double* v, const double* lam,
+                                   const double* t, Residuals& R, double* jl /* NW, += */) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
       const int ix = vidx(r);
-      if (lb[r] > -BIG) {
-        jl[ix] -= lam[r];
-        R.comp = dmax(R.comp, dabs(lam[r] * t[r] - pd.tau));
-        R.ineq = dmax(R.ineq, dabs(lb[r] - v[r] + t[r]));
-      }
-      if (ub[r] < BIG) {
-        jl[ix] += lam[NV + r];
-        R.comp = dmax(R.comp, dabs(lam[NV + r] * t[NV + r] - pd.tau));
-        R.ineq = dmax(R.ineq, dabs(v[r] - ub[r] + t[NV + r]));
+      MPC_UNROLL for (int side = 0; side < 2; ++side) {
+        const int q = side * NV + r;
+        const bool act = side ? (bd.ub[r] < BIG) : (bd.lb[r] > -BIG);
+        if (!act) continue;
+        const int qs = slack_of(bd, r, side);
+        double sl = 0.0;
+        if (NSX > 0 && qs >= 0) {
+          sl = t[qs];  // slack value
+          const double z = side ? bd.zu[qs - R_US] : bd.zl[qs - R_LS];
+          R.stat = dmax(R.stat, dabs(z - lam[q] - lam[qs]));
+          R.comp = dmax(R.comp, dabs(lam[qs] * t[qs] - pd.tau));
+        }
+        jl[ix] += side ? lam[q] : -lam[q];
+        R.comp = dmax(R.comp, dabs(lam[q] * t[q] - pd.tau));
+        const double h = side ? v[r] - bd.ub[r] - sl : bd.lb[r] - v[r] - sl;
+        R.ineq = dmax(R.ineq, dabs(h + t[q]));
       }
     }
+  }
+  // slack penalty of the stage, sum_j z_l sl_j + z_u su_j (scaled), part of the cost (nlp.py:1099-1134)
+  MPC_HD static double slack_cost(const Bnd& bd, const double* t) {
+    double c = 0.0;
+    MPC_UNROLL for (int j = 0; j < NSX; ++j) {
+      if (bd.zl[j] >= 0.0) c += bd.zl[j] * t[R_LS + j];
+      if (bd.zu[j] >= 0.0) c += bd.zu[j] * t[R_US + j];
+    }
+    return c;
   }
 
   // One backward Riccati step.  In: P (NX x NX full), p; stage data.  Out: P, p (overwritten), K, kff.
@@ -379,6 +488,14 @@ struct Engine {
   // k < N: A, B, b = F(x_k,u_k) - x_{k+1}, scaled cost gradient q, r, stage cost, defect norm.
   // k = N: terminal cost gradient and value.
   // =======================================================================================
+  MPC_HD static double stage_slack_cost(const ProblemData& pd, const Lane& L, int k) {
+    Bnd bd;
+    double t[NR];
+    stage_bounds(pd, k, bd);
+    ld<NR>(L.it + (size_t)it_t(pd.N, k) * TILE, TILE, t);
+    return slack_cost(bd, t);
+  }
+
   MPC_HD static void lin_stage(const ProblemData& pd, const Lane& L, int k) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
@@ -401,7 +518,8 @@ struct Engine {
       st<NX * NU>(w + (size_t)W_B * bs, bs, B);
       st<NX>(w + (size_t)W_b * bs, bs, bb);
       load_cost(k == 0 ? 0 : 1, L, ck);
-      const double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      if (NSX > 0) c += stage_slack_cost(pd, L, k);
       st<NW>(w + (size_t)W_q * bs, bs, g);
       w[(size_t)W_c * bs] = c;
       w[(size_t)W_e * bs] = eq;
@@ -444,19 +562,20 @@ struct Engine {
       MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] = g[i];
       load_W(2, pd.scale[N], L, Hm);
       if (NBX > 0) {
-        double lb[NV], ub[NV], x[NX], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
-        stage_bounds(pd, N, lb, ub);
+        Bnd bd;
+        double x[NX], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
+        stage_bounds(pd, N, bd);
         ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
         MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
         stage_vars(x, u0, v);
         ld<NR>(L.it + (size_t)it_lam(N, N) * bs, bs, lam);
         ld<NR>(L.it + (size_t)it_t(N, N) * bs, bs, t);
         MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
-        rows_residual(pd, lb, ub, v, lam, t, R, jl);
+        rows_residual(pd, bd, v, lam, t, R, jl);
         MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] += jl[i];
         if (warm) {
-          clip_rows(lb, ub, lam, t);
-          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+          clip_rows(bd, lam, t);
+          barrier_add(bd, v, lam, t, target, Hm, g);
         }
       }
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
@@ -466,7 +585,7 @@ struct Engine {
     }
     for (int k = N - 1; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
-      double A[NX * NX], B[NX * NU], bb[NX], g[NW], x[NX], u[NU], pik[NX], lam[NR], t[NR], lb[NV], ub[NV], v[NV];
+      double A[NX * NX], B[NX * NU], bb[NX], g[NW], x[NX], u[NU], pik[NX], lam[NR], t[NR], v[NV];
       ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
       ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
       ld<NX>(w + (size_t)W_b * bs, bs, bb);
@@ -481,13 +600,14 @@ struct Engine {
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-      stage_bounds(pd, k, lb, ub);
+      Bnd bd;
+      stage_bounds(pd, k, bd);
       stage_vars(x, u, v);
       // ---- residuals at the current iterate (raw multipliers) ----
       MPC_UNROLL for (int i = 0; i < NX; ++i) R.stat = dmax(R.stat, dabs(carry[i] - pik[i]));
       double jl[NW];
       MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
-      rows_residual(pd, lb, ub, v, lam, t, R, jl);
+      rows_residual(pd, bd, v, lam, t, R, jl);
       const bool ufixed = (k == 0 && pd.mode == MODE_Q);
       if (!ufixed) {
         MPC_UNROLL for (int i = 0; i < NU; ++i) {
@@ -505,8 +625,8 @@ struct Engine {
       if (warm) {
         double Hm[NW * NW], K[NU * NX], kff[NU];
         load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
-        clip_rows(lb, ub, lam, t);
-        barrier_add(lb, ub, v, lam, t, target, Hm, g);
+        clip_rows(bd, lam, t);
+        barrier_add(bd, v, lam, t, target, Hm, g);
         if (!ufixed) {
           if (!riccati_step(P, p, A, B, bb, Hm, g, K, kff, nullptr)) failed = true;
         } else {
@@ -555,8 +675,9 @@ struct Engine {
       }
       st<NX>(w + (size_t)W_dx * bs, bs, dw);
       if (k < N || NBX > 0) {
-        double lb[NV], ub[NV], x[NX], u[NU], v[NV], lam[NR], t[NR], lh[NR], th[NR];
-        stage_bounds(pd, k, lb, ub);
+        Bnd bd;
+        double x[NX], u[NU], v[NV], lam[NR], t[NR], lh[NR], th[NR];
+        stage_bounds(pd, k, bd);
         if (k < N) {
           ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
         } else {
@@ -566,8 +687,8 @@ struct Engine {
         stage_vars(x, u, v);
         ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
         ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-        if (clip) clip_rows(lb, ub, lam, t);
-        rows_forward(lb, ub, v, dw, lam, t, target, lh, th, S);
+        if (clip) clip_rows(bd, lam, t);
+        rows_forward(bd, v, dw, lam, t, target, lh, th, S);
         st<NR>(w + (size_t)W_lh * bs, bs, lh);
         st<NR>(w + (size_t)W_th * bs, bs, th);
       }
@@ -598,8 +719,9 @@ struct Engine {
     double mu = 0.0;
     for (int k = 0; k <= N; ++k) {
       if (k == N && NBX == 0) break;
-      double x[NX], u[NU], v[NV], lam[NR], t[NR], lb[NV], ub[NV];
-      stage_bounds(pd, k, lb, ub);
+      Bnd bd;
+      double x[NX], u[NU], v[NV], lam[NR], t[NR];
+      stage_bounds(pd, k, bd);
       if (k < N) {
         ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
       } else {
@@ -610,61 +732,32 @@ struct Engine {
       if (warm) {
         ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
         ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-        clip_rows(lb, ub, lam, t);
+        clip_rows(bd, lam, t);
       } else {
+        MPC_UNROLL for (int q = 0; q < NR; ++q) { lam[q] = 0.0; t[q] = 0.0; }
         MPC_UNROLL for (int r = 0; r < NV; ++r) {
-          const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
-          const double tmin = 1e-2 * range;
-          t[r] = dmax(v[r] - lb[r], tmin);
-          t[NV + r] = dmax(ub[r] - v[r], tmin);
-          lam[r] = pd.mu0 / t[r];
-          lam[NV + r] = pd.mu0 / t[NV + r];
-        }
-      }
-      MPC_UNROLL for (int r = 0; r < NV; ++r) {
-        if (lb[r] > -BIG) mu += lam[r] * t[r]; else { lam[r] = 0.0; t[r] = 0.0; }
-        if (ub[r] < BIG) mu += lam[NV + r] * t[NV + r]; else { lam[NV + r] = 0.0; t[NV + r] = 0.0; }
-      }
-      st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
-      st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-    }
-    return mu;
-  }
-
-  // Jammed warm start: the last Newton step (lam_hat, t_hat in the workspace) wanted slacks to
-  // cross zero (rows entering the active set) or multipliers to change sign (rows leaving it).
-  // Give exactly those rows room -- product pd.repair -- and keep every other row where it is.
-  // Returns sum(lam*t).
-  MPC_HD static double ipm_repair(const ProblemData& pd, const Lane& L) {
-    const int N = pd.N;
-    constexpr size_t bs = TILE;
-    double mu = 0.0;
-    for (int k = 0; k <= N; ++k) {
-      if (k == N && NBX == 0) break;
-      const double* w = L.ws + (size_t)k * W_REC * bs;
-      double lam[NR], t[NR], lh[NR], th[NR], lb[NV], ub[NV];
-      stage_bounds(pd, k, lb, ub);
-      ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
-      ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-      ld<NR>(w + (size_t)W_lh * bs, bs, lh);
-      ld<NR>(w + (size_t)W_th * bs, bs, th);
-      MPC_UNROLL for (int r = 0; r < NV; ++r) {
-        const double range = (lb[r] > -BIG && ub[r] < BIG) ? ub[r] - lb[r] : 1.0;
-        const double eps_t = 1e-3 * range;
-        MPC_UNROLL for (int side = 0; side < 2; ++side) {
-          const int q = side * NV + r;
-          const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
-          if (!act) continue;
-          if (th[q] < 0.5 * t[q] && th[q] < eps_t) {         // slack collapses: row becomes active
-            t[q] = dmax(t[q] < eps_t ? t[q] : eps_t, 1e-10 * range);
-            t[q] = eps_t;
-            lam[q] = dmax(dmax(lam[q], lh[q]), pd.repair / eps_t);
-          } else if (lh[q] < 0.5 * lam[q] && lam[q] * t[q] < pd.repair) {  // multiplier collapses: row is released
-            t[q] = dmax(dmax(t[q], th[q]), eps_t);
-            lam[q] = pd.repair / t[q];
+          const double tmin = 1e-2 * row_range(bd, r);
+          MPC_UNROLL for (int side = 0; side < 2; ++side) {
+            const int q = side * NV + r;
+            double d = side ? bd.ub[r] - v[r] : v[r] - bd.lb[r];
+            const int qs = slack_of(bd, r, side);
+            if (NSX > 0 && qs >= 0) {  // slack: cover a violated bound, stay strictly positive
+              t[qs] = dmax(-d, 0.0) + tmin;
+              lam[qs] = pd.mu0 / t[qs];
+              d += t[qs];
+            }
+            t[q] = dmax(d, tmin);
+            lam[q] = pd.mu0 / t[q];
           }
-          mu += lam[q] * t[q];
         }
+      }
+      MPC_UNROLL for (int r = 0; r < NV; ++r) {
+        if (bd.lb[r] > -BIG) mu += lam[r] * t[r]; else { lam[r] = 0.0; t[r] = 0.0; }
+        if (bd.ub[r] < BIG) mu += lam[NV + r] * t[NV + r]; else { lam[NV + r] = 0.0; t[NV + r] = 0.0; }
+      }
+      MPC_UNROLL for (int j = 0; j < NSX; ++j) {
+        if (bd.zl[j] >= 0.0) mu += lam[R_LS + j] * t[R_LS + j]; else { lam[R_LS + j] = 0.0; t[R_LS + j] = 0.0; }
+        if (bd.zu[j] >= 0.0) mu += lam[R_US + j] * t[R_US + j]; else { lam[R_US + j] = 0.0; t[R_US + j] = 0.0; }
       }
       st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
@@ -704,23 +797,15 @@ struct Engine {
     double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
     double sigma = warm ? pd.sigma_min : pd.sigma0;
     int iters = 0, warm_iters = 0;
-    bool converged = false, failed = false, repaired = false;
+    bool converged = false, failed = false, minstep = false;
     for (int j = 0; j < pd.max_ipm && !converged; ++j) {
       ++iters;
       if (warm && (warm_iters >= WARM_LIMIT || (warm_iters > 0 && alpha < 0.05))) {
-        if (pd.repair > 0.0 && !repaired && warm_iters < WARM_LIMIT) {
-          // the Newton step predicts an active-set change: re-centre only the rows that block it
-          repaired = true;
-          mu = ipm_repair(pd, L) / m_rows;
-          alpha = 0.0;
-          sigma = pd.sigma_min;
-        } else {
-          // the warm start is jammed (active set changed too much): restart from a cold point
-          warm = false;
-          mu = ipm_init(pd, L, false) / m_rows;
-          alpha = 0.0;
-          sigma = pd.sigma0;
-        }
+        // the warm start is jammed (active set changed too much): restart from a cold point
+        warm = false;
+        mu = ipm_init(pd, L, false) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma0;
       }
       if (warm) ++warm_iters;
       const double target = dmax(sigma * mu, pd.tau);
@@ -732,13 +817,14 @@ struct Engine {
         ld<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, g);
         MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
         if (NBX > 0) {
-          double lb[NV], ub[NV], x[NX], u0[NU], v[NV], lam[NR], t[NR];
-          stage_bounds(pd, N, lb, ub);
+          Bnd bd;
+        double x[NX], u0[NU], v[NV], lam[NR], t[NR];
+          stage_bounds(pd, N, bd);
           ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
           MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
           stage_vars(x, u0, v);
           rows_update(L, N, N, alpha, lam, t);
-          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+          barrier_add(bd, v, lam, t, target, Hm, g);
         }
         MPC_UNROLL for (int i = 0; i < NX; ++i) {
           p[i] = g[i];
@@ -755,13 +841,14 @@ struct Engine {
         double Hm[NW * NW];
         load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
         {
-          double lb[NV], ub[NV], x[NX], u[NU], v[NV], lam[NR], t[NR];
-          stage_bounds(pd, k, lb, ub);
+          Bnd bd;
+        double x[NX], u[NU], v[NV], lam[NR], t[NR];
+          stage_bounds(pd, k, bd);
           ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
           if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
           stage_vars(x, u, v);
           rows_update(L, N, k, alpha, lam, t);
-          barrier_add(lb, ub, v, lam, t, target, Hm, g);
+          barrier_add(bd, v, lam, t, target, Hm, g);
         }
         const bool ufixed = (k == 0 && qmode);
         if (!ufixed) {
@@ -779,6 +866,10 @@ struct Engine {
       forward_sweep(pd, L, target, /*clip=*/false, S);
       if (failed || !(S.amax == S.amax)) break;
       alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
+      if (alpha < 1e-9) {  // the iteration has collapsed onto the boundary (HPIPM: MIN_STEP), e.g. infeasible QP
+        minstep = true;
+        break;
+      }
       const double mu_new = (S.s0 + alpha * S.s1 + alpha * alpha * S.s2) / m_rows;
 #ifdef IPM_TRACE
       printf("  ipm it %2d warm %d sigma %.3f mu %.3e target %.3e amax %.4g alpha %.4g cmax %.3e mu_new %.3e\n", iters, (int)warm,
@@ -792,6 +883,7 @@ struct Engine {
     }
     *alpha_out = alpha;
     if (failed) return -1;
+    if (minstep) return -2;
     return converged ? iters : -(iters + 1000);
   }
 
@@ -799,13 +891,17 @@ struct Engine {
   // Apply the QP step: w += dw, (lam,t) <- last IPM update, pi <- QP multipliers (backward
   // recursion of the x-stationarity rows).
   // ---------------------------------------------------------------------------------------
-  MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha, bool clip) {
+  // damp_primal: the QP was not solved (iteration limit): move the primal variables by alpha * dw
+  // only, the interior iterate of the method, instead of the full Newton target.
+  MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha, bool clip, bool damp_primal = false) {
+    const double ap = damp_primal ? alpha : 1.0;
     const int N = pd.N;
     constexpr size_t bs = TILE;
     double pik[NX];  // pi_k (multiplier of x_{k+1} = F(x_k,u_k))
     for (int k = N; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
-      double dw[NW], g[NW], Wm[NW * NW], lam[NR], lb[NV], ub[NV];
+      Bnd bd;
+      double dw[NW], g[NW], Wm[NW * NW], lam[NR];
       ld<NX>(w + (size_t)W_dx * bs, bs, dw);
       if (k < N) {
         ld<NU>(w + (size_t)W_du * bs, bs, dw + NX);
@@ -815,22 +911,25 @@ struct Engine {
         ld<NX>(w + (size_t)W_q * bs, bs, g);
         MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
       }
-      stage_bounds(pd, k, lb, ub);
+      stage_bounds(pd, k, bd);
       MPC_UNROLL for (int i = 0; i < NR; ++i) lam[i] = 0.0;
       if (k < N || NBX > 0) {
         double t[NR], lh[NR], th[NR];
         ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
         ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-        if (clip) clip_rows(lb, ub, lam, t);
+        if (clip) clip_rows(bd, lam, t);
         ld<NR>(w + (size_t)W_lh * bs, bs, lh);
         ld<NR>(w + (size_t)W_th * bs, bs, th);
-        MPC_UNROLL for (int r = 0; r < NV; ++r) {
-          MPC_UNROLL for (int side = 0; side < 2; ++side) {
-            const int q = side * NV + r;
-            const bool act = side ? (ub[r] < BIG) : (lb[r] > -BIG);
-            lam[q] = act ? lam[q] + alpha * (lh[q] - lam[q]) : 0.0;
-            t[q] = act ? t[q] + alpha * (th[q] - t[q]) : 0.0;
+        MPC_UNROLL for (int q = 0; q < NR; ++q) {
+          bool act;
+          if (q < 2 * NV) {
+            const int r = q < NV ? q : q - NV;
+            act = q < NV ? (bd.lb[r] > -BIG) : (bd.ub[r] < BIG);
+          } else {
+            act = q < R_US ? (bd.zl[q - R_LS] >= 0.0) : (bd.zu[q - R_US] >= 0.0);
           }
+          lam[q] = act ? lam[q] + alpha * (lh[q] - lam[q]) : 0.0;
+          t[q] = act ? t[q] + alpha * (th[q] - t[q]) : 0.0;
         }
         st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
         st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
@@ -857,13 +956,13 @@ struct Engine {
         MPC_UNROLL for (int i = 0; i < NX; ++i) pik[i] = pin[i];
         double x[NX];
         ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
-        MPC_UNROLL for (int i = 0; i < NX; ++i) x[i] += dw[i];
+        MPC_UNROLL for (int i = 0; i < NX; ++i) x[i] += ap * dw[i];
         st<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       }
       if (k < N) {
         double u[NU];
         ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-        MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] += dw[NX + i];
+        MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] += ap * dw[NX + i];
         st<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
       }
     }
@@ -871,14 +970,21 @@ struct Engine {
   }
 
   // Sample function, slow path of one SQP iteration (after qp_fast returned FAST_HARD): the full
-  // interior-point loop and the step.  Returns the status so far (ST_OK or ST_QPFAIL).
+  // interior-point loop and the step.
+  enum Full : int {
+    FULL_OK = 0,       // QP solved, step applied
+    FULL_MAXITER = 1,  // interior-point iteration limit: the (damped) last step is applied and the SQP
+                       // goes on, like acados, which tolerates ACADOS_MAXITER from the QP solver
+    FULL_FAILED = 2,   // reduced Hessian not positive definite, or step length collapsed (HPIPM MIN_STEP):
+                       // iterate left untouched, acados would return ACADOS_QP_FAILURE (4)
+  };
   MPC_HD static int qp_full(const ProblemData& pd, const Lane& L, int* ipm_iters) {
     double alpha = 0.0;
     const int r = qp_ipm(pd, L, &alpha);
-    if (ipm_iters) *ipm_iters += (r > 0) ? r : ((r == -1) ? 0 : -(r + 1000));
-    if (r == -1) return ST_QPFAIL;  // reduced Hessian not positive definite: iterate left untouched
-    apply_step(pd, L, alpha, /*clip=*/false);
-    return (r < 0) ? ST_QPFAIL : ST_OK;  // r < 0: iteration limit, step applied anyway (like acados)
+    if (ipm_iters) *ipm_iters += (r > 0) ? r : ((r >= -2) ? 0 : -(r + 1000));
+    if (r == -1 || r == -2) return FULL_FAILED;
+    apply_step(pd, L, alpha, /*clip=*/false, /*damp_primal=*/r < 0);
+    return (r < 0) ? FULL_MAXITER : FULL_OK;
   }
 
   MPC_HD static void set_initial(const ProblemData& pd, const Lane& L, const double* x0, size_t x0s, const double* u0,
@@ -926,17 +1032,19 @@ struct Engine {
       double Hp[NWS];
       MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) Hp[pidx(i, j)] = Hww[i * NW + j];
       st<NWS>(w + (size_t)S_H * bs, bs, Hp);
-      st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
-      st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
       double gp[NPM];
       MPC_UNROLL for (int j = 0; j < NPM; ++j) {
         double a = 0.0;
         MPC_UNROLL for (int i = 0; i < NX; ++i) a += pik[i] * Fp[i * NPM + j];
         gp[j] = a;
       }
+      M::cost_sens(k == 0 ? 0 : 1, pd.scale[k], y, gp, Hwp);  // model parameters that enter the stage cost
+      st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+      st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
       st<NPM>(w + (size_t)S_gp * bs, bs, gp);
       load_cost(k == 0 ? 0 : 1, L, ck);
-      const double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      double c = cost_grad(ck, pd.scale[k], NW, y, g);
+      if (NSX > 0) c += stage_slack_cost(pd, L, k);
       st<NW>(w + (size_t)S_g * bs, bs, g);
       w[(size_t)S_c * bs] = c;
       w[(size_t)S_e * bs] = eq;
@@ -975,16 +1083,17 @@ struct Engine {
         ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
         if (pd.param_cost && dLdth) M::cost_param_grad(2, pd.scale[N], L.th, (size_t)TILE, x, nullptr, dLdth);
         if (NBX > 0) {
-          double lb[NV], ub[NV], u0[NU], v[NV], lam[NR], t[NR], jl[NW];
-          stage_bounds(pd, N, lb, ub);
+          Bnd bd;
+        double u0[NU], v[NV], lam[NR], t[NR], jl[NW];
+          stage_bounds(pd, N, bd);
           MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
           stage_vars(x, u0, v);
           ld<NR>(L.it + (size_t)it_lam(N, N) * bs, bs, lam);
           ld<NR>(L.it + (size_t)it_t(N, N) * bs, bs, t);
           MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
-          rows_residual(pd, lb, ub, v, lam, t, R, jl);
+          rows_residual(pd, bd, v, lam, t, R, jl);
           MPC_UNROLL for (int i = 0; i < NX; ++i) carry[i] += jl[i];
-          barrier_hess(lb, ub, lam, t, Hm);
+          barrier_hess(bd, lam, t, Hm);
         }
       }
       MPC_UNROLL for (int i = 0; i < NX; ++i) {
@@ -994,7 +1103,7 @@ struct Engine {
     }
     for (int k = N - 1; k >= 0; --k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
-      double A[NX * NX], B[NX * NU], g[NW], Hp[NWS], gpk[NPM], x[NX], u[NU], pik[NX], lam[NR], t[NR], lb[NV], ub[NV], v[NV];
+      double A[NX * NX], B[NX * NU], g[NW], Hp[NWS], gpk[NPM], x[NX], u[NU], pik[NX], lam[NR], t[NR], v[NV];
       ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
       ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
       ld<NW>(w + (size_t)S_g * bs, bs, g);
@@ -1012,13 +1121,14 @@ struct Engine {
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
       if (pd.param_cost && dLdth) M::cost_param_grad(k == 0 ? 0 : 1, pd.scale[k], L.th, (size_t)TILE, x, u, dLdth);
-      stage_bounds(pd, k, lb, ub);
+      Bnd bd;
+      stage_bounds(pd, k, bd);
       stage_vars(x, u, v);
       // ---- residuals ----
       MPC_UNROLL for (int i = 0; i < NX; ++i) R.stat = dmax(R.stat, dabs(carry[i] - pik[i]));
       double jl[NW];
       MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
-      rows_residual(pd, lb, ub, v, lam, t, R, jl);
+      rows_residual(pd, bd, v, lam, t, R, jl);
       const bool ufixed = (k == 0 && qmode);
       double su[NU];  // u-stationarity remainder (multiplier of the clamped u_0 in Q-mode)
       MPC_UNROLL for (int i = 0; i < NU; ++i) {
@@ -1044,7 +1154,7 @@ struct Engine {
           Hm[i * NW + j] += Hp[pidx(i, j)];
           if (j != i) Hm[j * NW + i] = Hm[i * NW + j];
         }
-        barrier_hess(lb, ub, lam, t, Hm);
+        barrier_hess(bd, lam, t, Hm);
         double Pp[NPS];
         {
           int c_ = 0;

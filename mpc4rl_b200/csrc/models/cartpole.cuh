@@ -25,7 +25,9 @@ struct CartpoleModelT {
   static constexpr int NBX = NBX_;
   static constexpr int NTH = 83;
   static constexpr int TH_W0 = 3, TH_W = 28, TH_WE = 53, TH_YREF0 = 69, TH_YREF = 74, TH_YREFE = 79;
+  static constexpr int NSX = 0;              // no soft bounds
   MPC_HD static int bx(int j) { return j; }  // idxbx (all states, in order)
+  MPC_HD static int sx(int) { return 0; }
 
   // ---- quadratic tracking cost  l = 1/2 (y-yref)' W (y-yref),  y=[x;u] -------------------
   // kind: 0 initial stage, 1 intermediate, 2 terminal (ny = NX).
@@ -42,7 +44,7 @@ struct CartpoleModelT {
   }
   // theta -> the engine's quadratic cost table (Engine::CT_*): per kind
   //   [W packed upper (15) | yref (5) | flin (5) | c0]
-  MPC_HD static void cost_table(const double* th, size_t ths, double* ct, size_t cts) {
+  MPC_HD static void cost_table(const double* th, size_t ths, double* ct, size_t cts, const double* /*mc*/) {
     constexpr int NWS = NW * (NW + 1) / 2, REC = NWS + 2 * NW + 1;
     for (int kind = 0; kind < 3; ++kind) {
       double* c = ct + (size_t)(kind * REC) * cts;
@@ -55,6 +57,7 @@ struct CartpoleModelT {
       c[(size_t)(NWS + 2 * NW) * cts] = 0.0;                              // no constant term
     }
   }
+  MPC_HD static void cost_sens(int, double, const double*, double*, double*) {}  // no model parameter in the cost
   // d(s * l)/d(W, yref) accumulated into the [NTH] row (parameterize_tracking_cost=True semantics,
   // nlp.py:1057-1074): dl/dW_ij = 1/2 e_i e_j, dl/dyref = -W_sym e.
   MPC_HD static void cost_param_grad(int kind, double s, const double* th, size_t ths, const double* x, const double* u,

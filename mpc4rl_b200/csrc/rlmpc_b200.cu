@@ -14,6 +14,7 @@
 #include "../../include/rlmpc_b200.h"
 #include "engine.cuh"
 #include "models/cartpole.cuh"
+#include "models/linear_system.cuh"
 
 using namespace rlmpc;
 
@@ -30,10 +31,27 @@ int fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess) return fail(RLMPC_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// launch shapes (tuned with tools/bench_variants.sh; -D overrides build the variants)
 #ifndef RLMPC_TPB
-#define RLMPC_TPB 64
+#define RLMPC_TPB 64  // threads per block of the sample-parallel kernels
 #endif
-constexpr int TPB = RLMPC_TPB;  // threads per block of the sample-parallel kernels
+#ifndef RLMPC_QP1_MINB
+#define RLMPC_QP1_MINB 8  // 128 registers: 0.58 -> 0.50 ms per 65 536 samples (profiles/r01_summary.md)
+#endif
+#ifndef RLMPC_SW_MINB
+#define RLMPC_SW_MINB 1
+#endif
+#ifndef RLMPC_STAGE_TPB
+#define RLMPC_STAGE_TPB 128  // threads per block of the (sample, stage) kernels
+#endif
+#ifndef RLMPC_LIN_MINB
+#define RLMPC_LIN_MINB 1
+#endif
+#ifndef RLMPC_SS_MINB
+#define RLMPC_SS_MINB 1
+#endif
+constexpr int TPB = RLMPC_TPB;
+constexpr int STPB = RLMPC_STAGE_TPB;
 
 // Per-call state shared by the kernels of one pipeline (device pointers into the handle).
 struct KArgs {
@@ -50,6 +68,8 @@ struct KArgs {
   int* status;  // acados status per sample
   double* cost; // cost of the last linearisation
   int* hard;    // queue of samples for the full interior-point pass
+  int* ishard;  // 1 if the sample was queued in this call (written by k_qp1 only)
+  int subset;   // sens kernels: 0 all samples, 1 samples not queued, 2 the queued samples (via the queue)
   int* counters;  // [0] queue length, [1] samples still active
   const double* x0;  // [B, NX] row-major or null
   const double* u0;  // [B, NU] row-major or null
@@ -88,7 +108,7 @@ __global__ void k_begin(const __grid_constant__ ProblemData pd, const KArgs a) {
 
 // (sample, stage) kernel: linearisation.  grid = (ceil(B / blockDim), N + 1)
 template <class M>
-__global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(STPB, RLMPC_LIN_MINB) k_lin(const __grid_constant__ ProblemData pd, const KArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B || a.work[b] != WK_ACTIVE) return;
   Engine<M>::lin_stage(pd, make_lane<M>(a, b), blockIdx.y);
@@ -96,7 +116,7 @@ __global__ void __launch_bounds__(128) k_lin(const __grid_constant__ ProblemData
 
 // sample kernel: convergence test + one warm interior-point Newton iteration (fast path)
 template <class M>
-__global__ void __launch_bounds__(TPB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B || a.work[b] != WK_ACTIVE) return;
@@ -104,6 +124,7 @@ __global__ void __launch_bounds__(TPB) k_qp1(const __grid_constant__ ProblemData
   typename E::Residuals R;
   const int code = E::qp_fast(pd, L, R);
   a.cost[b] = R.cost;
+  a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? 1 : 0;
   if (code == E::FAST_NAN) {
     a.status[b] = ST_NAN;
     a.work[b] = WK_DONE;
@@ -146,9 +167,10 @@ __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData 
   const int st = E::qp_full(pd, L, nullptr);
 #pragma unroll 8
   for (int i = 0; i < nit; ++i) Ls.it[(size_t)i * TILE] = L.it[(size_t)i * TILE];
-  if (pd.max_sqp == 1 || st == ST_QPFAIL) {
-    // RTI: done after one QP.  Otherwise a failed QP (not PD / iteration limit) ends the solve
-    a.status[b] = st;
+  if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
+    // RTI: done after one QP.  SQP: an indefinite reduced Hessian ends the solve; an interior-point
+    // iteration limit does not (the next linearisation may well be solvable)
+    a.status[b] = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL;
     a.work[b] = WK_DONE;
   } else {
     a.work[b] = WK_ACTIVE;
@@ -179,19 +201,28 @@ __global__ void k_out(const __grid_constant__ ProblemData pd, const KArgs a) {
 }
 
 // (sample, stage) kernel: exact second-order stage information.  grid = (ceil(B / blockDim), N + 1)
+__device__ __forceinline__ int subset_sample(const KArgs& a) {
+  // which sample does this thread own?  -1: none
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.subset == 2) return j < a.counters[0] ? a.hard[j] : -1;
+  if (j >= a.B) return -1;
+  if (a.subset == 1 && a.ishard[j]) return -1;
+  return j;
+}
+
 template <class M>
-__global__ void __launch_bounds__(128) k_sens_stage(const __grid_constant__ ProblemData pd, const KArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+__global__ void __launch_bounds__(STPB, RLMPC_SS_MINB) k_sens_stage(const __grid_constant__ ProblemData pd, const KArgs a) {
+  const int b = subset_sample(a);
+  if (b < 0) return;
   Engine<M>::sens_stage(pd, make_lane<M>(a, b), blockIdx.y);
 }
 
 // sample kernel: residuals, dL/dtheta, exact-Hessian factorisation, adjoint solves, outputs
 template <class M>
-__global__ void __launch_bounds__(TPB) k_sens_sweep(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(TPB, RLMPC_SW_MINB) k_sens_sweep(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+  const int b = subset_sample(a);
+  if (b < 0) return;
   const Lane L = make_lane<M>(a, b);
   int ok = 1;
   const int ng = E::grad_width(pd);
@@ -218,11 +249,11 @@ __global__ void __launch_bounds__(TPB) k_sens_sweep(const __grid_constant__ Prob
 
 // theta -> quadratic cost table (shared: one thread; per sample: one thread per sample)
 template <class M>
-__global__ void k_cost_table(const double* th, double* ct, int per_sample, int B) {
+__global__ void k_cost_table(const __grid_constant__ ProblemData pd, const double* th, double* ct, int per_sample, int B) {
   using E = Engine<M>;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= (per_sample ? B : TILE)) return;  // shared theta: the 32 lanes of tile 0
-  M::cost_table(th + tile_off(b, M::NTH), TILE, ct + tile_off(b, E::CT_SIZE), TILE);
+  M::cost_table(th + tile_off(b, M::NTH), TILE, ct + tile_off(b, E::CT_SIZE), TILE, pd.mc);
 }
 
 // MPC.reset: x_k = x0 for all stages, everything else zero
@@ -284,7 +315,7 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 
 }  // namespace
 
-enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1 };
+enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2 };
 
 struct rlmpc_handle {
   int model, variant, device, max_batch;
@@ -294,13 +325,19 @@ struct rlmpc_handle {
   ProblemData pd;
   double *it = nullptr, *ws = nullptr, *it2 = nullptr, *ws2 = nullptr, *th = nullptr, *ct = nullptr, *th_stage = nullptr;
   double* cost = nullptr;
-  int *work = nullptr, *status = nullptr, *hard = nullptr, *counters = nullptr;
+  int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
+  int overlap = 0;  // 1: RTI + sens runs the full interior-point pass of the queued samples on a side stream,
+                    // concurrently with the sensitivity kernels of all other samples.  Measured slower
+                    // (the few latency-bound warps of the queue lose issue slots to the bulk kernels).
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* h_counters = nullptr;  // pinned
   int th_per_sample = 0;
   int sync_every = 4;  // SQP rounds between host checks of the active-sample counter (max_sqp > 1)
   int timing = 0;      // 1: record CUDA events between the phases of a call (rlmpc_get_timings)
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  bool ev_set[6] = {false, false, false, false, false, false};
+  static constexpr int NEV = 7;
+  cudaEvent_t ev[NEV] = {};
+  bool ev_set[NEV] = {};
   long long launches = 0;
   // staging for the host-buffer entry point
   double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
@@ -315,6 +352,7 @@ namespace {
   switch ((h)->variant) {                                              \
     case VAR_CARTPOLE: { using M = CartpoleModel; expr; } break;       \
     case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; expr; } break;  \
+    case VAR_LINEAR: { using M = LinearSystemModel; expr; } break;     \
   }
 
 int check_batch(rlmpc_handle* h, int B) {
@@ -323,7 +361,8 @@ int check_batch(rlmpc_handle* h, int B) {
   return 0;
 }
 
-// phase boundaries: 0 start | 1 after k_lin | 2 after k_qp1 | 3 after k_qp2 | 4 after k_sens_stage | 5 after k_sens_sweep
+// phase boundaries: 0 start | 1 after k_lin | 2 after k_qp1 | 3 after k_qp2 | 4 after k_sens_stage | 5 after
+// k_sens_sweep | 6 end of the call (sens kernels of the queued samples when the side stream is used)
 void mark(rlmpc_handle* h, int i, cudaStream_t s) {
   if (!h->timing) return;
   cudaEventRecord(h->ev[i], s);
@@ -337,33 +376,41 @@ KArgs base_args(rlmpc_handle* h, int B) {
   a.it_size = h->it_size; a.ws_size = h->ws_size; a.th_size = h->nth; a.ct_size = h->ct_size;
   a.th = h->th; a.ct = h->ct; a.th_per_sample = h->th_per_sample; a.B = B;
   a.work = h->work; a.status = h->status; a.cost = h->cost; a.hard = h->hard; a.counters = h->counters;
+  a.ishard = h->ishard;
   return a;
 }
 
 // SQP: K rounds of (linearise | convergence test + fast QP | full interior point on the queue),
 // then one test-only round.  RTI (K = 1) is a single round without the final test.
 template <class M>
-int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s) {
+int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   const int B = a.B, N = h->pd.N, K = h->pd.max_sqp;
   const int gs = (B + TPB - 1) / TPB;
-  const dim3 gstage((B + 127) / 128, N + 1);
+  const dim3 gstage((B + STPB - 1) / STPB, N + 1);
   k_begin<M><<<(B + 127) / 128, 128, 0, s>>>(h->pd, a);
   h->launches++;
-  for (int i = 0; i < 6; ++i) h->ev_set[i] = false;
+  for (int i = 0; i < rlmpc_handle::NEV; ++i) h->ev_set[i] = false;
   const int rounds = (K == 1) ? 1 : K + 1;
   for (int r = 0; r < rounds; ++r) {
     a.last_round = (K > 1 && r == K) ? 1 : 0;
     CUDA_OK(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int), s));
     mark(h, 0, s);
-    k_lin<M><<<gstage, 128, 0, s>>>(h->pd, a);
+    k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
     mark(h, 1, s);
     k_qp1<M><<<gs, TPB, 0, s>>>(h->pd, a);
     mark(h, 2, s);
     h->launches += 2;
     if (!a.last_round) {
-      k_qp2<M><<<(B + 31) / 32, 32, 0, s>>>(h->pd, a);
-      mark(h, 3, s);
+      cudaStream_t sq = s;
+      if (fork_qp2) {  // queued samples continue on the side stream; the caller joins on ev_join
+        CUDA_OK(cudaEventRecord(h->ev_fork, s));
+        CUDA_OK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        sq = h->side_stream;
+      }
+      k_qp2<M><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, a);
+      mark(h, 3, sq);
       h->launches++;
+      if (fork_qp2) CUDA_OK(cudaEventRecord(h->ev_join, sq));
     }
     if (K > 1 && !a.last_round && (r % h->sync_every) == h->sync_every - 1) {
       // all samples converged?  (the only host synchronisation of the library; RTI never gets here)
@@ -379,29 +426,39 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s) {
 }
 
 template <class M>
-int pipeline_sens(rlmpc_handle* h, const KArgs& a, cudaStream_t s) {
+int pipeline_sens(rlmpc_handle* h, KArgs a, cudaStream_t s, bool forked) {
   const int B = a.B, N = h->pd.N;
-  const dim3 gstage((B + 127) / 128, N + 1);
+  const dim3 gstage((B + STPB - 1) / STPB, N + 1);
   if (!a.have_solve) {
-    for (int i = 0; i < 6; ++i) h->ev_set[i] = false;
+    for (int i = 0; i < rlmpc_handle::NEV; ++i) h->ev_set[i] = false;
     mark(h, 3, s);
   }
-  k_sens_stage<M><<<gstage, 128, 0, s>>>(h->pd, a);
+  a.subset = forked ? 1 : 0;
+  k_sens_stage<M><<<gstage, STPB, 0, s>>>(h->pd, a);
   mark(h, 4, s);
   k_sens_sweep<M><<<(B + TPB - 1) / TPB, TPB, 0, s>>>(h->pd, a);
   mark(h, 5, s);
   h->launches += 2;
+  if (forked) {  // join: the queued samples now have their step; same two kernels over the queue
+    CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    a.subset = 2;
+    k_sens_stage<M><<<gstage, STPB, 0, s>>>(h->pd, a);
+    k_sens_sweep<M><<<(B + 31) / 32, 32, 0, s>>>(h->pd, a);
+    h->launches += 2;
+  }
+  mark(h, 6, s);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <class M>
 int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s) {
+  const bool fork = do_solve && do_sens && h->pd.max_sqp == 1 && h->overlap;
   if (do_solve) {
-    if (int r = pipeline_solve<M>(h, a, s)) return r;
+    if (int r = pipeline_solve<M>(h, a, s, fork)) return r;
   }
   a.have_solve = do_solve;
-  if (do_sens) return pipeline_sens<M>(h, a, s);
+  if (do_sens) return pipeline_sens<M>(h, a, s, fork);
   k_out<M><<<(a.B + 127) / 128, 128, 0, s>>>(h->pd, a);
   h->launches++;
   CUDA_OK(cudaGetLastError());
@@ -468,7 +525,7 @@ int field_offset(rlmpc_handle* h, const char* field, int stage, int* off, int* d
 
 int refresh_cost_table(rlmpc_handle* h, int B) {
   DISPATCH_MODEL(h, (k_cost_table<M><<<h->th_per_sample ? (B + 127) / 128 : 1, h->th_per_sample ? 128 : 32>>>(
-                        h->th, h->ct, h->th_per_sample, B)));
+                        h->pd, h->th, h->ct, h->th_per_sample, B)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
@@ -503,6 +560,9 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
       h->variant = bx ? VAR_CARTPOLE_BX : VAR_CARTPOLE;
       break;
     }
+    case RLMPC_MODEL_LINEAR_SYSTEM:
+      h->variant = VAR_LINEAR;
+      break;
     default:
       delete h;
       return fail(RLMPC_EINVAL, "unknown model");
@@ -516,12 +576,13 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.repair = 0.0;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
   memcpy(pd.lbx_e, d->lbx_e, sizeof(pd.lbx_e)); memcpy(pd.ubx_e, d->ubx_e, sizeof(pd.ubx_e));
   memcpy(pd.mc, d->model_const, sizeof(pd.mc));
+  memcpy(pd.zl, d->zl, sizeof(pd.zl)); memcpy(pd.zu, d->zu, sizeof(pd.zu));
   cudaError_t e = cudaSetDevice(device);
   const size_t nio_in = (size_t)max_batch * (h->nx + h->nu);
   const size_t nio_out = (size_t)max_batch * (h->nu + 1 + 4 + (size_t)h->nth * (1 + h->nu));
@@ -537,6 +598,11 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMalloc(&h->work, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->status, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->hard, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ishard, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->ishard, 0, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
@@ -546,7 +612,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_status, sizeof(int) * max_batch);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_counters, sizeof(int) * 4);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < rlmpc_handle::NEV && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
   if (e == cudaSuccess) e = cudaMemset(h->it, 0, n_it);
   if (e == cudaSuccess) e = cudaMemset(h->ws, 0, n_ws);
   if (e == cudaSuccess) e = cudaMemset(h->it2, 0, n_it);
@@ -569,11 +635,14 @@ void rlmpc_destroy(rlmpc_handle* h) {
   cudaSetDevice(h->device);
   cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->th); cudaFree(h->ct);
   cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
-  cudaFree(h->counters);
+  cudaFree(h->counters); cudaFree(h->ishard);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_status);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status); cudaFreeHost(h->h_counters);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < rlmpc_handle::NEV; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
@@ -626,7 +695,10 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
   else if (!strcmp(field, "ubx")) dst = h->pd.ubx;
   else if (!strcmp(field, "lbx_e")) dst = h->pd.lbx_e;
   else if (!strcmp(field, "ubx_e")) dst = h->pd.ubx_e;
+  else if (!strcmp(field, "zl") || !strcmp(field, "zu")) dst = nullptr;
   else return fail(RLMPC_EINVAL, std::string("unknown bound field ") + field);
+  if (!strcmp(field, "zl")) dst = h->pd.zl;
+  if (!strcmp(field, "zu")) dst = h->pd.zu;
   if (is_x && h->variant == VAR_CARTPOLE) {
     for (int i = 0; i < n; ++i)
       if (v[i] > -BIG && v[i] < BIG)
@@ -643,12 +715,12 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "mu0")) h->pd.mu0 = value;
   else if (!strcmp(name, "sigma_min")) h->pd.sigma_min = value;
   else if (!strcmp(name, "sigma0")) h->pd.sigma0 = value;
-  else if (!strcmp(name, "repair")) h->pd.repair = value;
   else if (!strcmp(name, "max_ipm")) h->pd.max_ipm = (int)value;
   else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
   else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;
   else if (!strcmp(name, "sync_every")) h->sync_every = value < 1 ? 1 : (int)value;
   else if (!strcmp(name, "timing")) h->timing = (int)value;
+  else if (!strcmp(name, "overlap")) h->overlap = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }
@@ -765,15 +837,21 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 long long rlmpc_launch_count(const rlmpc_handle* h) { return h ? h->launches : 0; }
 
 int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
-  if (!h || !ms_out || n < 5) return fail(RLMPC_EINVAL, "bad arguments");
+  if (!h || !ms_out || n < 6) return fail(RLMPC_EINVAL, "bad arguments");
   if (!h->timing) return fail(RLMPC_EINVAL, "option \"timing\" is off");
   CUDA_OK(cudaSetDevice(h->device));
-  for (int i = 0; i < 5; ++i) {
+  // [lin | qp1 | qp2 (from the end of qp1, possibly on the side stream) | sens_stage | sens_sweep | tail]
+  const int from[6] = {0, 1, 2, 2, 4, 5}, to[6] = {1, 2, 3, 4, 5, 6};
+  for (int i = 0; i < 6; ++i) {
     ms_out[i] = 0.0;
-    if (h->ev_set[i] && h->ev_set[i + 1]) {
-      CUDA_OK(cudaEventSynchronize(h->ev[i + 1]));
+    int f = from[i];
+    if (i == 3 && !h->overlap && h->ev_set[3]) f = 3;  // serial: sens_stage starts when qp2 ends
+    if (i == 3 && !h->ev_set[2]) f = 3;                // sens-only call
+    if (h->ev_set[f] && h->ev_set[to[i]]) {
+      CUDA_OK(cudaEventSynchronize(h->ev[to[i]]));
+      CUDA_OK(cudaEventSynchronize(h->ev[f]));
       float ms = 0.f;
-      CUDA_OK(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+      CUDA_OK(cudaEventElapsedTime(&ms, h->ev[f], h->ev[to[i]]));
       ms_out[i] = ms;
     }
   }

@@ -33,16 +33,17 @@ def make_ocp_view(spec: ProblemSpec) -> SimpleNamespace:
         idxbx=idxbx, lbx=spec.lbx[idxbx].copy(), ubx=spec.ubx[idxbx].copy(),
         idxbx_e=idxbx_e, lbx_e=spec.lbx_e[idxbx_e].copy(), ubx_e=spec.ubx_e[idxbx_e].copy(),
         idxbx_0=np.arange(spec.nx), lbx_0=np.zeros(spec.nx), ubx_0=np.zeros(spec.nx),
-        idxsbx=np.array([], dtype=int), idxsbu=np.array([], dtype=int), idxsh=np.array([], dtype=int),
+        idxsbx=np.asarray(spec.idxsbx, dtype=int), idxsbu=np.array([], dtype=int), idxsh=np.array([], dtype=int),
         idxsbx_e=np.array([], dtype=int), idxsh_e=np.array([], dtype=int),
         lh=np.array([]), uh=np.array([]), lh_e=np.array([]), uh_e=np.array([]),
     )
     dims = SimpleNamespace(N=spec.N, nx=spec.nx, nu=spec.nu, np=spec.np_model, nbu=spec.nu, nbx=len(idxbx),
-                           nbx_0=spec.nx, nbx_e=len(idxbx_e), nh=0, nh_e=0, nsbx=0, nsbu=0, nsh=0, nsbx_e=0, nsh_e=0,
+                           nbx_0=spec.nx, nbx_e=len(idxbx_e), nh=0, nh_e=0, nsbx=len(spec.idxsbx), nsbu=0, nsh=0, nsbx_e=0, nsh_e=0,
                            ny_0=spec.nx + spec.nu, ny=spec.nx + spec.nu, ny_e=spec.nx)
     cost = SimpleNamespace(cost_type_0=spec.cost_type, cost_type=spec.cost_type, cost_type_e=spec.cost_type,
                            W_0=pv("W_0"), W=pv("W"), W_e=pv("W_e"), yref_0=pv("yref_0"), yref=pv("yref"), yref_e=pv("yref_e"),
-                           zl=np.array([]), zu=np.array([]), zl_e=np.array([]), zu_e=np.array([]))
+                           zl=np.asarray(spec.zl, dtype=float).copy(), zu=np.asarray(spec.zu, dtype=float).copy(),
+                           zl_e=np.array([]), zu_e=np.array([]))
     model = SimpleNamespace(name=spec.name, x_labels=list(spec.state_labels), u_labels=list(spec.input_labels),
                             p_labels=list(spec.parameter_labels))
     return SimpleNamespace(dims=dims, constraints=cons, cost=cost, model=model,
@@ -181,17 +182,27 @@ class OcpSolverShim:
         nx, nu, N = self.spec.nx, self.spec.nu, self.N
         if field in ("x", "u", "pi"):
             return self.engine.get(field, stage, 1)[0].cpu().numpy()
+        nbx, ns = self.engine.nbx, len(self.spec.idxsbx)
         if field in ("sl", "su"):
-            return np.zeros(0)
+            # slack values of the soft state bounds = slack of the rows -sl <= 0 / -su <= 0 (stages 1..N-1)
+            if ns == 0 or stage == 0 or stage == N:
+                return np.zeros(0)
+            v = self.engine.get("t", stage, 1)[0].cpu().numpy()
+            o = 2 * (nu + nbx) + (0 if field == "sl" else ns)
+            return v[o:o + ns].copy()
         if field in ("lam", "t"):
-            # acados order within a stage: [lbu, lbx, ubu, ubx] (rlmpc/common/utils.py:4-25)
-            if stage == N:
-                return np.zeros(0)  # no terminal bounds in this problem class
+            # acados order within a stage: [lbu, lbx, ubu, ubx, lsbx, usbx] (rlmpc/common/utils.py:4-25); the
+            # engine stores [lbu(nu), lbx(nbx), ubu(nu), ubx(nbx), lsbx(ns), usbx(ns)] for every stage 0..N
             v = self.engine.get(field, stage, 1)[0].cpu().numpy()
-            lo_u, up_u = v[:nu], v[nu:]
+            lo_u, lo_x, up_u, up_x = v[:nu], v[nu:nu + nbx], v[nu + nbx:2 * nu + nbx], v[2 * nu + nbx:2 * (nu + nbx)]
+            soft = v[2 * (nu + nbx):]
+            if stage == N:
+                if len(self.acados_ocp.constraints.idxbx_e) == 0:
+                    return np.zeros(0)
+                return np.concatenate([lo_x, up_x])
             if stage > 0:
-                return np.concatenate([lo_u, up_u])
-            # stage 0 carries the x_0 (and, in Q-mode, u_0) equalities as two opposing bounds
+                return np.concatenate([lo_u, lo_x, up_u, up_x, soft])
+            # stage 0 carries the x_0 (and, in Q-mode, u_0) equalities as two opposing bounds on all nx / nu
             rho_x = self.engine.get("rho_x0", 0, 1)[0].cpu().numpy()
             if self.qmode:
                 rho_u = self.engine.get("rho_u0", 0, 1)[0].cpu().numpy()
@@ -210,8 +221,8 @@ class OcpSolverShim:
             if k < self.N:
                 d[f"u_{k}"] = self.get(k, "u").tolist()
                 d[f"pi_{k}"] = self.get(k, "pi").tolist()
-                for f in ("lam", "t"):
-                    d[f"{f}_{k}"] = self.engine.get(f, k, 1)[0].cpu().numpy().tolist()
+            for f in ("lam", "t"):
+                d[f"{f}_{k}"] = self.engine.get(f, k, 1)[0].cpu().numpy().tolist()
         with open(filename, "w") as fh:
             json.dump(d, fh, indent=1)
 

@@ -35,6 +35,9 @@ class ProblemSpec:
     gamma: float = 1.0
     cost_type: str = "NONLINEAR_LS"
     parameterize_tracking_cost: bool = False
+    idxsbx: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))  # soft rows: positions within idxbx
+    zl: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    zu: np.ndarray = field(default_factory=lambda: np.zeros(0))
     state_labels: List[str] = field(default_factory=list)
     input_labels: List[str] = field(default_factory=list)
     parameter_labels: List[str] = field(default_factory=list)  # labels of p["model"]
@@ -83,6 +86,10 @@ class ProblemSpec:
                 arr[i] = v
         for i, v in enumerate(self.model_const):
             d.model_const[i] = v
+        for i, v in enumerate(np.asarray(self.zl, dtype=float).ravel()):
+            d.zl[i] = v
+        for i, v in enumerate(np.asarray(self.zu, dtype=float).ravel()):
+            d.zu[i] = v
         return d
 
 
@@ -146,3 +153,50 @@ def cartpole_original_config() -> dict:
                                                  "l": {"value": 0.5, "fixed": False}, "g": {"value": 9.8, "fixed": True}}},
         "constraints": {"constr_type": "BGH", "x0": [0.0, 0.0, 3.14, 0.0], "idxbu": [0], "lbu": [-80.0], "ubu": [80.0]},
     }
+
+
+def cartpole_config() -> dict:
+    """config/cartpole.yaml of the reference as a dict (``config["mpc"]``): N=30, tf=3.0, |u| <= 30,
+    box bounds on all four states on stages 1..N (config/cartpole.yaml:1-93)."""
+    c = cartpole_original_config()
+    W = np.diag([10.0, 0.1, 10.0, 0.1, 0.01]).tolist()
+    W_e = np.diag([10.0, 0.1, 10.0, 0.1]).tolist()
+    c["ocp_options"]["tf"] = 3.0
+    c["dimensions"]["N"] = 30
+    c["cost"].update({"W_0": W, "W": W, "W_e": W_e})
+    bx = [2.4, 10.0, 6.28, 10.0]
+    c["constraints"] = {"constr_type": "BGH", "x0": [0.0, 0.0, 3.14, 0.0], "idxbu": [0], "lbu": [-30.0], "ubu": [30.0],
+                        "idxbx_0": [0, 1, 2, 3], "idxbx": [0, 1, 2, 3], "lbx": [-v for v in bx], "ubx": bx,
+                        "idxbx_e": [0, 1, 2, 3], "lbx_e": [-v for v in bx], "ubx_e": bx}
+    return c
+
+
+def linear_system_param_nominal() -> dict:
+    """The parameter dict of tests/test_linear_example.py:9-17 / examples/linear_system_mpc_qlearning.py:109-117."""
+    return {
+        "A": np.array([[1.0, 0.25], [0.0, 1.0]]), "B": np.array([[0.03125], [0.25]]),
+        "Q": np.identity(2), "R": np.identity(1), "b": np.array([[0.0], [0.0]]),
+        "f": np.array([[0.0], [0.0], [0.0]]), "V_0": np.array([1e-3]),
+    }
+
+
+def linear_system_spec(param: dict | None = None, gamma: float = 0.99, N: int = 40,
+                       lbx=(-0.0, -1.0), ubx=(1.0, 1.0), lbu=(-1.0,), ubu=(1.0,)) -> ProblemSpec:
+    """rlmpc/mpc/linear_system/acados.py:73-131: x+ = Ax + Bu + b, EXTERNAL cost 1/2 y'y + f'y (+ V_0 at
+    stage 0), terminal 1/2 x'Px with P = DARE(A,B,Q,R) of THIS dict (a constant), soft bound on x[0]."""
+    from scipy.linalg import solve_discrete_are
+
+    param = linear_system_param_nominal() if param is None else param
+    P = solve_discrete_are(param["A"], param["B"], param["Q"], param["R"])
+    p_nom = np.concatenate([np.asarray(param[k], dtype=float).T.reshape(-1) for k in ["A", "B", "b", "V_0", "f"]])
+    labels = ["A_0", "A_1", "A_2", "A_3", "B_0", "B_1", "b_0", "b_1", "V_0", "f_0", "f_1", "f_2"]
+    return ProblemSpec(
+        name="lti", model=_cabi.MODEL_LINEAR_SYSTEM, N=N, nx=2, nu=1, tf=float(N),  # tf = N: dT = 1 (acados.py:120)
+        p_entries=[("model", (12,))], p_nominal=p_nom,
+        lbu=np.array(lbu, dtype=float), ubu=np.array(ubu, dtype=float),
+        lbx=np.array(lbx, dtype=float), ubx=np.array(ubx, dtype=float),
+        lbx_e=np.full(2, -INF), ubx_e=np.full(2, INF),
+        model_const=np.array([P[0, 0], P[0, 1], P[1, 1]]), gamma=gamma, cost_type="EXTERNAL",
+        idxsbx=np.array([0]), zl=np.array([1e2]), zu=np.array([1e2]),
+        state_labels=["x_0", "x_1"], input_labels=["u_0"], parameter_labels=labels,
+    )

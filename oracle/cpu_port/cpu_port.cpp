@@ -10,6 +10,7 @@
 
 #include "../../mpc4rl_b200/csrc/engine.cuh"
 #include "../../mpc4rl_b200/csrc/models/cartpole.cuh"
+#include "../../mpc4rl_b200/csrc/models/linear_system.cuh"
 
 using namespace rlmpc;
 
@@ -33,7 +34,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
   for (int b = 0; b < (per_sample ? B : TILE); ++b) {
     for (int i = 0; i < M::NTH; ++i)
       th[tile_off(b, M::NTH) + (size_t)i * TILE] = per_sample ? theta[(size_t)b * M::NTH + i] : theta[i];
-    M::cost_table(th.data() + tile_off(b, M::NTH), TILE, ct.data() + tile_off(b, E::CT_SIZE), TILE);
+    M::cost_table(th.data() + tile_off(b, M::NTH), TILE, ct.data() + tile_off(b, E::CT_SIZE), TILE, pd.mc);
   }
   for (int b = 0; b < B; ++b)  // caller's iterate is [it_size][B] batch-minor
     for (int i = 0; i < itn_; ++i) itt[tile_off(b, itn_) + (size_t)i * TILE] = iterate[(size_t)i * B + b];
@@ -66,7 +67,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
         }
         const int st = E::qp_full(pd, L, &ipm_iter);
         ++sqp_iter;
-        if (K == 1 || st == ST_QPFAIL) { status = st; break; }
+        if (K == 1 || st == E::FULL_FAILED) { status = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL; break; }
       }
       if (iters_out) {
         iters_out[3 * b] = sqp_iter;
@@ -118,11 +119,12 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     for (int i = 0; i < itn_; ++i) iterate[(size_t)i * B + b] = itt[tile_off(b, itn_) + (size_t)i * TILE];
 }
 
-// model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds
+// model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds, 3 = linear system
 #define PORT_DISPATCH(model, expr)                         \
   switch (model) {                                         \
     case 1: { using M = CartpoleModel; expr; } break;      \
     case 2: { using M = CartpoleModelBX; expr; } break;    \
+    case 3: { using M = LinearSystemModel; expr; } break;  \
     default: return -1;                                    \
   }
 

@@ -19,21 +19,30 @@ from .solver import DenseSolver
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def sample_states(n, seed):
-    """SURVEY.md 8(d) config 2 distribution."""
+def sample_states(n, seed, variant="original"):
+    """'original': SURVEY.md 8(d) config 2 distribution.  'default' (config/cartpole.yaml, state
+    bounds, |u| <= 30): states around the hanging position the YAML starts from (x0 = [0,0,3.14,0]);
+    far-away starts make the first linearised QP infeasible there (acados: status 4)."""
     rng = np.random.default_rng(seed)
-    lo = np.array([-1.0, -2.0, -np.pi, -4.0]); hi = -lo
-    x = rng.uniform(lo, hi, size=(n, 4))
-    a = rng.uniform(-80.0, 80.0, size=(n, 1))
+    if variant == "original":
+        lo = np.array([-1.0, -2.0, -np.pi, -4.0]); hi = -lo
+        x = rng.uniform(lo, hi, size=(n, 4))
+        a = rng.uniform(-80.0, 80.0, size=(n, 1))
+    else:
+        x = np.array([0.0, 0.0, np.pi, 0.0]) + rng.uniform(-1.0, 1.0, size=(n, 4)) * np.array([1.0, 1.0, 0.5, 1.0])
+        a = rng.uniform(-30.0, 30.0, size=(n, 1))
     return x, a
 
 
 def cartpole_golden(variant="original", n=20, seed=1234):
     pb = make_cartpole(variant)
     s = DenseSolver(pb)
-    x0s, acts = sample_states(n, seed)
-    # the reference's own test point (scripts/cartpole_mpc_sensitivities.py:80-81)
-    x0s[0] = [0.0, 0.0, np.pi / 2, 0.0]; acts[0] = [-30.0]
+    x0s, acts = sample_states(n, seed, variant)
+    if variant == "original":
+        # the reference's own test point (scripts/cartpole_mpc_sensitivities.py:80-81)
+        x0s[0] = [0.0, 0.0, np.pi / 2, 0.0]; acts[0] = [-30.0]
+    else:
+        x0s[0] = [0.0, 0.0, 3.14, 0.0]; acts[0] = [-30.0]  # config/cartpole.yaml:80, u0 on the bound
     out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "U", "X", "pi", "lam", "t", "UQ", "XQ", "status")}
     for i in range(n):
         sol, upd = s.unit(x0s[i], tol=1e-10)
@@ -52,7 +61,39 @@ def cartpole_golden(variant="original", n=20, seed=1234):
     print("wrote", path)
 
 
+def linear_system_golden(gamma=0.9, seed=7):
+    """Linear system (rlmpc/mpc/linear_system/acados.py) at the example's discount factor.  States
+    are drawn from the box the environment visits; samples whose optimum violates the soft bound on
+    x[0] exercise the slack rows.  Also the LQR known answers of SURVEY.md 8(c) (widened bounds)."""
+    from .problems import make_linear_system
+
+    pb = make_linear_system(gamma=gamma)
+    s = DenseSolver(pb)
+    rng = np.random.default_rng(seed)
+    x0s = np.vstack([[0.5, 0.5], [0.2, 0.2], [0.5, -0.2], [0.9, 0.8], [0.05, -0.6],
+                     rng.uniform([0.0, -1.0], [1.0, 1.0], size=(7, 2))])
+    acts = rng.uniform(-1.0, 1.0, size=(len(x0s), 1))
+    out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "U", "X", "lam", "t", "slmax", "status")}
+    for i in range(len(x0s)):
+        sol, upd = s.unit(x0s[i], tol=1e-10)
+        solq, updq = s.unit(x0s[i], u0=acts[i], tol=1e-10)
+        print(f"[linear {i}] V={sol.cost:.6f} u0={sol.U[0]} it={sol.sqp_iter} | Q={solq.cost:.6f} slack={max(sol.slbx.max(), sol.subx.max()):.3f}", flush=True)
+        out["status"].append([sol.status, solq.status])
+        out["V"].append(sol.cost); out["u0"].append(sol.U[0]); out["dV"].append(upd["dL_dp"][0]); out["dpi"].append(upd["dpi_dp"])
+        out["Q"].append(solq.cost); out["dQ"].append(updq["dL_dp"][0])
+        out["U"].append(sol.U); out["X"].append(sol.X); out["lam"].append(sol.lam); out["t"].append(sol.t)
+        out["slmax"].append(max(sol.slbx.max(), sol.subx.max(), solq.slbx.max(), solq.subx.max()))
+    out = {k: np.array(v) for k, v in out.items()}
+    out["x0"] = x0s; out["a"] = acts; out["theta"] = pb.p_nominal; out["gamma"] = gamma
+    path = os.path.join(ROOT, "tests", "golden", "linear_system.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["original"]
     for v in which:
-        cartpole_golden(v)
+        if v == "linear":
+            linear_system_golden()
+        else:
+            cartpole_golden(v, n=20 if v == "original" else 12)

@@ -1,0 +1,204 @@
+"""GPU parity tests for the other problem definitions the engine carries -- through the C ABI:
+
+* cartpole with state bounds (config/cartpole.yaml: N=30, |u|<=30, box on all four states),
+* the linear system of the reference's usage example / pytest (rlmpc/mpc/linear_system/acados.py,
+  tests/test_linear_example.py): EXTERNAL cost, discount factor, soft state bound with slack rows.
+
+Golden fixtures: oracle/make_golden.py (dense restatement; parity unpinned, see oracle/__init__.py).
+Tolerances as in test_gpu_cartpole.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _dev(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda:0")
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+# ------------------------------------------------------------------------------------------------
+# cartpole.yaml (state bounds)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def g_bx():
+    return np.load(os.path.join(ROOT, "tests", "golden", "cartpole_default.npz"))
+
+
+def _bx_engine(B):
+    from mpc4rl_b200 import BatchedMPC, cartpole_config, cartpole_spec
+
+    m = BatchedMPC(cartpole_spec(cartpole_config()), max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    return m
+
+
+def test_state_bounds_v_and_q_match_golden(g_bx):
+    x0 = _dev(g_bx["x0"])
+    B = x0.shape[0]
+    m = _bx_engine(B)
+    assert m.nbx == 4 and m.nrows == 10  # [lbu, lbx(4), ubu, ubx(4)]
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=300)
+    st = out["status"].cpu().numpy()
+    ok = (g_bx["status"][:, 0] == 0) & (st == 0)
+    assert ok.sum() >= B - 1
+    assert np.abs(out["u0"].cpu().numpy() - g_bx["u0"])[ok].max() < 1e-6
+    assert _rel(out["cost"].cpu().numpy()[ok], g_bx["V"][ok]) < 1e-9
+    assert _rel(m.full_grad(out["dL"]).cpu().numpy()[ok], g_bx["dV"][ok]) < 1e-6
+    assert np.abs(m.full_grad(out["dpi"]).cpu().numpy() - g_bx["dpi"])[ok].max() < 1e-5 * max(1.0, np.abs(g_bx["dpi"]).max())
+    assert out["res"][torch.tensor(ok, device="cuda:0")].max().item() < 1e-9
+    # the state trajectory touches its bounds: the golden solutions have 20-35 active rows each
+    X = np.stack([m.get("x", k, B).cpu().numpy() for k in range(31)], axis=1)
+    assert np.abs(X - g_bx["X"])[ok].max() < 1e-6
+    assert (np.abs(X[..., 1]).max(axis=1) > 10.0 - 1e-6).any()  # velocity bound active somewhere
+    # Q-mode
+    a = _dev(g_bx["a"])
+    m.reset(x0)
+    oq = m.solve_sens(x0, a, max_sqp=300)
+    okq = (g_bx["status"][:, 1] == 0) & (oq["status"].cpu().numpy() == 0)
+    assert okq.sum() >= B - 1
+    assert _rel(oq["cost"].cpu().numpy()[okq], g_bx["Q"][okq]) < 1e-9
+    assert _rel(m.full_grad(oq["dL"]).cpu().numpy()[okq], g_bx["dQ"][okq]) < 1e-6
+
+
+def test_state_bounds_through_the_mirrored_api(g_bx):
+    from mpc4rl_b200 import cartpole_config
+    from mpc4rl_b200.mpc.cartpole.acados import AcadosMPC
+
+    mpc = AcadosMPC(config=cartpole_config(), build=True)
+    x0 = g_bx["x0"][0]  # config/cartpole.yaml x0 = [0, 0, 3.14, 0]
+    mpc.reset(x0)
+    mpc.update(x0)
+    mpc.update_nlp()
+    assert abs(mpc.get_V() - g_bx["V"][0]) < 1e-6 * abs(g_bx["V"][0])
+    assert np.abs(mpc.get_pi() - g_bx["u0"][0]).max() < 1e-5
+    lam1 = mpc.ocp_solver.get(1, "lam")  # acados order [lbu, lbx(4), ubu, ubx(4)]
+    assert lam1.shape == (10,)
+    assert mpc.ocp_solver.get(30, "lam").shape == (8,)  # terminal: [lbx_e(4), ubx_e(4)]
+    assert mpc.ocp_solver.get(0, "lam").shape == (10,)  # stage 0: lbu, lbx_0 (all nx), ubu, ubx_0
+    mpc.nlp.assert_kkt_residual(1e-6)  # scripts/cartpole_mpc_kkt_conditions.py:74-85
+    # infeasible first QP (pendulum horizontal: no input authority in the linearisation) -> acados status 4
+    mpc.reset(np.array([0.0, 0.0, np.pi / 2, 0.0]))
+    with pytest.raises(RuntimeError, match="status 4"):
+        mpc.update(np.array([0.0, 0.0, np.pi / 2, 0.0]))
+
+
+# ------------------------------------------------------------------------------------------------
+# linear system
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def g_lin():
+    return np.load(os.path.join(ROOT, "tests", "golden", "linear_system.npz"))
+
+
+def _lin_engine(B, **kw):
+    from mpc4rl_b200 import BatchedMPC, linear_system_spec
+
+    m = BatchedMPC(linear_system_spec(**kw), max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    return m
+
+
+def test_linear_system_matches_golden(g_lin):
+    x0, a = _dev(g_lin["x0"]), _dev(g_lin["a"])
+    B = x0.shape[0]
+    m = _lin_engine(B, gamma=float(g_lin["gamma"]))
+    assert m.ngrad == 12 and m.nrows == 8  # [lbu, lbx(2), ubu, ubx(2), lsbx, usbx]
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=100)
+    ok = (g_lin["status"][:, 0] == 0) & (out["status"].cpu().numpy() == 0)
+    assert ok.all()
+    assert np.abs(out["u0"].cpu().numpy() - g_lin["u0"]).max() < 1e-8
+    assert _rel(out["cost"].cpu().numpy(), g_lin["V"]) < 1e-9
+    assert _rel(out["dL"].cpu().numpy(), g_lin["dV"]) < 1e-6
+    assert np.abs(out["dL"][:, 8].cpu().numpy() - 1.0).max() < 1e-12  # dV/dV_0 = 1 exactly
+    # dpi/dp: where a softened bound is violated the reference's formula (slack frozen, quirk Q4; x_0
+    # "fixed" by two barrier rows of finite stiffness, quirk Q7) is a ratio of IPM-sized stiffnesses --
+    # compared only on the samples without an active slack
+    soft = g_lin["slmax"] > 1e-6
+    assert soft.sum() >= 2
+    assert np.abs(out["dpi"].cpu().numpy() - g_lin["dpi"])[~soft].max() < 1e-5 * np.abs(g_lin["dpi"]).max()
+    # slack values of the violated soft bound (ocp_solver.get(stage, "su"))
+    T = np.stack([m.get("t", k, B).cpu().numpy() for k in range(1, 40)], axis=1)  # [B, 39, 8]
+    assert abs(T[3, :, 7].max() - 0.21875) < 1e-6  # x0 = [0.9, 0.8]: upper bound on x[0] exceeded by 0.21875
+    # Q-mode
+    m.reset(x0)
+    oq = m.solve_sens(x0, a, max_sqp=100)
+    okq = (g_lin["status"][:, 1] == 0) & (oq["status"].cpu().numpy() == 0)
+    assert okq.sum() >= B - 1  # one (s, a) pair makes the hard bound on x[1] infeasible
+    assert _rel(oq["cost"].cpu().numpy()[okq], g_lin["Q"][okq]) < 1e-9
+    assert _rel(oq["dL"].cpu().numpy()[okq], g_lin["dQ"][okq]) < 1e-6
+
+
+def test_linear_system_lqr_known_answer():
+    """gamma = 1 and bounds out of reach: the MPC is the LQR (terminal cost = DARE solution), closed form
+    from SURVEY.md 8(c): x0=[0.2,0.2] -> u0=-0.461877155042, V-V_0=0.460894064457; [0.5,-0.2] -> ..."""
+    m = _lin_engine(2, gamma=1.0, lbx=(-1e3, -1e3), ubx=(1e3, 1e3), lbu=(-1e3,), ubu=(1e3,))
+    x0 = _dev([[0.2, 0.2], [0.5, -0.2]])
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=20)
+    assert (out["status"] == 0).all()
+    assert np.abs(out["u0"].cpu().numpy().ravel() - [-0.461877155042, -0.102167673017]).max() < 1e-9
+    # + 78e-8: the tau-central slacks of the 2 x 39 soft rows (z * tau / z each)
+    assert np.abs(out["cost"].cpu().numpy() - 1e-3 - 78e-8 - [0.460894064457, 0.680269101675]).max() < 1e-8
+    assert np.isfinite(out["dpi"].cpu().numpy()).all()
+
+
+def test_linear_example_construction_like_the_reference_pytest():
+    """tests/test_linear_example.py:8-26 of the reference: construct and touch the attributes."""
+    from mpc4rl_b200.mpc.linear_system.acados import AcadosMPC
+    from mpc4rl_b200.problems import linear_system_param_nominal
+
+    mpc = AcadosMPC(linear_system_param_nominal(), discount_factor=0.99)
+    assert mpc is not None
+    assert mpc.ocp_solver is not None
+    assert mpc.nlp is not None
+    assert mpc.ocp_solver.acados_ocp is not None
+    assert mpc.ocp_solver.acados_ocp.model is not None
+    assert mpc.ocp_solver.acados_ocp.dims is not None
+    assert mpc.ocp_solver.acados_ocp.cost is not None
+    assert mpc.ocp_solver.acados_ocp.dims.N == 40 and mpc.get_p().shape == (12,)
+    assert mpc.get_parameter_labels()[8] == "V_0"
+    x0 = np.array([0.5, 0.5])
+    mpc.reset(x0)
+    mpc.q_update(x0, np.array([0.3]))
+    assert mpc.get_dQ_dp().shape == (1, 12) and abs(mpc.get_dQ_dp()[0, 8] - 1.0) < 1e-12
+    mpc.update(x0)
+    mpc.update_nlp()
+    assert mpc.get_dpi_dp().shape == (1, 12)
+    assert mpc.ocp_solver.get(1, "lam").shape == (8,) and mpc.ocp_solver.get(1, "su").shape == (1,)
+
+
+def test_qlearning_example_batched_equals_per_sample_loop():
+    """The usage example of the reference: the batched learning step gives the parameter update of the
+    per-sample q_update/update loop (examples/linear_system_mpc_qlearning.py:171-205)."""
+    from mpc4rl_b200.examples import linear_system_mpc_qlearning as ex
+    from mpc4rl_b200.mpc.linear_system.acados import AcadosMPC
+    from mpc4rl_b200.problems import linear_system_param_nominal
+
+    mpc = AcadosMPC(linear_system_param_nominal(), discount_factor=ex.GAMMA)
+    env = ex.LinearSystemEnv(mpc.ocp_solver.acados_ocp.constraints.lbx, mpc.ocp_solver.acados_ocp.constraints.ubx, seed=1)
+    S, A, C = ex.rollout(mpc, env, episode_length=24)
+    assert np.isfinite(C).all() and np.abs(A).max() <= 1.0 + 1e-9
+    dp_loop, td_loop, q_loop, v_loop = ex.learn_loop(mpc, S, A, C)
+    engine = mpc.batched(max_batch=32)
+    engine.set_option("tol", 1e-6)
+    dp_b, td_b, q_b, v_b = ex.learn_batched(engine, mpc, S, A, C)
+    assert np.abs(q_b - q_loop).max() < 1e-6 * max(1.0, np.abs(q_loop).max())
+    assert np.abs(v_b - v_loop).max() < 1e-6 * max(1.0, np.abs(v_loop).max())
+    assert np.abs(td_b - td_loop).max() < 1e-5
+    assert np.abs(dp_b - dp_loop).max() < 1e-6 * max(1e-6, np.abs(dp_loop).max()) + 1e-12
+    p0 = mpc.get_parameter_values().copy()
+    mpc.set_parameter(p0 + dp_b)
+    assert np.abs(mpc.get_p() - (p0 + dp_b)).max() == 0.0
+    log = ex.main(n_episodes=2, episode_length=16, verbose=False)
+    assert len(log) == 2 and np.isfinite(log[-1]["td_error"])

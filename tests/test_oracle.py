@@ -133,3 +133,66 @@ def test_host_port_of_engine_matches_oracle(golden):
     assert np.abs(q["cost"] - golden["Q"])[okq].max() < 1e-9 * np.abs(golden["Q"]).max()
     assert np.abs(q["dL"][:, :3] - golden["dQ"][:, :3])[okq].max() < 1e-6 * np.abs(golden["dQ"]).max()
     assert np.count_nonzero(q["dpi"]) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# other problem definitions: state-bounded cartpole (config/cartpole.yaml) and the linear system
+# ------------------------------------------------------------------------------------------------
+def test_host_port_with_state_bounds_matches_oracle_fixtures():
+    from oracle import cpu_port as cp
+    from oracle.problems import make_cartpole
+
+    pb = make_cartpole("default")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_default.npz"))
+    scale = np.array([pb.stage_scale(k) for k in range(pb.N + 1)])
+    pd = cp.make_pd(pb.N, scale, pb.lbu, pb.ubu, [pb.tf / pb.N / 4, 9.8], tol=1e-10, warm_ipm=1,
+                    lbx=pb.lbx, ubx=pb.ubx, lbx_e=pb.lbx_e, ubx_e=pb.ubx_e)
+    o = cp.unit(2, pd, 0, 300, pb.p_nominal, g["x0"])
+    ok = (g["status"][:, 0] == 0) & (o["status"] == 0)
+    assert ok.sum() >= len(ok) - 1
+    assert np.abs(o["u0"] - g["u0"])[ok].max() < 1e-8
+    assert (np.abs(o["cost"] - g["V"]) / np.abs(g["V"]))[ok].max() < 1e-10
+    assert np.abs(o["dL"] - g["dV"][:, :3])[ok].max() < 1e-8 * np.abs(g["dV"]).max()
+    assert np.abs(o["dpi"] - g["dpi"][:, :, :3])[ok].max() < 1e-6 * np.abs(g["dpi"]).max()
+    assert min((g["lam"][i] > 1e-6).sum() for i in range(len(ok))) >= 15  # many active rows, state bounds included
+
+
+def test_linear_system_oracle_lqr_and_host_port():
+    """Known answer: with gamma = 1 and the bounds out of reach the MPC is the LQR with
+    the DARE terminal cost -- for the dense oracle and for the host port of the engine; then the
+    committed fixtures (soft bound active in two of them) against the host port."""
+    from scipy.linalg import solve_discrete_are
+
+    from oracle import cpu_port as cp
+    from oracle.problems import linear_system_param_nominal, make_linear_system
+    from oracle.solver import DenseSolver
+
+    par = linear_system_param_nominal()
+    P = solve_discrete_are(par["A"], par["B"], par["Q"], par["R"])
+    K = np.linalg.solve(par["R"] + par["B"].T @ P @ par["B"], par["B"].T @ P @ par["A"])
+    assert np.abs(K.ravel() - [0.805778325799, 1.503607449412]).max() < 1e-10
+    pbw = make_linear_system(gamma=1.0, lbx=(-1e3, -1e3), ubx=(1e3, 1e3))
+    pbw.lbu = np.array([-1e3]); pbw.ubu = np.array([1e3])
+    x0 = np.array([0.2, 0.2])
+    sol, upd = DenseSolver(pbw).unit(x0, tol=1e-10)
+    assert abs(sol.U[0, 0] + 0.461877155042) < 1e-8
+    # the tau-central slacks of the 2 x 39 soft rows cost z * tau / z each: 78e-8 above the closed form
+    assert abs(sol.cost - 1e-3 - 0.460894064457 - 78e-8) < 1e-9
+    assert abs(upd["dL_dp"][0, 8] - 1.0) < 1e-12  # dV/dV_0
+    mc = [P[0, 0], P[0, 1], P[1, 1]]
+    pdw = cp.make_pd(40, np.ones(41), [-1e3], [1e3], mc, tol=1e-10, warm_ipm=1, lbx=[-1e3, -1e3], ubx=[1e3, 1e3],
+                     zl=[1e2], zu=[1e2])
+    o = cp.unit(3, pdw, 0, 20, pbw.p_nominal, x0[None, :], nx=2, nu=1)
+    assert o["status"][0] == 0 and abs(o["u0"][0, 0] + 0.461877155042) < 1e-9
+    # fixtures
+    g = np.load(os.path.join(ROOT, "tests", "golden", "linear_system.npz"))
+    pb = make_linear_system(gamma=float(g["gamma"]))
+    scale = np.array([pb.stage_scale(k) for k in range(pb.N + 1)])
+    pd = cp.make_pd(pb.N, scale, pb.lbu, pb.ubu, mc, tol=1e-10, warm_ipm=1, lbx=pb.lbx, ubx=pb.ubx, zl=pb.zl, zu=pb.zu)
+    o = cp.unit(3, pd, 0, 100, pb.p_nominal, g["x0"], nx=2, nu=1)
+    assert (o["status"] == 0).all() and (g["status"][:, 0] == 0).all()
+    assert np.abs(o["u0"] - g["u0"]).max() < 1e-8
+    assert (np.abs(o["cost"] - g["V"]) / np.abs(g["V"])).max() < 1e-9
+    assert np.abs(o["dL"] - g["dV"]).max() < 1e-6 * np.abs(g["dV"]).max()
+    soft = g["slmax"] > 1e-6
+    assert soft.sum() >= 2 and np.abs(o["dpi"] - g["dpi"])[~soft].max() < 1e-5 * np.abs(g["dpi"]).max()
