@@ -56,10 +56,10 @@ def test_state_bounds_v_and_q_match_golden(g_bx):
     assert _rel(m.full_grad(out["dL"]).cpu().numpy()[ok], g_bx["dV"][ok]) < 1e-6
     assert np.abs(m.full_grad(out["dpi"]).cpu().numpy() - g_bx["dpi"])[ok].max() < 1e-5 * max(1.0, np.abs(g_bx["dpi"]).max())
     assert out["res"][torch.tensor(ok, device="cuda:0")].max().item() < 1e-9
-    # the state trajectory touches its bounds: the golden solutions have 20-35 active rows each
+    # 20-35 active rows per solution (mostly the saturated input); sample 7 rides the cart-position bound
     X = np.stack([m.get("x", k, B).cpu().numpy() for k in range(31)], axis=1)
     assert np.abs(X - g_bx["X"])[ok].max() < 1e-6
-    assert (np.abs(X[..., 1]).max(axis=1) > 10.0 - 1e-6).any()  # velocity bound active somewhere
+    assert ok[7] and abs(np.abs(X[7, :, 0]).max() - 2.4) < 1e-6
     # Q-mode
     a = _dev(g_bx["a"])
     m.reset(x0)
