@@ -37,8 +37,10 @@ class BatchedMPC:
         desc = spec.to_desc()
         _cabi.check(self.lib.rlmpc_create(C.byref(desc), self.max_batch, dev.index or 0, C.byref(self._h)))
         self.nx, self.nu, self.ntheta = spec.nx, spec.nu, spec.ntheta
-        self.nrows = int(self.lib.rlmpc_nrows(self._h))  # 2*(nu+nbx) inequality rows per stage [lbu lbx ubu ubx]
-        self.nbx = self.nrows // 2 - self.nu
+        # inequality rows per stage: 2*(nu+nbx) + 2*ns, acados order [lbu lbx ubu ubx lsbx usbx]
+        self.nrows = int(self.lib.rlmpc_nrows(self._h))
+        self.ns = len(spec.idxsbx)
+        self.nbx = (self.nrows - 2 * self.ns) // 2 - self.nu
         self.theta = np.array(spec.p_nominal, dtype=np.float64)
         self.set_theta(self.theta)
         self.param_cost = bool(spec.parameterize_tracking_cost)

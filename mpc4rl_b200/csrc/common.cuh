@@ -51,6 +51,8 @@ struct ProblemData {
   double mu0;           // initial barrier parameter of a cold-started IPM
   double sigma_min;     // smallest centring parameter (barrier reduction per full step)
   double sigma0;        // centring parameter of the first iteration of a cold start
+  double as_steps;      // warm start: number of active-set (full step + projection) iterations tried
+                        // when the Newton step is not feasible, before the cold restart
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component

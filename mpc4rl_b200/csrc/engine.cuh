@@ -651,23 +651,61 @@ struct Engine {
     return FAST_HARD;
   }
 
+  // ---------------------------------------------------------------------------------------
+  // How a sweep READS the data of stage k (writes always go straight to the arrays).  The default
+  // reads in place.  The CUDA build also has a reader that prefetches whole stage records into a
+  // shared-memory ring with cp.async, two stages ahead of the recursion (rlmpc_b200.cu): the
+  // Riccati recursions are a dependent chain per sample, so when few samples are in flight (the
+  // queued full interior-point solves) global-memory latency, not bandwidth, is what they wait for.
+  // Interface: begin(k_first, dir, count) starts a sweep over `count` stages; ws(k) / rows(k) return
+  // stride-TILE views of the workspace record and of [lam(NR) t(NR) u(NU) x(NX)] of stage k, valid
+  // until done(k), which releases the stage and lets the reader fetch ahead.
+  // ---------------------------------------------------------------------------------------
+  static constexpr int RD_LAM = 0, RD_T = NR, RD_U = 2 * NR, RD_X = 2 * NR + NU, RD_ROWS = 2 * NR + NU + NX;
+  static constexpr int RD_WS = W_c;  // staged workspace elements [W_A, W_c)
+  struct DirectReader {
+    const Lane& L;
+    int N;
+    MPC_HD DirectReader(const Lane& L_, int N_) : L(L_), N(N_) {}
+    MPC_HD void begin(int, int, int) {}
+    MPC_HD const double* ws(int k) const { return L.ws + (size_t)k * W_REC * TILE; }
+    MPC_HD void rows(int k, double* lam, double* t, double* u, double* x) const {
+      ld<NR>(L.it + (size_t)it_lam(N, k) * TILE, TILE, lam);
+      ld<NR>(L.it + (size_t)it_t(N, k) * TILE, TILE, t);
+      if (k < N) {
+        ld<NU>(L.it + (size_t)it_u(N, k) * TILE, TILE, u);
+      } else {
+        MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
+      }
+      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * TILE, TILE, x);
+    }
+    MPC_HD void done(int) {}
+  };
+
   // Forward sweep of one interior-point iteration: dx, du from the feedback law, new slacks and
   // multipliers (lam_hat, t_hat) of every row, fraction-to-boundary statistics.
   MPC_HD static void forward_sweep(const ProblemData& pd, const Lane& L, double target, bool clip, StepStats& S) {
+    DirectReader rd(L, pd.N);
+    forward_sweep(pd, L, target, clip, S, rd);
+  }
+  template <class RD>
+  MPC_HD static void forward_sweep(const ProblemData& pd, const Lane& L, double target, bool clip, StepStats& S, RD& rd) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     double dw[NW];
     MPC_UNROLL for (int i = 0; i < NW; ++i) dw[i] = 0.0;
+    rd.begin(0, +1, N + 1);
     for (int k = 0; k <= N; ++k) {
       double* w = L.ws + (size_t)k * W_REC * bs;
+      const double* wr = rd.ws(k);
       double A[NX * NX], B[NX * NU], bb[NX];
       if (k < N) {
         double K[NU * NX];
-        ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
-        ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
-        ld<NX>(w + (size_t)W_b * bs, bs, bb);
-        ld<NU * NX>(w + (size_t)W_K * bs, bs, K);
-        ld<NU>(w + (size_t)W_k * bs, bs, dw + NX);
+        ld<NX * NX>(wr + (size_t)W_A * bs, bs, A);
+        ld<NX * NU>(wr + (size_t)W_B * bs, bs, B);
+        ld<NX>(wr + (size_t)W_b * bs, bs, bb);
+        ld<NU * NX>(wr + (size_t)W_K * bs, bs, K);
+        ld<NU>(wr + (size_t)W_k * bs, bs, dw + NX);
         MPC_UNROLL for (int i = 0; i < NU; ++i) MPC_UNROLL for (int l = 0; l < NX; ++l) dw[NX + i] += K[i * NX + l] * dw[l];
         st<NU>(w + (size_t)W_du * bs, bs, dw + NX);
       } else {
@@ -678,20 +716,14 @@ struct Engine {
         Bnd bd;
         double x[NX], u[NU], v[NV], lam[NR], t[NR], lh[NR], th[NR];
         stage_bounds(pd, k, bd);
-        if (k < N) {
-          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-        } else {
-          MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
-        }
-        if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+        rd.rows(k, lam, t, u, x);
         stage_vars(x, u, v);
-        ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
-        ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
         if (clip) clip_rows(bd, lam, t);
         rows_forward(bd, v, dw, lam, t, target, lh, th, S);
         st<NR>(w + (size_t)W_lh * bs, bs, lh);
         st<NR>(w + (size_t)W_th * bs, bs, th);
       }
+      rd.done(k);
       if (k < N) {
         double dxn[NX];
         MPC_UNROLL for (int i = 0; i < NX; ++i) {
@@ -765,16 +797,66 @@ struct Engine {
     return mu;
   }
 
-  // pending damped update (lam,t) += alpha ((lam_hat,t_hat) - (lam,t)) of the rows of stage k; returns them
-  MPC_HD static void rows_update(const Lane& L, int N, int k, double alpha, double* lam, double* t) {
+  // Active-set step of a warm start (primal-dual active-set idea, Hintermueller/Ito/Kunisch): the
+  // Newton step from the tau-central point of the previous QP is taken IN FULL, and the rows it
+  // drives through zero are flipped instead of cutting the step: a slack that collapses makes
+  // its row active (t <- eps, lam kept positive), a multiplier that turns negative releases its row
+  // (lam <- tau/t).  All other rows take their Newton values.  A handful of such steps identify the
+  // new active set when few rows change; the regular iteration then polishes to lam*t = tau.
+  // Returns sum(lam*t).
+  MPC_HD static double ipm_project(const ProblemData& pd, const Lane& L) {
+    const int N = pd.N;
     constexpr size_t bs = TILE;
-    const double* w = L.ws + (size_t)k * W_REC * bs;
-    ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
-    ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-    if (alpha > 0.0) {
-      double lh[NR], th[NR];
+    double mu = 0.0;
+    for (int k = 0; k <= N; ++k) {
+      if (k == N && NBX == 0) break;
+      const double* w = L.ws + (size_t)k * W_REC * bs;
+      Bnd bd;
+      double lam[NR], t[NR], lh[NR], th[NR];
+      stage_bounds(pd, k, bd);
+      ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
       ld<NR>(w + (size_t)W_lh * bs, bs, lh);
       ld<NR>(w + (size_t)W_th * bs, bs, th);
+      MPC_UNROLL for (int q = 0; q < NR; ++q) {
+        bool act;
+        double range;
+        if (q < 2 * NV) {
+          const int r = q < NV ? q : q - NV;
+          act = q < NV ? (bd.lb[r] > -BIG) : (bd.ub[r] < BIG);
+          range = row_range(bd, r);
+        } else {
+          act = q < R_US ? (bd.zl[q - R_LS] >= 0.0) : (bd.zu[q - R_US] >= 0.0);
+          range = row_range(bd, soft_row(q < R_US ? q - R_LS : q - R_US));
+        }
+        if (!act) continue;
+        const double eps_t = 1e-9 * range;
+        if (!(th[q] > eps_t)) {          // slack collapses: the row becomes (stays) active
+          t[q] = eps_t;
+          lam[q] = dmax(dmax(lh[q], lam[q]), 1e-3);
+        } else if (!(lh[q] > 0.0)) {     // multiplier changes sign: the row is released
+          t[q] = th[q];
+          lam[q] = pd.tau / th[q];
+        } else {
+          t[q] = th[q];
+          lam[q] = lh[q];
+        }
+        mu += lam[q] * t[q];
+      }
+      st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+      st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+    }
+    return mu;
+  }
+
+  // pending damped update (lam,t) += alpha ((lam_hat,t_hat) - (lam,t)) of the rows of stage k (lam, t
+  // in: current values; wr: read view of the stage record holding lam_hat, t_hat)
+  MPC_HD static void rows_update(const Lane& L, int N, int k, double alpha, const double* wr, double* lam, double* t) {
+    constexpr size_t bs = TILE;
+    if (alpha > 0.0) {
+      double lh[NR], th[NR];
+      ld<NR>(wr + (size_t)W_lh * bs, bs, lh);
+      ld<NR>(wr + (size_t)W_th * bs, bs, th);
       MPC_UNROLL for (int i = 0; i < NR; ++i) {
         lam[i] += alpha * (lh[i] - lam[i]);
         t[i] += alpha * (th[i] - t[i]);
@@ -785,6 +867,11 @@ struct Engine {
   }
 
   MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
+    DirectReader rd(L, pd.N);
+    return qp_ipm(pd, L, alpha_out, rd);
+  }
+  template <class RD>
+  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out, RD& rd) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     const bool qmode = pd.mode == MODE_Q;
@@ -796,11 +883,11 @@ struct Engine {
 
     double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
     double sigma = warm ? pd.sigma_min : pd.sigma0;
-    int iters = 0, warm_iters = 0;
+    int iters = 0, warm_iters = 0, as_iters = 0;
     bool converged = false, failed = false, minstep = false;
     for (int j = 0; j < pd.max_ipm && !converged; ++j) {
       ++iters;
-      if (warm && (warm_iters >= WARM_LIMIT || (warm_iters > 0 && alpha < 0.05))) {
+      if (warm && (warm_iters >= WARM_LIMIT + as_iters || (warm_iters > as_iters && alpha > 0.0 && alpha < 0.05))) {
         // the warm start is jammed (active set changed too much): restart from a cold point
         warm = false;
         mu = ipm_init(pd, L, false) / m_rows;
@@ -811,21 +898,23 @@ struct Engine {
       const double target = dmax(sigma * mu, pd.tau);
       // ---------------- backward sweep ----------------
       double P[NX * NX], p[NX];
+      rd.begin(N, -1, N + 1);
       {
         double Hm[NW * NW], g[NW];
+        const double* wr = rd.ws(N);
         load_W(2, pd.scale[N], L, Hm);
-        ld<NX>(L.ws + ((size_t)N * W_REC + W_q) * bs, bs, g);
+        ld<NX>(wr + (size_t)W_q * bs, bs, g);
         MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
         if (NBX > 0) {
           Bnd bd;
-        double x[NX], u0[NU], v[NV], lam[NR], t[NR];
+          double x[NX], u0[NU], v[NV], lam[NR], t[NR];
           stage_bounds(pd, N, bd);
-          ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, x);
-          MPC_UNROLL for (int i = 0; i < NU; ++i) u0[i] = 0.0;
+          rd.rows(N, lam, t, u0, x);
           stage_vars(x, u0, v);
-          rows_update(L, N, N, alpha, lam, t);
+          rows_update(L, N, N, alpha, wr, lam, t);
           barrier_add(bd, v, lam, t, target, Hm, g);
         }
+        rd.done(N);
         MPC_UNROLL for (int i = 0; i < NX; ++i) {
           p[i] = g[i];
           MPC_UNROLL for (int jj = 0; jj < NX; ++jj) P[i * NX + jj] = Hm[i * NW + jj];
@@ -833,23 +922,24 @@ struct Engine {
       }
       for (int k = N - 1; k >= 0; --k) {
         double* w = L.ws + (size_t)k * W_REC * bs;
+        const double* wr = rd.ws(k);
         double A[NX * NX], B[NX * NU], bb[NX], g[NW], K[NU * NX], kff[NU];
-        ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
-        ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
-        ld<NX>(w + (size_t)W_b * bs, bs, bb);
-        ld<NW>(w + (size_t)W_q * bs, bs, g);
+        ld<NX * NX>(wr + (size_t)W_A * bs, bs, A);
+        ld<NX * NU>(wr + (size_t)W_B * bs, bs, B);
+        ld<NX>(wr + (size_t)W_b * bs, bs, bb);
+        ld<NW>(wr + (size_t)W_q * bs, bs, g);
         double Hm[NW * NW];
         load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
         {
           Bnd bd;
-        double x[NX], u[NU], v[NV], lam[NR], t[NR];
+          double x[NX], u[NU], v[NV], lam[NR], t[NR];
           stage_bounds(pd, k, bd);
-          ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-          if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+          rd.rows(k, lam, t, u, x);
           stage_vars(x, u, v);
-          rows_update(L, N, k, alpha, lam, t);
+          rows_update(L, N, k, alpha, wr, lam, t);
           barrier_add(bd, v, lam, t, target, Hm, g);
         }
+        rd.done(k);
         const bool ufixed = (k == 0 && qmode);
         if (!ufixed) {
           if (!riccati_step(P, p, A, B, bb, Hm, g, K, kff, nullptr)) failed = true;
@@ -863,11 +953,19 @@ struct Engine {
       }
       // ---------------- forward sweep ----------------
       StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
-      forward_sweep(pd, L, target, /*clip=*/false, S);
+      forward_sweep(pd, L, target, /*clip=*/false, S, rd);
       if (failed || !(S.amax == S.amax)) break;
+      if (warm && S.amax < 1.0 / 0.995 && as_iters < (int)pd.as_steps) {
+        // infeasible Newton step of a warm start: full step + projection instead of a short step
+        ++as_iters;
+        mu = ipm_project(pd, L) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma_min;
+        continue;
+      }
       alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
-      if (alpha < 1e-9) {  // the iteration has collapsed onto the boundary (HPIPM: MIN_STEP), e.g. infeasible QP
-        minstep = true;
+      if (!warm && alpha < 1e-9) {  // a cold-started iteration has collapsed onto the boundary (HPIPM: MIN_STEP),
+        minstep = true;             // e.g. infeasible QP.  (A jammed WARM start restarts cold instead, above.)
         break;
       }
       const double mu_new = (S.s0 + alpha * S.s1 + alpha * alpha * S.s2) / m_rows;
@@ -979,8 +1077,13 @@ struct Engine {
                        // iterate left untouched, acados would return ACADOS_QP_FAILURE (4)
   };
   MPC_HD static int qp_full(const ProblemData& pd, const Lane& L, int* ipm_iters) {
+    DirectReader rd(L, pd.N);
+    return qp_full(pd, L, ipm_iters, rd);
+  }
+  template <class RD>
+  MPC_HD static int qp_full(const ProblemData& pd, const Lane& L, int* ipm_iters, RD& rd) {
     double alpha = 0.0;
-    const int r = qp_ipm(pd, L, &alpha);
+    const int r = qp_ipm(pd, L, &alpha, rd);
     if (ipm_iters) *ipm_iters += (r > 0) ? r : ((r >= -2) ? 0 : -(r + 1000));
     if (r == -1 || r == -2) return FULL_FAILED;
     apply_step(pd, L, alpha, /*clip=*/false, /*damp_primal=*/r < 0);

@@ -144,29 +144,147 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
   }
 }
 
-// sample kernel over the queue: full interior-point solve on a compact (coalesced) copy of the
-// sample's stage data and iterate; only the iterate is copied back.
+// Reader of the queued (latency-bound) interior-point solves: every lane copies the records of the
+// next RING_DEPTH stages of its own sample into a shared-memory ring with cp.async (LDGSTS, no
+// registers held across the copy) while the recursion works on the current stage.  ncu on the
+// direct-load version: 73 % of the warp stalls were long-scoreboard (profiles/r01_summary.md).
+// A lane only ever reads what it copied itself, so no barrier is needed, just wait_group.
+constexpr int RING_DEPTH = 3;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <class E>
+struct RingReader {
+  static constexpr int SLOT = E::RD_WS + E::RD_ROWS;  // doubles per stage and lane
+  const Lane& L;
+  int N;
+  double* ring;  // this lane's column: element e of slot s at ring[(s * SLOT + e) * TILE]
+  int k0, dir, count, consumed;
+  __device__ RingReader(const Lane& L_, int N_, double* ring_) : L(L_), N(N_), ring(ring_), k0(0), dir(1), count(0), consumed(0) {}
+  __device__ __forceinline__ void issue(int i) {
+    if (i < count) {
+      const int k = k0 + i * dir;
+      double* dst = ring + (size_t)((i % RING_DEPTH) * SLOT) * TILE;
+      const double* src = L.ws + (size_t)k * E::W_REC * TILE;
+#pragma unroll
+      for (int e = 0; e < E::RD_WS; ++e) cp_async8(dst + (size_t)e * TILE, src + (size_t)e * TILE);
+      double* dr = dst + (size_t)E::RD_WS * TILE;
+      const double* sl = L.it + (size_t)E::it_lam(N, k) * TILE;
+      const double* stt = L.it + (size_t)E::it_t(N, k) * TILE;
+#pragma unroll
+      for (int e = 0; e < E::NR; ++e) {
+        cp_async8(dr + (size_t)(E::RD_LAM + e) * TILE, sl + (size_t)e * TILE);
+        cp_async8(dr + (size_t)(E::RD_T + e) * TILE, stt + (size_t)e * TILE);
+      }
+      if (k < N) {
+        const double* su = L.it + (size_t)E::it_u(N, k) * TILE;
+#pragma unroll
+        for (int e = 0; e < E::NU; ++e) cp_async8(dr + (size_t)(E::RD_U + e) * TILE, su + (size_t)e * TILE);
+      }
+      if (E::NBX > 0) {
+        const double* sx = L.it + (size_t)E::it_x(N, k) * TILE;
+#pragma unroll
+        for (int e = 0; e < E::NX; ++e) cp_async8(dr + (size_t)(E::RD_X + e) * TILE, sx + (size_t)e * TILE);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per call, empty or not
+  }
+  __device__ __forceinline__ void begin(int k_first, int dir_, int count_) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // the previous sweep's stores (K, k, lam, t, lam_hat, t_hat) are re-read through the async copies
+    __threadfence();
+    k0 = k_first; dir = dir_; count = count_; consumed = 0;
+#pragma unroll
+    for (int i = 0; i < RING_DEPTH; ++i) issue(i);
+  }
+  __device__ __forceinline__ const double* ws(int) const {
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING_DEPTH - 1) : "memory");
+    return ring + (size_t)((consumed % RING_DEPTH) * SLOT) * TILE;
+  }
+  __device__ __forceinline__ void rows(int k, double* lam, double* t, double* u, double* x) const {
+    const double* r = ws(k) + (size_t)E::RD_WS * TILE;
+    E::template ld<E::NR>(r + (size_t)E::RD_LAM * TILE, TILE, lam);
+    E::template ld<E::NR>(r + (size_t)E::RD_T * TILE, TILE, t);
+    if (k < N) {
+      E::template ld<E::NU>(r + (size_t)E::RD_U * TILE, TILE, u);
+    } else {
+#pragma unroll
+      for (int i = 0; i < E::NU; ++i) u[i] = 0.0;
+    }
+    if (E::NBX > 0) E::template ld<E::NX>(r + (size_t)E::RD_X * TILE, TILE, x);
+  }
+  __device__ __forceinline__ void done(int) {
+    issue(consumed + RING_DEPTH);
+    ++consumed;
+  }
+};
+
+// Queue <-> compact copies.  The queued samples are scattered over the batch; these two kernels
+// move their iterate and the linearisation part of their workspace into / out of contiguous tiles
+// so that the long interior-point solve streams coalesced data.  One warp per (queue tile, chunk of
+// GATHER_CHUNK elements): reads are one sector per lane (scattered), writes are coalesced.
+constexpr int GATHER_CHUNK = 64;
+
+template <class M>
+__global__ void k_gather(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int j = blockIdx.x * TILE + (threadIdx.x & 31);
+  if (blockIdx.x * TILE >= a.counters[0]) return;
+  const bool live = j < a.counters[0];
+  const int b = live ? a.hard[j] : 0;
+  const int nit = E::it_size(pd.N), nws = (pd.N + 1) * E::W_K;  // iterate, then [W_A, W_K) of every stage
+  const int chunk = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int e0 = chunk * GATHER_CHUNK;
+  if (!live || e0 >= nit + nws) return;
+  const double* si = a.it + tile_off(b, a.it_size);
+  const double* sw = a.ws + tile_off(b, a.ws_size);
+  double* di = a.it2 + tile_off(j, a.it_size);
+  double* dw = a.ws2 + tile_off(j, a.ws_size);
+#pragma unroll 8
+  for (int e = e0; e < e0 + GATHER_CHUNK && e < nit + nws; ++e) {
+    if (e < nit) {
+      di[(size_t)e * TILE] = si[(size_t)e * TILE];
+    } else {
+      const int q = e - nit, k = q / E::W_K, i = q - k * E::W_K;
+      const size_t o = ((size_t)k * E::W_REC + i) * TILE;
+      dw[o] = sw[o];
+    }
+  }
+}
+
+template <class M>
+__global__ void k_scatter(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  const int j = blockIdx.x * TILE + (threadIdx.x & 31);
+  if (j >= a.counters[0]) return;
+  const int b = a.hard[j];
+  const int nit = E::it_size(pd.N);
+  const int chunk = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int e0 = chunk * GATHER_CHUNK;
+  const double* si = a.it2 + tile_off(j, a.it_size);
+  double* di = a.it + tile_off(b, a.it_size);
+#pragma unroll 8
+  for (int e = e0; e < e0 + GATHER_CHUNK && e < nit; ++e) di[(size_t)e * TILE] = si[(size_t)e * TILE];
+}
+
+// sample kernel over the queue: full interior-point solve on the compact copies.
 template <class M>
 __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.counters[0]) return;
   const int b = a.hard[j];
-  const Lane Ls = make_lane<M>(a, b);
-  Lane L = Ls;
+  Lane L = make_lane<M>(a, b);  // theta / cost table of the sample; iterate and workspace: the compact copies
   L.it = a.it2 + tile_off(j, a.it_size);
   L.ws = a.ws2 + tile_off(j, a.ws_size);
-  const int N = pd.N, nit = E::it_size(N);
-#pragma unroll 8
-  for (int i = 0; i < nit; ++i) L.it[(size_t)i * TILE] = Ls.it[(size_t)i * TILE];
-  for (int k = 0; k <= N; ++k) {
-    const size_t o = (size_t)k * E::W_REC;
-#pragma unroll
-    for (int i = E::W_A; i < E::W_K; ++i) L.ws[(o + i) * TILE] = Ls.ws[(o + i) * TILE];
-  }
-  const int st = E::qp_full(pd, L, nullptr);
-#pragma unroll 8
-  for (int i = 0; i < nit; ++i) Ls.it[(size_t)i * TILE] = L.it[(size_t)i * TILE];
+  const int N = pd.N;
+  extern __shared__ double ring_smem[];
+  RingReader<E> rd(L, N, ring_smem + threadIdx.x);
+  const int st = E::qp_full(pd, L, nullptr, rd);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
     // RTI: done after one QP.  SQP: an indefinite reduced Hessian ends the solve; an interior-point
     // iteration limit does not (the next linearisation may well be solvable)
@@ -380,6 +498,11 @@ KArgs base_args(rlmpc_handle* h, int B) {
   return a;
 }
 
+template <class M>
+constexpr size_t qp2_smem() {
+  return sizeof(double) * RING_DEPTH * RingReader<Engine<M>>::SLOT * TILE;
+}
+
 // SQP: K rounds of (linearise | convergence test + fast QP | full interior point on the queue),
 // then one test-only round.  RTI (K = 1) is a single round without the final test.
 template <class M>
@@ -407,9 +530,17 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         CUDA_OK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         sq = h->side_stream;
       }
-      k_qp2<M><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, a);
+      {
+        using E = Engine<M>;
+        const int wpb = 8;  // warps per block of the copy kernels
+        const int n_g = (E::it_size(N) + (N + 1) * E::W_K + GATHER_CHUNK - 1) / GATHER_CHUNK;
+        const int n_s = (E::it_size(N) + GATHER_CHUNK - 1) / GATHER_CHUNK;
+        k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
+        k_qp2<M><<<(B + 31) / 32, 32, qp2_smem<M>(), sq>>>(h->pd, a);
+        k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
+      }
       mark(h, 3, sq);
-      h->launches++;
+      h->launches += 3;
       if (fork_qp2) CUDA_OK(cudaEventRecord(h->ev_join, sq));
     }
     if (K > 1 && !a.last_round && (r % h->sync_every) == h->sync_every - 1) {
@@ -572,11 +703,23 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     h->nx = E::NX; h->nu = E::NU; h->nth = M::NTH; h->npm = E::NPM; h->nr = E::NR;
     h->it_size = E::it_size(d->N); h->ws_size = E::ws_size(d->N); h->ct_size = E::CT_SIZE;
   });
+  {
+    cudaError_t ea = cudaSetDevice(device);
+    DISPATCH_MODEL(h, {
+      if (ea == cudaSuccess)
+        ea = cudaFuncSetAttribute(k_qp2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp2_smem<M>());
+    });
+    if (ea != cudaSuccess) {
+      const std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ea);
+      delete h;
+      return fail(RLMPC_ECUDA, msg);
+    }
+  }
   ProblemData& pd = h->pd;
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -715,6 +858,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "mu0")) h->pd.mu0 = value;
   else if (!strcmp(name, "sigma_min")) h->pd.sigma_min = value;
   else if (!strcmp(name, "sigma0")) h->pd.sigma0 = value;
+  else if (!strcmp(name, "as_steps")) h->pd.as_steps = value;
   else if (!strcmp(name, "max_ipm")) h->pd.max_ipm = (int)value;
   else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
   else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;

@@ -59,7 +59,7 @@ def test_state_bounds_v_and_q_match_golden(g_bx):
     # 20-35 active rows per solution (mostly the saturated input); sample 7 rides the cart-position bound
     X = np.stack([m.get("x", k, B).cpu().numpy() for k in range(31)], axis=1)
     assert np.abs(X - g_bx["X"])[ok].max() < 1e-6
-    assert ok[7] and abs(np.abs(X[7, :, 0]).max() - 2.4) < 1e-6
+    assert ok[7] and abs(np.abs(X[7, :, 0]).max() - 2.4) < 1e-4  # tau-central: slack tau/lam below the bound
     # Q-mode
     a = _dev(g_bx["a"])
     m.reset(x0)

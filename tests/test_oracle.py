@@ -155,7 +155,7 @@ def test_host_port_with_state_bounds_matches_oracle_fixtures():
     assert np.abs(o["dL"] - g["dV"][:, :3])[ok].max() < 1e-8 * np.abs(g["dV"]).max()
     assert np.abs(o["dpi"] - g["dpi"][:, :, :3])[ok].max() < 1e-6 * np.abs(g["dpi"]).max()
     assert min((g["lam"][i] > 1e-6).sum() for i in range(len(ok))) >= 15  # many active rows
-    assert abs(np.abs(g["X"][7, :, 0]).max() - 2.4) < 1e-6  # sample 7 rides the cart-position bound
+    assert abs(np.abs(g["X"][7, :, 0]).max() - 2.4) < 1e-4  # sample 7 rides the cart-position bound
 
 
 def test_linear_system_oracle_lqr_and_host_port():

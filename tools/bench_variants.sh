@@ -1,4 +1,4 @@
-# Tuning helper: time bench.py against the default library and every mpc4rl_b200/variants_*.so, plus option sweeps.
+# Tuning helper: time bench.py with option sweeps and against every mpc4rl_b200/variants_*.so.
 run() {
   python bench.py --steps 5 --warmup 3 --no-cpu "$@" 2>&1 | python -c "
 import sys, json
@@ -10,8 +10,9 @@ for l in sys.stdin:
 "
 }
 echo "== default"; run
-for o in overlap=0 max_ipm=30 max_ipm=22 "max_ipm=22 --opt overlap=0"; do echo "== opt $o"; run --opt $o; done
+for o in "$@"; do echo "== opt $o"; run --opt $o; done
 for so in mpc4rl_b200/variants_*.so; do
+  [ -e "$so" ] || continue
   echo "== $so"
   RLMPC_B200_LIB=$PWD/$so run
 done
