@@ -954,6 +954,15 @@ struct Engine {
       // ---------------- forward sweep ----------------
       StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
       forward_sweep(pd, L, target, /*clip=*/false, S, rd);
+      if ((failed || !(S.amax == S.amax)) && warm) {
+        // a warm start (or its active-set steps) went wrong numerically: not an error, start over cold
+        warm = false;
+        failed = false;
+        mu = ipm_init(pd, L, false) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma0;
+        continue;
+      }
       if (failed || !(S.amax == S.amax)) break;
       if (warm && S.amax < 1.0 / 0.995 && as_iters < (int)pd.as_steps) {
         // infeasible Newton step of a warm start: full step + projection instead of a short step

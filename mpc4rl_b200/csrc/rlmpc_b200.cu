@@ -271,7 +271,7 @@ __global__ void k_scatter(const __grid_constant__ ProblemData pd, const KArgs a)
 }
 
 // sample kernel over the queue: full interior-point solve on the compact copies.
-template <class M>
+template <class M, bool RING>
 __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,10 +281,15 @@ __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData 
   L.it = a.it2 + tile_off(j, a.it_size);
   L.ws = a.ws2 + tile_off(j, a.ws_size);
   const int N = pd.N;
-  extern __shared__ double ring_smem[];
-  RingReader<E> rd(L, N, ring_smem + threadIdx.x);
-  const int st = E::qp_full(pd, L, nullptr, rd);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  int st;
+  if (RING) {
+    extern __shared__ double ring_smem[];
+    RingReader<E> rd(L, N, ring_smem + threadIdx.x);
+    st = E::qp_full(pd, L, nullptr, rd);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    st = E::qp_full(pd, L, nullptr);
+  }
   if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
     // RTI: done after one QP.  SQP: an indefinite reduced Hessian ends the solve; an interior-point
     // iteration limit does not (the next linearisation may well be solvable)
@@ -444,6 +449,7 @@ struct rlmpc_handle {
   double *it = nullptr, *ws = nullptr, *it2 = nullptr, *ws2 = nullptr, *th = nullptr, *ct = nullptr, *th_stage = nullptr;
   double* cost = nullptr;
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
+  int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
   int overlap = 0;  // 1: RTI + sens runs the full interior-point pass of the queued samples on a side stream,
                     // concurrently with the sensitivity kernels of all other samples.  Measured slower
                     // (the few latency-bound warps of the queue lose issue slots to the bulk kernels).
@@ -536,7 +542,10 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         const int n_g = (E::it_size(N) + (N + 1) * E::W_K + GATHER_CHUNK - 1) / GATHER_CHUNK;
         const int n_s = (E::it_size(N) + GATHER_CHUNK - 1) / GATHER_CHUNK;
         k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
-        k_qp2<M><<<(B + 31) / 32, 32, qp2_smem<M>(), sq>>>(h->pd, a);
+        if (h->ring)
+          k_qp2<M, true><<<(B + 31) / 32, 32, qp2_smem<M>(), sq>>>(h->pd, a);
+        else
+          k_qp2<M, false><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, a);
         k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
       }
       mark(h, 3, sq);
@@ -707,7 +716,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     cudaError_t ea = cudaSetDevice(device);
     DISPATCH_MODEL(h, {
       if (ea == cudaSuccess)
-        ea = cudaFuncSetAttribute(k_qp2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp2_smem<M>());
+        ea = cudaFuncSetAttribute(k_qp2<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp2_smem<M>());
     });
     if (ea != cudaSuccess) {
       const std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ea);
@@ -865,6 +874,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "sync_every")) h->sync_every = value < 1 ? 1 : (int)value;
   else if (!strcmp(name, "timing")) h->timing = (int)value;
   else if (!strcmp(name, "overlap")) h->overlap = (int)value;
+  else if (!strcmp(name, "ring")) h->ring = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }
