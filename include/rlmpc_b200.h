@@ -98,6 +98,9 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value);
 /* Replaces ocp_solver.reset() + set(stage,"x",x0) for all stages (mpc.py:204-210):
  * x_k = x0, u = 0, multipliers = 0 for samples [0,B). */
 int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream);
+/* Same for the samples with mask_dev[b] != 0 only (environments that were reset inside a vectorised
+ * closed loop); mask_dev NULL = all. */
+int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* mask_dev, void* stream);
 /* Replaces ocp_solver.get/set(stage, field). field in {"x","u","pi","lam","t"}; buf_dev is
  * [B, dim(field)] row-major; lam/t are in acados order [lbu, ubu] for this problem class. */
 int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, double* buf_dev, void* stream);
@@ -136,6 +139,14 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
  * caller all-reduces acc over ranks (NCCL) and divides. */
 int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const double* dQ_dtheta_dev,
                   const int* status_dev, double* acc_out_dev, void* stream);
+
+/* ---- vectorised environment (closed-loop training without host round trips) ------------------- */
+/* Replaces ContinuousCartPoleSwingUpVectorEnv.step (rlmpc/gym/continuous_cartpole/environment.py:372-426)
+ * for B environments on the current device.  par_dev[13] = [gravity, masscart, masspole, length,
+ * force_mag, tau, x_threshold, theta_threshold, max_episode_steps, reset_state(4)]; state_dev [B,4]
+ * in/out, action_dev [B] in [-1,1], steps_dev [B] in/out; finished environments are reset in place. */
+int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, const double* action_dev,
+                            double* reward_dev, int* terminated_dev, int* truncated_dev, int* steps_dev, void* stream);
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);

@@ -19,9 +19,10 @@ LIB_PATH = os.environ.get("RLMPC_B200_LIB", os.path.join(_PKG, "librlmpc_b200.so
 # every symbol include/rlmpc_b200.h declares
 SYMBOLS = [
     "rlmpc_create", "rlmpc_destroy", "rlmpc_last_error", "rlmpc_dims", "rlmpc_nrows", "rlmpc_set_theta",
-    "rlmpc_set_cost_scaling", "rlmpc_set_bounds", "rlmpc_set_option", "rlmpc_reset", "rlmpc_get_iterate",
+    "rlmpc_set_cost_scaling", "rlmpc_set_bounds", "rlmpc_set_option", "rlmpc_reset", "rlmpc_reset_masked",
+    "rlmpc_get_iterate",
     "rlmpc_put_iterate", "rlmpc_solve", "rlmpc_sens", "rlmpc_solve_sens", "rlmpc_solve_sens_host",
-    "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings",
+    "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings", "rlmpc_cartpole_env_step",
 ]
 
 
@@ -63,6 +64,7 @@ def load():
     lib.rlmpc_set_bounds.argtypes = [H, cp, vp, C.c_int]
     lib.rlmpc_set_option.argtypes = [H, cp, C.c_double]
     lib.rlmpc_reset.argtypes = [H, C.c_int, vp, vp]
+    lib.rlmpc_reset_masked.argtypes = [H, C.c_int, vp, vp, vp]
     lib.rlmpc_get_iterate.argtypes = [H, cp, C.c_int, C.c_int, vp, vp]
     lib.rlmpc_put_iterate.argtypes = [H, cp, C.c_int, C.c_int, vp, vp]
     lib.rlmpc_solve.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
@@ -71,6 +73,7 @@ def load():
     lib.rlmpc_solve_sens_host.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.rlmpc_td_grad.argtypes = [H, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     lib.rlmpc_get_timings.argtypes = [H, vp, C.c_int]
+    lib.rlmpc_cartpole_env_step.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.rlmpc_launch_count.argtypes = [H]; lib.rlmpc_launch_count.restype = C.c_longlong
     for name in SYMBOLS:
         f = getattr(lib, name)

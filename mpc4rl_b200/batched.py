@@ -104,11 +104,16 @@ class BatchedMPC:
         _cabi.check(self.lib.rlmpc_set_bounds(self._h, field.encode(), a.ctypes.data_as(C.c_void_p), len(a)))
 
     # ---- iterate ----
-    def reset(self, x0: Optional[torch.Tensor] = None, B: Optional[int] = None) -> None:
+    def reset(self, x0: Optional[torch.Tensor] = None, B: Optional[int] = None, mask: Optional[torch.Tensor] = None) -> None:
+        """MPC.reset for the batch (mpc.py:204-210); ``mask`` [B] restricts it to some samples."""
         if x0 is not None:
             x0 = self._chk_in(x0, self.nx, "x0")
             B = x0.shape[0]
-        _cabi.check(self.lib.rlmpc_reset(self._h, int(B), _ptr(x0), self._stream()))
+        if mask is None:
+            _cabi.check(self.lib.rlmpc_reset(self._h, int(B), _ptr(x0), self._stream()))
+        else:
+            m = mask.to(self.device, torch.int32).contiguous()
+            _cabi.check(self.lib.rlmpc_reset_masked(self._h, int(B), _ptr(x0), _ptr(m), self._stream()))
 
     def get(self, field: str, stage: int, B: int) -> torch.Tensor:
         dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": self.nrows, "t": self.nrows,

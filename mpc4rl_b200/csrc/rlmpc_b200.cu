@@ -379,12 +379,56 @@ __global__ void k_cost_table(const __grid_constant__ ProblemData pd, const doubl
   M::cost_table(th + tile_off(b, M::NTH), TILE, ct + tile_off(b, E::CT_SIZE), TILE, pd.mc);
 }
 
-// MPC.reset: x_k = x0 for all stages, everything else zero
-template <class M>
-__global__ void k_reset(int N, double* it, int B, const double* x0) {
-  using E = Engine<M>;
+// Vectorised continuous cart-pole swing-up environment, one thread per environment
+// (rlmpc/gym/continuous_cartpole/environment.py:372-426: explicit Euler, tau = 0.02; note the env uses
+// polemass_length = m*l in `temp` where the MPC model uses m, quirk Q9).
+// par: [gravity, masscart, masspole, length, force_mag, tau, x_threshold, theta_threshold,
+//       max_episode_steps, reset_state(4)]
+__global__ void k_cartpole_env_step(const double* __restrict__ par, int B, double* state, const double* action,
+                                    double* reward, int* terminated, int* truncated, int* steps) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const double g = par[0], mc = par[1], mp = par[2], len = par[3], fmag = par[4], tau = par[5];
+  const double xth = par[6], thth = par[7];
+  const int max_steps = (int)par[8];
+  double x = state[4 * b], xd = state[4 * b + 1], th = state[4 * b + 2], thd = state[4 * b + 3];
+  const double a = action[b];
+  const double force = a * fmag, total = mp + mc, pml = mp * len;
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  const double temp = (force + pml * thd * thd * sn) / total;
+  const double thacc = (g * sn - cs * temp) / (len * (4.0 / 3.0 - mp * cs * cs / total));
+  const double xacc = temp - pml * thacc * cs / total;
+  x += tau * xd;
+  xd += tau * xacc;
+  th += tau * thd;
+  thd += tau * thacc;
+  const int term = (x < -xth) || (x > xth) || (th < -thth) || (th > thth);
+  const int st = steps[b] + 1;
+  const int trunc = st >= max_steps;
+  // reward of the state reached (environment.py:448-456), angle wrapped to [-pi, pi)
+  const double pi = 3.14159265358979323846;
+  double an = fmod(th + pi, 2.0 * pi);
+  if (an < 0.0) an += 2.0 * pi;
+  an -= pi;
+  reward[b] = 2.0 * x * x + 0.01 * xd * xd + 2.0 * an * an + 0.01 * thd * thd + 0.001 * a * a;
+  terminated[b] = term;
+  truncated[b] = trunc;
+  if (term || trunc) {  // auto-reset (environment.py:416-419) to the reset state
+    x = par[9]; xd = par[10]; th = par[11]; thd = par[12];
+    steps[b] = 0;
+  } else {
+    steps[b] = st;
+  }
+  state[4 * b] = x; state[4 * b + 1] = xd; state[4 * b + 2] = th; state[4 * b + 3] = thd;
+}
+
+// MPC.reset: x_k = x0 for all stages, everything else zero
+template <class M>
+__global__ void k_reset(int N, double* it, int B, const double* x0, const int* mask) {
+  using E = Engine<M>;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || (mask && !mask[b])) return;
   const int n = E::it_size(N);
   double* p = it + tile_off(b, n);
   for (int i = 0; i < n; ++i) {
@@ -880,10 +924,14 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
 }
 
 int rlmpc_reset(rlmpc_handle* h, int B, const double* x0_dev, void* stream) {
+  return rlmpc_reset_masked(h, B, x0_dev, nullptr, stream);
+}
+
+int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* mask_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
-  DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, B, x0_dev)));
+  DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, B, x0_dev, mask_dev)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -984,6 +1032,17 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
   if (grid > 148 * 4) grid = 148 * 4;
   k_td_grad<<<grid, threads, sizeof(double) * (ncols + 2), s>>>(B, ncols, td_dev, dQ_dtheta_dev, status_dev, acc_out_dev);
   h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, const double* action_dev,
+                            double* reward_dev, int* terminated_dev, int* truncated_dev, int* steps_dev, void* stream) {
+  if (!par_dev || !state_dev || !action_dev || !reward_dev || !terminated_dev || !truncated_dev || !steps_dev || B < 0)
+    return fail(RLMPC_EINVAL, "bad arguments");
+  if (B == 0) return 0;
+  k_cartpole_env_step<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(par_dev, B, state_dev, action_dev, reward_dev,
+                                                                       terminated_dev, truncated_dev, steps_dev);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

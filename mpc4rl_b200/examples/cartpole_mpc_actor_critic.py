@@ -1,0 +1,91 @@
+"""Closed-loop MPC actor + MPC critic on vectorised cart-pole environments, all on the GPU
+(BASELINE.json configs[4]).
+
+Every environment step, for all environments at once:
+  actor   a_t = pi_theta(s_t): one SQP-RTI step of the MPC from the environment's own warm start
+          (the reference evaluates ``mpc.get_action`` per observation, rlmpc/td3/policies.py:197);
+          the same call returns V_theta(s_t)
+  env     (s_{t+1}, cost_t) = step(s_t, a_t)                      (rlmpc_cartpole_env_step)
+  critic  Q_theta(s_{t-1}, a_{t-1}) and dQ/dtheta: MPC with the first input clamped (mpc.py:52-96)
+  TD      td = cost_{t-1} + gamma V(s_t) - Q(s_{t-1}, a_{t-1});   theta += lr * mean(td * dQ/dtheta)
+          (examples/linear_system_mpc_qlearning.py:192-205); the sum over environments is reduced on the
+          device and, with several ranks, all-reduced (one small vector per step).
+Run on N GPUs with ``python -m torch.distributed.run --nproc-per-node N -m mpc4rl_b200.examples.cartpole_mpc_actor_critic``.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from ..batched import BatchedMPC
+from ..gym.continuous_cartpole import ContinuousCartPoleSwingUpVectorEnv
+from ..parallel import allreduce_accumulator, td_parameter_step
+from ..problems import cartpole_original_config, cartpole_spec
+
+
+def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float = 1e-6, device: int = 0,
+        explore: float = 0.05, seed: int = 0, critic_sqp: int = 10, verbose: bool = True):
+    spec = cartpole_spec(cartpole_original_config())
+    dev = torch.device("cuda", device)
+    actor = BatchedMPC(spec, max_batch=num_envs, device=device)    # owns one warm start per environment
+    critic = BatchedMPC(spec, max_batch=num_envs, device=device)
+    env = ContinuousCartPoleSwingUpVectorEnv(num_envs=num_envs, force_mag=float(spec.ubu[0]), device=device)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1000 * int(os.environ.get("RANK", "0")))
+    theta = torch.tensor(spec.p_nominal, dtype=torch.float64)
+    lo, hi = float(spec.lbu[0]), float(spec.ubu[0])
+
+    s, _ = env.reset()
+    actor.reset(s)
+    actor.solve(s, max_sqp=30)  # converge the warm starts once
+    prev = None
+    log = []
+    for t in range(n_steps):
+        out = actor.solve_sens(s, max_sqp=1)  # RTI: pi(s_t), V(s_t)
+        v_t, u_t = out["cost"], out["u0"]
+        if prev is not None:
+            q = critic.solve_sens(prev["s"], prev["u"], max_sqp=critic_sqp)
+            td = prev["cost"] + gamma * v_t * (~prev["term"]).double() - q["cost"]
+            valid = ((q["status"] == 0) & (out["status"] == 0) & ~prev["trunc"]).logical_not().to(torch.int32)
+            acc = critic.td_grad(td, q["dL"], valid)
+            allreduce_accumulator(acc)
+            n_valid = int(acc[-1].item())
+            new = td_parameter_step(theta[: critic.ngrad].to(dev), acc, lr)
+            theta[: critic.ngrad] = new.cpu()
+            actor.set_theta(theta.numpy())
+            critic.set_theta(theta.numpy())
+            log.append(dict(step=t, mean_td=float(acc[-2].item() / max(n_valid, 1)), n_valid=n_valid,
+                            mean_cost=float(prev["cost"].mean().item()), theta=theta[: critic.ngrad].numpy().copy()))
+            if verbose and int(os.environ.get("RANK", "0")) == 0:
+                print(f"step {t}: mean cost {log[-1]['mean_cost']:.3f} mean TD {log[-1]['mean_td']:.3f} "
+                      f"valid {n_valid} theta {log[-1]['theta']}")
+        a = 2.0 * (u_t - lo) / (hi - lo) - 1.0
+        a = (a + explore * torch.randn(a.shape, generator=g, dtype=torch.float64).to(dev)).clamp(-1.0, 1.0)
+        u_applied = 0.5 * (hi - lo) * (a + 1.0) + lo
+        s_next, cost, term, trunc, _ = env.step(a)
+        prev = dict(s=s, u=u_applied, cost=cost, term=term, trunc=trunc)
+        done = term | trunc
+        if bool(done.any()):
+            actor.reset(s_next, mask=done)  # like MPC.reset(obs) at the start of an episode
+        s = s_next
+    return log
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    run(num_envs=4096 // world, device=local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
