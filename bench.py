@@ -47,12 +47,52 @@ def synth_states(B, seed):
     return lo + (-2.0 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)
 
 
-def config_dict(B, n_gpus):
-    return {"workload": "cartpole_original N=40 nx=4 nu=1 ntheta=83 (3 with gradient), V-mode SQP-RTI (K=1) + "
-                        "dL/dtheta + dpi/dtheta, warm-started from the converged iterate, states perturbed every step",
+WORKLOADS = {
+    # BASELINE.json configs[1] -- the headline
+    "cartpole": dict(batch=65536, b_alg=8492, metric=METRIC,
+                     text="cartpole_original N=40 nx=4 nu=1 ntheta=83 (3 with gradient), V-mode SQP-RTI (K=1) + "
+                          "dL/dtheta + dpi/dtheta, warm-started from the converged iterate, states perturbed every step"),
+    # BASELINE.json configs[3] (secondary line, `--workload evaporation`): N=100, nu=3 (third input = slack), affine h rows
+    "evaporation": dict(batch=32768, b_alg=45228, metric="MPC solves+sensitivities/sec (evaporation N=100, batch 32k)",
+                        text="evaporation_process N=100 nx=2 nu=3 ntheta=60 (tracking-cost parameters), V-mode SQP-RTI "
+                             "(K=1) + dL/dtheta + dpi/dtheta, warm-started from the converged iterate, states perturbed every step"),
+}
+
+
+def config_dict(B, n_gpus, workload="cartpole"):
+    return {"workload": WORKLOADS[workload]["text"],
             "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, replicated theta)",
-            "l2": "working set (iterate 0.29 GB + stage scratch 1.5 GB per GPU) is larger than L2, no flush needed",
+            "l2": "working set (iterate + stage scratch, > 1.5 GB per GPU) is larger than L2, no flush needed",
             "seed": 1234}
+
+
+def make_workload(name, B, rank, dev):
+    """(spec, x0 [B,nx] on dev, perturbation scale, function that installs the initial guess)"""
+    import torch
+
+    if name == "cartpole":
+        from mpc4rl_b200 import cartpole_original_config, cartpole_spec
+
+        spec = cartpole_spec(cartpole_original_config())
+        x0 = synth_states(B, 1234 + rank).to(dev)
+        return spec, x0, 1e-3, lambda mpc: mpc.reset(x0)
+    from mpc4rl_b200 import evaporation_spec
+
+    spec = evaporation_spec(gamma=0.99)
+    g = torch.Generator(device="cpu").manual_seed(7 + rank)  # SURVEY.md 8(d) config 4: X_2~U(25,40), P_2~U(49.7,70)
+    lo, hi = torch.tensor([25.0, 49.7], dtype=torch.float64), torch.tensor([40.0, 70.0], dtype=torch.float64)
+    x0 = (lo + (hi - lo) * torch.rand(B, 2, generator=g, dtype=torch.float64)).to(dev)
+
+    def guess(mpc):  # every stage on the steady state (evaporation_process/acados.py:104-109)
+        mpc.reset(B=B)
+        xs = torch.tensor(spec.x_init, dtype=torch.float64, device=dev).repeat(B, 1)
+        us = torch.tensor(spec.u_init, dtype=torch.float64, device=dev).repeat(B, 1)
+        for k in range(spec.N + 1):
+            mpc.put("x", k, xs)
+        for k in range(spec.N):
+            mpc.put("u", k, us)
+
+    return spec, x0, 1e-2, guess
 
 
 class ClockSampler:
@@ -153,7 +193,7 @@ def run_reference(args, rank, world):
 def run_gpu(args, rank, world, local_rank):
     import torch
 
-    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+    from mpc4rl_b200 import BatchedMPC
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
@@ -165,24 +205,24 @@ def run_gpu(args, rank, world, local_rank):
 
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    spec = cartpole_spec(cartpole_original_config())
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    spec, x0, pert, install_guess = make_workload(args.workload, B, rank, dev)
     mpc = BatchedMPC(spec, max_batch=B, device=local_rank)
-    x0 = synth_states(B, 1234 + rank).to(dev)
     # untimed setup: converge the batch once (cold start like MPC.reset), this is the warm-start state
     mpc.set_option("tol", 1e-6)
     mpc.set_option("timing", 1)
     for kv in args.opt:
         k, v = kv.split("=")
         mpc.set_option(k, float(v))
-    mpc.reset(x0)
+    install_guess(mpc)
     _, _, st = mpc.solve(x0, max_sqp=60)
     torch.cuda.synchronize()
     conv_frac = float((st == 0).double().mean().item())
     n_steps = args.warmup + args.steps
     g = torch.Generator(device="cpu").manual_seed(99 + rank)
     # every step sees fresh states: the converged ones moved by a small "environment step"
-    xs = [(x0 + 1e-3 * torch.randn(B, 4, generator=g, dtype=torch.float64).to(dev)) for _ in range(n_steps)]
+    xs = [(x0 + pert * torch.randn(B, spec.nx, generator=g, dtype=torch.float64).to(dev)) for _ in range(n_steps)]
     td = torch.randn(B, generator=g, dtype=torch.float64).to(dev)
     out = mpc.alloc_outputs(B)
     stream = torch.cuda.current_stream()
@@ -233,7 +273,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through the C ABI, every step ----
     xs_host = [x.cpu().numpy() for x in xs]
-    mpc.reset(x0)
+    install_guess(mpc)
     mpc.solve(x0, max_sqp=60)
     for i in range(args.warmup):
         mpc.solve_sens_host(xs_host[i], max_sqp=1)
@@ -243,8 +283,9 @@ def run_gpu(args, rank, world, local_rank):
         o = mpc.solve_sens_host(xs_host[args.warmup + i], max_sqp=1)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = B * 4 * 8
-    d2h = B * ((1 + 1 + 4 + 3 + 3) * 8 + 4)
+    ng, nu = mpc.ngrad, spec.nu
+    h2d = B * spec.nx * 8
+    d2h = B * ((nu + 1 + 4 + ng + nu * ng) * 8 + 4)
 
     tt = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -254,11 +295,11 @@ def run_gpu(args, rank, world, local_rank):
         peaks, peak_src = measured_peaks()
         units = B * world * args.steps
         value = units / (total_ms * 1e-3)
-        achieved = B * B_ALG / (kernel_ms * 1e-3) / 1e9
+        achieved = B * wl["b_alg"] / (kernel_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(B, world),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(B, world, args.workload),
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
@@ -267,12 +308,12 @@ def run_gpu(args, rank, world, local_rank):
                          "kernel": "rlmpc_solve_sens = k_lin + k_qp1 + k_qp2 + k_sens_stage + k_sens_sweep "
                                    f"(dominant: {max(phase_ms, key=phase_ms.get)})",
                          "kernel_ms": kernel_ms, "kernels_ms": {k: round(v, 4) for k, v in phase_ms.items()},
-                         "algorithmic_bytes_per_unit": B_ALG,
+                         "algorithmic_bytes_per_unit": wl["b_alg"],
                          "note": "path is FP64 CUDA-core/latency bound, not HBM bound (SURVEY.md 8(d)); "
                                  "fraction reported as defined, bytes not padded"},
             "quality": {"status0_frac_after_setup": conv_frac, "status0_frac_last_step": ok_frac, "kkt_res_max_last_step": res_max},
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "cartpole":
             cval, cores, csec = cpu_port_run(args.cpu_samples, 3, 1)
             line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_samples} samples of the same workload x 3 steps ({csec:.2f} s per step); "
@@ -288,7 +329,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="samples per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cartpole", choices=sorted(WORKLOADS), help="cartpole = BASELINE.json configs[1] (headline)")
     ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning experiments)")

@@ -35,6 +35,7 @@ extern "C" {
 /* models (device code emitted per problem, the role of acados' c_generated_code) */
 #define RLMPC_MODEL_CARTPOLE 1      /* rlmpc/mpc/cartpole/acados.py:28-108 (config/cartpole*.yaml) */
 #define RLMPC_MODEL_LINEAR_SYSTEM 2 /* rlmpc/mpc/linear_system/acados.py:27-131 */
+#define RLMPC_MODEL_EVAPORATION 3   /* rlmpc/mpc/evaporation_process/acados.py:142-228 */
 
 #define RLMPC_MODE_V 0 /* x_0 fixed            -> V(s), pi(s)   mpc.py:177-202 (update, get_action) */
 #define RLMPC_MODE_Q 1 /* x_0 and u_0 fixed    -> Q(s,a)        mpc.py:52-96   (q_update) */
@@ -56,9 +57,11 @@ typedef struct rlmpc_problem_desc {
   double lbu[RLMPC_MAXD], ubu[RLMPC_MAXD]; /* input bounds, all stages (constraints.lbu/ubu) */
   double lbx[RLMPC_MAXD], ubx[RLMPC_MAXD]; /* state bounds stages 1..N-1 (+-1e30 = none) */
   double lbx_e[RLMPC_MAXD], ubx_e[RLMPC_MAXD];
-  double model_const[8];            /* cartpole: [0]=RK4 step h, [1]=g; linear system: [0..2] = P11,P12,P22 of
-                                       the constant terminal cost (linear_system/acados.py:51-57) */
+  double model_const[24];           /* cartpole: [0]=RK4 step h, [1]=g; linear system: [0..2] = P11,P12,P22 of
+                                       the constant terminal cost (linear_system/acados.py:51-57); evaporation:
+                                       [0..18] = environment.PARAM in dict order, [19] = RK4 step, [20] = #steps */
   double zl[RLMPC_MAXD], zu[RLMPC_MAXD]; /* linear penalties of the soft state bounds (cost.zl/zu), per idxsbx row */
+  double lg[RLMPC_MAXD], ug[RLMPC_MAXD]; /* bounds of the affine general constraints (constraints.lh/uh) */
 } rlmpc_problem_desc;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -105,6 +108,16 @@ int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* 
  * [B, dim(field)] row-major; lam/t are in acados order [lbu, ubu] for this problem class. */
 int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, double* buf_dev, void* stream);
 int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, const double* buf_dev, void* stream);
+
+/* Warm-start store next to a replay buffer: the reference keeps ONE iterate inside its solver object
+ * (mpc.py:204-210), so replayed samples always start cold; here every replay-buffer entry can keep its
+ * own primal-dual iterate, which is what keeps an SQP-RTI step (max_sqp = 1) accurate.  The store is a
+ * caller-owned device buffer of rlmpc_store_bytes(h, capacity) bytes; idx_dev[b] is the slot of batch
+ * sample b (entries outside [0, capacity) are skipped).  to_store = 1: handle iterate -> store,
+ * 0: store -> handle iterate. */
+size_t rlmpc_store_bytes(const rlmpc_handle* h, int capacity);
+int rlmpc_store_copy(rlmpc_handle* h, int B, const int* idx_dev, double* store_dev, int capacity, int to_store,
+                     void* stream);
 
 /* ---- the hot path ----------------------------------------------------------------------- */
 /* Replaces ocp_solver.set(0,"lbx"/"ubx",x0) [+ constraints_set(0,"lbu"/"ubu",u0)] + solve()

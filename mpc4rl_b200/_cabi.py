@@ -11,6 +11,7 @@ import os
 MAXN, MAXD = 128, 8
 MODEL_CARTPOLE = 1
 MODEL_LINEAR_SYSTEM = 2
+MODEL_EVAPORATION = 3
 MODE_V, MODE_Q = 0, 1
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -20,7 +21,7 @@ LIB_PATH = os.environ.get("RLMPC_B200_LIB", os.path.join(_PKG, "librlmpc_b200.so
 SYMBOLS = [
     "rlmpc_create", "rlmpc_destroy", "rlmpc_last_error", "rlmpc_dims", "rlmpc_nrows", "rlmpc_set_theta",
     "rlmpc_set_cost_scaling", "rlmpc_set_bounds", "rlmpc_set_option", "rlmpc_reset", "rlmpc_reset_masked",
-    "rlmpc_get_iterate",
+    "rlmpc_get_iterate", "rlmpc_store_bytes", "rlmpc_store_copy",
     "rlmpc_put_iterate", "rlmpc_solve", "rlmpc_sens", "rlmpc_solve_sens", "rlmpc_solve_sens_host",
     "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings", "rlmpc_cartpole_env_step",
 ]
@@ -34,8 +35,9 @@ class ProblemDesc(C.Structure):
         ("lbu", C.c_double * MAXD), ("ubu", C.c_double * MAXD),
         ("lbx", C.c_double * MAXD), ("ubx", C.c_double * MAXD),
         ("lbx_e", C.c_double * MAXD), ("ubx_e", C.c_double * MAXD),
-        ("model_const", C.c_double * 8),
+        ("model_const", C.c_double * 24),
         ("zl", C.c_double * MAXD), ("zu", C.c_double * MAXD),
+        ("lg", C.c_double * MAXD), ("ug", C.c_double * MAXD),
     ]
 
 
@@ -65,6 +67,8 @@ def load():
     lib.rlmpc_set_option.argtypes = [H, cp, C.c_double]
     lib.rlmpc_reset.argtypes = [H, C.c_int, vp, vp]
     lib.rlmpc_reset_masked.argtypes = [H, C.c_int, vp, vp, vp]
+    lib.rlmpc_store_bytes.argtypes = [H, C.c_int]; lib.rlmpc_store_bytes.restype = C.c_size_t
+    lib.rlmpc_store_copy.argtypes = [H, C.c_int, vp, vp, C.c_int, C.c_int, vp]
     lib.rlmpc_get_iterate.argtypes = [H, cp, C.c_int, C.c_int, vp, vp]
     lib.rlmpc_put_iterate.argtypes = [H, cp, C.c_int, C.c_int, vp, vp]
     lib.rlmpc_solve.argtypes = [H, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
@@ -77,7 +81,7 @@ def load():
     lib.rlmpc_launch_count.argtypes = [H]; lib.rlmpc_launch_count.restype = C.c_longlong
     for name in SYMBOLS:
         f = getattr(lib, name)
-        if name not in ("rlmpc_destroy", "rlmpc_last_error", "rlmpc_launch_count"):
+        if name not in ("rlmpc_destroy", "rlmpc_last_error", "rlmpc_launch_count", "rlmpc_store_bytes"):
             f.restype = C.c_int
     _lib = lib
     return lib

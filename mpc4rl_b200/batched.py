@@ -40,17 +40,22 @@ class BatchedMPC:
         # inequality rows per stage: 2*(nu+nbx) + 2*ns, acados order [lbu lbx ubu ubx lsbx usbx]
         self.nrows = int(self.lib.rlmpc_nrows(self._h))
         self.ns = len(spec.idxsbx)
-        self.nbx = (self.nrows - 2 * self.ns) // 2 - self.nu
+        self.ng = len(spec.lh)  # affine general constraint rows (lh/uh)
+        self.nbx = (self.nrows - 2 * self.ns) // 2 - self.nu - self.ng
         self.theta = np.array(spec.p_nominal, dtype=np.float64)
         self.set_theta(self.theta)
-        self.param_cost = bool(spec.parameterize_tracking_cost)
+        # cartpole only: gradient rows over the whole p (incl. W, yref) instead of the model parameters.  The
+        # other models have a fixed gradient width (all their parameters).
+        self.param_cost = bool(spec.parameterize_tracking_cost) and spec.model == _cabi.MODEL_CARTPOLE
         self.set_option("param_cost", 1.0 if self.param_cost else 0.0)
 
     @property
     def ngrad(self) -> int:
         """Width of the gradient rows: the model parameters (the only entries of the reference's p
         with non-zero gradient when parameterize_tracking_cost=False, quirk Q8) or all of p."""
-        return self.ntheta if self.param_cost else self.spec.np_model
+        ng = C.c_int()
+        _cabi.check(self.lib.rlmpc_dims(self._h, None, None, None, C.byref(ng), None))
+        return int(ng.value)
 
     def full_grad(self, g: torch.Tensor) -> torch.Tensor:
         """Pad [..., ngrad] gradient rows to the reference's [..., ntheta] layout."""
@@ -125,6 +130,10 @@ class BatchedMPC:
     def put(self, field: str, stage: int, value: torch.Tensor) -> None:
         value = value.contiguous()
         _cabi.check(self.lib.rlmpc_put_iterate(self._h, field.encode(), int(stage), value.shape[0], _ptr(value), self._stream()))
+
+    def iterate_store(self, capacity: int) -> "IterateStore":
+        """Per-replay-buffer-entry warm starts."""
+        return IterateStore(self, capacity)
 
     # ---- hot path ----
     def solve(self, x0: torch.Tensor, u0: Optional[torch.Tensor] = None, max_sqp: int = 1):
@@ -208,3 +217,26 @@ class BatchedMPC:
     @property
     def launch_count(self) -> int:
         return int(self.lib.rlmpc_launch_count(self._h))
+
+
+class IterateStore:
+    """``capacity`` primal-dual iterates on the device, addressed by replay-buffer index.
+
+    ``load(idx)`` puts the stored iterates of entries ``idx[b]`` into batch positions b of the engine (before
+    an RTI step on a sampled minibatch), ``save(idx)`` writes the engine's current iterates back."""
+
+    def __init__(self, engine: BatchedMPC, capacity: int):
+        self.engine, self.capacity = engine, int(capacity)
+        nbytes = int(engine.lib.rlmpc_store_bytes(engine._h, self.capacity))
+        self.buf = torch.zeros(nbytes // 8, dtype=torch.float64, device=engine.device)
+
+    def _copy(self, idx: torch.Tensor, to_store: int):
+        i = idx.to(self.engine.device, torch.int32).contiguous()
+        _cabi.check(self.engine.lib.rlmpc_store_copy(self.engine._h, i.numel(), _ptr(i), _ptr(self.buf), self.capacity,
+                                                     to_store, self.engine._stream()))
+
+    def save(self, idx: torch.Tensor) -> None:
+        self._copy(idx, 1)
+
+    def load(self, idx: torch.Tensor) -> None:
+        self._copy(idx, 0)

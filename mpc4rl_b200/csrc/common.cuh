@@ -58,7 +58,8 @@ struct ProblemData {
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component
   double lbx_e[MAXD], ubx_e[MAXD];  // stage N
   double zl[MAXD], zu[MAXD];        // linear penalties of the soft state bounds (cost.zl / cost.zu), per soft row
-  double mc[8];         // model constants (integrator step, gravity, ...)
+  double lg[MAXD], ug[MAXD];        // bounds of the general linear rows (constraints.lh / uh)
+  double mc[24];        // model constants (integrator step, gravity, plant parameters, ...)
 };
 
 // One sample's strided view: element i of a logical per-sample vector lives at p[i*TILE].

@@ -29,12 +29,14 @@ namespace rlmpc {
 template <class M>
 struct Engine {
   static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NPM = M::NPM, NBX = M::NBX;
-  static constexpr int NV = NU + NBX;   // box-constrained variables of a stage: [u ; x[bx]]
+  static constexpr int NG = M::NG;      // general linear rows lg <= g0 + C [x;u] <= ug (constraints.lh/uh with an affine h)
+  static constexpr int NV = NU + NBX + NG;  // constrained quantities of a stage: v = [u ; x[bx] ; g]
   static constexpr int NSX = M::NSX;    // soft state bounds (subset of bx, stages 1..N-1): slack rows
   static constexpr int NSXA = NSX > 0 ? NSX : 1;
-  // inequality rows per stage, acados order [lbu lbx ubu ubx lsbx usbx] (rlmpc/common/utils.py:4-25)
+  // inequality rows per stage, acados order [lbu lbx lh ubu ubx uh lsbx usbx] (rlmpc/common/utils.py:4-25)
   static constexpr int NR = 2 * NV + 2 * NSX;
   static constexpr int R_LS = 2 * NV, R_US = 2 * NV + NSX;  // first lower / upper slack row
+  static constexpr bool NEEDX = NBX > 0 || NG > 0;  // do the rows of a stage depend on x?
   static constexpr int NPS = NX * (NX + 1) / 2;
   static constexpr int NWS = NW * (NW + 1) / 2;
 
@@ -195,7 +197,35 @@ struct Engine {
     double lb[NV], ub[NV];
     double zl[NSXA], zu[NSXA];  // scaled penalties s_k * z of the soft pairs, < 0: pair not present at this stage
   };
-  MPC_HD static int vidx(int r) { return r < NU ? NX + r : M::bx(r - NU); }  // index into w = [x;u]
+  MPC_HD static int vidx(int r) { return r < NU ? NX + r : M::bx(r - NU); }  // r < NU + NBX: index into w = [x;u]
+  // Jacobian row of v_r w.r.t. w = [x;u]: a unit vector for the box rows, the model's constant row for g
+  MPC_HD static double jrow(int r, int i) {
+    if (r < NU + NBX) return vidx(r) == i ? 1.0 : 0.0;
+    return M::gC(r - NU - NBX, i);
+  }
+  // H += c J_r' J_r ;  gvec += a J_r
+  MPC_HD static void jr_rank1(int r, double c, double* Hm) {
+    if (r < NU + NBX) {
+      const int ix = vidx(r);
+      Hm[ix * NW + ix] += c;
+    } else {
+      MPC_UNROLL for (int a = 0; a < NW; ++a) MPC_UNROLL for (int b = 0; b < NW; ++b)
+        Hm[a * NW + b] += c * M::gC(r - NU - NBX, a) * M::gC(r - NU - NBX, b);
+    }
+  }
+  MPC_HD static void jr_axpy(int r, double a, double* gvec) {
+    if (r < NU + NBX) {
+      gvec[vidx(r)] += a;
+    } else {
+      MPC_UNROLL for (int i = 0; i < NW; ++i) gvec[i] += a * M::gC(r - NU - NBX, i);
+    }
+  }
+  MPC_HD static double jr_dot(int r, const double* dw) {
+    if (r < NU + NBX) return dw[vidx(r)];
+    double a = 0.0;
+    MPC_UNROLL for (int i = 0; i < NW; ++i) a += M::gC(r - NU - NBX, i) * dw[i];
+    return a;
+  }
   MPC_HD static int soft_row(int j) { return NU + M::sx(j); }               // variable index (in v) of soft pair j
   MPC_HD static void stage_bounds(const ProblemData& pd, int k, Bnd& bd) {
     const bool uact = (k < pd.N) && !(k == 0 && pd.mode == MODE_Q);
@@ -207,6 +237,10 @@ struct Engine {
       const int ix = M::bx(j);
       bd.lb[NU + j] = (k == 0) ? -1e300 : (k == pd.N ? pd.lbx_e[ix] : pd.lbx[ix]);
       bd.ub[NU + j] = (k == 0) ? 1e300 : (k == pd.N ? pd.ubx_e[ix] : pd.ubx[ix]);
+    }
+    MPC_UNROLL for (int j = 0; j < NG; ++j) {  // nh rows live on stages 0..N-1; constant when x_0 and u_0 are both fixed
+      bd.lb[NU + NBX + j] = uact ? pd.lg[j] : -1e300;
+      bd.ub[NU + NBX + j] = uact ? pd.ug[j] : 1e300;
     }
     MPC_UNROLL for (int j = 0; j < NSXA; ++j) {
       const bool sact = NSX > 0 && k >= 1 && k < pd.N;
@@ -235,6 +269,12 @@ struct Engine {
   MPC_HD static void stage_vars(const double* x, const double* u, double* v) {
     MPC_UNROLL for (int i = 0; i < NU; ++i) v[i] = u[i];
     MPC_UNROLL for (int j = 0; j < NBX; ++j) v[NU + j] = x[M::bx(j)];
+    MPC_UNROLL for (int j = 0; j < NG; ++j) {
+      double a = M::g0(j);
+      MPC_UNROLL for (int i = 0; i < NX; ++i) a += M::gC(j, i) * x[i];
+      MPC_UNROLL for (int i = 0; i < NU; ++i) a += M::gC(j, NX + i) * u[i];
+      v[NU + NBX + j] = a;
+    }
   }
   MPC_HD static double row_range(const Bnd& bd, int r) {
     return (bd.lb[r] > -BIG && bd.ub[r] < BIG) ? bd.ub[r] - bd.lb[r] : 1.0;
@@ -287,18 +327,17 @@ struct Engine {
   MPC_HD static void barrier_add(const Bnd& bd, const double* v, const double* lam, const double* t,
                                  double target, double* Hm, double* g) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
-      const int ix = vidx(r);
       if (bd.lb[r] > -BIG) {
         const int qs = slack_of(bd, r, 0);
         const RowC rc = row_coeffs(lam, t, r, qs, qs >= 0 ? bd.zl[qs - R_LS] : 0.0, target);
-        Hm[ix * NW + ix] += rc.c;
-        g[ix] -= rc.a - rc.c * (v[r] - bd.lb[r]);
+        jr_rank1(r, rc.c, Hm);
+        jr_axpy(r, -(rc.a - rc.c * (v[r] - bd.lb[r])), g);
       }
       if (bd.ub[r] < BIG) {
         const int qs = slack_of(bd, r, 1);
         const RowC rc = row_coeffs(lam, t, NV + r, qs, qs >= 0 ? bd.zu[qs - R_US] : 0.0, target);
-        Hm[ix * NW + ix] += rc.c;
-        g[ix] += rc.a - rc.c * (bd.ub[r] - v[r]);
+        jr_rank1(r, rc.c, Hm);
+        jr_axpy(r, rc.a - rc.c * (bd.ub[r] - v[r]), g);
       }
     }
   }
@@ -306,9 +345,8 @@ struct Engine {
   // reference (quirk Q4: slacks are not part of z), so a softened row counts with its own lam/t.
   MPC_HD static void barrier_hess(const Bnd& bd, const double* lam, const double* t, double* Hm) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
-      const int ix = vidx(r);
-      if (bd.lb[r] > -BIG) Hm[ix * NW + ix] += lam[r] / t[r];
-      if (bd.ub[r] < BIG) Hm[ix * NW + ix] += lam[NV + r] / t[NV + r];
+      if (bd.lb[r] > -BIG) jr_rank1(r, lam[r] / t[r], Hm);
+      if (bd.ub[r] < BIG) jr_rank1(r, lam[NV + r] / t[NV + r], Hm);
     }
   }
   struct StepStats {
@@ -331,7 +369,7 @@ struct Engine {
       th[q] = 0.0;
     }
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
-      const double dv = dw[vidx(r)];
+      const double dv = jr_dot(r, dw);
       MPC_UNROLL for (int side = 0; side < 2; ++side) {
         const int q = side * NV + r;
         const bool act = side ? (bd.ub[r] < BIG) : (bd.lb[r] > -BIG);
@@ -378,7 +416,6 @@ struct Engine {
   MPC_HD static void rows_residual(const ProblemData& pd, const Bnd& bd, const double* v, const double* lam,
                                    const double* t, Residuals& R, double* jl /* NW, += */) {
     MPC_UNROLL for (int r = 0; r < NV; ++r) {
-      const int ix = vidx(r);
       MPC_UNROLL for (int side = 0; side < 2; ++side) {
         const int q = side * NV + r;
         const bool act = side ? (bd.ub[r] < BIG) : (bd.lb[r] > -BIG);
@@ -391,7 +428,7 @@ struct Engine {
           R.stat = dmax(R.stat, dabs(z - lam[q] - lam[qs]));
           R.comp = dmax(R.comp, dabs(lam[qs] * t[qs] - pd.tau));
         }
-        jl[ix] += side ? lam[q] : -lam[q];
+        jr_axpy(r, side ? lam[q] : -lam[q], jl);
         R.comp = dmax(R.comp, dabs(lam[q] * t[q] - pd.tau));
         const double h = side ? v[r] - bd.ub[r] - sl : bd.lb[r] - v[r] - sl;
         R.ineq = dmax(R.ineq, dabs(h + t[q]));
@@ -596,7 +633,7 @@ struct Engine {
         R.eq = (e == e) ? dmax(R.eq, e) : e;
       }
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      if (NEEDX) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
@@ -677,7 +714,7 @@ struct Engine {
       } else {
         MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
       }
-      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * TILE, TILE, x);
+      if (NEEDX) ld<NX>(L.it + (size_t)it_x(N, k) * TILE, TILE, x);
     }
     MPC_HD void done(int) {}
   };
@@ -759,7 +796,7 @@ struct Engine {
       } else {
         MPC_UNROLL for (int i = 0; i < NU; ++i) u[i] = 0.0;
       }
-      if (NBX > 0) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      if (NEEDX) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       stage_vars(x, u, v);
       if (warm) {
         ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
@@ -1056,9 +1093,11 @@ struct Engine {
           ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
           MPC_UNROLL for (int i = 0; i < NX; ++i) MPC_UNROLL for (int l = 0; l < NX; ++l) pin[i] += A[l * NX + i] * pik[l];
         }
-        MPC_UNROLL for (int j = 0; j < NBX; ++j) {
-          const int ix = M::bx(j);
-          pin[ix] += -lam[NU + j] + lam[NV + NU + j];
+        {
+          double jl[NW];
+          MPC_UNROLL for (int i = 0; i < NW; ++i) jl[i] = 0.0;
+          MPC_UNROLL for (int r = NU; r < NV; ++r) jr_axpy(r, -lam[r] + lam[NV + r], jl);  // rows that touch x
+          MPC_UNROLL for (int i = 0; i < NX; ++i) pin[i] += jl[i];
         }
         MPC_UNROLL for (int i = 0; i < NX; ++i) pik[i] = pin[i];
         double x[NX];
@@ -1150,7 +1189,7 @@ struct Engine {
         MPC_UNROLL for (int i = 0; i < NX; ++i) a += pik[i] * Fp[i * NPM + j];
         gp[j] = a;
       }
-      M::cost_sens(k == 0 ? 0 : 1, pd.scale[k], y, gp, Hwp);  // model parameters that enter the stage cost
+      M::cost_sens(k == 0 ? 0 : 1, pd.scale[k], y, L.th, (size_t)TILE, gp, Hwp);  // model parameters that enter the stage cost
       st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
       st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
       st<NPM>(w + (size_t)S_gp * bs, bs, gp);
@@ -1228,7 +1267,7 @@ struct Engine {
       }
       MPC_UNROLL for (int j = 0; j < NPM; ++j) gp[j] += gpk[j];
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-      if (NBX > 0 || (pd.param_cost && dLdth)) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      if (NEEDX || (pd.param_cost && dLdth)) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);

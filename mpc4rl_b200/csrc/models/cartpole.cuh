@@ -26,6 +26,9 @@ struct CartpoleModelT {
   static constexpr int NTH = 83;
   static constexpr int TH_W0 = 3, TH_W = 28, TH_WE = 53, TH_YREF0 = 69, TH_YREF = 74, TH_YREFE = 79;
   static constexpr int NSX = 0;              // no soft bounds
+  static constexpr int NG = 0;               // no general linear rows
+  MPC_HD static double gC(int, int) { return 0.0; }
+  MPC_HD static double g0(int) { return 0.0; }
   MPC_HD static int bx(int j) { return j; }  // idxbx (all states, in order)
   MPC_HD static int sx(int) { return 0; }
 
@@ -57,7 +60,7 @@ struct CartpoleModelT {
       c[(size_t)(NWS + 2 * NW) * cts] = 0.0;                              // no constant term
     }
   }
-  MPC_HD static void cost_sens(int, double, const double*, double*, double*) {}  // no model parameter in the cost
+  MPC_HD static void cost_sens(int, double, const double*, const double*, size_t, double*, double*) {}  // no model parameter in the cost
   // d(s * l)/d(W, yref) accumulated into the [NTH] row (parameterize_tracking_cost=True semantics,
   // nlp.py:1057-1074): dl/dW_ij = 1/2 e_i e_j, dl/dyref = -W_sym e.
   MPC_HD static void cost_param_grad(int kind, double s, const double* th, size_t ths, const double* x, const double* u,

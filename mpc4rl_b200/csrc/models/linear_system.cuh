@@ -14,6 +14,9 @@ namespace rlmpc {
 struct LinearSystemModel {
   static constexpr int NX = 2, NU = 1, NW = 3, NPM = 12, NTH = 12;
   static constexpr int NBX = 2, NSX = 1;
+  static constexpr int NG = 0;               // no general linear rows
+  MPC_HD static double gC(int, int) { return 0.0; }
+  MPC_HD static double g0(int) { return 0.0; }
   static constexpr int TH_A = 0, TH_B = 4, TH_b = 6, TH_V0 = 8, TH_F = 9;
   MPC_HD static int bx(int j) { return j; }  // idxbx = [0, 1]
   MPC_HD static int sx(int) { return 0; }    // idxsbx = [0]: position in idxbx
@@ -34,7 +37,7 @@ struct LinearSystemModel {
   // no W / yref entries in p (EXTERNAL cost)
   MPC_HD static void cost_param_grad(int, double, const double*, size_t, const double*, const double*, double*) {}
   // cost terms that depend on model parameters: d(s l)/d theta -> gp, d(grad_w s l)/d theta -> Hwp
-  MPC_HD static void cost_sens(int kind, double s, const double* y, double* gp, double* Hwp) {
+  MPC_HD static void cost_sens(int kind, double s, const double* y, const double*, size_t, double* gp, double* Hwp) {
     if (kind == 2) return;
     if (kind == 0) gp[TH_V0] += s;
     MPC_UNROLL for (int i = 0; i < NW; ++i) {

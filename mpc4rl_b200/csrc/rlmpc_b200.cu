@@ -15,6 +15,7 @@
 #include "engine.cuh"
 #include "models/cartpole.cuh"
 #include "models/linear_system.cuh"
+#include "models/evaporation.cuh"
 
 using namespace rlmpc;
 
@@ -184,7 +185,7 @@ struct RingReader {
 #pragma unroll
         for (int e = 0; e < E::NU; ++e) cp_async8(dr + (size_t)(E::RD_U + e) * TILE, su + (size_t)e * TILE);
       }
-      if (E::NBX > 0) {
+      if (E::NEEDX) {
         const double* sx = L.it + (size_t)E::it_x(N, k) * TILE;
 #pragma unroll
         for (int e = 0; e < E::NX; ++e) cp_async8(dr + (size_t)(E::RD_X + e) * TILE, sx + (size_t)e * TILE);
@@ -214,7 +215,7 @@ struct RingReader {
 #pragma unroll
       for (int i = 0; i < E::NU; ++i) u[i] = 0.0;
     }
-    if (E::NBX > 0) E::template ld<E::NX>(r + (size_t)E::RD_X * TILE, TILE, x);
+    if (E::NEEDX) E::template ld<E::NX>(r + (size_t)E::RD_X * TILE, TILE, x);
   }
   __device__ __forceinline__ void done(int) {
     issue(consumed + RING_DEPTH);
@@ -379,6 +380,27 @@ __global__ void k_cost_table(const __grid_constant__ ProblemData pd, const doubl
   M::cost_table(th + tile_off(b, M::NTH), TILE, ct + tile_off(b, E::CT_SIZE), TILE, pd.mc);
 }
 
+// Warm-start store coupled to a replay buffer: slot idx[b] of a caller-owned store
+// (same tiled layout, `capacity` samples) <-> sample b of the handle's iterate.  One warp per
+// (batch tile, 64-element chunk); the side addressed through idx is sector-granular, the other coalesced.
+__global__ void k_store_copy(double* it, double* store, int it_size, int B, const int* idx, int capacity, int to_store) {
+  const int b = blockIdx.x * TILE + (threadIdx.x & 31);
+  if (b >= B) return;
+  const int slot = idx[b];
+  if (slot < 0 || slot >= capacity) return;
+  const int chunk = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int e0 = chunk * 64;
+  double* pi_ = it + tile_off(b, it_size);
+  double* ps = store + tile_off(slot, it_size);
+#pragma unroll 8
+  for (int e = e0; e < e0 + 64 && e < it_size; ++e) {
+    if (to_store)
+      ps[(size_t)e * TILE] = pi_[(size_t)e * TILE];
+    else
+      pi_[(size_t)e * TILE] = ps[(size_t)e * TILE];
+  }
+}
+
 // Vectorised continuous cart-pole swing-up environment, one thread per environment
 // (rlmpc/gym/continuous_cartpole/environment.py:372-426: explicit Euler, tau = 0.02; note the env uses
 // polemass_length = m*l in `temp` where the MPC model uses m, quirk Q9).
@@ -482,7 +504,7 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 
 }  // namespace
 
-enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2 };
+enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2, VAR_EVAPORATION = 3 };
 
 struct rlmpc_handle {
   int model, variant, device, max_batch;
@@ -521,6 +543,7 @@ namespace {
     case VAR_CARTPOLE: { using M = CartpoleModel; expr; } break;       \
     case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; expr; } break;  \
     case VAR_LINEAR: { using M = LinearSystemModel; expr; } break;     \
+    case VAR_EVAPORATION: { using M = EvaporationModel; expr; } break; \
   }
 
 int check_batch(rlmpc_handle* h, int B) {
@@ -747,6 +770,9 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     case RLMPC_MODEL_LINEAR_SYSTEM:
       h->variant = VAR_LINEAR;
       break;
+    case RLMPC_MODEL_EVAPORATION:
+      h->variant = VAR_EVAPORATION;
+      break;
     default:
       delete h;
       return fail(RLMPC_EINVAL, "unknown model");
@@ -779,6 +805,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memcpy(pd.lbx_e, d->lbx_e, sizeof(pd.lbx_e)); memcpy(pd.ubx_e, d->ubx_e, sizeof(pd.ubx_e));
   memcpy(pd.mc, d->model_const, sizeof(pd.mc));
   memcpy(pd.zl, d->zl, sizeof(pd.zl)); memcpy(pd.zu, d->zu, sizeof(pd.zu));
+  memcpy(pd.lg, d->lg, sizeof(pd.lg)); memcpy(pd.ug, d->ug, sizeof(pd.ug));
   cudaError_t e = cudaSetDevice(device);
   const size_t nio_in = (size_t)max_batch * (h->nx + h->nu);
   const size_t nio_out = (size_t)max_batch * (h->nu + 1 + 4 + (size_t)h->nth * (1 + h->nu));
@@ -1031,6 +1058,25 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
   int grid = (B + nwarp - 1) / nwarp;
   if (grid > 148 * 4) grid = 148 * 4;
   k_td_grad<<<grid, threads, sizeof(double) * (ncols + 2), s>>>(B, ncols, td_dev, dQ_dtheta_dev, status_dev, acc_out_dev);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t rlmpc_store_bytes(const rlmpc_handle* h, int capacity) {
+  if (!h || capacity <= 0) return 0;
+  return sizeof(double) * (size_t)h->it_size * (((size_t)capacity + TILE - 1) / TILE * TILE);
+}
+
+int rlmpc_store_copy(rlmpc_handle* h, int B, const int* idx_dev, double* store_dev, int capacity, int to_store,
+                     void* stream) {
+  if (int r = check_batch(h, B)) return r;
+  if (!idx_dev || !store_dev || capacity <= 0) return fail(RLMPC_EINVAL, "bad arguments");
+  if (B == 0) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  const int wpb = 8, chunks = (h->it_size + 63) / 64;
+  k_store_copy<<<dim3((B + 31) / 32, (chunks + wpb - 1) / wpb), 32 * wpb, 0, (cudaStream_t)stream>>>(
+      h->it, store_dev, h->it_size, B, idx_dev, capacity, to_store);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

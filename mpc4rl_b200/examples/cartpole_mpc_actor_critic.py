@@ -25,12 +25,13 @@ from ..parallel import allreduce_accumulator, td_parameter_step
 from ..problems import cartpole_original_config, cartpole_spec
 
 
-def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float = 1e-6, device: int = 0,
-        explore: float = 0.05, seed: int = 0, critic_sqp: int = 10, verbose: bool = True):
+def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float = 1e-9, device: int = 0,
+        explore: float = 0.05, seed: int = 0, critic_sqp: int = 40, verbose: bool = True):
     spec = cartpole_spec(cartpole_original_config())
     dev = torch.device("cuda", device)
     actor = BatchedMPC(spec, max_batch=num_envs, device=device)    # owns one warm start per environment
     critic = BatchedMPC(spec, max_batch=num_envs, device=device)
+    critic.set_option("tol", 1e-5)
     env = ContinuousCartPoleSwingUpVectorEnv(num_envs=num_envs, force_mag=float(spec.ubu[0]), device=device)
     g = torch.Generator(device="cpu").manual_seed(seed + 1000 * int(os.environ.get("RANK", "0")))
     theta = torch.tensor(spec.p_nominal, dtype=torch.float64)

@@ -35,10 +35,11 @@ def make_ocp_view(spec: ProblemSpec) -> SimpleNamespace:
         idxbx_0=np.arange(spec.nx), lbx_0=np.zeros(spec.nx), ubx_0=np.zeros(spec.nx),
         idxsbx=np.asarray(spec.idxsbx, dtype=int), idxsbu=np.array([], dtype=int), idxsh=np.array([], dtype=int),
         idxsbx_e=np.array([], dtype=int), idxsh_e=np.array([], dtype=int),
-        lh=np.array([]), uh=np.array([]), lh_e=np.array([]), uh_e=np.array([]),
+        lh=np.asarray(spec.lh, dtype=float).copy(), uh=np.asarray(spec.uh, dtype=float).copy(),
+        lh_e=np.array([]), uh_e=np.array([]),
     )
     dims = SimpleNamespace(N=spec.N, nx=spec.nx, nu=spec.nu, np=spec.np_model, nbu=spec.nu, nbx=len(idxbx),
-                           nbx_0=spec.nx, nbx_e=len(idxbx_e), nh=0, nh_e=0, nsbx=len(spec.idxsbx), nsbu=0, nsh=0, nsbx_e=0, nsh_e=0,
+                           nbx_0=spec.nx, nbx_e=len(idxbx_e), nh=len(spec.lh), nh_e=0, nsbx=len(spec.idxsbx), nsbu=0, nsh=0, nsbx_e=0, nsh_e=0,
                            ny_0=spec.nx + spec.nu, ny=spec.nx + spec.nu, ny_e=spec.nx)
     cost = SimpleNamespace(cost_type_0=spec.cost_type, cost_type=spec.cost_type, cost_type_e=spec.cost_type,
                            W_0=pv("W_0"), W=pv("W"), W_e=pv("W_e"), yref_0=pv("yref_0"), yref=pv("yref"), yref_e=pv("yref_e"),
@@ -188,27 +189,30 @@ class OcpSolverShim:
             if ns == 0 or stage == 0 or stage == N:
                 return np.zeros(0)
             v = self.engine.get("t", stage, 1)[0].cpu().numpy()
-            o = 2 * (nu + nbx) + (0 if field == "sl" else ns)
+            o = 2 * (nu + nbx + self.engine.ng) + (0 if field == "sl" else ns)
             return v[o:o + ns].copy()
         if field in ("lam", "t"):
             # acados order within a stage: [lbu, lbx, ubu, ubx, lsbx, usbx] (rlmpc/common/utils.py:4-25); the
             # engine stores [lbu(nu), lbx(nbx), ubu(nu), ubx(nbx), lsbx(ns), usbx(ns)] for every stage 0..N
             v = self.engine.get(field, stage, 1)[0].cpu().numpy()
-            lo_u, lo_x, up_u, up_x = v[:nu], v[nu:nu + nbx], v[nu + nbx:2 * nu + nbx], v[2 * nu + nbx:2 * (nu + nbx)]
-            soft = v[2 * (nu + nbx):]
+            ng = self.engine.ng
+            nv = nu + nbx + ng  # engine order per side: [u, x[bx], h]
+            lo_u, lo_x, lo_h = v[:nu], v[nu:nu + nbx], v[nu + nbx:nv]
+            up_u, up_x, up_h = v[nv:nv + nu], v[nv + nu:nv + nu + nbx], v[nv + nu + nbx:2 * nv]
+            soft = v[2 * nv:]
             if stage == N:
                 if len(self.acados_ocp.constraints.idxbx_e) == 0:
                     return np.zeros(0)
                 return np.concatenate([lo_x, up_x])
             if stage > 0:
-                return np.concatenate([lo_u, lo_x, up_u, up_x, soft])
+                return np.concatenate([lo_u, lo_x, lo_h, up_u, up_x, up_h, soft])
             # stage 0 carries the x_0 (and, in Q-mode, u_0) equalities as two opposing bounds on all nx / nu
             rho_x = self.engine.get("rho_x0", 0, 1)[0].cpu().numpy()
             if self.qmode:
                 rho_u = self.engine.get("rho_u0", 0, 1)[0].cpu().numpy()
                 lo_u, up_u = (np.maximum(rho_u, 0.0), np.maximum(-rho_u, 0.0)) if field == "lam" else (np.zeros(nu), np.zeros(nu))
             lo_x, up_x = (np.maximum(rho_x, 0.0), np.maximum(-rho_x, 0.0)) if field == "lam" else (np.zeros(nx), np.zeros(nx))
-            return np.concatenate([lo_u, lo_x, up_u, up_x])
+            return np.concatenate([lo_u, lo_x, lo_h, up_u, up_x, up_h])
         raise NotImplementedError(field)
 
     # ---- iterate hand-off (examples/chain_mass.py:119-120) ----

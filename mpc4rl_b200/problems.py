@@ -38,6 +38,10 @@ class ProblemSpec:
     idxsbx: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))  # soft rows: positions within idxbx
     zl: np.ndarray = field(default_factory=lambda: np.zeros(0))
     zu: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    lh: np.ndarray = field(default_factory=lambda: np.zeros(0))  # affine general constraints lh <= h(x,u) <= uh
+    uh: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    x_init: np.ndarray | None = None  # initial guess of every stage where the reference sets one
+    u_init: np.ndarray | None = None
     state_labels: List[str] = field(default_factory=list)
     input_labels: List[str] = field(default_factory=list)
     parameter_labels: List[str] = field(default_factory=list)  # labels of p["model"]
@@ -78,8 +82,12 @@ class ProblemSpec:
         for i, v in enumerate(self.cost_scaling()):
             d.scale[i] = v
         for i in range(_cabi.MAXD):
-            d.lbu[i] = d.lbx[i] = d.lbx_e[i] = -INF
-            d.ubu[i] = d.ubx[i] = d.ubx_e[i] = INF
+            d.lbu[i] = d.lbx[i] = d.lbx_e[i] = d.lg[i] = -INF
+            d.ubu[i] = d.ubx[i] = d.ubx_e[i] = d.ug[i] = INF
+        for i, v in enumerate(np.asarray(self.lh, dtype=float).ravel()):
+            d.lg[i] = v
+        for i, v in enumerate(np.asarray(self.uh, dtype=float).ravel()):
+            d.ug[i] = v
         for name in ("lbu", "ubu", "lbx", "ubx", "lbx_e", "ubx_e"):
             arr = getattr(d, name)
             for i, v in enumerate(np.asarray(getattr(self, name), dtype=float).ravel()):
@@ -199,4 +207,37 @@ def linear_system_spec(param: dict | None = None, gamma: float = 0.99, N: int = 
         model_const=np.array([P[0, 0], P[0, 1], P[1, 1]]), gamma=gamma, cost_type="EXTERNAL",
         idxsbx=np.array([0]), zl=np.array([1e2]), zu=np.array([1e2]),
         state_labels=["x_0", "x_1"], input_labels=["u_0"], parameter_labels=labels,
+    )
+
+
+EVAPORATION_PARAM = {
+    # rlmpc/gym/evaporation_process/environment.py:5-25 (dict order = order of the model constants)
+    "a": 0.5616, "b": 0.3126, "c": 48.43, "d": 0.507, "e": 55.0, "f": 0.1538, "g": 90.0, "h": 0.16, "M": 20.0,
+    "C": 4.0, "U_A2": 6.84, "C_p": 0.07, "lam": 38.5, "lam_s": 36.6, "F_1": 10.0, "X_1": 5.0, "F_3": 50.0,
+    "T_1": 40.0, "T_200": 25.0,
+}
+H_NOMINAL = np.diag([10.0, 10.0, 0.1, 0.1, 0.1])  # scripts/evaporation_process_mpc.py:33
+
+
+def evaporation_spec(model_param: dict | None = None, cost_param: dict | None = None, gamma: float = 1.0,
+                     H: np.ndarray | None = None, N: int = 100, n_sub: int = 4) -> ProblemSpec:
+    """rlmpc/mpc/evaporation_process/acados.py:142-228.  ``cost_param["H"]["l"]`` (or ``H``) is the 5x5
+    tracking weight; theta = [W_0, W, yref_0, yref] (parameterize_tracking_cost=True, acados.py:115)."""
+    mp = dict(EVAPORATION_PARAM if model_param is None else model_param)
+    if H is None:
+        H = cost_param["H"]["l"] if cost_param is not None else H_NOMINAL
+    H = np.asarray(H, dtype=float)
+    x_ss, u_ss = np.array([25.0, 49.743]), np.array([191.713, 215.888, 0.0])
+    yref = np.concatenate([x_ss, u_ss])
+    p_entries = [("model", (0,)), ("W_0", (5, 5)), ("W", (5, 5)), ("yref_0", (5,)), ("yref", (5,))]
+    p_nom = np.concatenate([H.T.ravel(), H.T.ravel(), yref, yref])
+    mc = np.array([mp[k] for k in EVAPORATION_PARAM] + [1.0 / n_sub, float(n_sub)])
+    return ProblemSpec(
+        name="evaporation_process", model=_cabi.MODEL_EVAPORATION, N=N, nx=2, nu=3, tf=float(N),
+        p_entries=p_entries, p_nominal=p_nom,
+        lbu=np.array([100.0, 100.0, 0.0]), ubu=np.array([400.0, 400.0, 10.0]),
+        lbx=np.full(2, -INF), ubx=np.full(2, INF), lbx_e=np.full(2, -INF), ubx_e=np.full(2, INF),
+        model_const=mc, gamma=gamma, cost_type="NONLINEAR_LS", parameterize_tracking_cost=True,
+        lh=np.array([-1e3, -1e3]), uh=np.array([0.0, 0.0]), x_init=x_ss, u_init=u_ss,
+        state_labels=["X_2", "P_2"], input_labels=["P_100", "F_200", "s"], parameter_labels=[],
     )

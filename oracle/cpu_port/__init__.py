@@ -27,7 +27,8 @@ class ProblemData(C.Structure):
         ("lbx", C.c_double * MAXD), ("ubx", C.c_double * MAXD),
         ("lbx_e", C.c_double * MAXD), ("ubx_e", C.c_double * MAXD),
         ("zl", C.c_double * MAXD), ("zu", C.c_double * MAXD),
-        ("mc", C.c_double * 8),
+        ("lg", C.c_double * MAXD), ("ug", C.c_double * MAXD),
+        ("mc", C.c_double * 24),
     ]
 
 
@@ -57,7 +58,7 @@ def lib():
 
 
 def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0,
-            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20) -> ProblemData:
+            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20, lg=(), ug=()) -> ProblemData:
     pd = ProblemData()
     pd.sigma_min = sigma_min; pd.sigma0 = sigma0; pd.as_steps = as_steps
     pd.N = N; pd.max_ipm = max_ipm; pd.warm_ipm = warm_ipm; pd.param_cost = param_cost
@@ -65,13 +66,14 @@ def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, war
     for i, v in enumerate(scale):
         pd.scale[i] = v
     for i in range(MAXD):
-        pd.lbx[i] = pd.lbx_e[i] = -1e30
-        pd.ubx[i] = pd.ubx_e[i] = 1e30
+        pd.lbx[i] = pd.lbx_e[i] = pd.lg[i] = -1e30
+        pd.ubx[i] = pd.ubx_e[i] = pd.ug[i] = 1e30
     for i, v in enumerate(lbu):
         pd.lbu[i] = v
     for i, v in enumerate(ubu):
         pd.ubu[i] = v
-    for name, vals in (("lbx", lbx), ("ubx", ubx), ("lbx_e", lbx_e), ("ubx_e", ubx_e), ("zl", zl), ("zu", zu)):
+    for name, vals in (("lbx", lbx), ("ubx", ubx), ("lbx_e", lbx_e), ("ubx_e", ubx_e), ("zl", zl), ("zu", zu),
+                       ("lg", lg), ("ug", ug)):
         for i, v in enumerate(vals):
             getattr(pd, name)[i] = v
     for i, v in enumerate(mc):

@@ -11,6 +11,7 @@
 #include "../../mpc4rl_b200/csrc/engine.cuh"
 #include "../../mpc4rl_b200/csrc/models/cartpole.cuh"
 #include "../../mpc4rl_b200/csrc/models/linear_system.cuh"
+#include "../../mpc4rl_b200/csrc/models/evaporation.cuh"
 
 using namespace rlmpc;
 
@@ -125,6 +126,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     case 1: { using M = CartpoleModel; expr; } break;      \
     case 2: { using M = CartpoleModelBX; expr; } break;    \
     case 3: { using M = LinearSystemModel; expr; } break;  \
+    case 4: { using M = EvaporationModel; expr; } break;   \
     default: return -1;                                    \
   }
 

@@ -90,10 +90,64 @@ def linear_system_golden(gamma=0.9, seed=7):
     print("wrote", path)
 
 
+def evaporation_golden(gamma=0.95, N=40, seed=7):
+    """Evaporation process (rlmpc/mpc/evaporation_process/acados.py): affine h rows shared with the slack
+    input, discounted tracking cost, theta = (W_0, W, yref_0, yref) = 60 entries.  Horizon N=40 instead of
+    the reference's 100: the dense oracle needs ~30 s per solve at N=40 and ~10 min at N=100 (one N=100
+    sample is added by ``evaporation_golden_full``)."""
+    from .problems import make_evaporation
+
+    pb = make_evaporation(gamma=gamma, N=N)
+    s = DenseSolver(pb)
+    rng = np.random.default_rng(seed)
+    # SURVEY.md 8(d) config 4 distribution X_2~U(25,40), P_2~U(49.7,70), plus one state below the soft bound
+    x0s = np.vstack([[30.0, 60.0], [25.5, 50.0], [24.0, 55.0], rng.uniform([25.0, 49.7], [40.0, 70.0], size=(2, 2))])
+    acts = np.column_stack([rng.uniform(150.0, 350.0, size=(len(x0s), 2)), np.full(len(x0s), 0.5)])
+    out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "U", "X", "status")}
+    nan = lambda *shape: np.full(shape, np.nan)
+    for i in range(len(x0s)):
+        res = []
+        for u0 in (None, acts[i]):
+            try:  # the dense IPM has no safeguards: a failed solve is recorded as status -1, not fixed up
+                sol, upd = s.unit(x0s[i], u0=u0, tol=1e-9)
+                res.append((sol.status, sol.cost, sol.U, sol.X, upd["dL_dp"][0], upd["dpi_dp"]))
+            except Exception as e:  # noqa: BLE001
+                print(f"[evaporation {i}] oracle failed: {type(e).__name__}: {e}", flush=True)
+                res.append((-1, np.nan, nan(N, 3), nan(N + 1, 2), nan(60), nan(3, 60)))
+        (sv, V, U, X, dV, dpi), (sq, Q, _, _, dQ, _) = res
+        print(f"[evaporation {i}] V={V:.6f} u0={U[0]} st={sv} | Q={Q:.6f} st={sq}", flush=True)
+        out["status"].append([sv, sq])
+        out["V"].append(V); out["u0"].append(U[0]); out["dV"].append(dV); out["dpi"].append(dpi)
+        out["Q"].append(Q); out["dQ"].append(dQ); out["U"].append(U); out["X"].append(X)
+    out = {k: np.array(v) for k, v in out.items()}
+    out["x0"] = x0s; out["a"] = acts; out["theta"] = pb.p_nominal; out["gamma"] = gamma; out["N"] = N
+    path = os.path.join(ROOT, "tests", "golden", "evaporation.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+def evaporation_golden_full(gamma=0.95):
+    """One V-mode sample at the reference's full horizon N=100."""
+    from .problems import make_evaporation
+
+    pb = make_evaporation(gamma=gamma, N=100)
+    x0 = np.array([30.0, 60.0])
+    sol, upd = DenseSolver(pb).unit(x0, tol=1e-9)
+    print(f"[evaporation N=100] V={sol.cost:.6f} u0={sol.U[0]} it={sol.sqp_iter} st={sol.status}", flush=True)
+    path = os.path.join(ROOT, "tests", "golden", "evaporation_n100.npz")
+    np.savez_compressed(path, x0=x0, V=sol.cost, u0=sol.U[0], dV=upd["dL_dp"][0], dpi=upd["dpi_dp"], X=sol.X, U=sol.U,
+                        status=sol.status, gamma=gamma, theta=pb.p_nominal)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["original"]
     for v in which:
-        if v == "linear":
+        if v == "evaporation":
+            evaporation_golden()
+        elif v == "evaporation_full":
+            evaporation_golden_full()
+        elif v == "linear":
             linear_system_golden()
         else:
             cartpole_golden(v, n=20 if v == "original" else 12)

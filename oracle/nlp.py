@@ -51,10 +51,13 @@ def build_rows(pb: Problem) -> List[Row]:
             iu, ix, isx = pb.idxbu, pb.idxbx, pb.idxsbx
         else:
             iu, ix, isx = np.zeros(0, dtype=int), pb.idxbx_e, pb.idxsbx_e
+        ih = range(len(pb.lh)) if k < N else range(0)  # nh rows on stages 0..N-1 (nh_e = 0)
         rows += [Row(k, "lbu", int(i)) for i in iu]
         rows += [Row(k, "lbx", int(i)) for i in ix]
+        rows += [Row(k, "lh", int(i)) for i in ih]
         rows += [Row(k, "ubu", int(i)) for i in iu]
         rows += [Row(k, "ubx", int(i)) for i in ix]
+        rows += [Row(k, "uh", int(i)) for i in ih]
         rows += [Row(k, "lsbx", int(j)) for j in range(len(isx))]
         rows += [Row(k, "usbx", int(j)) for j in range(len(isx))]
     return rows
@@ -162,6 +165,12 @@ class RestatedNLP:
                 if j in soft:
                     Jsu[i, k * ns + soft[j]] = -1.0
                 spec.append(("ubx", k, j))
+            elif r.kind in ("lh", "uh"):
+                # lh - h <= 0 / h - uh <= 0 with h = h0 + Ch [x_k; u_k]  (nlp.py:696-716, 745-762)
+                sgn = -1.0 if r.kind == "lh" else 1.0
+                Jw[i, N * nu + k * nx: N * nu + (k + 1) * nx] = sgn * pb.Ch[r.idx, :nx]
+                Jw[i, k * nu: (k + 1) * nu] = sgn * pb.Ch[r.idx, nx:]
+                spec.append((r.kind, k, r.idx))
             elif r.kind == "lsbx":
                 Jsl[i, k * ns + r.idx] = -1.0; spec.append(("zero", k, 0))
             elif r.kind == "usbx":
@@ -181,6 +190,10 @@ class RestatedNLP:
                 c[i] = b.lbx0[j] if k == 0 else (pb.lbx[j] if k < N else pb.lbx_e[j])
             elif kind == "ubx":
                 c[i] = -(b.ubx0[j] if k == 0 else (pb.ubx[j] if k < N else pb.ubx_e[j]))
+            elif kind == "lh":
+                c[i] = pb.lh[j] - pb.h0[j]
+            elif kind == "uh":
+                c[i] = pb.h0[j] - pb.uh[j]
         return torch.as_tensor(c, dtype=F64)
 
     def h(self, w, p, b: Bounds):

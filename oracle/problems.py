@@ -75,6 +75,15 @@ class Problem:
     idxsbx_e: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=int))
     zl_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
     zu_e: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    # general constraints lh <= h(x,u) <= uh on stages 0..N-1; the reference's h is affine:
+    # h = h0 + Ch [x;u]  (evaporation_process/acados.py:207-210)
+    Ch: np.ndarray = field(default_factory=lambda: np.zeros((0, 0)))
+    h0: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    lh: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    uh: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    # initial guess of every stage (the evaporation model needs a non-zero one, acados.py:104-109)
+    x_init: Optional[np.ndarray] = None
+    u_init: Optional[np.ndarray] = None
 
     # ---- parameter struct helpers (nlp.py:970-989; CasADi column-major) ----
     @property
@@ -131,6 +140,8 @@ def stage_cost_unscaled(pb: Problem, k: int, x, u, p):
                 return _nls(pb.y_fun(x, u), pb.p_get(p, "yref_0"), pb.p_get(p, "W_0"))
             if k < pb.N:
                 return _nls(pb.y_fun(x, u), pb.p_get(p, "yref"), pb.p_get(p, "W"))
+            if "W_e" not in dict(pb.p_entries):
+                return 0.0 * x.sum()  # no terminal cost (nlp.py:1069-1072)
             return _nls(pb.y_e_fun(x), pb.p_get(p, "yref_e"), pb.p_get(p, "W_e"))
         T = lambda a: torch.as_tensor(a, dtype=F64)
         if k == 0:
@@ -244,4 +255,56 @@ def make_linear_system(param: Optional[dict] = None, gamma: float = 0.99, N: int
         idxbu=np.array([0]), lbu=np.array([-1.0]), ubu=np.array([1.0]),
         idxbx=np.array([0, 1]), lbx=np.array(lbx, dtype=float), ubx=np.array(ubx, dtype=float),
         idxsbx=np.array([0]), zl=np.array([1e2]), zu=np.array([1e2]),
+    )
+
+
+# --------------------------------------------------------------------------------------
+# evaporation process  (rlmpc/mpc/evaporation_process/acados.py:142-228,
+#                       rlmpc/gym/evaporation_process/environment.py:5-25, 50-106)
+# --------------------------------------------------------------------------------------
+EVAPORATION_PARAM = {
+    "a": 0.5616, "b": 0.3126, "c": 48.43, "d": 0.507, "e": 55.0, "f": 0.1538, "g": 90.0, "h": 0.16, "M": 20.0,
+    "C": 4.0, "U_A2": 6.84, "C_p": 0.07, "lam": 38.5, "lam_s": 36.6, "F_1": 10.0, "X_1": 5.0, "F_3": 50.0,
+    "T_1": 40.0, "T_200": 25.0,
+}
+
+
+def evaporation_ode(x, u, pm):
+    """compute_data + f_expl with the plant parameters as constants (model.p is empty)."""
+    p = EVAPORATION_PARAM if pm is None or len(pm) == 0 else pm
+    X_2, P_2 = x[0], x[1]
+    P_100, F_200 = u[0], u[1]
+    T_2 = p["a"] * P_2 + p["b"] * X_2 + p["c"]
+    T_3 = p["d"] * P_2 + p["e"]
+    T_100 = p["f"] * P_100 + p["g"]
+    U_A1 = p["h"] * (p["F_1"] + p["F_3"])
+    Q_100 = U_A1 * (T_100 - T_2)
+    F_4 = (Q_100 - p["F_1"] * p["C_p"] * (T_2 - p["T_1"])) / p["lam"]
+    Q_200 = p["U_A2"] * (T_3 - p["T_200"]) / (1 + (p["U_A2"] / (2 * p["C_p"] * F_200)))
+    F_5 = Q_200 / p["lam"]
+    F_2 = p["F_1"] - F_4
+    return torch.stack([(p["F_1"] * p["X_1"] - F_2 * X_2) / p["M"], (F_4 - F_5) / p["C"]])
+
+
+def make_evaporation(H: Optional[np.ndarray] = None, gamma: float = 0.99, N: int = 100, n_sub: int = 4) -> Problem:
+    H = np.diag([10.0, 10.0, 0.1, 0.1, 0.1]) if H is None else np.asarray(H, float)  # H_nominal, scripts/evaporation_process_mpc.py:33
+    x_ss, u_ss = np.array([25.0, 49.743]), np.array([191.713, 215.888, 0.0])
+    yref = np.concatenate([x_ss, u_ss])
+    dt = 1.0 / n_sub
+
+    def f_disc(x, u, pm):
+        for _ in range(n_sub):  # acados.py:74-86
+            x = erk4(lambda xx, uu, _p: evaporation_ode(xx, uu, None), x, u, None, dt)
+        return x
+
+    p_entries = [("model", (0,)), ("W_0", (5, 5)), ("W", (5, 5)), ("yref_0", (5,)), ("yref", (5,))]
+    p_nom = np.concatenate([H.T.ravel(), H.T.ravel(), yref, yref])
+    Ch = np.array([[-1.0, 0.0, 0.0, 0.0, -1.0], [0.0, -1.0, 0.0, 0.0, -1.0]])  # h = 25 - x - s
+    return Problem(
+        name="evaporation_process", N=N, nx=2, nu=3, tf=float(N), p_entries=p_entries, p_nominal=p_nom,
+        cost_type="NLS", hessian_approx="GAUSS_NEWTON", gamma=gamma, parameterize_tracking_cost=True,
+        f_disc=f_disc, y_fun=lambda x, u: torch.cat([x, u]), y_e_fun=lambda x: x,
+        idxbu=np.array([0, 1, 2]), lbu=np.array([100.0, 100.0, 0.0]), ubu=np.array([400.0, 400.0, 10.0]),
+        Ch=Ch, h0=np.array([25.0, 25.0]), lh=np.array([-1e3, -1e3]), uh=np.array([0.0, 0.0]),
+        x_init=x_ss, u_init=u_ss,
     )

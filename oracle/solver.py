@@ -149,7 +149,9 @@ class DenseSolver:
         free, genuine = self._masks(qmode)
         gi = np.where(genuine)[0]
         # initial guess like MPC.reset (mpc.py:204-210): all stages = x0, u = 0
-        if init is None:
+        if init is None and pb.x_init is not None:
+            U = np.tile(np.asarray(pb.u_init, float), (N, 1)); X = np.tile(np.asarray(pb.x_init, float), (N + 1, 1))
+        elif init is None:
             U = np.zeros((N, nu)); X = np.tile(np.asarray(x0, float), (N + 1, 1))
         else:
             U, X = np.array(init[0], float), np.array(init[1], float)

@@ -29,8 +29,8 @@ def test_header_symbols_are_exported(built_library):
 def test_desc_struct_matches_header(built_library):
     from mpc4rl_b200 import _cabi
 
-    # struct rlmpc_problem_desc: 2 ints + (129 + 6*8 + 8 + 2*8) doubles
-    assert C.sizeof(_cabi.ProblemDesc) == 8 + 8 * (129 + 48 + 8 + 16)
+    # struct rlmpc_problem_desc: 2 ints + (129 + 6*8 + 24 + 4*8) doubles
+    assert C.sizeof(_cabi.ProblemDesc) == 8 + 8 * (129 + 48 + 24 + 32)
 
 
 def test_no_gpu_means_loud_failure(built_library):

@@ -126,3 +126,28 @@ def test_closed_loop_actor_critic_example_runs():
     assert len(log) == 5
     assert all(np.isfinite(l["mean_td"]) and l["n_valid"] > 48 for l in log)
     assert not np.array_equal(log[0]["theta"], log[-1]["theta"])
+
+
+def test_iterate_store_keeps_rti_accurate(golden):
+    """warm starts stored per replay-buffer entry.  A minibatch sampled in a different
+    order gets its own iterates back, so one RTI step reproduces the converged solution, while the same RTI
+    step from the wrong (permuted) warm starts does not."""
+    ok = np.where(golden["status"][:, 0] == 0)[0][:16]
+    x = torch.tensor(golden["x0"][ok], dtype=torch.float64, device="cuda:0")
+    eng = _engine(16)
+    store = eng.iterate_store(capacity=100)
+    slots = torch.arange(16, device="cuda:0", dtype=torch.int32) * 5 + 3
+    eng.reset(x)
+    u_conv = eng.solve(x, max_sqp=200)[0]
+    store.save(slots)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(1)).cuda()
+    # minibatch = the same entries in another order; engine still holds the iterates in the OLD order
+    u_wrong = eng.solve(x[perm], max_sqp=1)[0]
+    store.load(slots[perm])
+    out = eng.solve_sens(x[perm], max_sqp=1)
+    assert (out["status"] == 0).all()
+    assert (out["u0"] - u_conv[perm]).abs().max().item() < 1e-8
+    assert out["res"].max().item() < 1e-8
+    assert (u_wrong - u_conv[perm]).abs().max().item() > 1e-3
+    # out-of-range slots are skipped
+    store.load(torch.full((16,), -1, dtype=torch.int32))

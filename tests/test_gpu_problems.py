@@ -202,3 +202,86 @@ def test_qlearning_example_batched_equals_per_sample_loop():
     assert np.abs(mpc.get_p() - (p0 + dp_b)).max() == 0.0
     log = ex.main(n_episodes=2, episode_length=16, verbose=False)
     assert len(log) == 2 and np.isfinite(log[-1]["td_error"])
+
+
+# ------------------------------------------------------------------------------------------------
+# evaporation process (affine h rows through the slack input, N = 100, theta = (W_0, W, yref_0, yref))
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def g_evap():
+    return np.load(os.path.join(ROOT, "tests", "golden", "evaporation.npz"))
+
+
+def _evap_engine(B, gamma, N=100):
+    from mpc4rl_b200 import BatchedMPC, evaporation_spec
+
+    spec = evaporation_spec(gamma=gamma, N=N)
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-9)
+    return m, spec
+
+
+def _evap_guess(m, spec, B):
+    """The reference starts every stage at the steady state (evaporation_process/acados.py:104-109)."""
+    m.reset(B=B)
+    for k in range(spec.N + 1):
+        m.put("x", k, _dev(np.tile(spec.x_init, (B, 1))))
+    for k in range(spec.N):
+        m.put("u", k, _dev(np.tile(spec.u_init, (B, 1))))
+
+
+def test_evaporation_matches_golden(g_evap):
+    x0, a = _dev(g_evap["x0"]), _dev(g_evap["a"])
+    B = x0.shape[0]
+    m, spec = _evap_engine(B, float(g_evap["gamma"]), int(g_evap["N"]))  # fixtures: N=40 (dense oracle cost)
+    assert m.ngrad == 60 and m.nrows == 10 and m.ng == 2 and m.nbx == 0  # [lbu(3), lh(2), ubu(3), uh(2)]
+    _evap_guess(m, spec, B)
+    out = m.solve_sens(x0, max_sqp=100)
+    ok = (g_evap["status"][:, 0] == 0) & (out["status"].cpu().numpy() == 0)
+    assert ok.sum() >= B - 1
+    assert np.abs(out["u0"].cpu().numpy() - g_evap["u0"])[ok].max() < 1e-6
+    assert _rel(out["cost"].cpu().numpy()[ok], g_evap["V"][ok]) < 1e-9
+    assert _rel(out["dL"].cpu().numpy()[ok], g_evap["dV"][ok]) < 1e-6     # d/d(W_0, W, yref_0, yref)
+    assert _rel(out["dpi"].cpu().numpy()[ok], g_evap["dpi"][ok]) < 1e-5
+    X = np.stack([m.get("x", k, B).cpu().numpy() for k in range(spec.N + 1)], axis=1)
+    assert np.abs(X - g_evap["X"])[ok].max() < 1e-6
+    # the soft constraint x + s >= 25 is active for the state that starts below it
+    U = np.stack([m.get("u", k, B).cpu().numpy() for k in range(spec.N)], axis=1)
+    assert U[2, 0, 2] > 0.5  # x0 = [24, 55]: slack input used at stage 0
+    _evap_guess(m, spec, B)
+    oq = m.solve_sens(x0, a, max_sqp=100)
+    okq = (g_evap["status"][:, 1] == 0) & (oq["status"].cpu().numpy() == 0)
+    assert okq.sum() >= B - 2
+    assert _rel(oq["cost"].cpu().numpy()[okq], g_evap["Q"][okq]) < 1e-9
+    assert _rel(oq["dL"].cpu().numpy()[okq], g_evap["dQ"][okq]) < 1e-6
+
+
+def test_evaporation_through_the_mirrored_api():
+    """The reference's class at its full horizon N=100 against the one N=100 oracle sample."""
+    from mpc4rl_b200.mpc.evaporation_process.acados import AcadosMPC
+    from mpc4rl_b200.problems import EVAPORATION_PARAM, H_NOMINAL
+
+    g1 = np.load(os.path.join(ROOT, "tests", "golden", "evaporation_n100.npz"))
+    g_evap = {k: (g1[k][None] if g1[k].ndim >= 1 and k != "theta" else g1[k]) for k in g1.files}
+    g_evap["V"] = np.array([float(g1["V"])])
+    gamma = float(g_evap["gamma"])
+    mpc = AcadosMPC(model_param=EVAPORATION_PARAM, cost_param={"H": {"l": H_NOMINAL}}, gamma=gamma)
+    assert mpc.get_p().shape == (60,) and mpc.ocp_solver.acados_ocp.dims.N == 100 and mpc.ocp_solver.acados_ocp.dims.nh == 2
+    x0 = g_evap["x0"][0]
+    u = mpc.get_action(x0)
+    assert np.abs(u - g_evap["u0"][0]).max() < 1e-4  # default tol 1e-6
+    mpc.reset()
+    mpc.update(x0)
+    mpc.update_nlp()
+    assert abs(mpc.get_V() - g_evap["V"][0]) < 1e-7 * abs(g_evap["V"][0])
+    assert mpc.get_dV_dp().shape == (1, 60) and mpc.get_dpi_dp().shape == (3, 60)
+    assert _rel(mpc.get_dV_dp()[0], g_evap["dV"][0]) < 1e-5
+    assert mpc.ocp_solver.get(1, "lam").shape == (10,) and mpc.ocp_solver.get(0, "lam").shape == (14,)
+    assert mpc.ocp_solver.get(100, "lam").shape == (0,)
+    # learning W through set_parameter keeps solver and NLP consistent (mpc.py:233-257)
+    p = mpc.get_p()
+    p[25] *= 1.1  # W[0,0]
+    mpc.set_parameter(p)
+    mpc.reset()
+    mpc.update(x0)
+    assert mpc.get_V() > g_evap["V"][0]

@@ -197,3 +197,47 @@ def test_linear_system_oracle_lqr_and_host_port():
     assert np.abs(o["dL"] - g["dV"]).max() < 1e-6 * np.abs(g["dV"]).max()
     soft = g["slmax"] > 1e-6
     assert soft.sum() >= 2 and np.abs(o["dpi"] - g["dpi"])[~soft].max() < 1e-5 * np.abs(g["dpi"]).max()
+
+
+def test_evaporation_host_port_matches_oracle_fixtures():
+    """Evaporation process: host port of the engine against the dense-oracle fixtures (N=40 set and the one
+    full-horizon N=100 sample; u0, V, dV/dtheta and dpi/dtheta over the 60 tracking-cost parameters), plus
+    a live short-horizon oracle solve."""
+    from oracle import cpu_port as cp
+    from oracle.problems import EVAPORATION_PARAM, make_evaporation
+    from oracle.solver import DenseSolver
+
+    def port(pb, x0s, gamma):
+        scale = np.array([pb.stage_scale(k) for k in range(pb.N + 1)])
+        mc = list(EVAPORATION_PARAM.values()) + [0.25, 4]
+        pd = cp.make_pd(pb.N, scale, pb.lbu, pb.ubu, mc, tol=1e-9, warm_ipm=1, lg=pb.lh, ug=pb.uh)
+        B, nx, nu, N = len(x0s), 2, 3, pb.N
+        it = np.zeros((cp.lib().cpu_port_iterate_size(4, N), B))
+        for k in range(N + 1):
+            it[k * nx:(k + 1) * nx, :] = pb.x_init[:, None]
+        for k in range(N):
+            it[(N + 1) * nx + k * nu:(N + 1) * nx + (k + 1) * nu, :] = pb.u_init[:, None]
+        return cp.unit(4, pd, 0, 100, pb.p_nominal, x0s, iterate=it, nx=2, nu=3)
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "evaporation.npz"))
+    pb = make_evaporation(gamma=float(g["gamma"]), N=int(g["N"]))
+    o = port(pb, g["x0"], float(g["gamma"]))
+    ok = (g["status"][:, 0] == 0) & (o["status"] == 0)
+    assert ok.sum() >= len(ok) - 1
+    assert np.abs(o["u0"] - g["u0"])[ok].max() < 1e-7
+    assert (np.abs(o["cost"] - g["V"]) / np.abs(g["V"]))[ok].max() < 1e-10
+    assert np.abs(o["dL"] - g["dV"])[ok].max() < 1e-7 * np.abs(g["dV"]).max()
+    assert np.abs(o["dpi"] - g["dpi"])[ok].max() < 1e-6 * np.abs(g["dpi"]).max()
+    g1 = np.load(os.path.join(ROOT, "tests", "golden", "evaporation_n100.npz"))
+    o1 = port(make_evaporation(gamma=float(g1["gamma"]), N=100), g1["x0"][None, :], float(g1["gamma"]))
+    assert int(g1["status"]) == 0 and o1["status"][0] == 0
+    assert np.abs(o1["u0"][0] - g1["u0"]).max() < 1e-7 and abs(o1["cost"][0] - float(g1["V"])) < 1e-10 * abs(float(g1["V"]))
+    assert np.abs(o1["dpi"][0] - g1["dpi"]).max() < 1e-6 * np.abs(g1["dpi"]).max()
+    # live: N = 10 horizon, the oracle finishes in seconds
+    pbs = make_evaporation(gamma=0.95, N=10)
+    x0 = np.array([[30.0, 60.0]])
+    sol, upd = DenseSolver(pbs).unit(x0[0], tol=1e-9)
+    os_ = port(pbs, x0, 0.95)
+    assert sol.status == 0 and os_["status"][0] == 0
+    assert np.abs(sol.U[0] - os_["u0"][0]).max() < 1e-8 and abs(sol.cost - os_["cost"][0]) < 1e-9 * abs(sol.cost)
+    assert np.abs(upd["dpi_dp"] - os_["dpi"][0]).max() < 1e-6 * np.abs(upd["dpi_dp"]).max()
