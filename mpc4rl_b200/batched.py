@@ -184,14 +184,22 @@ class BatchedMPC:
                     dL=torch.zeros(B, self.ngrad, **f64), dpi=torch.zeros(B, self.nu, self.ngrad, **f64),
                     res=torch.empty(B, 4, **f64))
 
-    def solve_sens_host(self, x0: np.ndarray, u0: Optional[np.ndarray] = None, max_sqp: int = 1) -> dict:
+    def alloc_host_outputs(self, B: int, pinned: bool = True) -> dict:
+        """Host result buffers for ``solve_sens_host``; page-locked ones are DMA targets (no staging copy)."""
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned).numpy()
+        return dict(u0=mk((B, self.nu), torch.float64), cost=mk((B,), torch.float64), status=mk((B,), torch.int32),
+                    dL=mk((B, self.ngrad), torch.float64), dpi=mk((B, self.nu, self.ngrad), torch.float64),
+                    res=mk((B, 4), torch.float64))
+
+    def solve_sens_host(self, x0: np.ndarray, u0: Optional[np.ndarray] = None, max_sqp: int = 1, out: dict | None = None) -> dict:
         """Host buffers in/out through the C ABI (H2D + kernels + D2H + sync inside the call)."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         B = x0.shape[0]
         mode = _cabi.MODE_V if u0 is None else _cabi.MODE_Q
         u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, self.nu)
-        out = dict(u0=np.empty((B, self.nu)), cost=np.empty(B), status=np.empty(B, dtype=np.int32),
-                   dL=np.empty((B, self.ngrad)), dpi=np.empty((B, self.nu, self.ngrad)), res=np.empty((B, 4)))
+        if out is None:
+            out = dict(u0=np.empty((B, self.nu)), cost=np.empty(B), status=np.empty(B, dtype=np.int32),
+                       dL=np.empty((B, self.ngrad)), dpi=np.empty((B, self.nu, self.ngrad)), res=np.empty((B, 4)))
         p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
         _cabi.check(self.lib.rlmpc_solve_sens_host(self._h, mode, int(max_sqp), B, p(x0), p(u0a), p(out["u0"]),
                                                    p(out["cost"]), p(out["status"]), p(out["dL"]), p(out["dpi"]),

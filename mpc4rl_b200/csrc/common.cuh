@@ -53,6 +53,7 @@ struct ProblemData {
   double sigma0;        // centring parameter of the first iteration of a cold start
   double as_steps;      // warm start: number of active-set (full step + projection) iterations tried
                         // when the Newton step is not feasible, before the cold restart
+  double condense;      // > 0: queued QPs are solved in partially condensed form (condense.cuh) where applicable
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component

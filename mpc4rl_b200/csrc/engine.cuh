@@ -72,13 +72,14 @@ struct Engine {
   static constexpr int W_b = W_B + NX * NU;
   static constexpr int W_q = W_b + NX;          // scaled cost gradient wrt x
   static constexpr int W_r = W_q + NX;          // ... wrt u
-  static constexpr int W_K = W_r + NU;
+  static constexpr int W_H = W_r + NU;          // only with M::STAGE_HESS: stage Hessian [Q S'; S R], packed upper (NWS)
+  static constexpr int W_K = W_H + (M::STAGE_HESS ? NWS : 0);
   static constexpr int W_k = W_K + NU * NX;
-  static constexpr int W_dx = W_k + NU;
-  static constexpr int W_du = W_dx + NX;
-  static constexpr int W_lh = W_du + NU;        // lam_hat (NR)
+  static constexpr int W_lh = W_k + NU;         // lam_hat (NR)
   static constexpr int W_th = W_lh + NR;        // t_hat   (NR)
-  static constexpr int W_c = W_th + NR;         // scaled stage cost
+  static constexpr int W_dx = W_th + NR;        // primal step (written by the forward sweep, read by the step)
+  static constexpr int W_du = W_dx + NX;
+  static constexpr int W_c = W_du + NU;         // scaled stage cost
   static constexpr int W_e = W_c + 1;           // |F(x_k,u_k) - x_{k+1}|_inf
   static constexpr int W_SOLVE_END = W_e + 1;
   // sensitivity phase (overlays the solve record; A, B stay where they are)
@@ -169,6 +170,18 @@ struct Engine {
       const double v = s * p[(size_t)pidx(i, j) * (size_t)TILE];
       Wm[i * NW + j] = v;
       Wm[j * NW + i] = v;
+    }
+  }
+  // Hessian of the stage QP: the scaled cost table, or (M::STAGE_HESS, e.g. condensed blocks) the record
+  MPC_HD static void stage_hess(int kind, double s, const Lane& L, const double* wr, double* Hm) {
+    if (M::STAGE_HESS) {
+      MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) {
+        const double v = wr[(size_t)(W_H + pidx(i, j)) * TILE];
+        Hm[i * NW + j] = v;
+        Hm[j * NW + i] = v;
+      }
+    } else {
+      load_W(kind, s, L, Hm);
     }
   }
   // gradient g = s (W (y - yref) + flin) and value s l(y) of one stage, y = [x;u] (n = NW or NX)
@@ -699,7 +712,7 @@ struct Engine {
   // until done(k), which releases the stage and lets the reader fetch ahead.
   // ---------------------------------------------------------------------------------------
   static constexpr int RD_LAM = 0, RD_T = NR, RD_U = 2 * NR, RD_X = 2 * NR + NU, RD_ROWS = 2 * NR + NU + NX;
-  static constexpr int RD_WS = W_c;  // staged workspace elements [W_A, W_c)
+  static constexpr int RD_WS = W_dx;  // staged workspace elements [W_A, W_dx): everything a sweep reads
   struct DirectReader {
     const Lane& L;
     int N;
@@ -939,7 +952,7 @@ struct Engine {
       {
         double Hm[NW * NW], g[NW];
         const double* wr = rd.ws(N);
-        load_W(2, pd.scale[N], L, Hm);
+        stage_hess(2, pd.scale[N], L, wr, Hm);
         ld<NX>(wr + (size_t)W_q * bs, bs, g);
         MPC_UNROLL for (int i = 0; i < NU; ++i) g[NX + i] = 0.0;
         if (NBX > 0) {
@@ -966,7 +979,7 @@ struct Engine {
         ld<NX>(wr + (size_t)W_b * bs, bs, bb);
         ld<NW>(wr + (size_t)W_q * bs, bs, g);
         double Hm[NW * NW];
-        load_W(k == 0 ? 0 : 1, pd.scale[k], L, Hm);
+        stage_hess(k == 0 ? 0 : 1, pd.scale[k], L, wr, Hm);
         {
           Bnd bd;
           double x[NX], u[NU], v[NV], lam[NR], t[NR];

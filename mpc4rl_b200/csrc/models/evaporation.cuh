@@ -28,6 +28,7 @@ struct EvaporationModel {
   // g_j = 25 - x_j - s,  lh <= g <= uh
   MPC_HD static double gC(int j, int i) { return (i == j || i == NX + 2) ? -1.0 : 0.0; }
   MPC_HD static double g0(int) { return 25.0; }
+  static constexpr bool STAGE_HESS = false;
 
   // ---- cost --------------------------------------------------------------------------------
   MPC_HD static int w_off(int kind) { return kind == 0 ? TH_W0 : TH_W; }

@@ -13,6 +13,7 @@
 
 #include "../../include/rlmpc_b200.h"
 #include "engine.cuh"
+#include "condense.cuh"
 #include "models/cartpole.cuh"
 #include "models/linear_system.cuh"
 #include "models/evaporation.cuh"
@@ -61,6 +62,9 @@ struct KArgs {
   int it_size, ws_size, th_size, ct_size;  // doubles per sample of each tiled array
   double* it2;  // compact copies used by the full interior-point pass (one slot per queued sample)
   double* ws2;
+  double* itb;  // block-form iterate / workspace of the partially condensed queue path
+  double* wsb;
+  int itb_size, wsb_size;
   const double* th;
   const double* ct;
   int th_per_sample;
@@ -150,14 +154,15 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
 // registers held across the copy) while the recursion works on the current stage.  ncu on the
 // direct-load version: 73 % of the warp stalls were long-scoreboard (profiles/r01_summary.md).
 // A lane only ever reads what it copied itself, so no barrier is needed, just wait_group.
-constexpr int RING_DEPTH = 3;
+constexpr int RING_DEPTH = 3;   // stage-form records (13 KB per stage and warp)
+constexpr int RING_DEPTH_B = 2; // condensed block records (38 KB per block and warp)
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
-template <class E>
+template <class E, int DEPTH = RING_DEPTH>
 struct RingReader {
   static constexpr int SLOT = E::RD_WS + E::RD_ROWS;  // doubles per stage and lane
   const Lane& L;
@@ -168,7 +173,7 @@ struct RingReader {
   __device__ __forceinline__ void issue(int i) {
     if (i < count) {
       const int k = k0 + i * dir;
-      double* dst = ring + (size_t)((i % RING_DEPTH) * SLOT) * TILE;
+      double* dst = ring + (size_t)((i % DEPTH) * SLOT) * TILE;
       const double* src = L.ws + (size_t)k * E::W_REC * TILE;
 #pragma unroll
       for (int e = 0; e < E::RD_WS; ++e) cp_async8(dst + (size_t)e * TILE, src + (size_t)e * TILE);
@@ -199,11 +204,11 @@ struct RingReader {
     __threadfence();
     k0 = k_first; dir = dir_; count = count_; consumed = 0;
 #pragma unroll
-    for (int i = 0; i < RING_DEPTH; ++i) issue(i);
+    for (int i = 0; i < DEPTH; ++i) issue(i);
   }
   __device__ __forceinline__ const double* ws(int) const {
-    asm volatile("cp.async.wait_group %0;" ::"n"(RING_DEPTH - 1) : "memory");
-    return ring + (size_t)((consumed % RING_DEPTH) * SLOT) * TILE;
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    return ring + (size_t)((consumed % DEPTH) * SLOT) * TILE;
   }
   __device__ __forceinline__ void rows(int k, double* lam, double* t, double* u, double* x) const {
     const double* r = ws(k) + (size_t)E::RD_WS * TILE;
@@ -218,7 +223,7 @@ struct RingReader {
     if (E::NEEDX) E::template ld<E::NX>(r + (size_t)E::RD_X * TILE, TILE, x);
   }
   __device__ __forceinline__ void done(int) {
-    issue(consumed + RING_DEPTH);
+    issue(consumed + DEPTH);
     ++consumed;
   }
 };
@@ -294,6 +299,63 @@ __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData 
   if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
     // RTI: done after one QP.  SQP: an indefinite reduced Hessian ends the solve; an interior-point
     // iteration limit does not (the next linearisation may well be solvable)
+    a.status[b] = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL;
+    a.work[b] = WK_DONE;
+  } else {
+    a.work[b] = WK_ACTIVE;
+  }
+}
+
+// ---- partially condensed queue path (condense.cuh): input-bounds-only problems, V-mode ----
+constexpr int CBLK = 4;  // stages per block
+template <class M>
+struct Condensable {
+  static constexpr bool value = M::NBX == 0 && M::NSX == 0 && M::NG == 0 && CBLK * M::NU <= MAXD;
+};
+
+// (queue sample, block) kernel: build the block records and the block-form iterate.  grid = (tiles, N/S + 1)
+template <class M>
+__global__ void __launch_bounds__(64) k_condense(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using Cn = Condenser<M, CBLK>;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.counters[0]) return;
+  const int b = a.hard[j];
+  Lane L = make_lane<M>(a, b);
+  L.it = a.it2 + tile_off(j, a.it_size);
+  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  Lane Lb = L;
+  Lb.it = a.itb + tile_off(j, a.itb_size);
+  Lb.ws = a.wsb + tile_off(j, a.wsb_size);
+  Cn::condense_block(pd, L, Lb, blockIdx.y);
+}
+
+// queue sample kernel: interior-point loop on the blocks, expansion, step
+template <class M, bool RING>
+__global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData pd, const __grid_constant__ ProblemData pdb,
+                                             const KArgs a) {
+  using E = Engine<M>;
+  using Cn = Condenser<M, CBLK>;
+  using EB = typename Cn::EB;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.counters[0]) return;
+  const int b = a.hard[j];
+  Lane L = make_lane<M>(a, b);
+  L.it = a.it2 + tile_off(j, a.it_size);
+  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  Lane Lb = L;
+  Lb.it = a.itb + tile_off(j, a.itb_size);
+  Lb.ws = a.wsb + tile_off(j, a.wsb_size);
+  int st;
+  if (RING) {
+    extern __shared__ double ring_smem[];
+    RingReader<EB, RING_DEPTH_B> rd(Lb, pdb.N, ring_smem + threadIdx.x);
+    st = Cn::solve_expand(pd, pdb, L, Lb, nullptr, rd);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    typename EB::DirectReader rd(Lb, pdb.N);
+    st = Cn::solve_expand(pd, pdb, L, Lb, nullptr, rd);
+  }
+  if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
     a.status[b] = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL;
     a.work[b] = WK_DONE;
   } else {
@@ -513,6 +575,10 @@ struct rlmpc_handle {
   int ng() const { return pd.param_cost ? nth : npm; }
   ProblemData pd;
   double *it = nullptr, *ws = nullptr, *it2 = nullptr, *ws2 = nullptr, *th = nullptr, *ct = nullptr, *th_stage = nullptr;
+  double *itb = nullptr, *wsb = nullptr;  // partially condensed queue path (only for condensable models)
+  int itb_size = 0, wsb_size = 0;
+  int condense = 1;    // 1: queued QPs in partially condensed form where applicable (input bounds only, V-mode, N % 4 == 0)
+  int ring_b = 0;      // ring reader for the condensed kernel: measured slower (3.3 vs 2.3 ms), blocks carry enough work per load batch
   double* cost = nullptr;
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
   int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
@@ -538,12 +604,12 @@ struct rlmpc_handle {
 namespace {
 
 // run `expr` with M bound to the model type of the handle
-#define DISPATCH_MODEL(h, expr)                                        \
-  switch ((h)->variant) {                                              \
-    case VAR_CARTPOLE: { using M = CartpoleModel; expr; } break;       \
-    case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; expr; } break;  \
-    case VAR_LINEAR: { using M = LinearSystemModel; expr; } break;     \
-    case VAR_EVAPORATION: { using M = EvaporationModel; expr; } break; \
+#define DISPATCH_MODEL(h, ...)                                                \
+  switch ((h)->variant) {                                                     \
+    case VAR_CARTPOLE: { using M = CartpoleModel; __VA_ARGS__; } break;       \
+    case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; __VA_ARGS__; } break;  \
+    case VAR_LINEAR: { using M = LinearSystemModel; __VA_ARGS__; } break;     \
+    case VAR_EVAPORATION: { using M = EvaporationModel; __VA_ARGS__; } break; \
   }
 
 int check_batch(rlmpc_handle* h, int B) {
@@ -564,6 +630,7 @@ KArgs base_args(rlmpc_handle* h, int B) {
   KArgs a;
   memset(&a, 0, sizeof(a));
   a.it = h->it; a.ws = h->ws; a.it2 = h->it2; a.ws2 = h->ws2;
+  a.itb = h->itb; a.wsb = h->wsb; a.itb_size = h->itb_size; a.wsb_size = h->wsb_size;
   a.it_size = h->it_size; a.ws_size = h->ws_size; a.th_size = h->nth; a.ct_size = h->ct_size;
   a.th = h->th; a.ct = h->ct; a.th_per_sample = h->th_per_sample; a.B = B;
   a.work = h->work; a.status = h->status; a.cost = h->cost; a.hard = h->hard; a.counters = h->counters;
@@ -574,6 +641,51 @@ KArgs base_args(rlmpc_handle* h, int B) {
 template <class M>
 constexpr size_t qp2_smem() {
   return sizeof(double) * RING_DEPTH * RingReader<Engine<M>>::SLOT * TILE;
+}
+template <class M>
+constexpr size_t qp2c_smem() {
+  return sizeof(double) * RING_DEPTH_B * RingReader<typename Condenser<M, CBLK>::EB, RING_DEPTH_B>::SLOT * TILE;
+}
+
+template <class M>
+cudaError_t alloc_condensed(rlmpc_handle* h, int N, cudaError_t e) {
+  if constexpr (Condensable<M>::value) {
+    using EB = typename Condenser<M, CBLK>::EB;
+    if (N % CBLK == 0) {
+      h->itb_size = EB::it_size(N / CBLK);
+      h->wsb_size = EB::ws_size(N / CBLK);
+      if (e == cudaSuccess) e = cudaMalloc(&h->itb, sizeof(double) * h->itb_size * h->bs);
+      if (e == cudaSuccess) e = cudaMalloc(&h->wsb, sizeof(double) * h->wsb_size * h->bs);
+      if (e == cudaSuccess) e = cudaMemset(h->itb, 0, sizeof(double) * h->itb_size * h->bs);
+      if (e == cudaSuccess) e = cudaMemset(h->wsb, 0, sizeof(double) * h->wsb_size * h->bs);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_qp2c<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qp2c_smem<M>());
+    }
+  }
+  return e;
+}
+
+// the queue pass between gather and scatter: condensed where possible, else stage form
+template <class M>
+void launch_queue_solve(rlmpc_handle* h, const KArgs& a, int B, cudaStream_t sq) {
+  if constexpr (Condensable<M>::value) {
+    using Cn = Condenser<M, CBLK>;
+    if (h->condense && h->itb && Cn::applicable(h->pd)) {
+      const ProblemData pdb = Cn::block_pd(h->pd);
+      k_condense<M><<<dim3((B + 63) / 64, pdb.N + 1), 64, 0, sq>>>(h->pd, a);
+      if (h->ring_b)
+        k_qp2c<M, true><<<(B + 31) / 32, 32, qp2c_smem<M>(), sq>>>(h->pd, pdb, a);
+      else
+        k_qp2c<M, false><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, pdb, a);
+      h->launches += 2;
+      return;
+    }
+  }
+  if (h->ring)
+    k_qp2<M, true><<<(B + 31) / 32, 32, qp2_smem<M>(), sq>>>(h->pd, a);
+  else
+    k_qp2<M, false><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, a);
+  h->launches++;
 }
 
 // SQP: K rounds of (linearise | convergence test + fast QP | full interior point on the queue),
@@ -609,14 +721,11 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         const int n_g = (E::it_size(N) + (N + 1) * E::W_K + GATHER_CHUNK - 1) / GATHER_CHUNK;
         const int n_s = (E::it_size(N) + GATHER_CHUNK - 1) / GATHER_CHUNK;
         k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
-        if (h->ring)
-          k_qp2<M, true><<<(B + 31) / 32, 32, qp2_smem<M>(), sq>>>(h->pd, a);
-        else
-          k_qp2<M, false><<<(B + 31) / 32, 32, 0, sq>>>(h->pd, a);
+        launch_queue_solve<M>(h, a, B, sq);
         k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
       }
       mark(h, 3, sq);
-      h->launches += 3;
+      h->launches += 2;
       if (fork_qp2) CUDA_OK(cudaEventRecord(h->ev_join, sq));
     }
     if (K > 1 && !a.last_round && (r % h->sync_every) == h->sync_every - 1) {
@@ -798,7 +907,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -814,6 +923,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMalloc(&h->ws, n_ws);
   if (e == cudaSuccess) e = cudaMalloc(&h->it2, n_it);
   if (e == cudaSuccess) e = cudaMalloc(&h->ws2, n_ws);
+  DISPATCH_MODEL(h, e = alloc_condensed<M>(h, d->N, e));
   if (e == cudaSuccess) e = cudaMalloc(&h->th, sizeof(double) * h->nth * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->ct, sizeof(double) * h->ct_size * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->th_stage, sizeof(double) * h->nth * (size_t)max_batch);
@@ -856,7 +966,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
 void rlmpc_destroy(rlmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->th); cudaFree(h->ct);
+  cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->itb); cudaFree(h->wsb); cudaFree(h->th); cudaFree(h->ct);
   cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
   cudaFree(h->counters); cudaFree(h->ishard);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -946,6 +1056,8 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "timing")) h->timing = (int)value;
   else if (!strcmp(name, "overlap")) h->overlap = (int)value;
   else if (!strcmp(name, "ring")) h->ring = (int)value;
+  else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
+  else if (!strcmp(name, "condense")) h->condense = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }
@@ -1019,10 +1131,28 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = h->own_stream;
   const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->ng();
-  // stage inputs through pinned memory so the copies are real DMA transfers
-  memcpy(h->h_in, x0_host, sizeof(double) * nB * nx);
-  if (u0_host) memcpy(h->h_in + nB * nx, u0_host, sizeof(double) * nB * nu);
-  CUDA_OK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(double) * nB * (nx + (u0_host ? nu : 0)), cudaMemcpyHostToDevice, s));
+  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used
+  // directly as DMA source / destination; pageable ones go through the handle's pinned staging area.
+  auto pinned = [](const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool in_pinned = pinned(x0_host) && pinned(u0_host);
+  double* d_x0 = h->d_in;
+  double* d_u0 = u0_host ? h->d_in + nB * nx : nullptr;
+  if (in_pinned) {
+    CUDA_OK(cudaMemcpyAsync(d_x0, x0_host, sizeof(double) * nB * nx, cudaMemcpyHostToDevice, s));
+    if (u0_host) CUDA_OK(cudaMemcpyAsync(d_u0, u0_host, sizeof(double) * nB * nu, cudaMemcpyHostToDevice, s));
+  } else {
+    memcpy(h->h_in, x0_host, sizeof(double) * nB * nx);
+    if (u0_host) memcpy(h->h_in + nB * nx, u0_host, sizeof(double) * nB * nu);
+    CUDA_OK(cudaMemcpyAsync(h->d_in, h->h_in, sizeof(double) * nB * (nx + (u0_host ? nu : 0)), cudaMemcpyHostToDevice, s));
+  }
   double* d_u0o = h->d_out;
   double* d_cost = d_u0o + nB * nu;
   double* d_res = d_cost + nB;
@@ -1030,9 +1160,20 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   double* d_dpi = d_dL + nB * nth;
   const size_t n_out = nB * (nu + 1 + 4 + nth * (1 + nu));
   CUDA_OK(cudaMemsetAsync(d_dL, 0, sizeof(double) * nB * nth * (1 + nu), s));
-  if (int r = run_unit(h, mode, max_sqp, B, h->d_in, u0_host ? h->d_in + nB * nx : nullptr, d_u0o, d_cost, h->d_status,
-                       d_dL, d_dpi, d_res, 1, 1, s))
-    return r;
+  if (int r = run_unit(h, mode, max_sqp, B, d_x0, d_u0, d_u0o, d_cost, h->d_status, d_dL, d_dpi, d_res, 1, 1, s)) return r;
+  const bool out_pinned = pinned(u0_out_host) && pinned(cost_out_host) && pinned(res_out_host) && pinned(dL_dtheta_host) &&
+                          pinned(dpi_dtheta_host) && pinned(status_out_host);
+  if (out_pinned) {
+    if (u0_out_host) CUDA_OK(cudaMemcpyAsync(u0_out_host, d_u0o, sizeof(double) * nB * nu, cudaMemcpyDeviceToHost, s));
+    if (cost_out_host) CUDA_OK(cudaMemcpyAsync(cost_out_host, d_cost, sizeof(double) * nB, cudaMemcpyDeviceToHost, s));
+    if (res_out_host) CUDA_OK(cudaMemcpyAsync(res_out_host, d_res, sizeof(double) * nB * 4, cudaMemcpyDeviceToHost, s));
+    if (dL_dtheta_host) CUDA_OK(cudaMemcpyAsync(dL_dtheta_host, d_dL, sizeof(double) * nB * nth, cudaMemcpyDeviceToHost, s));
+    if (dpi_dtheta_host)
+      CUDA_OK(cudaMemcpyAsync(dpi_dtheta_host, d_dpi, sizeof(double) * nB * nth * nu, cudaMemcpyDeviceToHost, s));
+    if (status_out_host) CUDA_OK(cudaMemcpyAsync(status_out_host, h->d_status, sizeof(int) * nB, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+  }
   CUDA_OK(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int) * nB, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../mpc4rl_b200/csrc/engine.cuh"
+#include "../../mpc4rl_b200/csrc/condense.cuh"
 #include "../../mpc4rl_b200/csrc/models/cartpole.cuh"
 #include "../../mpc4rl_b200/csrc/models/linear_system.cuh"
 #include "../../mpc4rl_b200/csrc/models/evaporation.cuh"
@@ -16,6 +17,27 @@
 using namespace rlmpc;
 
 static int g_threads = 0;  // 0 = all hardware threads
+
+// queued QP: partially condensed (blocks of 4 stages) where the product does that too
+template <class M>
+static int qp_full_maybe_condensed(const ProblemData& pd, const Lane& L, int* ipm_iter) {
+  using E = Engine<M>;
+  if constexpr (M::NBX == 0 && M::NSX == 0 && M::NG == 0 && M::NX * 1 == 4) {
+    using Cn = Condenser<M, 4>;
+    if (pd.condense > 0 && Cn::applicable(pd)) {
+      using EB = typename Cn::EB;
+      const ProblemData pdb = Cn::block_pd(pd);
+      std::vector<double> itb((size_t)EB::it_size(pdb.N) * TILE, 0.0), wsb((size_t)EB::ws_size(pdb.N) * TILE, 0.0);
+      Lane Lb = L;
+      Lb.it = itb.data();
+      Lb.ws = wsb.data();
+      for (int i = 0; i <= pdb.N; ++i) Cn::condense_block(pd, L, Lb, i);
+      typename EB::DirectReader rd(Lb, pdb.N);
+      return Cn::solve_expand(pd, pdb, L, Lb, ipm_iter, rd);
+    }
+  }
+  return E::qp_full(pd, L, ipm_iter);
+}
 
 // Same pipeline as rlmpc_b200.cu, one sample at a time: K rounds of (linearise all stages |
 // convergence test + fast QP | full interior point), one test-only round, then the sensitivities.
@@ -66,7 +88,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
           if (K == 1) { status = ST_OK; break; }
           continue;
         }
-        const int st = E::qp_full(pd, L, &ipm_iter);
+        const int st = qp_full_maybe_condensed<M>(pd, L, &ipm_iter);
         ++sqp_iter;
         if (K == 1 || st == E::FULL_FAILED) { status = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL; break; }
       }

@@ -92,6 +92,12 @@ def test_host_entry_point_equals_device_path(spec, golden):
     for k in ("u0", "cost", "dL", "dpi", "res"):
         assert np.array_equal(o_dev[k].cpu().numpy(), o_host[k]), k
     assert np.array_equal(o_dev["status"].cpu().numpy(), o_host["status"])
+    # page-locked caller buffers are used as DMA source / target directly: same results
+    m.reset(_dev(x0))
+    pin = m.alloc_host_outputs(x0.shape[0], pinned=True)
+    o_pin = m.solve_sens_host(torch.tensor(x0).pin_memory().numpy(), max_sqp=100, out=pin)
+    for k in ("u0", "cost", "dL", "dpi", "res", "status"):
+        assert np.array_equal(o_pin[k], o_host[k]), k
 
 
 def test_live_oracle_kkt_and_sensitivities(spec):
