@@ -106,7 +106,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -155,7 +155,7 @@ def cpu_port_run(n_samples, steps, warmup, threads=0, seed=1234):
     from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
 
     spec = cartpole_spec(cartpole_original_config())
-    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-6)
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-6, warm_ipm=1, condense=1)
     x0 = synth_states(n_samples, seed).numpy()
     o = cp.unit(1, pd, 0, 30, spec.p_nominal, x0, threads=threads)  # converge (untimed)
     it = o["iterate"]
