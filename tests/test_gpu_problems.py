@@ -285,3 +285,79 @@ def test_evaporation_through_the_mirrored_api():
     mpc.reset()
     mpc.update(x0)
     assert mpc.get_V() > g_evap["V"][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size property tests (BASELINE.json sizes; the oracle is too slow there)
+# ------------------------------------------------------------------------------------------------
+def test_evaporation_full_batch_properties():
+    """BASELINE configs[3] size (32 768 samples, N=100): every sample converges from the steady-state guess,
+    KKT residuals at tolerance, replicated inputs give bit-identical outputs, the constraint x + s >= 25 holds
+    along the horizon, and dV/dyref agrees with central differences through per-sample theta."""
+    from mpc4rl_b200 import BatchedMPC, evaporation_spec
+
+    B = 32768
+    spec = evaporation_spec(gamma=0.99)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    lo, hi = torch.tensor([25.0, 49.7], dtype=torch.float64), torch.tensor([40.0, 70.0], dtype=torch.float64)
+    x0 = (lo + (hi - lo) * torch.rand(B, 2, generator=g, dtype=torch.float64)).cuda()
+    x0[B // 2:] = x0[: B // 2]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-8)
+    _evap_guess(m, spec, B)
+    out = m.solve_sens(x0, max_sqp=100)
+    st = out["status"].cpu().numpy()
+    assert (st == 0).mean() > 0.999, np.bincount(st)
+    okm = out["status"] == 0
+    assert out["res"][okm].max().item() < 1e-8 * (1 + 1e-3)
+    for k in ("u0", "cost", "dL", "dpi"):
+        assert torch.equal(out[k][: B // 2], out[k][B // 2:]), k
+    for k in (0, 1, 50, 99):
+        x, u = m.get("x", k, B), m.get("u", k, B)
+        assert ((x + u[:, 2:3])[okm] >= 25.0 - 1e-6).all()
+        assert ((u >= torch.tensor(spec.lbu, device="cuda:0") - 1e-9) & (u <= torch.tensor(spec.ubu, device="cuda:0") + 1e-9))[okm].all()
+    # FD of V w.r.t. yref[0] (theta index 55) and W[0,0] (index 25) through per-sample theta
+    n, d = 32, 1e-5
+    idx = [25, 55]
+    th = np.tile(spec.p_nominal, (2 * len(idx) * n, 1))
+    for c, j in enumerate(idx):
+        th[(2 * c) * n:(2 * c + 1) * n, j] += d
+        th[(2 * c + 1) * n:(2 * c + 2) * n, j] -= d
+    m2 = BatchedMPC(spec, max_batch=th.shape[0], device=0)
+    m2.set_option("tol", 1e-11)
+    m2.set_theta(th)
+    xx = x0[:n].repeat(2 * len(idx), 1)
+    _evap_guess(m2, spec, th.shape[0])
+    o2 = m2.solve_sens(xx, max_sqp=200)
+    assert (o2["status"] == 0).all()
+    V = o2["cost"].cpu().numpy().reshape(2 * len(idx), n)
+    an = out["dL"][:n].cpu().numpy()
+    for c, j in enumerate(idx):
+        fd = (V[2 * c] - V[2 * c + 1]) / (2 * d)
+        assert np.abs(fd - an[:, j]).max() < 1e-4 * max(1.0, np.abs(an[:, j]).max()), j
+
+
+def test_linear_system_batch_properties():
+    """4 096 random states of the linear system in one call: converged, |u| <= 1, the hard bound on x[1] holds,
+    V >= V_0, V is (weakly) convex along a line of states, dV/dV_0 = 1 everywhere."""
+    B = 4096
+    m = _lin_engine(B, gamma=0.9)
+    m.set_option("tol", 1e-8)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x0 = torch.rand(B, 2, generator=g, dtype=torch.float64)
+    x0[:, 1] = 1.6 * x0[:, 1] - 0.8
+    t = torch.linspace(0.0, 1.0, 33, dtype=torch.float64)
+    x0[:33] = torch.stack([0.1 + 0.7 * t, 0.3 - 0.5 * t], dim=1)  # a line segment for the convexity check
+    x0 = x0.cuda()
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=100)
+    okm = out["status"] == 0
+    assert okm.double().mean().item() > 0.98
+    assert out["res"][okm].max().item() < 1e-8 * (1 + 1e-3)
+    assert (out["u0"][okm].abs() <= 1.0 + 1e-8).all()
+    assert (out["cost"][okm] >= 1e-3 - 1e-12).all()
+    assert (out["dL"][okm][:, 8] - 1.0).abs().max().item() < 1e-12
+    x1 = m.get("x", 1, B)
+    assert (x1[okm][:, 1].abs() <= 1.0 + 1e-7).all()
+    V = out["cost"][:33].cpu().numpy()
+    assert okm[:33].all() and (V[:-2] + V[2:] - 2 * V[1:-1] >= -1e-9).all()
