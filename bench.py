@@ -34,8 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "MPC solves+sensitivities/sec (cartpole N=40, batch 65k)"
 UNIT = "units/s"
-BATCH = 65536
-B_ALG = 8492  # algorithmic bytes per unit, SURVEY.md 8(d): 8*(2*524 + 4+1 + 1+1+3+3) + 4
+BATCH = 65536  # headline workload; algorithmic bytes per unit: 8*(2*524 + 4+1 + 1+1+3+3) + 4 = 8492
 
 
 def synth_states(B, seed):
@@ -308,7 +307,12 @@ def run_gpu(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step, ncu launch list
+                         # profiles/r01f_launches_rti_steps.csv (headline workload at its default batch only)
+                         "traffic": 12.645e9 if (args.workload == "cartpole" and B == 65536) else None,
+                         "traffic_source": "profiles/r01f_launches_rti_steps.csv (sum over the 9 kernels of one call)",
+                         "peak_source": peak_src,
                          "kernel": "rlmpc_solve_sens = k_lin + k_qp1 + k_qp2 + k_sens_stage + k_sens_sweep "
                                    f"(dominant: {max(phase_ms, key=phase_ms.get)})",
                          "kernel_ms": kernel_ms, "kernels_ms": {k: round(v, 4) for k, v in phase_ms.items()},
