@@ -46,6 +46,7 @@ struct ProblemData {
   int max_ipm;          // max interior-point iterations per QP
   int warm_ipm;         // 1: start the IPM from the stored (lam,t)
   int param_cost;       // 1: gradient wrt cost parameters requested (parameterize_tracking_cost)
+  int fix0;             // leading inputs of stage 0 that carry no rows (the clamped u_0 of Q-mode in block form)
   double tol;           // SQP convergence tolerance on the 4 KKT residual norms
   double tau;           // complementarity target lam*t = tau (nlp.py:1199)
   double mu0;           // initial barrier parameter of a cold-started IPM

@@ -13,7 +13,9 @@
 //     block dynamics  dx_{k0+S} = Phi_S dx_{k0} + Gam_S dU + beta_S
 //   Bounds are on inputs only, so the block rows are the stage rows re-ordered and the barrier terms
 //   stay diagonal: the interior-point iteration on the blocks IS the iteration on the stages.
-// Applies to problems with input bounds only (NBX = NSX = NG = 0), V-mode, N divisible by S.
+// Applies to problems with input bounds only (NBX = NSX = NG = 0), N divisible by S.  Q-mode (u_0
+// clamped): the inputs of stage 0 stay in block 0 as decoupled dummy variables (unit Hessian, zero
+// gradient, zero column in Gam, no rows), so their step is exactly zero.
 // condense_block() is a (sample, block) function, solve + expand a sample function.
 #pragma once
 #include "engine.cuh"
@@ -40,10 +42,12 @@ struct Condenser {
   static_assert(M::NBX == 0 && M::NSX == 0 && M::NG == 0, "partial condensing: input bounds only");
 
   // block problem data: N/S stages, input bounds replicated, mode V
-  static bool applicable(const ProblemData& pd) { return pd.mode == MODE_V && pd.N % S == 0 && NUB <= MAXD; }
+  static bool applicable(const ProblemData& pd) { return pd.N % S == 0 && NUB <= MAXD; }
   static ProblemData block_pd(const ProblemData& pd) {
     ProblemData b = pd;
     b.N = pd.N / S;
+    b.fix0 = (pd.mode == MODE_Q) ? NU : 0;
+    b.mode = MODE_V;
     for (int j = 0; j < S; ++j)
       for (int c = 0; c < NU; ++c) {
         b.lbu[j * NU + c] = pd.lbu[c];
@@ -129,6 +133,16 @@ struct Condenser {
       }
       MPC_UNROLL for (int a = 0; a < NX * NWB; ++a) Z[a] = Zn[a];
       MPC_UNROLL for (int a = 0; a < NX; ++a) beta[a] = bn[a];
+    }
+    if (i == 0 && pd.mode == MODE_Q) {  // clamped u_0: decouple the inputs of stage 0
+      MPC_UNROLL for (int c = 0; c < NU; ++c) {
+        const int q = NX + c;
+        MPC_UNROLL for (int a = 0; a < NWB; ++a) {
+          Hb[(a < q ? a : q) * NWB + (a < q ? q : a)] = (a == q) ? 1.0 : 0.0;
+        }
+        gb[q] = 0.0;
+        MPC_UNROLL for (int a = 0; a < NX; ++a) Z[a * NWB + q] = 0.0;
+      }
     }
     // block record: A = Phi_S, B = Gam_S, b = beta_S, g = gb, H = Hb
     double Ab[NX * NX], Bb[NX * NUB], Hp[EB::NWS];

@@ -243,8 +243,9 @@ struct Engine {
   MPC_HD static void stage_bounds(const ProblemData& pd, int k, Bnd& bd) {
     const bool uact = (k < pd.N) && !(k == 0 && pd.mode == MODE_Q);
     MPC_UNROLL for (int i = 0; i < NU; ++i) {
-      bd.lb[i] = uact ? pd.lbu[i] : -1e300;
-      bd.ub[i] = uact ? pd.ubu[i] : 1e300;
+      const bool act = uact && !(k == 0 && i < pd.fix0);
+      bd.lb[i] = act ? pd.lbu[i] : -1e300;
+      bd.ub[i] = act ? pd.ubu[i] : 1e300;
     }
     MPC_UNROLL for (int j = 0; j < NBX; ++j) {
       const int ix = M::bx(j);

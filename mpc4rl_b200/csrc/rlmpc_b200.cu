@@ -84,6 +84,7 @@ struct KArgs {
   double* dL;        // [B, ng]
   double* dpi;       // [B, NU, ng]
   double* res_out;   // [B, 4]
+  int inplace;       // queue kernels work in place on all samples marked WK_HARD (dense queue: no compact copies)
   int last_round;    // this SQP round only evaluates the convergence test
   int have_solve;    // sens: a solve preceded in this call (keep its status)
 };
@@ -97,6 +98,25 @@ __device__ __forceinline__ Lane make_lane(const KArgs& a, int b) {
   L.th = a.th + (a.th_per_sample ? tile_off(b, a.th_size) : (size_t)(b % TILE));
   L.ct = a.ct + (a.th_per_sample ? tile_off(b, a.ct_size) : (size_t)(b % TILE));
   return L;
+}
+
+// Which sample does thread j of a queue kernel own, and where are its iterate / workspace?  Sparse queue:
+// the j-th queued sample, compact copies in slot j.  Dense queue (inplace): sample j itself if it is queued.
+template <class M>
+__device__ __forceinline__ bool queue_lane(const KArgs& a, int j, int& b, int& slot, Lane& L) {
+  if (a.inplace) {
+    if (j >= a.B || a.work[j] != WK_HARD) return false;
+    b = slot = j;
+    L = make_lane<M>(a, b);
+    return true;
+  }
+  if (j >= a.counters[0]) return false;
+  b = a.hard[j];
+  slot = j;
+  L = make_lane<M>(a, b);
+  L.it = a.it2 + tile_off(j, a.it_size);
+  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  return true;
 }
 
 // start of a solve call: x_0 (and u_0 in Q-mode) into the iterate, pipeline state reset
@@ -281,11 +301,9 @@ template <class M, bool RING>
 __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.counters[0]) return;
-  const int b = a.hard[j];
-  Lane L = make_lane<M>(a, b);  // theta / cost table of the sample; iterate and workspace: the compact copies
-  L.it = a.it2 + tile_off(j, a.it_size);
-  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  int b, slot;
+  Lane L;  // theta / cost table of the sample; iterate and workspace: the compact copies (or in place)
+  if (!queue_lane<M>(a, j, b, slot, L)) return;
   const int N = pd.N;
   int st;
   if (RING) {
@@ -318,14 +336,12 @@ template <class M>
 __global__ void __launch_bounds__(64) k_condense(const __grid_constant__ ProblemData pd, const KArgs a) {
   using Cn = Condenser<M, CBLK>;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.counters[0]) return;
-  const int b = a.hard[j];
-  Lane L = make_lane<M>(a, b);
-  L.it = a.it2 + tile_off(j, a.it_size);
-  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  int b, slot;
+  Lane L;
+  if (!queue_lane<M>(a, j, b, slot, L)) return;
   Lane Lb = L;
-  Lb.it = a.itb + tile_off(j, a.itb_size);
-  Lb.ws = a.wsb + tile_off(j, a.wsb_size);
+  Lb.it = a.itb + tile_off(slot, a.itb_size);
+  Lb.ws = a.wsb + tile_off(slot, a.wsb_size);
   Cn::condense_block(pd, L, Lb, blockIdx.y);
 }
 
@@ -337,14 +353,12 @@ __global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData
   using Cn = Condenser<M, CBLK>;
   using EB = typename Cn::EB;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.counters[0]) return;
-  const int b = a.hard[j];
-  Lane L = make_lane<M>(a, b);
-  L.it = a.it2 + tile_off(j, a.it_size);
-  L.ws = a.ws2 + tile_off(j, a.ws_size);
+  int b, slot;
+  Lane L;
+  if (!queue_lane<M>(a, j, b, slot, L)) return;
   Lane Lb = L;
-  Lb.it = a.itb + tile_off(j, a.itb_size);
-  Lb.ws = a.wsb + tile_off(j, a.wsb_size);
+  Lb.it = a.itb + tile_off(slot, a.itb_size);
+  Lb.ws = a.wsb + tile_off(slot, a.wsb_size);
   int st;
   if (RING) {
     extern __shared__ double ring_smem[];
@@ -582,6 +596,7 @@ struct rlmpc_handle {
   double* cost = nullptr;
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
   int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
+  int inplace_queue = 0;
   int overlap = 0;  // 1: RTI + sens runs the full interior-point pass of the queued samples on a side stream,
                     // concurrently with the sensitivity kernels of all other samples.  Measured slower
                     // (the few latency-bound warps of the queue lose issue slots to the bulk kernels).
@@ -699,8 +714,14 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   h->launches++;
   for (int i = 0; i < rlmpc_handle::NEV; ++i) h->ev_set[i] = false;
   const int rounds = (K == 1) ? 1 : K + 1;
+  // Option "inplace_queue": the queue kernels work in place on the samples marked WK_HARD and the gather /
+  // scatter copies are skipped.  Only pays when (nearly) every sample is queued; measured slower for a
+  // cold SQP-to-convergence solve as a whole (90 vs 86 ms per 65 536: after the first round the queue is
+  // sparse and in-place warps carry few active lanes), so it is off by default.
+  bool dense_queue = (K > 1) && h->inplace_queue;
   for (int r = 0; r < rounds; ++r) {
     a.last_round = (K > 1 && r == K) ? 1 : 0;
+    a.inplace = dense_queue ? 1 : 0;
     CUDA_OK(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int), s));
     mark(h, 0, s);
     k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
@@ -720,9 +741,9 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         const int wpb = 8;  // warps per block of the copy kernels
         const int n_g = (E::it_size(N) + (N + 1) * E::W_K + GATHER_CHUNK - 1) / GATHER_CHUNK;
         const int n_s = (E::it_size(N) + GATHER_CHUNK - 1) / GATHER_CHUNK;
-        k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
+        if (!a.inplace) k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
         launch_queue_solve<M>(h, a, B, sq);
-        k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
+        if (!a.inplace) k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
       }
       mark(h, 3, sq);
       h->launches += 2;
@@ -735,6 +756,7 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
       CUDA_OK(cudaMemcpyAsync(h->h_counters, h->counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_OK(cudaStreamSynchronize(s));
       if (h->h_counters[1] == 0) break;
+      dense_queue = dense_queue && h->h_counters[0] > B / 2;
     }
   }
   CUDA_OK(cudaGetLastError());
@@ -1058,6 +1080,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "ring")) h->ring = (int)value;
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
+  else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }

@@ -19,7 +19,7 @@ class ProblemData(C.Structure):
     """Mirror of rlmpc::ProblemData (mpc4rl_b200/csrc/common.cuh)."""
     _fields_ = [
         ("N", C.c_int), ("mode", C.c_int), ("max_sqp", C.c_int), ("max_ipm", C.c_int),
-        ("warm_ipm", C.c_int), ("param_cost", C.c_int),
+        ("warm_ipm", C.c_int), ("param_cost", C.c_int), ("fix0", C.c_int),
         ("tol", C.c_double), ("tau", C.c_double), ("mu0", C.c_double),
         ("sigma_min", C.c_double), ("sigma0", C.c_double), ("as_steps", C.c_double), ("condense", C.c_double),
         ("scale", C.c_double * (MAXN + 1)),
