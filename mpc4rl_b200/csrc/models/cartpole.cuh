@@ -194,7 +194,7 @@ struct CartpoleModelT {
         if (b >= 4) v += Hf[p][b - 2];
         T[p][b] = v;
       }
-      MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+      MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {  // symmetric: upper triangle
         double v = Sr0[a] * T[0][b] + Sr1[a] * T[1][b];
         if (a >= 4) v += T[a - 2][b];
         Hacc[a][b] += v;
@@ -217,7 +217,7 @@ struct CartpoleModelT {
       }
     }
     MPC_UNROLL for (int a = 0; a < 5; ++a) {
-      MPC_UNROLL for (int b = 0; b < 5; ++b) Hww[a * 5 + b] = Hacc[a][b];
+      MPC_UNROLL for (int b = 0; b < 5; ++b) Hww[a * 5 + b] = (a <= b) ? Hacc[a][b] : Hacc[b][a];
       MPC_UNROLL for (int b = 0; b < 3; ++b) Hwp[a * 3 + b] = Hacc[a][5 + b];
     }
   }

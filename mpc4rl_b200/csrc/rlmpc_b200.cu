@@ -325,7 +325,10 @@ __global__ void __launch_bounds__(32) k_qp2(const __grid_constant__ ProblemData 
 }
 
 // ---- partially condensed queue path (condense.cuh): input-bounds-only problems, V-mode ----
-constexpr int CBLK = 4;  // stages per block
+#ifndef RLMPC_CBLK
+#define RLMPC_CBLK 4
+#endif
+constexpr int CBLK = RLMPC_CBLK;  // stages per block
 template <class M>
 struct Condensable {
   static constexpr bool value = M::NBX == 0 && M::NSX == 0 && M::NG == 0 && CBLK * M::NU <= MAXD;

@@ -73,3 +73,20 @@ def test_cartpole_spec_follows_reference_config():
     sl = s.p_slices()
     assert sl["W_0"][0] == slice(3, 28) and sl["yref_e"][0] == slice(79, 83)
     assert s.p_nominal[3] == 200.0 and s.p_nominal[3 + 6] == 0.02  # column-major diag
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/config"), reason="reference checkout not present")
+def test_builtin_configs_equal_reference_yaml():
+    """cartpole_config()/cartpole_original_config() restate config/cartpole{,_original}.yaml; where the
+    reference checkout is available, read the YAML files themselves and compare the resulting specs."""
+    import numpy as np
+
+    from mpc4rl_b200 import cartpole_config, cartpole_original_config, cartpole_spec
+    from mpc4rl_b200.common.utils import read_config
+
+    for name, mine in (("cartpole.yaml", cartpole_config()), ("cartpole_original.yaml", cartpole_original_config())):
+        ref = read_config(os.path.join("/root/reference/config", name))["mpc"]
+        a, b = cartpole_spec(ref), cartpole_spec(mine)
+        assert (a.N, a.nx, a.nu, a.tf) == (b.N, b.nx, b.nu, b.tf), name
+        for k in ("p_nominal", "lbu", "ubu", "lbx", "ubx", "lbx_e", "ubx_e", "model_const"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (name, k)
