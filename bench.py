@@ -262,10 +262,14 @@ def run_gpu(args, rank, world, local_rank):
     # per-kernel device times (CUDA events recorded by the library on the launching stream between
     # the kernels of a call); separate pass because reading them waits for the call
     n_ph = 3
+    queue = {}
     for i in range(n_ph):
         mpc.solve_sens(xs[args.warmup + (i % args.steps)], max_sqp=1, out=out)
         for k, v in mpc.timings().items():
-            phase_ms[k] += v / n_ph
+            if k in phase_ms:
+                phase_ms[k] += v / n_ph
+            else:
+                queue[k] = queue.get(k, 0.0) + v / n_ph
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     ok_frac = float((out["status"] == 0).double().mean().item())
     rmax = out["res"].max(dim=1).values
@@ -323,7 +327,10 @@ def run_gpu(args, rank, world, local_rank):
             # the max comes from the states on which full-step Gauss-Newton SQP 2-cycles (status 2 in the setup solve)
             "quality": {"status0_frac_after_setup": conv_frac, "status0_frac_last_step": ok_frac,
                         "kkt_res_median_last_step": res_med, "kkt_res_lt_1e-3_frac_last_step": res_small,
-                        "kkt_res_max_last_step": res_max},
+                        "kkt_res_max_last_step": res_max,
+                        # samples handed to the full interior-point pass per step, and its mean iteration count
+                        "queue_frac": queue.get("queue_len", 0.0) / B,
+                        "queue_ipm_iters_mean": queue.get("queue_ipm_iters", 0.0) / max(queue.get("queue_len", 0.0), 1.0)},
         }
         if world == 1 and not args.no_cpu and args.workload == "cartpole":
             cval, cores, csec = cpu_port_run(args.cpu_samples, 3, 1)

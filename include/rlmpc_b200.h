@@ -170,7 +170,8 @@ long long rlmpc_launch_count(const rlmpc_handle* h);
  * of a solve / sens call.  ms_out[0..6) = device time of the last call's
  * [linearise | convergence test + fast QP | full interior point of the queued samples | sens stage
  * evaluation | sens sweeps | tail = sens kernels of the queued samples] (of the last SQP round when
- * max_sqp > 1); waits for the call to finish.  n >= 6.  With option "overlap" = 1 (default 0) an RTI
+ * max_sqp > 1); waits for the call to finish.  n >= 6; with n >= 8 also ms_out[6] = number of queued samples and
+ * ms_out[7] = their interior-point iterations (warp-per-sample queue kernel) in that round.  With option "overlap" = 1 (default 0) an RTI
  * solve_sens call runs the third phase on a side stream concurrently with the fourth and fifth.  The reference's
  * analogue is the nlp_timing dict of update_nlp (nlp.py:1397-1422). */
 int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n);

@@ -218,9 +218,11 @@ class BatchedMPC:
 
     def timings(self) -> dict:
         """Device milliseconds of the phases of the last call (needs set_option("timing", 1))."""
-        ms = np.zeros(6)
-        _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 6))
-        return dict(zip(self.PHASES, ms.tolist()))
+        ms = np.zeros(8)
+        _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 8))
+        d = dict(zip(self.PHASES, ms[:6].tolist()))
+        d["queue_len"], d["queue_ipm_iters"] = int(ms[6]), int(ms[7])
+        return d
 
     @property
     def launch_count(self) -> int:

@@ -17,7 +17,7 @@ NVCC_FLAGS = [
 
 def _sources():
     out = [os.path.join(CSRC, "rlmpc_b200.cu")]
-    deps = [os.path.join(CSRC, f) for f in ("engine.cuh", "condense.cuh", "common.cuh")]
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
     deps += [os.path.join(CSRC, "models", f) for f in sorted(os.listdir(os.path.join(CSRC, "models")))]
     deps.append(os.path.join(os.path.dirname(PKG_DIR), "include", "rlmpc_b200.h"))
     return out, deps

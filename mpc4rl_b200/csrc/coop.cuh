@@ -1,0 +1,471 @@
+// Warp-per-sample interior-point solve of the queued stage QPs (CUDA only).
+//
+// The queue (samples whose warm Newton iteration of qp_fast() was not enough) is a small part of the
+// batch, but each of its solves is a long dependent chain: interior-point iterations x 2 sweeps x N
+// stages.  With one thread per sample (Engine::qp_full / Condenser::solve_expand) the kernel lasts as
+// long as its slowest sample, ~100 us per iteration.  Here ONE WARP owns one sample:
+//   * the whole stage QP (A, B, b, q, r of every stage, the multipliers and slacks of the rows) is
+//     staged once in shared memory (50 doubles per stage),
+//   * everything that is independent between stages (row updates, barrier terms, new slacks and
+//     multipliers, step-length statistics, the final step) runs with one lane per stage,
+//   * the two Riccati recursions run with one lane per matrix entry: [P A  P B  P b + p] on NX x (NW+1)
+//     lanes, then [A B]'[...] + cost on NW x (NW+1) lanes, exchanged through shared memory,
+//   * all control flow (warm start, active-set steps, cold restart, exits) is warp-uniform.
+// The iteration is the one of Engine::qp_ipm / apply_step, statement by statement (same operation order
+// inside every dot product), so both paths walk through the same iterates up to the rounding of the
+// reductions over the rows.  Applicable to input-bounds-only problems with NU = 1 and NX <= 4 (cart-pole,
+// config/cartpole_original.yaml); everything else keeps the thread-per-sample queue kernels.
+#pragma once
+
+#include "engine.cuh"
+
+namespace rlmpc {
+
+template <class M>
+struct CoopOK {
+  static constexpr int NW = M::NX + M::NU;
+  static constexpr bool value = M::NU == 1 && M::NBX == 0 && M::NSX == 0 && M::NG == 0 && !M::STAGE_HESS &&
+                                M::NX * (NW + 1) <= 32 && NW * (NW + 1) <= 32;
+};
+
+#ifdef __CUDACC__
+template <class M>
+struct CoopQP {
+  using E = Engine<M>;
+  static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NC = NW + 1, NWS = E::NWS;
+  static constexpr int PER_STAGE = NX * NC + NW + NW + NX + 12;  // Mk, g, K|kff, dx, 12 row/scalar fields
+  static constexpr int SCRATCH = NX * NX + 2 * NX + NX * NC + NW * NC + 3 * NWS;
+  __host__ __device__ static constexpr int smem_doubles(int N) { return PER_STAGE * (N + 1) + SCRATCH; }
+
+  __device__ static __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+  }
+  __device__ static __forceinline__ double wmin(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+  }
+  __device__ static __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+  }
+
+  __device__ static __forceinline__ double lds(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+  }
+  __device__ static __forceinline__ void sts(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+  }
+
+  // One sample, executed by the 32 lanes of a warp.  S: this warp's shared memory (smem_doubles(N)).
+  // Returns Engine::FULL_OK / FULL_MAXITER / FULL_FAILED; the step is applied to the iterate in global
+  // memory (L.it) unless FULL_FAILED.
+  __device__ static int solve(const ProblemData& pd, const Lane& L, double* S, const int lane, int* iters_out) {
+    const int N = pd.N, NS = N + 1;
+    constexpr size_t bs = TILE;
+    double* Mk = S;                  // [k][NX][NC]  = [A | B | b]
+    double* Gk = Mk + NS * NX * NC;  // [k][NW]      = [q ; r]      (later: x-part of the costate recursion)
+    double* Kk = Gk + NS * NW;       // [k][NW]      = [K | kff]    (later: pi_k)
+    double* DX = Kk + NS * NW;       // [k][NX]
+    double* DU = DX + NS * NX;       // [k]
+    double* U = DU + NS;
+    double* LL = U + NS;    // lam of the lower / upper input bound
+    double* LU = LL + NS;
+    double* TL = LU + NS;   // slacks
+    double* TU = TL + NS;
+    double* LHL = TU + NS;  // lam_hat, t_hat of the last Newton step
+    double* LHU = LHL + NS;
+    double* THL = LHU + NS;
+    double* THU = THL + NS;
+    double* HB = THU + NS;  // barrier terms of the stage: Hessian (u,u) and gradient (u)
+    double* GB = HB + NS;
+    double* P = GB + NS;    // scratch
+    double* pv = P + NX * NX;
+    double* pv2 = pv + NX;
+    double* PM = pv2 + NX;
+    double* T = PM + NX * NC;
+    double* Wc = T + NW * NC;
+
+    // explicit shared-window addresses for the two recursions (plain ld/st.shared with immediate offsets)
+    const unsigned sT = (unsigned)__cvta_generic_to_shared(T), sPM = (unsigned)__cvta_generic_to_shared(PM);
+    const unsigned sDX = (unsigned)__cvta_generic_to_shared(DX);
+
+    const bool qmode = pd.mode == MODE_Q;
+    const double lb = pd.lbu[0], ub = pd.ubu[0];
+    const bool has_l = lb > -BIG, has_u = ub < BIG;
+    const double range = (has_l && has_u) ? ub - lb : 1.0;
+    const int k_first = qmode ? 1 : 0;  // stages [k_first, N) carry the input rows
+    const double m_rows = (double)((N - k_first) * ((has_l ? 1 : 0) + (has_u ? 1 : 0)));
+
+    // ---------------- stage the QP ----------------
+    constexpr int NAB = NX * NX + NX * NU + NX;  // record elements [W_A, W_q): A, B, b
+    for (int idx = lane; idx < N * NAB; idx += 32) {
+      const int k = idx / NAB, e = idx - k * NAB;
+      const double v = L.ws[((size_t)k * E::W_REC + e) * bs];
+      int row, col;
+      if (e < NX * NX) {
+        row = e / NX; col = e - row * NX;
+      } else if (e < NX * NX + NX * NU) {
+        row = e - NX * NX; col = NX;
+      } else {
+        row = e - NX * NX - NX * NU; col = NX + 1;
+      }
+      Mk[k * NX * NC + row * NC + col] = v;
+    }
+    for (int idx = lane; idx < NS * NW; idx += 32) {
+      const int k = idx / NW, e = idx - k * NW;
+      Gk[idx] = (k < N || e < NX) ? L.ws[((size_t)k * E::W_REC + E::W_q + e) * bs] : 0.0;
+    }
+    for (int k = lane; k < NS; k += 32) {
+      U[k] = (k < N) ? L.it[(size_t)E::it_u(N, k) * bs] : 0.0;
+      LL[k] = L.it[(size_t)E::it_lam(N, k) * bs];
+      LU[k] = L.it[(size_t)(E::it_lam(N, k) + 1) * bs];
+      TL[k] = L.it[(size_t)E::it_t(N, k) * bs];
+      TU[k] = L.it[(size_t)(E::it_t(N, k) + 1) * bs];
+      LHL[k] = LHU[k] = THL[k] = THU[k] = 0.0;
+    }
+    for (int idx = lane; idx < 3 * NWS; idx += 32) {
+      const int kind = idx / NWS, e = idx - kind * NWS;
+      Wc[idx] = L.ct[(size_t)(kind * E::CT_REC + E::CT_W + e) * bs];
+    }
+    bool warm = pd.warm_ipm && L.it[(size_t)E::it_meta(N) * bs] > 0.5;
+    __syncwarp();
+
+    // (lam,t) of a warm / cold start; returns sum(lam*t)           [Engine::ipm_init]
+    auto init_rows = [&](bool w) -> double {
+      double mu = 0.0;
+      for (int k = lane; k < NS; k += 32) {
+        const bool act = k >= k_first && k < N;
+        double ll, lu, tl, tu;
+        if (w) {
+          tl = dmax(TL[k], 1e-10 * range); tu = dmax(TU[k], 1e-10 * range);
+          ll = dmax(LL[k], 1e-14); lu = dmax(LU[k], 1e-14);
+        } else {
+          const double tmin = 1e-2 * range, u = U[k];
+          tl = dmax(u - lb, tmin); ll = pd.mu0 / tl;
+          tu = dmax(ub - u, tmin); lu = pd.mu0 / tu;
+        }
+        if (act && has_l) mu += ll * tl; else { ll = 0.0; tl = 0.0; }
+        if (act && has_u) mu += lu * tu; else { lu = 0.0; tu = 0.0; }
+        LL[k] = ll; LU[k] = lu; TL[k] = tl; TU[k] = tu;
+      }
+      __syncwarp();
+      return wsum(mu);
+    };
+
+    double mu = init_rows(warm) / m_rows;
+    double alpha = 0.0;
+    double sigma = warm ? pd.sigma_min : pd.sigma0;
+    int iters = 0, warm_iters = 0, as_iters = 0;
+    bool converged = false, failed = false, minstep = false;
+
+    for (int j = 0; j < pd.max_ipm && !converged; ++j) {
+      ++iters;
+      if (warm && (warm_iters >= E::WARM_LIMIT + as_iters || (warm_iters > as_iters && alpha > 0.0 && alpha < 0.05))) {
+        warm = false;  // jammed warm start: restart cold
+        mu = init_rows(false) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma0;
+      }
+      if (warm) ++warm_iters;
+      const double target = dmax(sigma * mu, pd.tau);
+
+      // ---- rows: pending damped update, barrier terms (one lane per stage) ----
+      for (int k = lane; k < NS; k += 32) {
+        double ll = LL[k], lu = LU[k], tl = TL[k], tu = TU[k];
+        if (alpha > 0.0) {
+          ll += alpha * (LHL[k] - ll); tl += alpha * (THL[k] - tl);
+          lu += alpha * (LHU[k] - lu); tu += alpha * (THU[k] - tu);
+          LL[k] = ll; LU[k] = lu; TL[k] = tl; TU[k] = tu;
+        }
+        const bool act = k >= k_first && k < N;
+        double hb = 0.0, gb = 0.0;
+        const double u = U[k];
+        if (act && has_l) {
+          const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
+          hb += cb;
+          gb += -(ab - cb * (u - lb));
+        }
+        if (act && has_u) {
+          const double itb = 1.0 / tu, cb = lu * itb, ab = target * itb + lu;
+          hb += cb;
+          gb += ab - cb * (ub - u);
+        }
+        HB[k] = hb; GB[k] = gb;
+      }
+      __syncwarp();
+      // ---- backward Riccati sweep ----
+      // Two exchanges per stage through shared memory.  T holds stage k+1's [A B]'[P A | P B | v] + cost
+      // (rows 0..NX-1: the x-block and gradient, row NX: H, G, gv); phase A of stage k finishes it on the
+      // fly, P = T_xx + H'K, p = T_x5 + H'kff with K = -H/G, and multiplies by [A B b] of stage k; phase B
+      // forms stage k's T.  The stage data of the next stage is fetched into registers ahead of the chain.
+      const int iA = lane / NC, cA = lane - iA * NC;  // roles: phase A lane (iA, cA), phase B lane (rB = iA, cB = cA)
+      const bool inA = lane < NX * NC, inB = lane < NW * NC;
+      const int k_last = qmode ? 1 : 0;  // last stage with a feedback law
+      if (inB) {  // terminal "T": P_N = scaled W_e, p_N = q_N, no input
+        double v = 0.0;
+        if (iA < NX && cA < NX) v = pd.scale[N] * Wc[2 * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
+        if (iA < NX && cA == NC - 1) v = Gk[N * NW + iA];
+        if (iA == NX && cA == NX) v = 1.0;
+        T[lane] = v;
+      }
+      double mA[NX], mB[NX], baseB = 0.0;
+      auto fetch = [&](int k) {
+        const double* Mc = Mk + k * NX * NC;
+#pragma unroll
+        for (int l = 0; l < NX; ++l) {
+          mA[l] = inA ? Mc[l * NC + cA] : 0.0;
+          mB[l] = inB ? Mc[l * NC + iA] : 0.0;
+        }
+        if (inB) {
+          if (cA < NW) {
+            baseB = pd.scale[k] * Wc[(k == 0 ? 0 : 1) * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
+            if (iA == NX && cA == NX) baseB += HB[k];
+          } else {
+            baseB = Gk[k * NW + iA];
+            if (iA == NX) baseB += GB[k];
+          }
+        }
+      };
+      fetch(N - 1);
+      __syncwarp();
+      for (int k = N - 1; k >= k_last; --k) {
+        // ---- phase A ----
+        const double G = lds(sT + 8 * (NX * NC + NX));
+        if (!(G > 0.0)) failed = true;
+        const double inv = 1.0 / G;
+        if (inA) {
+          const double hi = lds(sT + 8 * (NX * NC + iA));
+          double acc = 0.0;
+          if (cA == NC - 1) {
+            const double kff = -lds(sT + 8 * (NX * NC + NC - 1)) * inv;
+            acc = lds(sT + 8 * (iA * NC + NC - 1)) + hi * kff;
+          }
+#pragma unroll
+          for (int l = 0; l < NX; ++l) {
+            // P_il = T_ab + H_a K_b, (a, b) = (min, max) of (i, l): the same expression on both sides of the diagonal
+            const double hl = lds(sT + 8 * (NX * NC + l));
+            const double ha = iA < l ? hi : hl, hb = iA < l ? hl : hi;
+            const double Pil = lds(sT + 8 * ((iA < l ? iA : l) * NC + (iA < l ? l : iA))) + ha * (-hb * inv);
+            acc += Pil * mA[l];
+          }
+          sts(sPM + 8 * lane, acc);
+        } else if (lane < NX * NC + NW && k + 1 < N) {  // feedback law of stage k+1
+          const int c = lane - NX * NC;
+          Kk[(k + 1) * NW + c] = -lds(sT + 8 * (NX * NC + (c < NX ? c : NC - 1))) * inv;
+        }
+        __syncwarp();
+        // ---- phase B ----
+        if (inB) {
+          double acc = baseB;
+#pragma unroll
+          for (int l = 0; l < NX; ++l) acc += mB[l] * lds(sPM + 8 * (l * NC + cA));
+          sts(sT + 8 * lane, acc);
+        }
+        if (k > k_last) fetch(k - 1);
+        __syncwarp();
+      }
+      {  // feedback law of the last stage; u_0 fixed (Q-mode): none
+        const double G = lds(sT + 8 * (NX * NC + NX));
+        if (!(G > 0.0)) failed = true;
+        const double inv = 1.0 / G;
+        if (lane < NW) {
+          Kk[k_last * NW + lane] = -lds(sT + 8 * (NX * NC + (lane < NX ? lane : NC - 1))) * inv;
+          if (qmode) Kk[lane] = 0.0;
+        }
+      }
+      // ---- forward sweep: dx, du ----
+      if (lane < NX) DX[lane] = 0.0;
+      __syncwarp();
+      {
+        double kr[NW], ar[NC];
+        auto fetch_f = [&](int k) {
+#pragma unroll
+          for (int l = 0; l < NW; ++l) kr[l] = Kk[k * NW + l];
+#pragma unroll
+          for (int l = 0; l < NC; ++l) ar[l] = (lane < NX) ? Mk[k * NX * NC + lane * NC + l] : 0.0;
+        };
+        fetch_f(0);
+        for (int k = 0; k < N; ++k) {
+          double dxl[NX];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) dxl[l] = lds(sDX + 8 * (k * NX + l));
+          double du = kr[NX];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) du += kr[l] * dxl[l];
+          double a = ar[NC - 1];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) a += ar[l] * dxl[l];
+          a += ar[NX] * du;
+          if (lane < NX) sts(sDX + 8 * ((k + 1) * NX + lane), a);
+          if (lane == 0) DU[k] = du;
+          if (k + 1 < N) fetch_f(k + 1);
+          __syncwarp();
+        }
+      }
+      if (lane == 0) DU[N] = 0.0;
+      __syncwarp();
+      // ---- rows: new slacks and multipliers, step-length statistics (one lane per stage) ----
+      double amax = 1e300, s0 = 0.0, s1 = 0.0, s2 = 0.0, cmax = 0.0;
+      for (int k = lane; k < NS; k += 32) {
+        const bool act = k >= k_first && k < N;
+        const double dv = DU[k], u = U[k];
+        double lhl = 0.0, thl = 0.0, lhu = 0.0, thu = 0.0;
+        if (act && has_l) {
+          const double ll = LL[k], tl = TL[k];
+          const double d = (u - lb) + dv;
+          const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
+          thl = d;
+          lhl = ab - cb * d;
+          const double dt = thl - tl, dl = lhl - ll;
+          if (dt < 0.0) amax = dmin(amax, -tl / dt);
+          if (dl < 0.0) amax = dmin(amax, -ll / dl);
+          s0 += ll * tl; s1 += ll * dt + tl * dl; s2 += dl * dt;
+          cmax = dmax(cmax, dabs(dl * dt));
+        }
+        if (act && has_u) {
+          const double lu = LU[k], tu = TU[k];
+          const double d = (ub - u) - dv;
+          const double itb = 1.0 / tu, cb = lu * itb, ab = target * itb + lu;
+          thu = d;
+          lhu = ab - cb * d;
+          const double dt = thu - tu, dl = lhu - lu;
+          if (dt < 0.0) amax = dmin(amax, -tu / dt);
+          if (dl < 0.0) amax = dmin(amax, -lu / dl);
+          s0 += lu * tu; s1 += lu * dt + tu * dl; s2 += dl * dt;
+          cmax = dmax(cmax, dabs(dl * dt));
+        }
+        LHL[k] = lhl; THL[k] = thl; LHU[k] = lhu; THU[k] = thu;
+      }
+      __syncwarp();
+      {  // NaN anywhere in the step must reach amax like in the scalar code (a NaN slack fails "dt < 0")
+        const double probe = DU[0] + DX[N * NX];
+        if (!(probe == probe)) amax = probe;
+      }
+      const bool nan_step = __any_sync(0xffffffffu, !(amax == amax));
+      amax = wmin(amax); s0 = wsum(s0); s1 = wsum(s1); s2 = wsum(s2); cmax = wmax(cmax);
+      failed = __any_sync(0xffffffffu, failed);
+
+      if ((failed || nan_step) && warm) {  // numerically broken warm start: not an error, start over cold
+        warm = false;
+        failed = false;
+        mu = init_rows(false) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma0;
+        continue;
+      }
+      if (failed || nan_step) { failed = true; break; }
+      if (warm && amax < 1.0 / 0.995 && as_iters < (int)pd.as_steps) {
+        // active-set step of a warm start                         [Engine::ipm_project]
+        ++as_iters;
+        double m2 = 0.0;
+        const double eps_t = 1e-9 * range;
+        for (int k = lane; k < NS; k += 32) {
+          const bool act = k >= k_first && k < N;
+          if (act && has_l) {
+            double ll = LL[k], tl;
+            const double lh = LHL[k], th = THL[k];
+            if (!(th > eps_t)) { tl = eps_t; ll = dmax(dmax(lh, ll), 1e-3); }
+            else if (!(lh > 0.0)) { tl = th; ll = pd.tau / th; }
+            else { tl = th; ll = lh; }
+            LL[k] = ll; TL[k] = tl;
+            m2 += ll * tl;
+          }
+          if (act && has_u) {
+            double lu = LU[k], tu;
+            const double lh = LHU[k], th = THU[k];
+            if (!(th > eps_t)) { tu = eps_t; lu = dmax(dmax(lh, lu), 1e-3); }
+            else if (!(lh > 0.0)) { tu = th; lu = pd.tau / th; }
+            else { tu = th; lu = lh; }
+            LU[k] = lu; TU[k] = tu;
+            m2 += lu * tu;
+          }
+        }
+        __syncwarp();
+        mu = wsum(m2) / m_rows;
+        alpha = 0.0;
+        sigma = pd.sigma_min;
+        continue;
+      }
+      alpha = (amax >= 1.0 / 0.995) ? 1.0 : 0.995 * amax;
+      if (!warm && alpha < 1e-9) {
+        minstep = true;
+        break;
+      }
+      const double mu_new = (s0 + alpha * s1 + alpha * alpha * s2) / m_rows;
+      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
+      const double r = 1.0 - alpha;
+      sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
+      mu = mu_new;
+    }
+    *iters_out = iters;
+    if (failed || minstep) return E::FULL_FAILED;
+
+    // ---------------- the step                                      [Engine::apply_step] ----------------
+    const double ap = converged ? 1.0 : alpha;  // iteration limit: damped primal step
+    for (int k = lane; k < NS; k += 32) {
+      const bool act = k >= k_first && k < N;
+      const double ll = (act && has_l) ? LL[k] + alpha * (LHL[k] - LL[k]) : 0.0;
+      const double tl = (act && has_l) ? TL[k] + alpha * (THL[k] - TL[k]) : 0.0;
+      const double lu = (act && has_u) ? LU[k] + alpha * (LHU[k] - LU[k]) : 0.0;
+      const double tu = (act && has_u) ? TU[k] + alpha * (THU[k] - TU[k]) : 0.0;
+      if (k < N) {
+        L.it[(size_t)E::it_lam(N, k) * bs] = ll;
+        L.it[(size_t)(E::it_lam(N, k) + 1) * bs] = lu;
+        L.it[(size_t)E::it_t(N, k) * bs] = tl;
+        L.it[(size_t)(E::it_t(N, k) + 1) * bs] = tu;
+        L.it[(size_t)E::it_u(N, k) * bs] = U[k] + ap * DU[k];
+      }
+    }
+    // x-part of the costate recursion: c_k = q_k + (W dw)_x, in place of q_k;  x_k += ap dx_k  (k >= 1)
+    for (int idx = lane; idx < NS * NX; idx += 32) {
+      const int k = idx / NX, i = idx - k * NX;
+      if (k == 0) continue;
+      const double s = pd.scale[k];
+      const double* W = Wc + (k == N ? 2 : 1) * NWS;
+      double a = Gk[k * NW + i];
+#pragma unroll
+      for (int jj = 0; jj < NW; ++jj) {
+        const double dwj = jj < NX ? DX[k * NX + jj] : DU[k];
+        a += (s * W[E::pidx(i < jj ? i : jj, i < jj ? jj : i)]) * dwj;
+      }
+      Gk[k * NW + i] = a;
+      const size_t o = (size_t)(E::it_x(N, k) + i) * bs;
+      L.it[o] = L.it[o] + ap * DX[k * NX + i];
+    }
+    __syncwarp();
+    // pi_{k-1} = c_k + A_k' pi_k, k = N .. 1   (pi_k kept in Kk[k][0..NX), ping-pong through pv / pv2)
+    double* cur = pv;
+    double* nxt = pv2;
+    if (lane < NX) cur[lane] = Gk[N * NW + lane];
+    __syncwarp();
+    for (int k = N - 1; k >= 0; --k) {
+      if (lane < NX) {
+        Kk[k * NW + lane] = cur[lane];  // pi_k
+        if (k > 0) {
+          const double* Mc = Mk + k * NX * NC;
+          double a = Gk[k * NW + lane];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) a += Mc[l * NC + lane] * cur[l];
+          nxt[lane] = a;
+        }
+      }
+      __syncwarp();
+      double* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    for (int idx = lane; idx < N * NX; idx += 32) {
+      const int k = idx / NX, i = idx - k * NX;
+      L.it[(size_t)(E::it_pi(N, k) + i) * bs] = Kk[k * NW + i];
+    }
+    if (lane == 0) L.it[(size_t)E::it_meta(N) * bs] = 1.0;
+    return converged ? E::FULL_OK : E::FULL_MAXITER;
+  }
+};
+#endif  // __CUDACC__
+
+}  // namespace rlmpc

@@ -14,6 +14,7 @@
 #include "../../include/rlmpc_b200.h"
 #include "engine.cuh"
 #include "condense.cuh"
+#include "coop.cuh"
 #include "models/cartpole.cuh"
 #include "models/linear_system.cuh"
 #include "models/evaporation.cuh"
@@ -75,7 +76,7 @@ struct KArgs {
   int* hard;    // queue of samples for the full interior-point pass
   int* ishard;  // 1 if the sample was queued in this call (written by k_qp1 only)
   int subset;   // sens kernels: 0 all samples, 1 samples not queued, 2 the queued samples (via the queue)
-  int* counters;  // [0] queue length, [1] samples still active
+  int* counters;  // [0] queue length, [1] samples still active, [2] work counter of k_qp3, [3] its interior-point iterations
   const double* x0;  // [B, NX] row-major or null
   const double* u0;  // [B, NU] row-major or null
   double* u0_out;    // [B, NU]
@@ -380,6 +381,44 @@ __global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData
   }
 }
 
+// ---- warp-per-sample queue path (coop.cuh): one warp solves one queued sample in shared memory ----
+#ifndef RLMPC_COOP_WARPS
+#define RLMPC_COOP_WARPS 4
+#endif
+constexpr int COOP_WARPS = RLMPC_COOP_WARPS;  // samples in flight per block
+
+// persistent grid; warps fetch queue positions from counters[2].  Works on the samples' own iterate and
+// stage records (no compact copies: the QP lives in shared memory for the whole solve).
+template <class M>
+__global__ void __launch_bounds__(COOP_WARPS * 32) k_qp3(const __grid_constant__ ProblemData pd, const KArgs a) {
+  using E = Engine<M>;
+  using Cq = CoopQP<M>;
+  extern __shared__ double coop_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* S = coop_smem + (size_t)wib * Cq::smem_doubles(pd.N);
+  const int n = a.counters[0];
+  for (;;) {
+    int j = 0;
+    if (lane == 0) j = atomicAdd(&a.counters[2], 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= n) break;
+    const int b = a.hard[j];
+    const Lane L = make_lane<M>(a, b);
+    int iters = 0;
+    const int st = Cq::solve(pd, L, S, lane, &iters);
+    if (lane == 0) {
+      atomicAdd(&a.counters[3], iters);
+      if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
+        a.status[b] = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL;
+        a.work[b] = WK_DONE;
+      } else {
+        a.work[b] = WK_ACTIVE;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <class M>
 __global__ void k_count_active(const KArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -595,7 +634,10 @@ struct rlmpc_handle {
   double *itb = nullptr, *wsb = nullptr;  // partially condensed queue path (only for condensable models)
   int itb_size = 0, wsb_size = 0;
   int condense = 1;    // 1: queued QPs in partially condensed form where applicable (input bounds only, V-mode, N % 4 == 0)
+  int coop = 1;        // warp-per-sample queue kernel (coop.cuh) where the model allows it (NU = 1, NX <= 4, input bounds only)
+  int coop_grid = 0;   // its persistent grid (blocks), sized at create time from the occupancy
   int ring_b = 0;      // ring reader for the condensed kernel: measured slower (3.3 vs 2.3 ms), blocks carry enough work per load batch
+                       // (an L1 prefetch of the next block record, CCTL.E.PF1, measured the same 3.3 ms: profiles/r01g_variants_prefetch_overlap.log)
   double* cost = nullptr;
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
   int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
@@ -683,6 +725,28 @@ cudaError_t alloc_condensed(rlmpc_handle* h, int N, cudaError_t e) {
   return e;
 }
 
+template <class M>
+size_t coop_smem(int N) {
+  if constexpr (CoopOK<M>::value) return sizeof(double) * COOP_WARPS * CoopQP<M>::smem_doubles(N);
+  return 0;
+}
+// persistent grid of the warp-per-sample queue kernel: as many blocks as fit on the device
+template <class M>
+cudaError_t setup_coop(rlmpc_handle* h, int N, cudaError_t e) {
+  if constexpr (CoopOK<M>::value) {
+    const size_t smem = coop_smem<M>(N);
+    int dev = 0, sms = 0, per_sm = 0, max_optin = 0;
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess || smem > (size_t)max_optin) return e;  // horizon too long for shared memory: coop_grid stays 0
+    e = cudaFuncSetAttribute(k_qp3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp3<M>, COOP_WARPS * 32, smem);
+    if (e == cudaSuccess) h->coop_grid = sms * per_sm;
+  }
+  return e;
+}
+
 // the queue pass between gather and scatter: condensed where possible, else stage form
 template <class M>
 void launch_queue_solve(rlmpc_handle* h, const KArgs& a, int B, cudaStream_t sq) {
@@ -725,7 +789,7 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   for (int r = 0; r < rounds; ++r) {
     a.last_round = (K > 1 && r == K) ? 1 : 0;
     a.inplace = dense_queue ? 1 : 0;
-    CUDA_OK(cudaMemsetAsync(h->counters, 0, 2 * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(int), s));
     mark(h, 0, s);
     k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
     mark(h, 1, s);
@@ -739,7 +803,15 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         CUDA_OK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         sq = h->side_stream;
       }
-      {
+      bool coop_done = false;
+      if constexpr (CoopOK<M>::value) {
+        if (h->coop && h->coop_grid > 0 && !a.inplace) {
+          k_qp3<M><<<h->coop_grid, COOP_WARPS * 32, coop_smem<M>(N), sq>>>(h->pd, a);
+          h->launches++;
+          coop_done = true;
+        }
+      }
+      if (!coop_done) {
         using E = Engine<M>;
         const int wpb = 8;  // warps per block of the copy kernels
         const int n_g = (E::it_size(N) + (N + 1) * E::W_K + GATHER_CHUNK - 1) / GATHER_CHUNK;
@@ -747,9 +819,9 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         if (!a.inplace) k_gather<M><<<dim3((B + 31) / 32, (n_g + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
         launch_queue_solve<M>(h, a, B, sq);
         if (!a.inplace) k_scatter<M><<<dim3((B + 31) / 32, (n_s + wpb - 1) / wpb), 32 * wpb, 0, sq>>>(h->pd, a);
+        h->launches += 2;
       }
       mark(h, 3, sq);
-      h->launches += 2;
       if (fork_qp2) CUDA_OK(cudaEventRecord(h->ev_join, sq));
     }
     if (K > 1 && !a.last_round && (r % h->sync_every) == h->sync_every - 1) {
@@ -949,6 +1021,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMalloc(&h->it2, n_it);
   if (e == cudaSuccess) e = cudaMalloc(&h->ws2, n_ws);
   DISPATCH_MODEL(h, e = alloc_condensed<M>(h, d->N, e));
+  DISPATCH_MODEL(h, e = setup_coop<M>(h, d->N, e));
   if (e == cudaSuccess) e = cudaMalloc(&h->th, sizeof(double) * h->nth * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->ct, sizeof(double) * h->ct_size * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->th_stage, sizeof(double) * h->nth * (size_t)max_batch);
@@ -958,7 +1031,11 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMalloc(&h->hard, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->ishard, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMemset(h->ishard, 0, sizeof(int) * h->bs);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {  // side stream of the "overlap" option: highest priority, so that the few queue blocks are placed first
+    int prio_lo = 0, prio_hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4);
@@ -1082,6 +1159,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "overlap")) h->overlap = (int)value;
   else if (!strcmp(name, "ring")) h->ring = (int)value;
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
+  else if (!strcmp(name, "coop")) h->coop = (int)value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
@@ -1280,6 +1358,13 @@ int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
       CUDA_OK(cudaEventElapsedTime(&ms, h->ev[f], h->ev[to[i]]));
       ms_out[i] = ms;
     }
+  }
+  if (n >= 8) {  // queue statistics of the last SQP round: length, interior-point iterations (warp-per-sample kernel only)
+    CUDA_OK(cudaDeviceSynchronize());
+    int c[4] = {0, 0, 0, 0};
+    CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    ms_out[6] = c[0];
+    ms_out[7] = c[3];
   }
   return 0;
 }

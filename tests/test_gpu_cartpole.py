@@ -222,3 +222,40 @@ def test_errors_are_reported(spec):
         m.solve(torch.zeros(2, 4, dtype=torch.float32, device="cuda:0"))
     with pytest.raises(RuntimeError):
         m.set_option("no_such_option", 1.0)
+
+
+def test_warp_per_sample_queue_equals_thread_per_sample(spec):
+    """The warp-cooperative queue kernel (csrc/coop.cuh, option coop=1, the default for this model) runs
+    the interior-point iteration of the thread-per-sample kernels statement by statement: same statuses,
+    u0 / V / gradients equal to rounding -- from a cold start (SQP to convergence: every sample goes
+    through the queue in the first rounds), for RTI steps at perturbed states, and in Q-mode."""
+    B = 4096
+    g = torch.Generator(device="cpu").manual_seed(7)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    dx = 1e-3 * torch.randn(3, B, 4, generator=g, dtype=torch.float64).cuda()
+    a0 = (-80.0 + 160.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)).cuda()
+    runs = {}
+    for coop in (1, 0):
+        m = _mpc(spec, B)
+        m.set_option("tol", 1e-8)
+        m.set_option("coop", coop)
+        m.reset(x0)
+        n0 = m.launch_count
+        outs = [m.solve_sens(x0, max_sqp=60)]
+        for i in range(3):
+            outs.append(m.solve_sens(x0 + dx[i], max_sqp=1))
+        outs.append(m.solve_sens(x0, u0=a0, max_sqp=60))
+        runs[coop] = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
+        runs[coop].append(m.launch_count - n0)
+    assert runs[1][-1] < runs[0][-1]  # one queue kernel instead of gather + condense + solve + scatter
+    for step, (a, b) in enumerate(zip(runs[1][:-1], runs[0][:-1])):
+        same = a["status"] == b["status"]
+        assert same.mean() > 0.995, (step, same.mean())
+        ok = same & (a["status"] == 0)
+        assert ok.mean() > 0.85, (step, ok.mean())
+        assert np.abs(a["u0"] - b["u0"])[ok].max() < 1e-7, step
+        assert _rel(a["cost"][ok], b["cost"][ok]) < 1e-9, step
+        assert _rel(a["dL"][ok], b["dL"][ok]) < 1e-6, step
+        if step < 4:  # Q-mode: dpi/dtheta is ~0 by construction (quirk Q7)
+            assert _rel(a["dpi"][ok], b["dpi"][ok]) < 1e-5, step

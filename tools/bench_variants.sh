@@ -5,7 +5,7 @@ import sys, json
 for l in sys.stdin:
     l=l.strip()
     if l.startswith('{'):
-        d=json.loads(l); print('value', round(d['value']), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), d['roofline']['kernels_ms'], d['quality']['status0_frac_last_step'])
+        d=json.loads(l); print('value', round(d['value']), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value']), d['roofline']['kernels_ms'], d['quality']['status0_frac_last_step'], d['quality'].get('queue_frac'), d['quality'].get('queue_ipm_iters_mean'))
     elif l: print(l[:300])
 "
 }
