@@ -34,7 +34,7 @@ struct CoopQP {
   using E = Engine<M>;
   static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NC = NW + 1, NWS = E::NWS;
   static constexpr int PER_STAGE = NX * NC + NW + NW + NX + 12;  // Mk, g, K|kff, dx, 12 row/scalar fields
-  static constexpr int SCRATCH = NX * NX + 2 * NX + NX * NC + NW * NC + 3 * NWS;
+  static constexpr int SCRATCH = NX * NX + 2 * NX + NX * NC + NW * NC + 3 * NWS + 1;
   __host__ __device__ static constexpr int smem_doubles(int N) { return PER_STAGE * (N + 1) + SCRATCH; }
 
   __device__ static __forceinline__ double wsum(double v) {
@@ -90,6 +90,7 @@ struct CoopQP {
     double* PM = pv2 + NX;
     double* T = PM + NX * NC;
     double* Wc = T + NW * NC;
+    double* ZERO = Wc + 3 * NWS;  // one 0.0
 
     // explicit shared-window addresses for the two recursions (plain ld/st.shared with immediate offsets)
     const unsigned sT = (unsigned)__cvta_generic_to_shared(T), sPM = (unsigned)__cvta_generic_to_shared(PM);
@@ -133,6 +134,7 @@ struct CoopQP {
       const int kind = idx / NWS, e = idx - kind * NWS;
       Wc[idx] = L.ct[(size_t)(kind * E::CT_REC + E::CT_W + e) * bs];
     }
+    if (lane == 0) ZERO[0] = 0.0;
     bool warm = pd.warm_ipm && L.it[(size_t)E::it_meta(N) * bs] > 0.5;
     __syncwarp();
 
@@ -157,6 +159,31 @@ struct CoopQP {
       __syncwarp();
       return wsum(mu);
     };
+
+    // ---- per-lane roles of the two recursions (constant over the solve) ----
+    const int iA = lane / NC, cA = lane - iA * NC;  // phase A: entry (iA, cA) of [P A | P B | v]; phase B: entry (iA, cA) of T
+    const bool inA = lane < NX * NC, inB = lane < NW * NC;
+    const int iAx = iA < NX ? iA : NX - 1;          // lanes beyond the roles compute on valid addresses, never store
+    const int k_last = qmode ? 1 : 0;               // last stage with a feedback law
+    const unsigned sMk = (unsigned)__cvta_generic_to_shared(Mk);
+    const unsigned sMA = sMk + 8 * cA, sMB = sMk + 8 * (iA < NW ? iA : 0);
+    unsigned oT[NX];
+#pragma unroll
+    for (int l = 0; l < NX; ++l) oT[l] = 8 * ((iAx < l ? iAx : l) * NC + (iAx < l ? l : iAx));
+    double wB0 = 0.0, wB1 = 0.0;  // cost Hessian entry (stage 0 / stages 1..N-1), unscaled
+    unsigned sBase = (unsigned)__cvta_generic_to_shared(ZERO), baseStride = 0;
+    if (inB) {
+      if (cA < NW && !(iA == NX && cA == NX)) {
+        wB0 = Wc[0 * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
+        wB1 = Wc[1 * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
+      } else if (cA < NW) {  // (u,u): scaled cost + barrier, written by the row phase
+        sBase = (unsigned)__cvta_generic_to_shared(HB); baseStride = 8;
+      } else if (iA < NX) {  // gradient wrt x
+        sBase = (unsigned)__cvta_generic_to_shared(Gk + iA); baseStride = 8 * NW;
+      } else {               // gradient wrt u + barrier
+        sBase = (unsigned)__cvta_generic_to_shared(GB); baseStride = 8;
+      }
+    }
 
     double mu = init_rows(warm) / m_rows;
     double alpha = 0.0;
@@ -184,7 +211,8 @@ struct CoopQP {
           LL[k] = ll; LU[k] = lu; TL[k] = tl; TU[k] = tu;
         }
         const bool act = k >= k_first && k < N;
-        double hb = 0.0, gb = 0.0;
+        // (u,u) Hessian entry and u-gradient of the stage with the barrier terms   [Engine::barrier_add]
+        double hb = pd.scale[k] * Wc[(k == 0 ? 0 : 1) * NWS + E::pidx(NX, NX)], gb = Gk[k * NW + NX];
         const double u = U[k];
         if (act && has_l) {
           const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
@@ -204,68 +232,57 @@ struct CoopQP {
       // (rows 0..NX-1: the x-block and gradient, row NX: H, G, gv); phase A of stage k finishes it on the
       // fly, P = T_xx + H'K, p = T_x5 + H'kff with K = -H/G, and multiplies by [A B b] of stage k; phase B
       // forms stage k's T.  The stage data of the next stage is fetched into registers ahead of the chain.
-      const int iA = lane / NC, cA = lane - iA * NC;  // roles: phase A lane (iA, cA), phase B lane (rB = iA, cB = cA)
-      const bool inA = lane < NX * NC, inB = lane < NW * NC;
-      const int k_last = qmode ? 1 : 0;  // last stage with a feedback law
-      if (inB) {  // terminal "T": P_N = scaled W_e, p_N = q_N, no input
+      if (lane < NW * NC) {  // terminal "T": P_N = scaled W_e, p_N = q_N, no input
         double v = 0.0;
         if (iA < NX && cA < NX) v = pd.scale[N] * Wc[2 * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
         if (iA < NX && cA == NC - 1) v = Gk[N * NW + iA];
         if (iA == NX && cA == NX) v = 1.0;
         T[lane] = v;
       }
-      double mA[NX], mB[NX], baseB = 0.0;
+      // stage data of stage k for this lane's two roles: column cA of [A B b] (phase A), column iA (phase B),
+      // and the cost / gradient term of entry (iA, cA) of T:  scale_k * w + (per-lane array)[k]
+      double mA[NX], mB[NX], baseB;
       auto fetch = [&](int k) {
-        const double* Mc = Mk + k * NX * NC;
+        const unsigned ma = sMA + (unsigned)k * (8 * NX * NC), mb = sMB + (unsigned)k * (8 * NX * NC);
 #pragma unroll
         for (int l = 0; l < NX; ++l) {
-          mA[l] = inA ? Mc[l * NC + cA] : 0.0;
-          mB[l] = inB ? Mc[l * NC + iA] : 0.0;
+          mA[l] = lds(ma + 8 * l * NC);
+          mB[l] = lds(mb + 8 * l * NC);
         }
-        if (inB) {
-          if (cA < NW) {
-            baseB = pd.scale[k] * Wc[(k == 0 ? 0 : 1) * NWS + E::pidx(iA < cA ? iA : cA, iA < cA ? cA : iA)];
-            if (iA == NX && cA == NX) baseB += HB[k];
-          } else {
-            baseB = Gk[k * NW + iA];
-            if (iA == NX) baseB += GB[k];
-          }
-        }
+        baseB = pd.scale[k] * (k == 0 ? wB0 : wB1) + lds(sBase + (unsigned)k * baseStride);
       };
       fetch(N - 1);
       __syncwarp();
       for (int k = N - 1; k >= k_last; --k) {
-        // ---- phase A ----
+        // ---- phase A (all lanes compute, lanes (i, c) with i < NX store) ----
         const double G = lds(sT + 8 * (NX * NC + NX));
         if (!(G > 0.0)) failed = true;
         const double inv = 1.0 / G;
-        if (inA) {
-          const double hi = lds(sT + 8 * (NX * NC + iA));
-          double acc = 0.0;
-          if (cA == NC - 1) {
-            const double kff = -lds(sT + 8 * (NX * NC + NC - 1)) * inv;
-            acc = lds(sT + 8 * (iA * NC + NC - 1)) + hi * kff;
-          }
+        const double hi = lds(sT + 8 * NX * NC + 8 * iAx);
+        double acc = 0.0;
+        if (cA == NC - 1) {
+          const double kff = -lds(sT + 8 * (NX * NC + NC - 1)) * inv;
+          acc = lds(sT + 8 * NC * iAx + 8 * (NC - 1)) + hi * kff;
+        }
 #pragma unroll
-          for (int l = 0; l < NX; ++l) {
-            // P_il = T_ab + H_a K_b, (a, b) = (min, max) of (i, l): the same expression on both sides of the diagonal
-            const double hl = lds(sT + 8 * (NX * NC + l));
-            const double ha = iA < l ? hi : hl, hb = iA < l ? hl : hi;
-            const double Pil = lds(sT + 8 * ((iA < l ? iA : l) * NC + (iA < l ? l : iA))) + ha * (-hb * inv);
-            acc += Pil * mA[l];
-          }
-          sts(sPM + 8 * lane, acc);
-        } else if (lane < NX * NC + NW && k + 1 < N) {  // feedback law of stage k+1
+        for (int l = 0; l < NX; ++l) {
+          // P_il = T_ab - (H_i H_l) / G, (a, b) = (min, max) of (i, l): bitwise symmetric
+          const double hl = lds(sT + 8 * (NX * NC + l));
+          const double Pil = lds(sT + oT[l]) - (hi * hl) * inv;
+          acc += Pil * mA[l];
+        }
+        if (inA) sts(sPM + 8 * lane, acc);
+        if (lane >= NX * NC && lane < NX * NC + NW && k + 1 < N) {  // feedback law of stage k+1
           const int c = lane - NX * NC;
           Kk[(k + 1) * NW + c] = -lds(sT + 8 * (NX * NC + (c < NX ? c : NC - 1))) * inv;
         }
         __syncwarp();
         // ---- phase B ----
-        if (inB) {
-          double acc = baseB;
+        {
+          double accB = baseB;
 #pragma unroll
-          for (int l = 0; l < NX; ++l) acc += mB[l] * lds(sPM + 8 * (l * NC + cA));
-          sts(sT + 8 * lane, acc);
+          for (int l = 0; l < NX; ++l) accB += mB[l] * lds(sPM + 8 * (l * NC) + 8 * cA);
+          if (inB) sts(sT + 8 * lane, accB);
         }
         if (k > k_last) fetch(k - 1);
         __syncwarp();
