@@ -65,7 +65,7 @@ struct CoopQP {
   // One sample, executed by the 32 lanes of a warp.  S: this warp's shared memory (smem_doubles(N)).
   // Returns Engine::FULL_OK / FULL_MAXITER / FULL_FAILED; the step is applied to the iterate in global
   // memory (L.it) unless FULL_FAILED.
-  __device__ static int solve(const ProblemData& pd, const Lane& L, double* S, const int lane, int* iters_out) {
+  __device__ static int solve(const ProblemData& pd, const Lane& L, double* S, const int lane, const bool swept, int* iters_out) {
     const int N = pd.N, NS = N + 1;
     constexpr size_t bs = TILE;
     double* Mk = S;                  // [k][NX][NC]  = [A | B | b]
@@ -201,7 +201,10 @@ struct CoopQP {
       }
       if (warm) ++warm_iters;
       const double target = dmax(sigma * mu, pd.tau);
-
+      // first iteration of a warm start at target tau: k_qp1 (Engine::qp_fast) has just done exactly this
+      // Newton iteration and left lam_hat, t_hat in the stage records; pick them up instead of repeating it
+      const bool reuse = swept && j == 0 && warm && target == pd.tau && pd.max_ipm > 1;
+      if (!reuse) {
       // ---- rows: pending damped update, barrier terms (one lane per stage) ----
       for (int k = lane; k < NS; k += 32) {
         double ll = LL[k], lu = LU[k], tl = TL[k], tu = TU[k];
@@ -327,6 +330,7 @@ struct CoopQP {
       }
       if (lane == 0) DU[N] = 0.0;
       __syncwarp();
+      }  // !reuse
       // ---- rows: new slacks and multipliers, step-length statistics (one lane per stage) ----
       double amax = 1e300, s0 = 0.0, s1 = 0.0, s2 = 0.0, cmax = 0.0;
       for (int k = lane; k < NS; k += 32) {
@@ -335,10 +339,15 @@ struct CoopQP {
         double lhl = 0.0, thl = 0.0, lhu = 0.0, thu = 0.0;
         if (act && has_l) {
           const double ll = LL[k], tl = TL[k];
-          const double d = (u - lb) + dv;
-          const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
-          thl = d;
-          lhl = ab - cb * d;
+          if (reuse) {
+            lhl = L.ws[((size_t)k * E::W_REC + E::W_lh) * bs];
+            thl = L.ws[((size_t)k * E::W_REC + E::W_th) * bs];
+          } else {
+            const double d = (u - lb) + dv;
+            const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
+            thl = d;
+            lhl = ab - cb * d;
+          }
           const double dt = thl - tl, dl = lhl - ll;
           if (dt < 0.0) amax = dmin(amax, -tl / dt);
           if (dl < 0.0) amax = dmin(amax, -ll / dl);
@@ -347,10 +356,15 @@ struct CoopQP {
         }
         if (act && has_u) {
           const double lu = LU[k], tu = TU[k];
-          const double d = (ub - u) - dv;
-          const double itb = 1.0 / tu, cb = lu * itb, ab = target * itb + lu;
-          thu = d;
-          lhu = ab - cb * d;
+          if (reuse) {
+            lhu = L.ws[((size_t)k * E::W_REC + E::W_lh + 1) * bs];
+            thu = L.ws[((size_t)k * E::W_REC + E::W_th + 1) * bs];
+          } else {
+            const double d = (ub - u) - dv;
+            const double itb = 1.0 / tu, cb = lu * itb, ab = target * itb + lu;
+            thu = d;
+            lhu = ab - cb * d;
+          }
           const double dt = thu - tu, dl = lhu - lu;
           if (dt < 0.0) amax = dmin(amax, -tu / dt);
           if (dl < 0.0) amax = dmin(amax, -lu / dl);
@@ -361,7 +375,7 @@ struct CoopQP {
       }
       __syncwarp();
       {  // NaN anywhere in the step must reach amax like in the scalar code (a NaN slack fails "dt < 0")
-        const double probe = DU[0] + DX[N * NX];
+        const double probe = reuse ? 0.0 : DU[0] + DX[N * NX];
         if (!(probe == probe)) amax = probe;
       }
       const bool nan_step = __any_sync(0xffffffffu, !(amax == amax));

@@ -595,7 +595,9 @@ struct Engine {
   // =======================================================================================
   enum Fast : int { FAST_CONVERGED = 0, FAST_STEPPED = 1, FAST_HARD = 2, FAST_NAN = 3 };
 
-  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R) {
+  // swept (optional): set when FAST_HARD is returned AFTER the forward sweep, i.e. the workspace holds the
+  // complete first warm iteration (K, k, dx, du, lam_hat, t_hat at target tau) for the queue kernel to reuse
+  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, bool* swept = nullptr) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     const bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
@@ -699,6 +701,7 @@ struct Engine {
       apply_step(pd, L, 1.0, /*clip=*/true);
       return FAST_STEPPED;
     }
+    if (swept) *swept = true;
     return FAST_HARD;
   }
 

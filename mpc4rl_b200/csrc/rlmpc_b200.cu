@@ -74,7 +74,7 @@ struct KArgs {
   int* status;  // acados status per sample
   double* cost; // cost of the last linearisation
   int* hard;    // queue of samples for the full interior-point pass
-  int* ishard;  // 1 if the sample was queued in this call (written by k_qp1 only)
+  int* ishard;  // != 0 if the sample was queued in this call (written by k_qp1 only); 2: its workspace holds the first warm iteration
   int subset;   // sens kernels: 0 all samples, 1 samples not queued, 2 the queued samples (via the queue)
   int* counters;  // [0] queue length, [1] samples still active, [2] work counter of k_qp3, [3] its interior-point iterations
   const double* x0;  // [B, NX] row-major or null
@@ -148,9 +148,10 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
   if (b >= a.B || a.work[b] != WK_ACTIVE) return;
   const Lane L = make_lane<M>(a, b);
   typename E::Residuals R;
-  const int code = E::qp_fast(pd, L, R);
+  bool swept = false;
+  const int code = E::qp_fast(pd, L, R, &swept);
   a.cost[b] = R.cost;
-  a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? 1 : 0;
+  a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? (swept ? 2 : 1) : 0;
   if (code == E::FAST_NAN) {
     a.status[b] = ST_NAN;
     a.work[b] = WK_DONE;
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32) k_qp3(const __grid_constant__
     const int b = a.hard[j];
     const Lane L = make_lane<M>(a, b);
     int iters = 0;
-    const int st = Cq::solve(pd, L, S, lane, &iters);
+    const int st = Cq::solve(pd, L, S, lane, a.ishard[b] == 2, &iters);
     if (lane == 0) {
       atomicAdd(&a.counters[3], iters);
       if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
