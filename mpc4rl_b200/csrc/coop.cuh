@@ -33,8 +33,8 @@ template <class M>
 struct CoopQP {
   using E = Engine<M>;
   static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NC = NW + 1, NWS = E::NWS;
-  static constexpr int PER_STAGE = NX * NC + NW + NW + NX + 12;  // Mk, g, K|kff, dx, 12 row/scalar fields
-  static constexpr int SCRATCH = NX * NX + 2 * NX + NX * NC + NW * NC + 3 * NWS + 1;
+  static constexpr int PER_STAGE = NX * NC + NW + NW + 9;  // Mk, g, K|kff (later dx, du), 9 row/scalar fields
+  static constexpr int SCRATCH = 2 * NX + NX * NC + NW * NC + 3 * NWS + 1;
   __host__ __device__ static constexpr int smem_doubles(int N) { return PER_STAGE * (N + 1) + SCRATCH; }
 
   __device__ static __forceinline__ double wsum(double v) {
@@ -70,10 +70,10 @@ struct CoopQP {
     constexpr size_t bs = TILE;
     double* Mk = S;                  // [k][NX][NC]  = [A | B | b]
     double* Gk = Mk + NS * NX * NC;  // [k][NW]      = [q ; r]      (later: x-part of the costate recursion)
-    double* Kk = Gk + NS * NW;       // [k][NW]      = [K | kff]    (later: pi_k)
-    double* DX = Kk + NS * NW;       // [k][NX]
-    double* DU = DX + NS * NX;       // [k]
-    double* U = DU + NS;
+    // [k][NW] = [K_k | kff_k] after the backward sweep; the forward sweep overwrites stage k's slot with
+    // [dx_{k+1} | du_k] once the feedback law of stage k is in registers (dx_0 = 0); finally pi_k
+    double* Kk = Gk + NS * NW;
+    double* U = Kk + NS * NW;
     double* LL = U + NS;    // lam of the lower / upper input bound
     double* LU = LL + NS;
     double* TL = LU + NS;   // slacks
@@ -82,10 +82,11 @@ struct CoopQP {
     double* LHU = LHL + NS;
     double* THL = LHU + NS;
     double* THU = THL + NS;
-    double* HB = THU + NS;  // barrier terms of the stage: Hessian (u,u) and gradient (u)
-    double* GB = HB + NS;
-    double* P = GB + NS;    // scratch
-    double* pv = P + NX * NX;
+    // (u,u) Hessian entry and u-gradient of the stage incl. barrier terms: live from the row phase to the end
+    // of the backward sweep, when lam_hat of the previous step is dead, so they share its storage
+    double* HB = LHL;
+    double* GB = LHU;
+    double* pv = THU + NS;  // scratch
     double* pv2 = pv + NX;
     double* PM = pv2 + NX;
     double* T = PM + NX * NC;
@@ -94,7 +95,7 @@ struct CoopQP {
 
     // explicit shared-window addresses for the two recursions (plain ld/st.shared with immediate offsets)
     const unsigned sT = (unsigned)__cvta_generic_to_shared(T), sPM = (unsigned)__cvta_generic_to_shared(PM);
-    const unsigned sDX = (unsigned)__cvta_generic_to_shared(DX);
+    const unsigned sKk = (unsigned)__cvta_generic_to_shared(Kk);
 
     const bool qmode = pd.mode == MODE_Q;
     const double lb = pd.lbu[0], ub = pd.ubu[0];
@@ -300,7 +301,6 @@ struct CoopQP {
         }
       }
       // ---- forward sweep: dx, du ----
-      if (lane < NX) DX[lane] = 0.0;
       __syncwarp();
       {
         double kr[NW], ar[NC];
@@ -314,7 +314,7 @@ struct CoopQP {
         for (int k = 0; k < N; ++k) {
           double dxl[NX];
 #pragma unroll
-          for (int l = 0; l < NX; ++l) dxl[l] = lds(sDX + 8 * (k * NX + l));
+          for (int l = 0; l < NX; ++l) dxl[l] = (k > 0) ? lds(sKk + 8 * ((k - 1) * NW + l)) : 0.0;
           double du = kr[NX];
 #pragma unroll
           for (int l = 0; l < NX; ++l) du += kr[l] * dxl[l];
@@ -322,20 +322,18 @@ struct CoopQP {
 #pragma unroll
           for (int l = 0; l < NX; ++l) a += ar[l] * dxl[l];
           a += ar[NX] * du;
-          if (lane < NX) sts(sDX + 8 * ((k + 1) * NX + lane), a);
-          if (lane == 0) DU[k] = du;
           if (k + 1 < N) fetch_f(k + 1);
+          if (lane < NX) sts(sKk + 8 * (k * NW + lane), a);  // dx_{k+1}
+          if (lane == NX) sts(sKk + 8 * (k * NW + NX), du);   // du_k
           __syncwarp();
         }
       }
-      if (lane == 0) DU[N] = 0.0;
-      __syncwarp();
       }  // !reuse
       // ---- rows: new slacks and multipliers, step-length statistics (one lane per stage) ----
       double amax = 1e300, s0 = 0.0, s1 = 0.0, s2 = 0.0, cmax = 0.0;
       for (int k = lane; k < NS; k += 32) {
         const bool act = k >= k_first && k < N;
-        const double dv = DU[k], u = U[k];
+        const double dv = (k < N) ? Kk[k * NW + NX] : 0.0, u = U[k];
         double lhl = 0.0, thl = 0.0, lhu = 0.0, thu = 0.0;
         if (act && has_l) {
           const double ll = LL[k], tl = TL[k];
@@ -375,7 +373,7 @@ struct CoopQP {
       }
       __syncwarp();
       {  // NaN anywhere in the step must reach amax like in the scalar code (a NaN slack fails "dt < 0")
-        const double probe = reuse ? 0.0 : DU[0] + DX[N * NX];
+        const double probe = reuse ? 0.0 : Kk[NX] + Kk[(N - 1) * NW];
         if (!(probe == probe)) amax = probe;
       }
       const bool nan_step = __any_sync(0xffffffffu, !(amax == amax));
@@ -450,7 +448,7 @@ struct CoopQP {
         L.it[(size_t)(E::it_lam(N, k) + 1) * bs] = lu;
         L.it[(size_t)E::it_t(N, k) * bs] = tl;
         L.it[(size_t)(E::it_t(N, k) + 1) * bs] = tu;
-        L.it[(size_t)E::it_u(N, k) * bs] = U[k] + ap * DU[k];
+        L.it[(size_t)E::it_u(N, k) * bs] = U[k] + ap * Kk[k * NW + NX];
       }
     }
     // x-part of the costate recursion: c_k = q_k + (W dw)_x, in place of q_k;  x_k += ap dx_k  (k >= 1)
@@ -462,12 +460,12 @@ struct CoopQP {
       double a = Gk[k * NW + i];
 #pragma unroll
       for (int jj = 0; jj < NW; ++jj) {
-        const double dwj = jj < NX ? DX[k * NX + jj] : DU[k];
+        const double dwj = jj < NX ? Kk[(k - 1) * NW + jj] : (k < N ? Kk[k * NW + NX] : 0.0);
         a += (s * W[E::pidx(i < jj ? i : jj, i < jj ? jj : i)]) * dwj;
       }
       Gk[k * NW + i] = a;
       const size_t o = (size_t)(E::it_x(N, k) + i) * bs;
-      L.it[o] = L.it[o] + ap * DX[k * NX + i];
+      L.it[o] = L.it[o] + ap * Kk[(k - 1) * NW + i];
     }
     __syncwarp();
     // pi_{k-1} = c_k + A_k' pi_k, k = N .. 1   (pi_k kept in Kk[k][0..NX), ping-pong through pv / pv2)
