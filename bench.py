@@ -322,7 +322,8 @@ def run_gpu(args, rank, world, local_rank):
                          "kernel_ms": kernel_ms, "kernels_ms": {k: round(v, 4) for k, v in phase_ms.items()},
                          "algorithmic_bytes_per_unit": wl["b_alg"],
                          "note": "path is FP64 CUDA-core/latency bound, not HBM bound (SURVEY.md 8(d)); "
-                                 "fraction reported as defined, bytes not padded"},
+                                 "fraction reported as defined, bytes not padded; k_qp1 and k_sens_sweep run at "
+                                 "70-100 % of the measured HBM peak on the bytes they actually move (profiles/r01_summary.md)"},
             # KKT residual of the iterate after the RTI step (one SQP iteration, so not converged by construction);
             # the max comes from the states on which full-step Gauss-Newton SQP 2-cycles (status 2 in the setup solve)
             "quality": {"status0_frac_after_setup": conv_frac, "status0_frac_last_step": ok_frac,

@@ -259,3 +259,24 @@ def test_warp_per_sample_queue_equals_thread_per_sample(spec):
         assert _rel(a["dL"][ok], b["dL"][ok]) < 1e-6, step
         if step < 4:  # Q-mode: dpi/dtheta is ~0 by construction (quirk Q7)
             assert _rel(a["dpi"][ok], b["dpi"][ok]) < 1e-5, step
+
+
+def test_phase_timings_and_queue_statistics(spec):
+    """rlmpc_get_timings: six phase times of the last call plus the queue length and the interior-point
+    iterations spent on it (the reference's analogue is update_nlp's nlp_timing dict, nlp.py:1397-1422)."""
+    B = 2048
+    g = torch.Generator(device="cpu").manual_seed(3)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    m = _mpc(spec, B)
+    with pytest.raises(RuntimeError):
+        m.timings()  # option "timing" is off
+    m.set_option("timing", 1)
+    m.reset(x0)
+    m.solve(x0, max_sqp=60)
+    m.solve_sens(x0 + 1e-3, max_sqp=1)
+    t = m.timings()
+    assert set(m.PHASES) <= set(t) and all(t[k] >= 0.0 for k in m.PHASES)
+    assert t["linearize"] > 0.0 and t["qp_fast"] > 0.0 and t["sens_sweep"] > 0.0
+    assert 0 < t["queue_len"] < B  # some, not all, samples need more than the one warm Newton iteration
+    assert t["queue_ipm_iters"] >= 2 * t["queue_len"]  # each of them at least a second iteration
