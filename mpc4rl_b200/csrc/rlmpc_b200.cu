@@ -741,7 +741,9 @@ cudaError_t setup_coop(rlmpc_handle* h, int N, cudaError_t e) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (e != cudaSuccess || smem > (size_t)max_optin) return e;  // horizon too long for shared memory: coop_grid stays 0
-    e = cudaFuncSetAttribute(k_qp3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the attribute belongs to the kernel, not to the handle: opt in to the device maximum once, so that handles
+    // with different horizons can coexist (the launch passes the size this handle needs)
+    e = cudaFuncSetAttribute(k_qp3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp3<M>, COOP_WARPS * 32, smem);
     if (e == cudaSuccess) h->coop_grid = sms * per_sm;
   }

@@ -280,3 +280,41 @@ def test_phase_timings_and_queue_statistics(spec):
     assert t["linearize"] > 0.0 and t["qp_fast"] > 0.0 and t["sens_sweep"] > 0.0
     assert 0 < t["queue_len"] < B  # some, not all, samples need more than the one warm Newton iteration
     assert t["queue_ipm_iters"] >= 2 * t["queue_len"]  # each of them at least a second iteration
+
+
+def test_handles_with_different_horizons_coexist(spec):
+    """Kernel attributes (dynamic shared memory of the warp-per-sample queue kernel) are per kernel, not
+    per handle: a long-horizon and a short-horizon handle alive at the same time, used alternately,
+    give what each gives alone."""
+    import copy
+
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    B = 512
+    g = torch.Generator(device="cpu").manual_seed(11)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    cfgs = []
+    for N in (80, 20):
+        c = copy.deepcopy(cartpole_original_config())
+        c["dimensions"]["N"] = N
+        c["ocp_options"]["tf"] = 0.02 * N
+        cfgs.append(cartpole_spec(c))
+
+    def run(m):
+        m.reset(x0)
+        o = m.solve_sens(x0, max_sqp=40)
+        return {k: v.clone() for k, v in o.items()}
+
+    alone = []
+    for s in cfgs:
+        m = BatchedMPC(s, max_batch=B, device=0)
+        alone.append(run(m))
+        m.close()
+    both = [BatchedMPC(s, max_batch=B, device=0) for s in cfgs]  # the short horizon is created last
+    for rep in range(2):
+        for m, ref in zip(both, alone):
+            o = run(m)
+            assert (o["status"] == 0).double().mean().item() > 0.5  # N=80 from random states: a third hits the 40-iteration limit
+            for k in ("status", "u0", "cost", "dL", "dpi"):
+                assert torch.equal(o[k], ref[k]), k
