@@ -51,6 +51,10 @@ WORKLOADS = {
     "cartpole": dict(batch=65536, b_alg=8492, metric=METRIC,
                      text="cartpole_original N=40 nx=4 nu=1 ntheta=83 (3 with gradient), V-mode SQP-RTI (K=1) + "
                           "dL/dtheta + dpi/dtheta, warm-started from the converged iterate, states perturbed every step"),
+    # SURVEY.md 8(d) config 2, secondary: config/cartpole.yaml (N=30, box bounds on all states) -- `--workload cartpole_bx`
+    "cartpole_bx": dict(batch=65536, b_alg=14092, metric="MPC solves+sensitivities/sec (cartpole.yaml N=30 with state bounds, batch 65k)",
+                        text="cartpole.yaml N=30 nx=4 nu=1, input and state bounds, V-mode SQP-RTI (K=1) + dL/dtheta + dpi/dtheta, "
+                             "warm-started from the converged iterate, states perturbed every step"),
     # BASELINE.json configs[3] (secondary line, `--workload evaporation`): N=100, nu=3 (third input = slack), affine h rows
     "evaporation": dict(batch=32768, b_alg=45228, metric="MPC solves+sensitivities/sec (evaporation N=100, batch 32k)",
                         text="evaporation_process N=100 nx=2 nu=3 ntheta=60 (tracking-cost parameters), V-mode SQP-RTI "
@@ -74,6 +78,13 @@ def make_workload(name, B, rank, dev):
 
         spec = cartpole_spec(cartpole_original_config())
         x0 = synth_states(B, 1234 + rank).to(dev)
+        return spec, x0, 1e-3, lambda mpc: mpc.reset(x0)
+    if name == "cartpole_bx":
+        from mpc4rl_b200 import cartpole_config, cartpole_spec
+
+        spec = cartpole_spec(cartpole_config())
+        x0 = synth_states(B, 1234 + rank).to(dev)
+        x0[:, 1:] *= 0.5  # keep the start inside the state box (|s_dot| <= 10, |theta| <= 6.28, |theta_dot| <= 10)
         return spec, x0, 1e-3, lambda mpc: mpc.reset(x0)
     from mpc4rl_b200 import evaporation_spec
 

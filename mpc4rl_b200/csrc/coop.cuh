@@ -29,6 +29,33 @@ struct CoopOK {
 };
 
 #ifdef __CUDACC__
+// warp reductions and plain shared-window accesses used by the cooperative solvers
+struct CoopQPBase {
+  __device__ static __forceinline__ double wsum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+  }
+  __device__ static __forceinline__ double wmin(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = dmin(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+  }
+  __device__ static __forceinline__ double wmax(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = dmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+  }
+  __device__ static __forceinline__ double lds(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+  }
+  __device__ static __forceinline__ void sts(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+  }
+};
+
 template <class M>
 struct CoopQP {
   using E = Engine<M>;
@@ -311,6 +338,7 @@ struct CoopQP {
           for (int l = 0; l < NC; ++l) ar[l] = (lane < NX) ? Mk[k * NX * NC + lane * NC + l] : 0.0;
         };
         fetch_f(0);
+        __syncwarp();  // every lane holds stage 0's feedback law before its slot is overwritten
         for (int k = 0; k < N; ++k) {
           double dxl[NX];
 #pragma unroll

@@ -422,6 +422,22 @@ struct Engine {
     }
   }
 
+  // step-length statistics of given (lam_hat, t_hat), same traversal as rows_forward (used when the Newton
+  // step of a stage was computed elsewhere and only its rows are at hand)
+  MPC_HD static void rows_stats(const Bnd& bd, const double* lam, const double* t, const double* lh, const double* th,
+                                StepStats& S) {
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      MPC_UNROLL for (int side = 0; side < 2; ++side) {
+        const int q = side * NV + r;
+        const bool act = side ? (bd.ub[r] < BIG) : (bd.lb[r] > -BIG);
+        if (!act) continue;
+        const int qs = slack_of(bd, r, side);
+        if (NSX > 0 && qs >= 0) step_stats(lam[qs], t[qs], lh[qs], th[qs], S);
+        step_stats(lam[q], t[q], lh[q], th[q], S);
+      }
+    }
+  }
+
   struct Residuals {
     double stat, eq, ineq, comp, cost;
   };
@@ -798,6 +814,40 @@ struct Engine {
   // ---------------------------------------------------------------------------------------
   static constexpr int WARM_LIMIT = 6;  // IPM iterations granted to a warm start before a cold restart
 
+  // (lam,t) of the rows of one stage at the start of an interior-point solve.  warm: the stored values,
+  // clipped into the cone; cold: slacks from the current point, lam = mu0 / t.  Returns sum(lam*t).
+  MPC_HD static double ipm_init_stage(const ProblemData& pd, const Bnd& bd, const double* v, bool warm, double* lam, double* t) {
+    double mu = 0.0;
+    if (warm) {
+      clip_rows(bd, lam, t);
+    } else {
+      MPC_UNROLL for (int q = 0; q < NR; ++q) { lam[q] = 0.0; t[q] = 0.0; }
+      MPC_UNROLL for (int r = 0; r < NV; ++r) {
+        const double tmin = 1e-2 * row_range(bd, r);
+        MPC_UNROLL for (int side = 0; side < 2; ++side) {
+          const int q = side * NV + r;
+          double d = side ? bd.ub[r] - v[r] : v[r] - bd.lb[r];
+          const int qs = slack_of(bd, r, side);
+          if (NSX > 0 && qs >= 0) {  // slack: cover a violated bound, stay strictly positive
+            t[qs] = dmax(-d, 0.0) + tmin;
+            lam[qs] = pd.mu0 / t[qs];
+            d += t[qs];
+          }
+          t[q] = dmax(d, tmin);
+          lam[q] = pd.mu0 / t[q];
+        }
+      }
+    }
+    MPC_UNROLL for (int r = 0; r < NV; ++r) {
+      if (bd.lb[r] > -BIG) mu += lam[r] * t[r]; else { lam[r] = 0.0; t[r] = 0.0; }
+      if (bd.ub[r] < BIG) mu += lam[NV + r] * t[NV + r]; else { lam[NV + r] = 0.0; t[NV + r] = 0.0; }
+    }
+    MPC_UNROLL for (int j = 0; j < NSX; ++j) {
+      if (bd.zl[j] >= 0.0) mu += lam[R_LS + j] * t[R_LS + j]; else { lam[R_LS + j] = 0.0; t[R_LS + j] = 0.0; }
+      if (bd.zu[j] >= 0.0) mu += lam[R_US + j] * t[R_US + j]; else { lam[R_US + j] = 0.0; t[R_US + j] = 0.0; }
+    }
+    return mu;
+  }
   // returns sum(lam*t)
   MPC_HD static double ipm_init(const ProblemData& pd, const Lane& L, bool warm) {
     const int N = pd.N;
@@ -818,33 +868,8 @@ struct Engine {
       if (warm) {
         ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
         ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
-        clip_rows(bd, lam, t);
-      } else {
-        MPC_UNROLL for (int q = 0; q < NR; ++q) { lam[q] = 0.0; t[q] = 0.0; }
-        MPC_UNROLL for (int r = 0; r < NV; ++r) {
-          const double tmin = 1e-2 * row_range(bd, r);
-          MPC_UNROLL for (int side = 0; side < 2; ++side) {
-            const int q = side * NV + r;
-            double d = side ? bd.ub[r] - v[r] : v[r] - bd.lb[r];
-            const int qs = slack_of(bd, r, side);
-            if (NSX > 0 && qs >= 0) {  // slack: cover a violated bound, stay strictly positive
-              t[qs] = dmax(-d, 0.0) + tmin;
-              lam[qs] = pd.mu0 / t[qs];
-              d += t[qs];
-            }
-            t[q] = dmax(d, tmin);
-            lam[q] = pd.mu0 / t[q];
-          }
-        }
       }
-      MPC_UNROLL for (int r = 0; r < NV; ++r) {
-        if (bd.lb[r] > -BIG) mu += lam[r] * t[r]; else { lam[r] = 0.0; t[r] = 0.0; }
-        if (bd.ub[r] < BIG) mu += lam[NV + r] * t[NV + r]; else { lam[NV + r] = 0.0; t[NV + r] = 0.0; }
-      }
-      MPC_UNROLL for (int j = 0; j < NSX; ++j) {
-        if (bd.zl[j] >= 0.0) mu += lam[R_LS + j] * t[R_LS + j]; else { lam[R_LS + j] = 0.0; t[R_LS + j] = 0.0; }
-        if (bd.zu[j] >= 0.0) mu += lam[R_US + j] * t[R_US + j]; else { lam[R_US + j] = 0.0; t[R_US + j] = 0.0; }
-      }
+      mu += ipm_init_stage(pd, bd, v, warm, lam, t);
       st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
     }
@@ -858,6 +883,35 @@ struct Engine {
   // (lam <- tau/t).  All other rows take their Newton values.  A handful of such steps identify the
   // new active set when few rows change; the regular iteration then polishes to lam*t = tau.
   // Returns sum(lam*t).
+  MPC_HD static bool row_active(const Bnd& bd, int q) {
+    if (q < 2 * NV) {
+      const int r = q < NV ? q : q - NV;
+      return q < NV ? (bd.lb[r] > -BIG) : (bd.ub[r] < BIG);
+    }
+    return q < R_US ? (bd.zl[q - R_LS] >= 0.0) : (bd.zu[q - R_US] >= 0.0);
+  }
+  // the rows of one stage; returns their sum(lam*t)
+  MPC_HD static double ipm_project_stage(const ProblemData& pd, const Bnd& bd, double* lam, double* t, const double* lh,
+                                         const double* th) {
+    double mu = 0.0;
+    MPC_UNROLL for (int q = 0; q < NR; ++q) {
+      if (!row_active(bd, q)) continue;
+      const double range = row_range(bd, q < 2 * NV ? (q < NV ? q : q - NV) : soft_row(q < R_US ? q - R_LS : q - R_US));
+      const double eps_t = 1e-9 * range;
+      if (!(th[q] > eps_t)) {          // slack collapses: the row becomes (stays) active
+        t[q] = eps_t;
+        lam[q] = dmax(dmax(lh[q], lam[q]), 1e-3);
+      } else if (!(lh[q] > 0.0)) {     // multiplier changes sign: the row is released
+        t[q] = th[q];
+        lam[q] = pd.tau / th[q];
+      } else {
+        t[q] = th[q];
+        lam[q] = lh[q];
+      }
+      mu += lam[q] * t[q];
+    }
+    return mu;
+  }
   MPC_HD static double ipm_project(const ProblemData& pd, const Lane& L) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
@@ -872,31 +926,7 @@ struct Engine {
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
       ld<NR>(w + (size_t)W_lh * bs, bs, lh);
       ld<NR>(w + (size_t)W_th * bs, bs, th);
-      MPC_UNROLL for (int q = 0; q < NR; ++q) {
-        bool act;
-        double range;
-        if (q < 2 * NV) {
-          const int r = q < NV ? q : q - NV;
-          act = q < NV ? (bd.lb[r] > -BIG) : (bd.ub[r] < BIG);
-          range = row_range(bd, r);
-        } else {
-          act = q < R_US ? (bd.zl[q - R_LS] >= 0.0) : (bd.zu[q - R_US] >= 0.0);
-          range = row_range(bd, soft_row(q < R_US ? q - R_LS : q - R_US));
-        }
-        if (!act) continue;
-        const double eps_t = 1e-9 * range;
-        if (!(th[q] > eps_t)) {          // slack collapses: the row becomes (stays) active
-          t[q] = eps_t;
-          lam[q] = dmax(dmax(lh[q], lam[q]), 1e-3);
-        } else if (!(lh[q] > 0.0)) {     // multiplier changes sign: the row is released
-          t[q] = th[q];
-          lam[q] = pd.tau / th[q];
-        } else {
-          t[q] = th[q];
-          lam[q] = lh[q];
-        }
-        mu += lam[q] * t[q];
-      }
+      mu += ipm_project_stage(pd, bd, lam, t, lh, th);
       st<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       st<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
     }

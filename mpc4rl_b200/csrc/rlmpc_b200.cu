@@ -14,7 +14,7 @@
 #include "../../include/rlmpc_b200.h"
 #include "engine.cuh"
 #include "condense.cuh"
-#include "coop.cuh"
+#include "coop_general.cuh"
 #include "models/cartpole.cuh"
 #include "models/linear_system.cuh"
 #include "models/evaporation.cuh"
@@ -388,12 +388,32 @@ __global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData
 #endif
 constexpr int COOP_WARPS = RLMPC_COOP_WARPS;  // samples in flight per block
 
+// Which cooperative solver, and how many samples per block: the lean one (coop.cuh) where it applies, else the
+// general one (coop_general.cuh; more shared memory per sample, one warp per block), else none.
+template <class M, bool LEAN = CoopOK<M>::value, bool GEN = CoopGenOK<M>::value>
+struct CoopSel {
+  static constexpr bool value = false;
+  static constexpr int WARPS = 1;
+};
+template <class M, bool GEN>
+struct CoopSel<M, true, GEN> {
+  static constexpr bool value = true;
+  static constexpr int WARPS = COOP_WARPS;
+  using Solver = CoopQP<M>;
+};
+template <class M>
+struct CoopSel<M, false, true> {
+  static constexpr bool value = true;
+  static constexpr int WARPS = 1;
+  using Solver = CoopGen<M>;
+};
+
 // persistent grid; warps fetch queue positions from counters[2].  Works on the samples' own iterate and
 // stage records (no compact copies: the QP lives in shared memory for the whole solve).
 template <class M>
-__global__ void __launch_bounds__(COOP_WARPS * 32) k_qp3(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(CoopSel<M>::WARPS * 32) k_qp3(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
-  using Cq = CoopQP<M>;
+  using Cq = typename CoopSel<M>::Solver;
   extern __shared__ double coop_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* S = coop_smem + (size_t)wib * Cq::smem_doubles(pd.N);
@@ -635,7 +655,7 @@ struct rlmpc_handle {
   double *itb = nullptr, *wsb = nullptr;  // partially condensed queue path (only for condensable models)
   int itb_size = 0, wsb_size = 0;
   int condense = 1;    // 1: queued QPs in partially condensed form where applicable (input bounds only, V-mode, N % 4 == 0)
-  int coop = 1;        // warp-per-sample queue kernel (coop.cuh) where the model allows it (NU = 1, NX <= 4, input bounds only)
+  int coop = 1;        // warp-per-sample queue kernel (coop.cuh / coop_general.cuh) where the model's blocks fit a warp
   int coop_grid = 0;   // its persistent grid (blocks), sized at create time from the occupancy
   int ring_b = 0;      // ring reader for the condensed kernel: measured slower (3.3 vs 2.3 ms), blocks carry enough work per load batch
                        // (an L1 prefetch of the next block record, CCTL.E.PF1, measured the same 3.3 ms: profiles/r01g_variants_prefetch_overlap.log)
@@ -728,13 +748,13 @@ cudaError_t alloc_condensed(rlmpc_handle* h, int N, cudaError_t e) {
 
 template <class M>
 size_t coop_smem(int N) {
-  if constexpr (CoopOK<M>::value) return sizeof(double) * COOP_WARPS * CoopQP<M>::smem_doubles(N);
+  if constexpr (CoopSel<M>::value) return sizeof(double) * CoopSel<M>::WARPS * CoopSel<M>::Solver::smem_doubles(N);
   return 0;
 }
 // persistent grid of the warp-per-sample queue kernel: as many blocks as fit on the device
 template <class M>
 cudaError_t setup_coop(rlmpc_handle* h, int N, cudaError_t e) {
-  if constexpr (CoopOK<M>::value) {
+  if constexpr (CoopSel<M>::value) {
     const size_t smem = coop_smem<M>(N);
     int dev = 0, sms = 0, per_sm = 0, max_optin = 0;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
@@ -744,7 +764,7 @@ cudaError_t setup_coop(rlmpc_handle* h, int N, cudaError_t e) {
     // the attribute belongs to the kernel, not to the handle: opt in to the device maximum once, so that handles
     // with different horizons can coexist (the launch passes the size this handle needs)
     e = cudaFuncSetAttribute(k_qp3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp3<M>, COOP_WARPS * 32, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp3<M>, CoopSel<M>::WARPS * 32, smem);
     if (e == cudaSuccess) h->coop_grid = sms * per_sm;
   }
   return e;
@@ -807,9 +827,9 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         sq = h->side_stream;
       }
       bool coop_done = false;
-      if constexpr (CoopOK<M>::value) {
+      if constexpr (CoopSel<M>::value) {
         if (h->coop && h->coop_grid > 0 && !a.inplace) {
-          k_qp3<M><<<h->coop_grid, COOP_WARPS * 32, coop_smem<M>(N), sq>>>(h->pd, a);
+          k_qp3<M><<<h->coop_grid, CoopSel<M>::WARPS * 32, coop_smem<M>(N), sq>>>(h->pd, a);
           h->launches++;
           coop_done = true;
         }

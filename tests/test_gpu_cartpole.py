@@ -249,10 +249,13 @@ def test_warp_per_sample_queue_equals_thread_per_sample(spec):
         runs[coop] = [{k: v.cpu().numpy() for k, v in o.items()} for o in outs]
         runs[coop].append(m.launch_count - n0)
     assert runs[1][-1] < runs[0][-1]  # one queue kernel instead of gather + condense + solve + scatter
+    conv = None  # samples converged in the cold solve: only those start the later calls from the same iterate
     for step, (a, b) in enumerate(zip(runs[1][:-1], runs[0][:-1])):
         same = a["status"] == b["status"]
         assert same.mean() > 0.995, (step, same.mean())
         ok = same & (a["status"] == 0)
+        conv = ok if conv is None else conv
+        ok = ok & conv
         assert ok.mean() > 0.85, (step, ok.mean())
         assert np.abs(a["u0"] - b["u0"])[ok].max() < 1e-7, step
         assert _rel(a["cost"][ok], b["cost"][ok]) < 1e-9, step

@@ -361,3 +361,73 @@ def test_linear_system_batch_properties():
     assert (x1[okm][:, 1].abs() <= 1.0 + 1e-7).all()
     V = out["cost"][:33].cpu().numpy()
     assert okm[:33].all() and (V[:-2] + V[2:] - 2 * V[1:-1] >= -1e-9).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# warp-per-sample queue kernel, general version (csrc/coop_general.cuh) against the thread-per-sample kernels
+# ------------------------------------------------------------------------------------------------
+def _compare_queue_kernels(make, x0, starts, steps, u0=None, min_ok=0.6):
+    """Same calls with option coop = 1 (default) and 0; statuses equal, outputs equal to rounding."""
+    runs = {}
+    for coop in (1, 0):
+        m = make()
+        m.set_option("tol", 1e-8)
+        m.set_option("coop", coop)
+        m.set_option("timing", 1)
+        starts(m)
+        outs = [m.solve_sens(x0, max_sqp=60)]
+        used = False
+        for dx in steps:
+            outs.append(m.solve_sens(x0 + dx, max_sqp=1))
+            used = used or m.timings()["queue_ipm_iters"] > 0  # (counted per SQP round; an RTI call has one)
+        if u0 is not None:
+            outs.append(m.solve_sens(x0, u0=u0, max_sqp=60))
+        runs[coop] = ([{k: v.cpu().numpy() for k, v in o.items()} for o in outs], used)
+    assert runs[1][1] and not runs[0][1]  # the warp-per-sample kernel ran with coop=1 and only then
+    conv = None  # samples converged in the cold solve: only those start the later calls from the same iterate in
+    for step, (a, b) in enumerate(zip(runs[1][0], runs[0][0])):  # both runs (an unconverged SQP amplifies rounding)
+        same = a["status"] == b["status"]
+        assert same.mean() > 0.99, (step, same.mean())
+        ok = same & (a["status"] == 0)
+        conv = ok if conv is None else conv
+        ok = ok & conv
+        assert ok.mean() > min_ok, (step, ok.mean())
+        assert np.abs(a["u0"] - b["u0"])[ok].max() < 1e-6 * max(1.0, np.abs(b["u0"][ok]).max()), step
+        assert _rel(a["cost"][ok], b["cost"][ok]) < 1e-8, step
+        assert _rel(a["dL"][ok], b["dL"][ok]) < 1e-5, step
+
+
+def test_general_warp_per_sample_kernel_state_bounds():
+    B = 2048
+    g = torch.Generator(device="cpu").manual_seed(5)
+    lo = torch.tensor([-1.0, -1.0, -0.5 * np.pi, -2.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    dx = [1e-3 * torch.randn(B, 4, generator=g, dtype=torch.float64).cuda() for _ in range(2)]
+    a0 = (-30.0 + 60.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)).cuda()
+    # random swing-up starts against |u| <= 30 and the state box: about half of them converge (the rest: status 2 / 4, equal in both paths)
+    _compare_queue_kernels(lambda: _bx_engine(B), x0, lambda m: m.reset(x0), dx, u0=a0, min_ok=0.3)
+
+
+def test_general_warp_per_sample_kernel_soft_bounds():
+    B = 2048
+    g = torch.Generator(device="cpu").manual_seed(6)
+    x0 = (torch.tensor([-0.2, -1.0]) + torch.tensor([1.4, 2.0]) * torch.rand(B, 2, generator=g)).double().cuda()
+    dx = [1e-2 * torch.randn(B, 2, generator=g, dtype=torch.float64).cuda() for _ in range(2)]
+    a0 = (-1.0 + 2.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)).cuda()
+    _compare_queue_kernels(lambda: _lin_engine(B), x0, lambda m: m.reset(x0), dx, u0=a0, min_ok=0.9)
+
+
+def test_general_warp_per_sample_kernel_general_rows():
+    B = 1024
+    g = torch.Generator(device="cpu").manual_seed(8)
+    lo, hi = torch.tensor([25.0, 49.7], dtype=torch.float64), torch.tensor([40.0, 70.0], dtype=torch.float64)
+    x0 = (lo + (hi - lo) * torch.rand(B, 2, generator=g, dtype=torch.float64)).cuda()
+    dx = [1e-2 * torch.randn(B, 2, generator=g, dtype=torch.float64).cuda() for _ in range(2)]
+    spec_box = {}
+
+    def make():
+        m, spec = _evap_engine(B, 0.99)
+        spec_box["spec"] = spec
+        return m
+
+    _compare_queue_kernels(make, x0, lambda m: _evap_guess(m, spec_box["spec"], B), dx, min_ok=0.95)
