@@ -92,9 +92,9 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * "sync_every" (4: SQP rounds between host checks "has every sample converged" when max_sqp > 1),
  * "timing" (0; 1 = record per-phase CUDA events, see rlmpc_get_timings), "overlap" (0),
  * "sigma_min" (0.05), "sigma0" (0.3): centring parameters of the interior-point iteration,
- * "coop" (1): queued QPs of small input-bounds-only models (NU = 1, NX <= 4: cart-pole without state
- * bounds) are solved by the warp-per-sample kernel, the whole QP resident in shared memory; 0 = use the
- * thread-per-sample queue kernels that every other model uses,
+ * "coop" (1): queued QPs are solved by the warp-per-sample kernel, the whole stage QP of a sample resident in
+ * shared memory (all shipped models; needs the horizon to fit: 43..99 doubles per stage); 0 = use the
+ * thread-per-sample queue kernels,
  * "condense" (1): (thread-per-sample path) queued QPs of input-bounds-only problems are solved in partially condensed form
  * (blocks of 4 stages, like the reference's PARTIAL_CONDENSING_HPIPM) in V-mode when N % 4 == 0,
  * "ring" (1) / "ring_b" (0): cp.async shared-memory ring reader of the stage-form / condensed queue kernel,
