@@ -98,6 +98,10 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * "condense" (1): (thread-per-sample path) queued QPs of input-bounds-only problems are solved in partially condensed form
  * (blocks of 4 stages, like the reference's PARTIAL_CONDENSING_HPIPM) in V-mode when N % 4 == 0,
  * "ring" (1) / "ring_b" (0): cp.async shared-memory ring reader of the stage-form / condensed queue kernel,
+ * "comp_accept" (0.5): an interior-point solve (and the single warm Newton iteration of the fast path) ends on
+ * a full step whose rows all land within lam*t = tau (1 +- comp_accept) -- a neighbourhood of the tau-central
+ * point, far inside HPIPM's own complementarity tolerance; at SQP convergence the step vanishes and lam*t = tau
+ * holds to rounding whatever the value (0.05 = the strict setting of the first builds),
  * "as_steps" (20): active-set (full Newton step + projection) iterations a warm start may take when
  * its Newton step is infeasible, before it falls back to a cold start,
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */

@@ -55,6 +55,8 @@ struct ProblemData {
   double as_steps;      // warm start: number of active-set (full step + projection) iterations tried
                         // when the Newton step is not feasible, before the cold restart
   double condense;      // > 0: queued QPs are solved in partially condensed form (condense.cuh) where applicable
+  double comp_accept;   // a Newton step / interior-point solve is accepted when it is a full step and every row ends
+                        // within lam*t = tau (1 +- comp_accept), i.e. max |dlam dt| <= comp_accept * tau
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component

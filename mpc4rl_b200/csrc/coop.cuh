@@ -455,7 +455,7 @@ struct CoopQP {
         break;
       }
       const double mu_new = (s0 + alpha * s1 + alpha * alpha * s2) / m_rows;
-      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
+      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) converged = true;
       const double r = 1.0 - alpha;
       sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
       mu = mu_new;

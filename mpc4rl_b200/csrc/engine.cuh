@@ -613,7 +613,11 @@ struct Engine {
 
   // swept (optional): set when FAST_HARD is returned AFTER the forward sweep, i.e. the workspace holds the
   // complete first warm iteration (K, k, dx, du, lam_hat, t_hat at target tau) for the queue kernel to reuse
-  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, bool* swept = nullptr) {
+  // polish: "converged" additionally requires the iterate to sit ON the central path (|lam*t - tau| <= 5 % tau,
+  // the accuracy update_nlp's R = 0 assumes for the sensitivities), not merely within the acceptance
+  // neighbourhood comp_accept of the steps on the way; otherwise one more (cheap, warm) Newton iteration
+  // follows.  Off for the final test-only round of an SQP solve, where the plain acados criterion decides.
+  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, bool* swept = nullptr, bool polish = true) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     const bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
@@ -708,12 +712,12 @@ struct Engine {
     }
     const double rmax = dmax(dmax(R.stat, R.eq), dmax(R.ineq, R.comp));
     if (!(rmax == rmax) || !(R.cost == R.cost)) return FAST_NAN;
-    if (rmax < pd.tol) return FAST_CONVERGED;
+    if (rmax < pd.tol && (!polish || !warm || R.comp <= 0.05 * pd.tau)) return FAST_CONVERGED;
     if (!warm || failed) return FAST_HARD;
     StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
     forward_sweep(pd, L, target, /*clip=*/true, S);
     if (!(S.amax == S.amax)) return FAST_HARD;
-    if (S.amax >= 1.0 / 0.995 && S.cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) {
+    if (S.amax >= 1.0 / 0.995 && S.cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) {
       apply_step(pd, L, 1.0, /*clip=*/true);
       return FAST_STEPPED;
     }
@@ -1066,7 +1070,7 @@ struct Engine {
       printf("  ipm it %2d warm %d sigma %.3f mu %.3e target %.3e amax %.4g alpha %.4g cmax %.3e mu_new %.3e\n", iters, (int)warm,
              sigma, mu, target, S.amax, alpha, S.cmax, mu_new);
 #endif
-      if (target <= pd.tau && alpha == 1.0 && S.cmax <= dmin(0.05 * pd.tau, 0.1 * pd.tol)) converged = true;
+      if (target <= pd.tau && alpha == 1.0 && S.cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) converged = true;
       // centring heuristic: aggressive after long steps, conservative after short ones
       const double r = 1.0 - alpha;
       sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));

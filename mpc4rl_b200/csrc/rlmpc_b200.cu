@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
   const Lane L = make_lane<M>(a, b);
   typename E::Residuals R;
   bool swept = false;
-  const int code = E::qp_fast(pd, L, R, &swept);
+  const int code = E::qp_fast(pd, L, R, &swept, /*polish=*/!a.last_round);
   a.cost[b] = R.cost;
   a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? (swept ? 2 : 1) : 0;
   if (code == E::FAST_NAN) {
@@ -1027,7 +1027,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0; pd.comp_accept = 0.5;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -1183,6 +1183,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "ring")) h->ring = (int)value;
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
   else if (!strcmp(name, "coop")) h->coop = (int)value;
+  else if (!strcmp(name, "comp_accept")) h->pd.comp_accept = value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);

@@ -78,7 +78,7 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
         const bool last = (K > 1 && r == K);
         for (int k = 0; k <= pd.N; ++k) E::lin_stage(pd, L, k);
         typename E::Residuals R;
-        const int code = E::qp_fast(pd, L, R);
+        const int code = E::qp_fast(pd, L, R, nullptr, /*polish=*/!last);
         cost = R.cost;
         if (code == E::FAST_NAN) { status = ST_NAN; break; }
         if (code == E::FAST_CONVERGED) { status = ST_OK; break; }
