@@ -102,6 +102,9 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * a full step whose rows all land within lam*t = tau (1 +- comp_accept) -- a neighbourhood of the tau-central
  * point, far inside HPIPM's own complementarity tolerance; at SQP convergence the step vanishes and lam*t = tau
  * holds to rounding whatever the value (0.05 = the strict setting of the first builds),
+ * "split" (2): an RTI solve(+sens) call on >= 4096 samples runs the two halves of the batch as two independent
+ * chains of kernels on two streams (the caller's and an internal one, joined before the call returns to the
+ * stream): kernels bound by different units overlap; 1 = one chain; rlmpc_get_timings then describes the first half,
  * "as_steps" (20): active-set (full Newton step + projection) iterations a warm start may take when
  * its Newton step is infeasible, before it falls back to a cold start,
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */

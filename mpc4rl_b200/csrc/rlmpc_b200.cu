@@ -88,6 +88,7 @@ struct KArgs {
   int inplace;       // queue kernels work in place on all samples marked WK_HARD (dense queue: no compact copies)
   int last_round;    // this SQP round only evaluates the convergence test
   int have_solve;    // sens: a solve preceded in this call (keep its status)
+  int b0;            // first sample of the range [b0, b0 + B) this launch works on (0 unless the batch is split over two streams)
 };
 
 template <class M>
@@ -124,8 +125,9 @@ __device__ __forceinline__ bool queue_lane(const KArgs& a, int j, int& b, int& s
 template <class M>
 __global__ void k_begin(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= a.B) return;
+  const int b = a.b0 + bi;
   const Lane L = make_lane<M>(a, b);
   E::set_initial(pd, L, a.x0 + (size_t)b * M::NX, 1, a.u0 ? a.u0 + (size_t)b * M::NU : nullptr, 1);
   a.work[b] = WK_ACTIVE;
@@ -135,8 +137,9 @@ __global__ void k_begin(const __grid_constant__ ProblemData pd, const KArgs a) {
 // (sample, stage) kernel: linearisation.  grid = (ceil(B / blockDim), N + 1)
 template <class M>
 __global__ void __launch_bounds__(STPB, RLMPC_LIN_MINB) k_lin(const __grid_constant__ ProblemData pd, const KArgs a) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B || a.work[b] != WK_ACTIVE) return;
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = a.b0 + bi;
+  if (bi >= a.B || a.work[b] != WK_ACTIVE) return;
   Engine<M>::lin_stage(pd, make_lane<M>(a, b), blockIdx.y);
 }
 
@@ -144,8 +147,9 @@ __global__ void __launch_bounds__(STPB, RLMPC_LIN_MINB) k_lin(const __grid_const
 template <class M>
 __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B || a.work[b] != WK_ACTIVE) return;
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = a.b0 + bi;
+  if (bi >= a.B || a.work[b] != WK_ACTIVE) return;
   const Lane L = make_lane<M>(a, b);
   typename E::Residuals R;
   bool swept = false;
@@ -452,8 +456,9 @@ __global__ void k_count_active(const KArgs a) {
 template <class M>
 __global__ void k_out(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= a.B) return;
+  const int b = a.b0 + bi;
   if (a.u0_out) {
 #pragma unroll
     for (int i = 0; i < M::NU; ++i)
@@ -469,8 +474,8 @@ __device__ __forceinline__ int subset_sample(const KArgs& a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (a.subset == 2) return j < a.counters[0] ? a.hard[j] : -1;
   if (j >= a.B) return -1;
-  if (a.subset == 1 && a.ishard[j]) return -1;
-  return j;
+  if (a.subset == 1 && a.ishard[a.b0 + j]) return -1;
+  return a.b0 + j;
 }
 
 template <class M>
@@ -645,6 +650,8 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 
 enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2, VAR_EVAPORATION = 3 };
 
+constexpr int MAX_SPLIT = 4;
+
 struct rlmpc_handle {
   int model, variant, device, max_batch;
   size_t bs;
@@ -655,6 +662,10 @@ struct rlmpc_handle {
   double *itb = nullptr, *wsb = nullptr;  // partially condensed queue path (only for condensable models)
   int itb_size = 0, wsb_size = 0;
   int condense = 1;    // 1: queued QPs in partially condensed form where applicable (input bounds only, V-mode, N % 4 == 0)
+  int split = 2;       // n > 1: an RTI call runs n parts of its batch on n streams (see pipeline())
+  cudaStream_t part_stream[MAX_SPLIT - 1] = {};
+  cudaEvent_t ev_part[MAX_SPLIT - 1] = {};
+  bool marks_off = false;
   int coop = 1;        // warp-per-sample queue kernel (coop.cuh / coop_general.cuh) where the model's blocks fit a warp
   int coop_grid = 0;   // its persistent grid (blocks), sized at create time from the occupancy
   int ring_b = 0;      // ring reader for the condensed kernel: measured slower (3.3 vs 2.3 ms), blocks carry enough work per load batch
@@ -702,7 +713,7 @@ int check_batch(rlmpc_handle* h, int B) {
 // phase boundaries: 0 start | 1 after k_lin | 2 after k_qp1 | 3 after k_qp2 | 4 after k_sens_stage | 5 after
 // k_sens_sweep | 6 end of the call (sens kernels of the queued samples when the side stream is used)
 void mark(rlmpc_handle* h, int i, cudaStream_t s) {
-  if (!h->timing) return;
+  if (!h->timing || h->marks_off) return;
   cudaEventRecord(h->ev[i], s);
   h->ev_set[i] = true;
 }
@@ -802,7 +813,8 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   const dim3 gstage((B + STPB - 1) / STPB, N + 1);
   k_begin<M><<<(B + 127) / 128, 128, 0, s>>>(h->pd, a);
   h->launches++;
-  for (int i = 0; i < rlmpc_handle::NEV; ++i) h->ev_set[i] = false;
+  if (!h->marks_off)
+    for (int i = 0; i < rlmpc_handle::NEV; ++i) h->ev_set[i] = false;
   const int rounds = (K == 1) ? 1 : K + 1;
   // Option "inplace_queue": the queue kernels work in place on the samples marked WK_HARD and the gather /
   // scatter copies are skipped.  Only pays when (nearly) every sample is queued; measured slower for a
@@ -812,7 +824,7 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   for (int r = 0; r < rounds; ++r) {
     a.last_round = (K > 1 && r == K) ? 1 : 0;
     a.inplace = dense_queue ? 1 : 0;
-    CUDA_OK(cudaMemsetAsync(h->counters, 0, 4 * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), s));
     mark(h, 0, s);
     k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
     mark(h, 1, s);
@@ -888,7 +900,7 @@ int pipeline_sens(rlmpc_handle* h, KArgs a, cudaStream_t s, bool forked) {
 }
 
 template <class M>
-int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s) {
+int pipeline_range(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s) {
   const bool fork = do_solve && do_sens && h->pd.max_sqp == 1 && h->overlap;
   if (do_solve) {
     if (int r = pipeline_solve<M>(h, a, s, fork)) return r;
@@ -899,6 +911,43 @@ int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// One RTI call = a chain of dependent kernels that are bound by different units (k_lin, k_sens_stage: FP64
+// issue; k_qp1, k_sens_sweep: HBM; k_qp3: shared memory and latency).  Samples are independent, so with option
+// "split" = 2 the batch is cut in two halves that run the same chain on two streams: the kernels of one half
+// overlap with kernels of the other half that wait for a different unit.
+template <class M>
+int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s) {
+  bool split = h->split > 1 && do_solve && h->pd.max_sqp == 1 && !h->overlap && a.B >= 4096;
+  if constexpr (CoopSel<M>::value) {
+    split = split && h->coop && h->coop_grid > 0;
+  } else {
+    split = false;
+  }
+  if (!split) return pipeline_range<M>(h, a, do_solve, do_sens, s);
+  const int parts = h->split < MAX_SPLIT ? h->split : MAX_SPLIT;
+  const int per = ((a.B + parts - 1) / parts + TILE - 1) / TILE * TILE;
+  CUDA_OK(cudaEventRecord(h->ev_fork, s));
+  int rc = 0;
+  for (int p = 0; p < parts && rc == 0; ++p) {
+    KArgs ap = a;
+    ap.b0 = p * per;
+    ap.B = a.B - ap.b0 < per ? a.B - ap.b0 : per;
+    if (ap.B <= 0) break;
+    ap.hard = a.hard + ap.b0;
+    ap.counters = a.counters + 4 * p;
+    cudaStream_t sp = (p == 0) ? s : h->part_stream[p - 1];
+    if (p > 0) CUDA_OK(cudaStreamWaitEvent(sp, h->ev_fork, 0));
+    h->marks_off = p > 0;  // phase events (option "timing") describe the first part
+    rc = pipeline_range<M>(h, ap, do_solve, do_sens, sp);
+    h->marks_off = false;
+    if (p > 0 && rc == 0) {
+      CUDA_OK(cudaEventRecord(h->ev_part[p - 1], sp));
+      CUDA_OK(cudaStreamWaitEvent(s, h->ev_part[p - 1], 0));
+    }
+  }
+  return rc;
 }
 
 int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, const double* u0, double* u0_out,
@@ -1059,9 +1108,16 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
   }
+  for (int i = 0; i < MAX_SPLIT - 1 && e == cudaSuccess; ++i) {
+    int prio_lo = 0, prio_hi = 0;  // later parts first: their blocks fill in wherever an earlier part leaves room
+    e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->part_stream[i], cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_part[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4 * MAX_SPLIT);  // 4 per part of a split batch
+  if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(int) * 4 * MAX_SPLIT);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int) * max_batch);
@@ -1095,6 +1151,10 @@ void rlmpc_destroy(rlmpc_handle* h) {
   cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
   cudaFree(h->counters); cudaFree(h->ishard);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (int i = 0; i < MAX_SPLIT - 1; ++i) {
+    if (h->part_stream[i]) cudaStreamDestroy(h->part_stream[i]);
+    if (h->ev_part[i]) cudaEventDestroy(h->ev_part[i]);
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_status);
@@ -1184,6 +1244,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
   else if (!strcmp(name, "coop")) h->coop = (int)value;
   else if (!strcmp(name, "comp_accept")) h->pd.comp_accept = value;
+  else if (!strcmp(name, "split")) h->split = (int)value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
@@ -1385,10 +1446,14 @@ int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
   }
   if (n >= 8) {  // queue statistics of the last SQP round: length, interior-point iterations (warp-per-sample kernel only)
     CUDA_OK(cudaDeviceSynchronize());
-    int c[4] = {0, 0, 0, 0};
+    int c[4 * MAX_SPLIT] = {};
     CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
-    ms_out[6] = c[0];
-    ms_out[7] = c[3];
+    const int parts = h->split > 1 ? (h->split < MAX_SPLIT ? h->split : MAX_SPLIT) : 1;  // the parts of a split batch count separately
+    ms_out[6] = ms_out[7] = 0.0;
+    for (int p = 0; p < parts; ++p) {
+      ms_out[6] += c[4 * p];
+      ms_out[7] += c[4 * p + 3];
+    }
   }
   return 0;
 }

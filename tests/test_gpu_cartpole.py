@@ -321,3 +321,32 @@ def test_handles_with_different_horizons_coexist(spec):
             assert (o["status"] == 0).double().mean().item() > 0.5  # N=80 from random states: a third hits the 40-iteration limit
             for k in ("status", "u0", "cost", "dL", "dpi"):
                 assert torch.equal(o[k], ref[k]), k
+
+
+def test_split_batch_on_two_streams_is_bit_identical(spec):
+    """Option split (default 2): an RTI call runs the two halves of the batch as two chains of kernels on two
+    streams.  Samples are independent, so every output is bit-identical to the single-chain call, also for
+    a batch that does not divide into whole tiles."""
+    B = 8192 + 40
+    g = torch.Generator(device="cpu").manual_seed(21)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    dx = 1e-3 * torch.randn(2, B, 4, generator=g, dtype=torch.float64).cuda()
+    a0 = (-80.0 + 160.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)).cuda()
+    runs = []
+    for split in (2, 1, 3):
+        m = _mpc(spec, B)
+        m.set_option("tol", 1e-8)
+        m.set_option("split", split)
+        m.set_option("timing", 1)
+        m.reset(x0)
+        m.solve(x0, max_sqp=40)
+        outs = [m.solve_sens(x0 + dx[0], max_sqp=1), m.solve_sens(x0 + dx[1], u0=a0, max_sqp=1)]
+        q = m.timings()["queue_len"]
+        outs.append(dict(zip(("u0", "cost", "status"), m.solve(x0 + dx[0], max_sqp=1))))
+        runs.append(([{k: v.clone() for k, v in o.items()} for o in outs], q))
+    assert runs[0][1] == runs[1][1] == runs[2][1] > 0  # queue statistics add up over the parts
+    for other in (runs[1], runs[2]):
+        for a, b in zip(runs[0][0], other[0]):
+            for k in a:
+                assert torch.equal(a[k], b[k]), k
