@@ -329,9 +329,9 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step, ncu launch list
-                         # profiles/r01g_launches_rti_steps.csv (headline workload at its default batch only)
-                         "traffic": 9.127e9 if (args.workload == "cartpole" and B == 65536) else None,
-                         "traffic_source": "profiles/r01g_launches_rti_steps.csv (sum over the 7 kernels of one call)",
+                         # profiles/r01h_launches_rti_steps.csv (headline workload at its default batch only)
+                         "traffic": 8.960e9 if (args.workload == "cartpole" and B == 65536) else None,
+                         "traffic_source": "profiles/r01h_launches_rti_steps.csv (sum over the 7 kernels of one un-split call)",
                          "peak_source": peak_src,
                          "kernel": "rlmpc_solve_sens = k_lin + k_qp1 + k_qp3 + k_sens_stage + k_sens_sweep "
                                    f"(dominant: {max(phase_ms, key=phase_ms.get)})",

@@ -2,9 +2,10 @@
 # --set full capture of every kernel of one step.  Run under gpurun (1 GPU).
 set -x
 mkdir -p gpurun_out
+# (split=1: the kernels of ONE chain over the whole batch; the default runs two half-batch chains on two streams)
 # launch list of the whole run (setup solve, warm-up, timed steps, per-kernel timing pass, e2e pass)
 timeout 1200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active \
-  --clock-control none -k regex:"k_" --csv --log-file gpurun_out/launches_all.csv python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/b_ncu_l.log 2>&1
+  --clock-control none -k regex:"k_" --csv --log-file gpurun_out/launches_all.csv python bench.py --steps 4 --warmup 3 --no-cpu --opt split=1 > gpurun_out/b_ncu_l.log 2>&1
 # keep the last 4 RTI calls of the device-resident pass (k_begin .. k_sens_sweep), and find how many
 # launches of the step kernels precede the first of them
 python - <<'PY' > gpurun_out/skip.txt
@@ -33,5 +34,5 @@ with open("gpurun_out/launches_rti.csv", "w") as f:
 PY
 read SKIP COUNT < gpurun_out/skip.txt
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_lin|k_qp1|k_qp3|k_gather|k_condense|k_qp2|k_sens_stage|k_sens_sweep" -s $SKIP -c $COUNT \
-  -o gpurun_out/prof_step python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/b_ncu_f.log 2>&1
+  -o gpurun_out/prof_step python bench.py --steps 4 --warmup 3 --no-cpu --opt split=1 > gpurun_out/b_ncu_f.log 2>&1
 tail -3 gpurun_out/b_ncu_f.log
