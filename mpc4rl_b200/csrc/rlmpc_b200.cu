@@ -950,10 +950,13 @@ int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s
   return rc;
 }
 
+// Works on the samples [b0, b0 + B); array arguments are indexed by the absolute sample number.  part > 0: a
+// further range of the same logical call, issued on another stream by the caller (own queue counters, no
+// phase events, no internal split).
 int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, const double* u0, double* u0_out,
              double* cost_out, int* status_out, double* dL, double* dpi, double* res_out, int do_solve, int do_sens,
-             cudaStream_t s) {
-  if (int r = check_batch(h, B)) return r;
+             cudaStream_t s, int b0 = 0, int part = -1) {
+  if (int r = check_batch(h, b0 + B)) return r;
   if (B == 0) return 0;
   if (mode != RLMPC_MODE_V && mode != RLMPC_MODE_Q) return fail(RLMPC_EINVAL, "bad mode");
   if (do_solve && !x0) return fail(RLMPC_EINVAL, "x0 is required");
@@ -967,7 +970,16 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
   a.u0_out = u0_out; a.cost_out = cost_out; a.status_out = status_out;
   a.dL = dL; a.dpi = dpi; a.res_out = res_out;
   int rc = fail(RLMPC_EINVAL, "unknown model");
-  DISPATCH_MODEL(h, rc = pipeline<M>(h, a, do_solve, do_sens, s));
+  if (part < 0) {
+    DISPATCH_MODEL(h, rc = pipeline<M>(h, a, do_solve, do_sens, s));
+    return rc;
+  }
+  a.b0 = b0;
+  a.hard = h->hard + b0;
+  a.counters = h->counters + 4 * part;
+  h->marks_off = part > 0;
+  DISPATCH_MODEL(h, rc = pipeline_range<M>(h, a, do_solve, do_sens, s));
+  h->marks_off = false;
   return rc;
 }
 
@@ -1332,6 +1344,47 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
     return at.type == cudaMemoryTypeHost;
   };
   const bool in_pinned = pinned(x0_host) && pinned(u0_host);
+  const bool all_pinned = in_pinned && pinned(u0_out_host) && pinned(cost_out_host) && pinned(res_out_host) &&
+                          pinned(dL_dtheta_host) && pinned(dpi_dtheta_host) && pinned(status_out_host);
+  if (all_pinned && max_sqp == 1 && h->split > 1 && B >= 4096 && !h->overlap) {
+    // Page-locked buffers, RTI: the parts of the batch (option "split") are complete pipelines of their own --
+    // copy in, kernel chain, copy out -- on separate streams, so that the copies of one part overlap with the
+    // kernels of another.
+    const int parts = h->split < MAX_SPLIT ? h->split : MAX_SPLIT;
+    const int per = ((B + parts - 1) / parts + TILE - 1) / TILE * TILE;
+    double* d_x0 = h->d_in;
+    double* d_u0 = u0_host ? h->d_in + nB * nx : nullptr;
+    double* d_u0o = h->d_out;
+    double* d_cost = d_u0o + nB * nu;
+    double* d_res = d_cost + nB;
+    double* d_dL = d_res + nB * 4;
+    double* d_dpi = d_dL + nB * nth;
+    int rc = 0, used = 0;
+    for (int p = 0; p < parts && rc == 0; ++p) {
+      const size_t b0 = (size_t)p * per;
+      if (b0 >= nB) break;
+      const size_t nb = nB - b0 < (size_t)per ? nB - b0 : (size_t)per;
+      cudaStream_t sp = (p == 0) ? s : h->part_stream[p - 1];
+      CUDA_OK(cudaMemcpyAsync(d_x0 + b0 * nx, x0_host + b0 * nx, sizeof(double) * nb * nx, cudaMemcpyHostToDevice, sp));
+      if (u0_host) CUDA_OK(cudaMemcpyAsync(d_u0 + b0 * nu, u0_host + b0 * nu, sizeof(double) * nb * nu, cudaMemcpyHostToDevice, sp));
+      CUDA_OK(cudaMemsetAsync(d_dL + b0 * nth, 0, sizeof(double) * nb * nth, sp));
+      CUDA_OK(cudaMemsetAsync(d_dpi + b0 * nth * nu, 0, sizeof(double) * nb * nth * nu, sp));
+      rc = run_unit(h, mode, max_sqp, (int)nb, d_x0, d_u0, d_u0o, d_cost, h->d_status, d_dL, d_dpi, d_res, 1, 1, sp, (int)b0, p);
+      if (rc) break;
+      if (u0_out_host) CUDA_OK(cudaMemcpyAsync(u0_out_host + b0 * nu, d_u0o + b0 * nu, sizeof(double) * nb * nu, cudaMemcpyDeviceToHost, sp));
+      if (cost_out_host) CUDA_OK(cudaMemcpyAsync(cost_out_host + b0, d_cost + b0, sizeof(double) * nb, cudaMemcpyDeviceToHost, sp));
+      if (res_out_host) CUDA_OK(cudaMemcpyAsync(res_out_host + b0 * 4, d_res + b0 * 4, sizeof(double) * nb * 4, cudaMemcpyDeviceToHost, sp));
+      if (dL_dtheta_host) CUDA_OK(cudaMemcpyAsync(dL_dtheta_host + b0 * nth, d_dL + b0 * nth, sizeof(double) * nb * nth, cudaMemcpyDeviceToHost, sp));
+      if (dpi_dtheta_host)
+        CUDA_OK(cudaMemcpyAsync(dpi_dtheta_host + b0 * nth * nu, d_dpi + b0 * nth * nu, sizeof(double) * nb * nth * nu, cudaMemcpyDeviceToHost, sp));
+      if (status_out_host) CUDA_OK(cudaMemcpyAsync(status_out_host + b0, h->d_status + b0, sizeof(int) * nb, cudaMemcpyDeviceToHost, sp));
+      used = p + 1;
+    }
+    for (int p = 0; p < used; ++p) cudaStreamSynchronize(p == 0 ? s : h->part_stream[p - 1]);
+    if (rc) return rc;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   double* d_x0 = h->d_in;
   double* d_u0 = u0_host ? h->d_in + nB * nx : nullptr;
   if (in_pinned) {

@@ -350,3 +350,33 @@ def test_split_batch_on_two_streams_is_bit_identical(spec):
         for a, b in zip(runs[0][0], other[0]):
             for k in a:
                 assert torch.equal(a[k], b[k]), k
+
+
+def test_pipelined_host_entry_point_is_bit_identical(spec):
+    """rlmpc_solve_sens_host with page-locked buffers runs an RTI call as per-part pipelines (copy in, kernel
+    chain, copy out) on separate streams; same numbers as the device-resident call, V- and Q-mode, ragged batch."""
+    B = 8192 + 72
+    g = torch.Generator(device="cpu").manual_seed(22)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)
+    x1 = (x0 + 1e-3 * torch.randn(B, 4, generator=g, dtype=torch.float64)).pin_memory()
+    a0 = (-80.0 + 160.0 * torch.rand(B, 1, generator=g, dtype=torch.float64)).pin_memory()
+    res = []
+    for host in (False, True):
+        m = _mpc(spec, B)
+        m.set_option("tol", 1e-8)
+        m.reset(x0.cuda())
+        m.solve(x0.cuda(), max_sqp=40)
+        outs = []
+        for u in (None, a0):
+            if host:
+                pin = m.alloc_host_outputs(B, pinned=True)
+                o = m.solve_sens_host(x1.numpy(), None if u is None else u.numpy(), max_sqp=1, out=pin)
+                outs.append({k: np.array(v) for k, v in o.items()})
+            else:
+                o = m.solve_sens(x1.cuda(), None if u is None else u.cuda(), max_sqp=1)
+                outs.append({k: v.cpu().numpy() for k, v in o.items()})
+        res.append(outs)
+    for a, b in zip(res[0], res[1]):
+        for k in ("u0", "cost", "dL", "dpi", "res", "status"):
+            assert np.array_equal(a[k], b[k]), k
