@@ -140,6 +140,33 @@ def evaporation_golden_full(gamma=0.95):
     print("wrote", path)
 
 
+def chain_mass_golden(n_mass=3, n=4, seed=50):
+    """Chain of masses (rlmpc/mpc/chain_mass/ocp_utils.py) at n_mass = 3 (nx = 9, nu = 3, ntheta = 113; what
+    rlmpc/examples/chain_mass.py:__main__ runs): define_x0 and perturbations of it (perturb_scale = 1e-2, seed 50 as
+    in get_chain_params), V-mode and Q-mode with |u0| <= 1.  The specification the CUDA path for this problem
+     has to meet."""
+    from .problems import make_chain_mass
+
+    pb = make_chain_mass(n_mass)
+    s = DenseSolver(pb)
+    rng = np.random.default_rng(seed)
+    x0s = np.vstack([pb.x0_example] + [pb.x0_example + 1e-2 * rng.standard_normal(pb.nx) for _ in range(n - 1)])
+    acts = rng.uniform(-0.8, 0.8, size=(n, 3))
+    out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "U", "X", "pi", "status")}
+    for i in range(n):
+        sol, upd = s.unit(x0s[i], tol=1e-10)
+        solq, updq = s.unit(x0s[i], u0=acts[i], tol=1e-10)
+        print(f"[chain_mass_{n_mass} {i}] V={sol.cost:.8f} u0={sol.U[0]} it={sol.sqp_iter} st={sol.status} | Q={solq.cost:.8f} st={solq.status}", flush=True)
+        out["status"].append([sol.status, solq.status])
+        out["V"].append(sol.cost); out["u0"].append(sol.U[0]); out["dV"].append(upd["dL_dp"][0]); out["dpi"].append(upd["dpi_dp"])
+        out["Q"].append(solq.cost); out["dQ"].append(updq["dL_dp"][0]); out["U"].append(sol.U); out["X"].append(sol.X); out["pi"].append(sol.pi)
+    out = {k: np.array(v) for k, v in out.items()}
+    out["x0"] = x0s; out["a"] = acts; out["theta"] = pb.p_nominal; out["x_ss"] = pb.x_ss; out["n_mass"] = n_mass
+    path = os.path.join(ROOT, "tests", "golden", f"chain_mass_{n_mass}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["original"]
     for v in which:
@@ -149,5 +176,7 @@ if __name__ == "__main__":
             evaporation_golden_full()
         elif v == "linear":
             linear_system_golden()
+        elif v == "chain_mass":
+            chain_mass_golden()
         else:
             cartpole_golden(v, n=20 if v == "original" else 12)

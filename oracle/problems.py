@@ -308,3 +308,135 @@ def make_evaporation(H: Optional[np.ndarray] = None, gamma: float = 0.99, N: int
         Ch=Ch, h0=np.array([25.0, 25.0]), lh=np.array([-1e3, -1e3]), uh=np.array([0.0, 0.0]),
         x_init=x_ss, u_init=u_ss,
     )
+
+
+# --------------------------------------------------------------------------------------
+# chain of masses  (rlmpc/mpc/chain_mass/ocp_utils.py:42-56, 59-147, 195-316, 319-371)
+# --------------------------------------------------------------------------------------
+def chain_params() -> dict:
+    """get_chain_params() (ocp_utils.py:319-341), the entries the OCP uses."""
+    return {"n_mass": 5, "Ts": 0.2, "N": 40, "m": 0.033, "D": 1.0, "L": 0.033, "C": 0.1, "xPosFirstMass": np.zeros(3)}
+
+
+def chain_param_layout(n_mass: int):
+    """define_param_struct_symSX(disturbance=True) (ocp_utils.py:353-371): [m | D | L | C | Q | R | w], entries with
+    `repeat` laid out repetition by repetition, matrices column-major.  Returns {name: slice} and the total length."""
+    n_link, M = n_mass - 1, n_mass - 2
+    nx = (2 * M + 1) * 3
+    sizes = [("m", n_link), ("D", 3 * n_link), ("L", 3 * n_link), ("C", 3 * n_link), ("Q", nx * nx), ("R", 9), ("w", 3 * M)]
+    out, o = {}, 0
+    for name, n in sizes:
+        out[name] = slice(o, o + n)
+        o += n
+    return out, o
+
+
+def chain_ode(x, u, pm, n_mass: int):
+    """f_expl = [xvel ; u ; f] (ocp_utils.py:59-147).  Spring force of link i on its masses:
+    F_j = D_ij / m_i (1 - L_ij / |dist|) dist_j; damping F_j = C_ij vel_j (not divided by the mass, as in the
+    reference); gravity -9.81 on z; disturbance w_i added to the acceleration of intermediate mass i."""
+    M = n_mass - 2
+    sl, _ = chain_param_layout(n_mass)
+    m, D, L, C, w = pm[sl["m"]], pm[sl["D"]].reshape(M + 1, 3), pm[sl["L"]].reshape(M + 1, 3), pm[sl["C"]].reshape(M + 1, 3), pm[sl["w"]].reshape(M, 3)
+    xpos = x[: 3 * (M + 1)].reshape(M + 1, 3)
+    xvel = x[3 * (M + 1):].reshape(M, 3)
+    zero3 = torch.zeros(3, dtype=x.dtype)
+    f = [torch.stack([zero3[0], zero3[0], zero3[0] - 9.81]) for _ in range(M)]
+    for i in range(M + 1):
+        dist = xpos[i] - (xpos[i - 1] if i > 0 else zero3)
+        F = D[i] / m[i] * (1.0 - L[i] / torch.linalg.vector_norm(dist)) * dist
+        if i < M:
+            f[i] = f[i] - F
+        if i > 0:
+            f[i - 1] = f[i - 1] + F
+    for i in range(M + 1):
+        if i == 0:
+            vel = xvel[0]
+        elif i == M:
+            vel = u - xvel[M - 1]
+        else:
+            vel = xvel[i] - xvel[i - 1]
+        F = C[i] * vel
+        if i < M:
+            f[i] = f[i] - F
+        if i > 0:
+            f[i - 1] = f[i - 1] + F
+    f = [f[i] + w[i] for i in range(M)]
+    return torch.cat([xvel.reshape(-1), u, torch.cat(f)])
+
+
+def chain_steady_state(n_mass: int, pm: np.ndarray, x_end: np.ndarray) -> np.ndarray:
+    """compute_parametric_steady_state (ocp_utils.py:150-192) without IPOPT: xdot = 0 with the last mass held at
+    x_end and u = 0, i.e. zero velocities and force balance on the intermediate masses (Newton on 3M unknowns,
+    started on the straight line like the reference's initial guess)."""
+    M = n_mass - 2
+    nx = (2 * M + 1) * 3
+    pmt = torch.as_tensor(pm, dtype=F64)
+
+    def resid(q):  # q: positions of the M intermediate masses
+        x = torch.cat([q, torch.as_tensor(x_end, dtype=F64), torch.zeros(3 * M, dtype=F64)])
+        return chain_ode(x, torch.zeros(3, dtype=F64), pmt, n_mass)[3 * (M + 1):]
+
+    q = torch.zeros(3 * M, dtype=F64)
+    q[0::3] = torch.linspace(0.0, float(x_end[0]), M + 2, dtype=F64)[1:-1]
+    for _ in range(50):
+        r = resid(q)
+        if float(r.abs().max()) < 1e-13:
+            break
+        J = torch.func.jacrev(resid)(q)
+        q = q - torch.linalg.solve(J, r)
+    x = np.zeros(nx)
+    x[: 3 * M] = q.numpy()
+    x[3 * M: 3 * (M + 1)] = x_end
+    return x
+
+
+def make_chain_mass(n_mass: int = 5, gamma: float = 1.0, params: Optional[dict] = None) -> Problem:
+    """export_parametric_ocp(chain_params, integrator_type="DISCRETE") as chain_mass/acados.py:32-45 builds it:
+    disturbance parameters present (w = 0), EXTERNAL cost 1/2 (x-x_ss)'Q(x-x_ss) + 1/2 u'Ru with Q, R part of p,
+    |u| <= 1, ERK4 with two sub-steps of Ts/2, GAUSS_NEWTON (= exact Hessian of the quadratic cost), gamma = 1 in
+    examples/chain_mass.py:main_nlp.  theta = p has 113 / 499 / 800 entries for n_mass = 3 / 5 / 6."""
+    cp = dict(chain_params() if params is None else params)
+    cp["n_mass"] = n_mass
+    M, n_link = n_mass - 2, n_mass - 1
+    nx, nu, N, Ts = (2 * M + 1) * 3, 3, cp["N"], cp["Ts"]
+    sl, nth = chain_param_layout(n_mass)
+    p = np.zeros(nth)
+    p[sl["m"]] = cp["m"]; p[sl["D"]] = cp["D"]; p[sl["L"]] = cp["L"]; p[sl["C"]] = cp["C"]  # random_scale = 0 (ocp_utils.py:205)
+    q_diag = np.ones(nx)
+    q_diag[3 * M: 3 * M + 3] = M + 1
+    p[sl["Q"]] = (2.0 * np.diag(q_diag)).T.ravel()
+    p[sl["R"]] = (2.0 * 1e-2 * np.eye(nu)).T.ravel()
+    x_end = np.array([cp["L"] * (M + 1) * 6, 0.0, 0.0])
+    x_ss = chain_steady_state(n_mass, p, x_end)
+    xss_t = torch.as_tensor(x_ss, dtype=F64)
+    h = Ts / 2
+
+    def f_disc(x, u, pm):
+        ode = lambda xx, uu, pp: chain_ode(xx, uu, pp, n_mass)
+        for _ in range(2):  # export_discrete_erk4_integrator_step, n_stages = 2 (ocp_utils.py:42-56)
+            x = erk4(ode, x, u, pm, h)
+        return x
+
+    def Qm(pm):
+        return pm[sl["Q"]].reshape(nx, nx).T
+
+    def ext(x, u, pm):
+        e = x - xss_t
+        return 0.5 * (e @ (Qm(pm) @ e) + u @ (pm[sl["R"]].reshape(nu, nu).T @ u))
+
+    def exte(x, pm):
+        e = x - xss_t
+        return 0.5 * (e @ (Qm(pm) @ e))
+
+    x0 = np.zeros(nx)  # define_x0 (examples/chain_mass.py:17-25): masses on the straight line to x_end, at rest
+    x0[: 3 * (M + 1): 3] = np.linspace(cp["xPosFirstMass"][0], x_end[0], M + 2)[1:]
+    pb = Problem(
+        name=f"chain_mass_{n_mass}", N=N, nx=nx, nu=nu, tf=N * Ts, p_entries=[("model", (nth,))], p_nominal=p,
+        cost_type="EXTERNAL", hessian_approx="GAUSS_NEWTON", gamma=gamma, f_disc=f_disc,
+        ext_cost_0=ext, ext_cost=ext, ext_cost_e=exte,
+        idxbu=np.arange(nu), lbu=-np.ones(nu), ubu=np.ones(nu),
+    )
+    pb.x_ss = x_ss
+    pb.x0_example = x0
+    return pb

@@ -241,3 +241,61 @@ def test_evaporation_host_port_matches_oracle_fixtures():
     assert sol.status == 0 and os_["status"][0] == 0
     assert np.abs(sol.U[0] - os_["u0"][0]).max() < 1e-8 and abs(sol.cost - os_["cost"][0]) < 1e-9 * abs(sol.cost)
     assert np.abs(upd["dpi_dp"] - os_["dpi"][0]).max() < 1e-6 * np.abs(upd["dpi_dp"]).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# chain of masses: oracle and fixture only -- the CUDA path for nx = 21 / 27 blocks
+# is the next round's work; these tests pin the specification it has to meet.
+# ------------------------------------------------------------------------------------------------
+def test_chain_mass_layout_matches_reference_counts():
+    from oracle.nlp import RestatedNLP
+    from oracle.problems import chain_param_layout, make_chain_mass
+
+    # define_nx_nu / define_param_struct_symSX (ocp_utils.py:344-371): n_mass = 3, 5, 6
+    assert [chain_param_layout(n)[1] for n in (3, 5, 6)] == [113, 499, 800]
+    pb = make_chain_mass(5)
+    nlp = RestatedNLP(pb)
+    # chain n_mass=5: nw=981, npi=840, nlam=282 => nz=2385, ntheta=499
+    assert (pb.nx, pb.nu, nlp.nw, nlp.npi, nlp.nlam, nlp.nz, pb.ntheta) == (21, 3, 981, 840, 282, 2385, 499)
+    sl, _ = chain_param_layout(5)
+    Q = pb.p_nominal[sl["Q"]].reshape(21, 21).T
+    assert np.array_equal(np.diag(Q), 2.0 * np.array([1.0] * 9 + [4.0] * 3 + [1.0] * 9))  # ocp_utils.py:263-266
+    assert np.array_equal(pb.p_nominal[sl["R"]].reshape(3, 3), 0.02 * np.eye(3))
+    # steady state: at rest, last mass at x_end, force balance on the intermediate masses (ocp_utils.py:150-192)
+    import torch
+
+    from oracle.problems import chain_ode
+
+    f = chain_ode(torch.as_tensor(pb.x_ss), torch.zeros(3, dtype=torch.float64), torch.as_tensor(pb.p_nominal), 5)
+    assert float(f.abs().max()) < 1e-12 and np.allclose(pb.x_ss[9:12], [0.033 * 4 * 6, 0.0, 0.0])
+
+
+def test_chain_mass_policy_gradient_against_parameter_sweep():
+    """What the reference's own test does (tests/test_chain_mass.py -> examples/chain_mass.py:main_nlp): sweep the
+    damping C_{M}_0 of the last link, solve from define_x0, and compare d pi / d p from update_nlp with the
+    numerical gradient of u_opt along the sweep -- here n_mass = 3 and central differences around the fixture."""
+    from oracle.problems import chain_param_layout, make_chain_mass
+    from oracle.solver import DenseSolver
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "chain_mass_3.npz"))
+    pb = make_chain_mass(3)
+    assert np.array_equal(pb.p_nominal, g["theta"]) and np.allclose(pb.x_ss, g["x_ss"], atol=1e-13)
+    s = DenseSolver(pb)
+    sl, _ = chain_param_layout(3)
+    M = 1
+    idx = sl["C"].start + 3 * M + 0  # C_{M}_0
+    d = 1e-4 * pb.p_nominal[idx]
+    us, Vs = [], []
+    for sgn in (+1.0, -1.0):
+        p = pb.p_nominal.copy()
+        p[idx] += sgn * d
+        sol = s.solve(g["x0"][0], p=p, tol=1e-10, init=(g["U"][0], g["X"][0]))
+        assert sol.status == 0
+        us.append(sol.U[0]); Vs.append(sol.cost)
+    fd_pi = (us[0] - us[1]) / (2 * d)
+    fd_V = (Vs[0] - Vs[1]) / (2 * d)
+    assert abs(g["u0"][0][2] - 1.0) < 1e-6  # third input sits on its bound: its sensitivity is the IPM-smoothed ~0
+    assert np.abs(fd_pi - g["dpi"][0][:, idx]).max() < 1e-5 * max(1.0, np.abs(g["dpi"][0][:, idx]).max())
+    assert abs(fd_V - g["dV"][0][idx]) < 1e-6 * max(1.0, abs(g["dV"][0][idx]))
+    # Q-mode fixes u_0; V <= Q
+    assert (g["status"] == 0).all() and (g["Q"] >= g["V"] - 1e-9).all()
