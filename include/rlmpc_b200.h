@@ -153,7 +153,10 @@ int rlmpc_solve_sens(rlmpc_handle* h, int mode, int max_sqp, int B, const double
                      double* u0_out_dev, double* cost_out_dev, int* status_out_dev, double* dL_dtheta_dev,
                      double* dpi_dtheta_dev, double* res_out_dev, void* stream);
 /* Host-buffer variant of rlmpc_solve_sens: copies x0/u0 in, runs, copies all outputs back and
- * synchronises.  This is the end-to-end call the reference-side binding would make. */
+ * synchronises.  This is the end-to-end call the reference-side binding would make.  It runs on streams of the
+ * handle and first waits for everything queued on the device (so it is ordered after earlier stream-ordered
+ * calls on the handle).  With page-locked buffers an RTI call is pipelined per part of the batch (option
+ * "split"): copy in, kernel chain and copy out of one part overlap with those of the other. */
 int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_host,
                           const double* u0_host, double* u0_out_host, double* cost_out_host, int* status_out_host,
                           double* dL_dtheta_host, double* dpi_dtheta_host, double* res_out_host);

@@ -1331,6 +1331,9 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   if (mode == RLMPC_MODE_Q && !u0_host) return fail(RLMPC_EINVAL, "u0 is required in Q-mode");
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = h->own_stream;
+  // This entry point runs on the handle's own streams and is synchronous; order it after whatever the caller
+  // has queued for this handle through the stream-ordered entry points (rlmpc_reset, rlmpc_solve, ...).
+  CUDA_OK(cudaDeviceSynchronize());
   const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->ng();
   // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used
   // directly as DMA source / destination; pageable ones go through the handle's pinned staging area.
