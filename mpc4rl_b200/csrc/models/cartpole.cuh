@@ -116,6 +116,13 @@ struct CartpoleModelT {
       const double k[4] = {s[1], xdd, s[3], thdd};
       double Dk[4][NC];
       MPC_UNROLL for (int c = 0; c < NC; ++c) {
+        if (st == 0) {  // S = I at the first stage: written out, a product with an exact zero is not folded away in IEEE arithmetic
+          Dk[0][c] = (c == 1) ? 1.0 : 0.0;
+          Dk[2][c] = (c == 3) ? 1.0 : 0.0;
+          Dk[1][c] = (c == 2) ? jx[0] : (c == 3) ? jx[1] : (c >= 4) ? jx[2 + (c - 4)] : 0.0;
+          Dk[3][c] = (c == 2) ? jt[0] : (c == 3) ? jt[1] : (c >= 4) ? jt[2 + (c - 4)] : 0.0;
+          continue;
+        }
         Dk[0][c] = S[1][c];
         Dk[2][c] = S[3][c];
         double a = jx[0] * S[2][c] + jx[1] * S[3][c];
@@ -189,15 +196,24 @@ struct CartpoleModelT {
       const double* Sr0 = kp + 4;       // d s[2] / d zeta
       const double* Sr1 = kp + 4 + NC;  // d s[3] / d zeta
       double T[6][NC];
-      MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
-        double v = Hf[p][0] * Sr0[b] + Hf[p][1] * Sr1[b];
-        if (b >= 4) v += Hf[p][b - 2];
-        T[p][b] = v;
-      }
-      MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {  // symmetric: upper triangle
-        double v = Sr0[a] * T[0][b] + Sr1[a] * T[1][b];
-        if (a >= 4) v += T[a - 2][b];
-        Hacc[a][b] += v;
+      if (st == 0) {  // d s / d zeta = [I 0] at the first stage: rows 2, 3 of S are the unit vectors e_2, e_3
+        MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b)
+          T[p][b] = (b == 2) ? Hf[p][0] : (b == 3) ? Hf[p][1] : (b >= 4) ? Hf[p][b - 2] : 0.0;
+        MPC_UNROLL for (int a = 2; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {
+          if (b < 2) continue;
+          Hacc[a][b] += (a == 2) ? T[0][b] : (a == 3) ? T[1][b] : T[a - 2][b];
+        }
+      } else {
+        MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+          double v = Hf[p][0] * Sr0[b] + Hf[p][1] * Sr1[b];
+          if (b >= 4) v += Hf[p][b - 2];
+          T[p][b] = v;
+        }
+        MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {  // symmetric: upper triangle
+          double v = Sr0[a] * T[0][b] + Sr1[a] * T[1][b];
+          if (a >= 4) v += T[a - 2][b];
+          Hacc[a][b] += v;
+        }
       }
       if (st > 0) {
         // adjoint of the stage point s_st = x + a*k_{st-1}:  mu_{st-1} = w*h/6*pi + a * (df/ds)' mu_st
