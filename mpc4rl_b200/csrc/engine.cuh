@@ -611,13 +611,13 @@ struct Engine {
   // =======================================================================================
   enum Fast : int { FAST_CONVERGED = 0, FAST_STEPPED = 1, FAST_HARD = 2, FAST_NAN = 3 };
 
-  // swept (optional): set when FAST_HARD is returned AFTER the forward sweep, i.e. the workspace holds the
+  // swept (optional): set (1 or 2) when FAST_HARD is returned AFTER the forward sweep, i.e. the workspace holds the
   // complete first warm iteration (K, k, dx, du, lam_hat, t_hat at target tau) for the queue kernel to reuse
   // polish: "converged" additionally requires the iterate to sit ON the central path (|lam*t - tau| <= 5 % tau,
   // the accuracy update_nlp's R = 0 assumes for the sensitivities), not merely within the acceptance
   // neighbourhood comp_accept of the steps on the way; otherwise one more (cheap, warm) Newton iteration
   // follows.  Off for the final test-only round of an SQP solve, where the plain acados criterion decides.
-  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, bool* swept = nullptr, bool polish = true) {
+  MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, int* swept = nullptr, bool polish = true) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     const bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
@@ -721,7 +721,7 @@ struct Engine {
       apply_step(pd, L, 1.0, /*clip=*/true);
       return FAST_STEPPED;
     }
-    if (swept) *swept = true;
+    if (swept) *swept = (S.amax >= 1.0 / 0.995) ? 2 : 1;  // 2: a full step, only complementarity left to polish (one more iteration)
     return FAST_HARD;
   }
 

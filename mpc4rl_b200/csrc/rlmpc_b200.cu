@@ -76,7 +76,8 @@ struct KArgs {
   int* hard;    // queue of samples for the full interior-point pass
   int* ishard;  // != 0 if the sample was queued in this call (written by k_qp1 only); 2: its workspace holds the first warm iteration
   int subset;   // sens kernels: 0 all samples, 1 samples not queued, 2 the queued samples (via the queue)
-  int* counters;  // [0] queue length, [1] samples still active, [2] work counter of k_qp3, [3] its interior-point iterations
+  int* counters;  // [0] queue length (front), [1] samples still active, [2] work counter of k_qp3, [3] its interior-point
+                  // iterations, [4] samples queued from the end of the array (two_ended)
   const double* x0;  // [B, NX] row-major or null
   const double* u0;  // [B, NU] row-major or null
   double* u0_out;    // [B, NU]
@@ -88,6 +89,7 @@ struct KArgs {
   int inplace;       // queue kernels work in place on all samples marked WK_HARD (dense queue: no compact copies)
   int last_round;    // this SQP round only evaluates the convergence test
   int have_solve;    // sens: a solve preceded in this call (keep its status)
+  int two_ended;     // k_qp1 files samples that probably need one more iteration at the END of the queue array (see k_qp3)
   int b0;            // first sample of the range [b0, b0 + B) this launch works on (0 unless the batch is split over two streams)
 };
 
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
   if (bi >= a.B || a.work[b] != WK_ACTIVE) return;
   const Lane L = make_lane<M>(a, b);
   typename E::Residuals R;
-  bool swept = false;
+  int swept = 0;
   const int code = E::qp_fast(pd, L, R, &swept, /*polish=*/!a.last_round);
   a.cost[b] = R.cost;
   a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? (swept ? 2 : 1) : 0;
@@ -171,7 +173,13 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
     }
   } else {
     a.work[b] = WK_HARD;
-    a.hard[atomicAdd(&a.counters[0], 1)] = b;
+    // Longest jobs first: samples whose step was cut short (active-set change: 3..20 iterations) go to the front of
+    // the queue array, full steps that only miss the complementarity bound (one more iteration) to its end; the
+    // warp-per-sample kernel hands out positions front to back, so the short jobs fill the tail of the launch.
+    if (a.two_ended && swept == 2)
+      a.hard[a.B - 1 - atomicAdd(&a.counters[4], 1)] = b;
+    else
+      a.hard[atomicAdd(&a.counters[0], 1)] = b;
   }
 }
 
@@ -421,13 +429,13 @@ __global__ void __launch_bounds__(CoopSel<M>::WARPS * 32) k_qp3(const __grid_con
   extern __shared__ double coop_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   double* S = coop_smem + (size_t)wib * Cq::smem_doubles(pd.N);
-  const int n = a.counters[0];
+  const int nf = a.counters[0], n = nf + a.counters[4];  // queue: [0, nf) from the front, the rest from the end of the array
   for (;;) {
     int j = 0;
     if (lane == 0) j = atomicAdd(&a.counters[2], 1);
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= n) break;
-    const int b = a.hard[j];
+    const int b = a.hard[j < nf ? j : a.B - 1 - (j - nf)];
     const Lane L = make_lane<M>(a, b);
     int iters = 0;
     const int st = Cq::solve(pd, L, S, lane, a.ishard[b] == 2, &iters);
@@ -651,6 +659,7 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2, VAR_EVAPORATION = 3 };
 
 constexpr int MAX_SPLIT = 4;
+constexpr int NCNT = 8;  // ints per set of queue counters
 
 struct rlmpc_handle {
   int model, variant, device, max_batch;
@@ -824,8 +833,9 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
   for (int r = 0; r < rounds; ++r) {
     a.last_round = (K > 1 && r == K) ? 1 : 0;
     a.inplace = dense_queue ? 1 : 0;
-    CUDA_OK(cudaMemsetAsync(a.counters, 0, 4 * sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(a.counters, 0, NCNT * sizeof(int), s));
     mark(h, 0, s);
+    if constexpr (CoopSel<M>::value) a.two_ended = (h->coop && h->coop_grid > 0 && !a.inplace && !fork_qp2) ? 1 : 0;
     k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
     mark(h, 1, s);
     k_qp1<M><<<gs, TPB, 0, s>>>(h->pd, a);
@@ -936,7 +946,7 @@ int pipeline(rlmpc_handle* h, KArgs a, int do_solve, int do_sens, cudaStream_t s
     ap.B = a.B - ap.b0 < per ? a.B - ap.b0 : per;
     if (ap.B <= 0) break;
     ap.hard = a.hard + ap.b0;
-    ap.counters = a.counters + 4 * p;
+    ap.counters = a.counters + NCNT * p;
     cudaStream_t sp = (p == 0) ? s : h->part_stream[p - 1];
     if (p > 0) CUDA_OK(cudaStreamWaitEvent(sp, h->ev_fork, 0));
     h->marks_off = p > 0;  // phase events (option "timing") describe the first part
@@ -976,7 +986,7 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
   }
   a.b0 = b0;
   a.hard = h->hard + b0;
-  a.counters = h->counters + 4 * part;
+  a.counters = h->counters + NCNT * part;
   h->marks_off = part > 0;
   DISPATCH_MODEL(h, rc = pipeline_range<M>(h, a, do_solve, do_sens, s));
   h->marks_off = false;
@@ -1128,8 +1138,8 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * 4 * MAX_SPLIT);  // 4 per part of a split batch
-  if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(int) * 4 * MAX_SPLIT);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(int) * NCNT * MAX_SPLIT);  // one set per part of a split batch
+  if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(int) * NCNT * MAX_SPLIT);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int) * max_batch);
@@ -1502,13 +1512,13 @@ int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
   }
   if (n >= 8) {  // queue statistics of the last SQP round: length, interior-point iterations (warp-per-sample kernel only)
     CUDA_OK(cudaDeviceSynchronize());
-    int c[4 * MAX_SPLIT] = {};
+    int c[NCNT * MAX_SPLIT] = {};
     CUDA_OK(cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     const int parts = h->split > 1 ? (h->split < MAX_SPLIT ? h->split : MAX_SPLIT) : 1;  // the parts of a split batch count separately
     ms_out[6] = ms_out[7] = 0.0;
     for (int p = 0; p < parts; ++p) {
-      ms_out[6] += c[4 * p];
-      ms_out[7] += c[4 * p + 3];
+      ms_out[6] += c[NCNT * p] + c[NCNT * p + 4];
+      ms_out[7] += c[NCNT * p + 3];
     }
   }
   return 0;
