@@ -27,6 +27,7 @@ struct BlockModel {
   static constexpr int NX = M::NX, NU = S * M::NU, NPM = 1, NTH = 1;
   static constexpr int NBX = 0, NSX = 0, NG = 0;
   static constexpr bool STAGE_HESS = true;
+  static constexpr bool PARAMS_COST_ONLY = false;
   MPC_HD static int bx(int j) { return j; }
   MPC_HD static int sx(int) { return 0; }
   MPC_HD static double gC(int, int) { return 0.0; }

@@ -1234,16 +1234,18 @@ struct Engine {
       double Hp[NWS];
       MPC_UNROLL for (int i = 0; i < NW; ++i) MPC_UNROLL for (int j = i; j < NW; ++j) Hp[pidx(i, j)] = Hww[i * NW + j];
       st<NWS>(w + (size_t)S_H * bs, bs, Hp);
-      double gp[NPM];
-      MPC_UNROLL for (int j = 0; j < NPM; ++j) {
-        double a = 0.0;
-        MPC_UNROLL for (int i = 0; i < NX; ++i) a += pik[i] * Fp[i * NPM + j];
-        gp[j] = a;
-      }
-      M::cost_sens(k == 0 ? 0 : 1, pd.scale[k], y, L.th, (size_t)TILE, gp, Hwp);  // model parameters that enter the stage cost
-      st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
-      st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
-      st<NPM>(w + (size_t)S_gp * bs, bs, gp);
+      if constexpr (!M::PARAMS_COST_ONLY) {
+        double gp[NPM];
+        MPC_UNROLL for (int j = 0; j < NPM; ++j) {
+          double a = 0.0;
+          MPC_UNROLL for (int i = 0; i < NX; ++i) a += pik[i] * Fp[i * NPM + j];
+          gp[j] = a;
+        }
+        M::cost_sens(k == 0 ? 0 : 1, pd.scale[k], y, L.th, (size_t)TILE, gp, Hwp);  // model parameters that enter the stage cost
+        st<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+        st<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
+        st<NPM>(w + (size_t)S_gp * bs, bs, gp);
+      }  // else: the parameters sit in the cost only; sens_sweep evaluates the contractions it needs on the fly
       load_cost(k == 0 ? 0 : 1, L, ck);
       double c = cost_grad(ck, pd.scale[k], NW, y, g);
       if (NSX > 0) c += stage_slack_cost(pd, L, k);
@@ -1310,15 +1312,22 @@ struct Engine {
       ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
       ld<NW>(w + (size_t)S_g * bs, bs, g);
       ld<NWS>(w + (size_t)S_H * bs, bs, Hp);
-      ld<NPM>(w + (size_t)S_gp * bs, bs, gpk);
+      if constexpr (!M::PARAMS_COST_ONLY) ld<NPM>(w + (size_t)S_gp * bs, bs, gpk);
       R.cost += w[(size_t)S_c * bs];
       {
         const double e = w[(size_t)S_e * bs];
         R.eq = (e == e) ? dmax(R.eq, e) : e;
       }
-      MPC_UNROLL for (int j = 0; j < NPM; ++j) gp[j] += gpk[j];
       ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, u);
-      if (NEEDX || (pd.param_cost && dLdth)) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      if (NEEDX || M::PARAMS_COST_ONLY || (pd.param_cost && dLdth)) ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, x);
+      if constexpr (M::PARAMS_COST_ONLY) {
+        double yk[NW];
+        MPC_UNROLL for (int i = 0; i < NX; ++i) yk[i] = x[i];
+        MPC_UNROLL for (int i = 0; i < NU; ++i) yk[NX + i] = u[i];
+        M::cost_sens_grad(k == 0 ? 0 : 1, pd.scale[k], yk, L.th, (size_t)TILE, gp);
+      } else {
+        MPC_UNROLL for (int j = 0; j < NPM; ++j) gp[j] += gpk[j];
+      }
       ld<NX>(L.it + (size_t)it_pi(N, k) * bs, bs, pik);
       ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
       ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
@@ -1389,13 +1398,19 @@ struct Engine {
         MPC_UNROLL for (int i = 0; i < NU * NX; ++i) yx[i] = 0.0;
         for (int k = 0; k < N; ++k) {
           const double* w = L.ws + (size_t)k * W_REC * bs;
-          double A[NX * NX], B[NX * NU], K[NU * NX], Pp[NPS], Hwp[NW * NPM], Fp[NX * NPM];
+          constexpr int NDP = M::PARAMS_COST_ONLY ? 1 : NPM;  // dense per-stage parameter derivatives: only if stored
+          double A[NX * NX], B[NX * NU], K[NU * NX], Pp[NPS], Hwp[NW * NDP], Fp[NX * NDP], yk[NW];
           ld<NX * NX>(w + (size_t)W_A * bs, bs, A);
           ld<NX * NU>(w + (size_t)W_B * bs, bs, B);
           ld<NU * NX>(w + (size_t)S_K * bs, bs, K);
           ld<NPS>(w + (size_t)S_P * bs, bs, Pp);
-          ld<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
-          ld<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
+          if constexpr (M::PARAMS_COST_ONLY) {
+            ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, yk);
+            ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, yk + NX);
+          } else {
+            ld<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+            ld<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
+          }
           double Pf[NX * NX];
           {
             int c_ = 0;
@@ -1424,11 +1439,18 @@ struct Engine {
               MPC_UNROLL for (int l = 0; l < NX; ++l) a += Pf[i * NX + l] * yxn[l];
               ypi[i] = a;
             }
-            MPC_UNROLL for (int j = 0; j < NPM; ++j) {
-              double a = 0.0;
-              MPC_UNROLL for (int i = 0; i < NX; ++i) a += yx[r * NX + i] * Hwp[i * NPM + j] + ypi[i] * Fp[i * NPM + j];
-              MPC_UNROLL for (int i = 0; i < NU; ++i) a += yu[i] * Hwp[(NX + i) * NPM + j];
-              acc[r * NPM + j] -= a;
+            if constexpr (M::PARAMS_COST_ONLY) {
+              double yw[NW];
+              MPC_UNROLL for (int i = 0; i < NX; ++i) yw[i] = yx[r * NX + i];
+              MPC_UNROLL for (int i = 0; i < NU; ++i) yw[NX + i] = yu[i];
+              M::cost_sens_adj(k == 0 ? 0 : 1, pd.scale[k], yk, L.th, (size_t)TILE, yw, acc + r * NPM);
+            } else {
+              MPC_UNROLL for (int j = 0; j < NPM; ++j) {
+                double a = 0.0;
+                MPC_UNROLL for (int i = 0; i < NX; ++i) a += yx[r * NX + i] * Hwp[i * NPM + j] + ypi[i] * Fp[i * NPM + j];
+                MPC_UNROLL for (int i = 0; i < NU; ++i) a += yu[i] * Hwp[(NX + i) * NPM + j];
+                acc[r * NPM + j] -= a;
+              }
             }
             MPC_UNROLL for (int i = 0; i < NX; ++i) yx[r * NX + i] = yxn[i];
           }

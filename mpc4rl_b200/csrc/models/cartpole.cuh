@@ -29,7 +29,8 @@ struct CartpoleModelT {
   static constexpr int NG = 0;               // no general linear rows
   MPC_HD static double gC(int, int) { return 0.0; }
   MPC_HD static double g0(int) { return 0.0; }
-  static constexpr bool STAGE_HESS = false;  // stage Hessians come from the cost table
+  static constexpr bool STAGE_HESS = false;
+  static constexpr bool PARAMS_COST_ONLY = false;  // parameters enter the dynamics: dense per-stage parameter derivatives  // stage Hessians come from the cost table
   MPC_HD static int bx(int j) { return j; }  // idxbx (all states, in order)
   MPC_HD static int sx(int) { return 0; }
 

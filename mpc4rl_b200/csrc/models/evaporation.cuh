@@ -72,6 +72,40 @@ struct EvaporationModel {
     }
   }
 
+  // All 60 parameters sit in the stage cost only (model.p is empty): the engine then does not store the dense
+  // d(grad_w L)/d theta (5 x 60) and dF/d theta (2 x 60) of every stage but asks for the two contractions it
+  // needs while it sweeps:  gp += d(s l)/d theta   and   acc -= yw' d(grad_w s l)/d theta  (yw: adjoint of [x;u]).
+  static constexpr bool PARAMS_COST_ONLY = true;
+  MPC_HD static void cost_sens_grad(int kind, double s, const double* y, const double* th, size_t ths, double* gp) {
+    if (kind == 2) return;
+    const int wo = w_off(kind), yo = y_off(kind);
+    double e[NW];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) e[i] = y[i] - th[(size_t)(yo + i) * ths];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      double a = 0.0;
+      MPC_UNROLL for (int j = 0; j < NW; ++j) {
+        a += Wsym(kind, i, j, th, ths) * e[j];
+        gp[wo + j * NW + i] += 0.5 * s * e[i] * e[j];
+      }
+      gp[yo + i] -= s * a;
+    }
+  }
+  MPC_HD static void cost_sens_adj(int kind, double s, const double* y, const double* th, size_t ths, const double* yw,
+                                   double* acc) {
+    if (kind == 2) return;
+    const int wo = w_off(kind), yo = y_off(kind);
+    double e[NW];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) e[i] = y[i] - th[(size_t)(yo + i) * ths];
+    MPC_UNROLL for (int j = 0; j < NW; ++j) {
+      double a = 0.0;
+      MPC_UNROLL for (int i = 0; i < NW; ++i) {
+        a += yw[i] * Wsym(kind, i, j, th, ths);
+        acc[wo + j * NW + i] -= 0.5 * s * (yw[i] * e[j] + yw[j] * e[i]);  // W_ij, column-major
+      }
+      acc[yo + j] += s * a;  // d(grad l)/d yref = -W_s
+    }
+  }
+
   // ---- dynamics ------------------------------------------------------------------------------
   // One RK4 step Phi(x, ud) of length h with forward propagation of d/d(x, ud) (ud = the two inputs
   // that enter f).  D: 2 x 4 row-major.  keep (optional): per RK stage [s(2) | S(2x4) | jac(2x4)].

@@ -17,7 +17,8 @@ struct LinearSystemModel {
   static constexpr int NG = 0;               // no general linear rows
   MPC_HD static double gC(int, int) { return 0.0; }
   MPC_HD static double g0(int) { return 0.0; }
-  static constexpr bool STAGE_HESS = false;  // stage Hessians come from the cost table
+  static constexpr bool STAGE_HESS = false;
+  static constexpr bool PARAMS_COST_ONLY = false;  // parameters enter the dynamics: dense per-stage parameter derivatives  // stage Hessians come from the cost table
   static constexpr int TH_A = 0, TH_B = 4, TH_b = 6, TH_V0 = 8, TH_F = 9;
   MPC_HD static int bx(int j) { return j; }  // idxbx = [0, 1]
   MPC_HD static int sx(int) { return 0; }    // idxsbx = [0]: position in idxbx
