@@ -36,6 +36,7 @@ extern "C" {
 #define RLMPC_MODEL_CARTPOLE 1      /* rlmpc/mpc/cartpole/acados.py:28-108 (config/cartpole*.yaml) */
 #define RLMPC_MODEL_LINEAR_SYSTEM 2 /* rlmpc/mpc/linear_system/acados.py:27-131 */
 #define RLMPC_MODEL_EVAPORATION 3   /* rlmpc/mpc/evaporation_process/acados.py:142-228 */
+#define RLMPC_MODEL_CHAIN_MASS 4    /* rlmpc/mpc/chain_mass/ocp_utils.py:59-147,195-316 (n_mass = 3, 5, 6: nx = 9, 21, 27) */
 
 #define RLMPC_MODE_V 0 /* x_0 fixed            -> V(s), pi(s)   mpc.py:177-202 (update, get_action) */
 #define RLMPC_MODE_Q 1 /* x_0 and u_0 fixed    -> Q(s,a)        mpc.py:52-96   (q_update) */
@@ -59,7 +60,9 @@ typedef struct rlmpc_problem_desc {
   double lbx_e[RLMPC_MAXD], ubx_e[RLMPC_MAXD];
   double model_const[24];           /* cartpole: [0]=RK4 step h, [1]=g; linear system: [0..2] = P11,P12,P22 of
                                        the constant terminal cost (linear_system/acados.py:51-57); evaporation:
-                                       [0..18] = environment.PARAM in dict order, [19] = RK4 step, [20] = #steps */
+                                       [0..18] = environment.PARAM in dict order, [19] = RK4 step, [20] = #steps;
+                                       chain mass: [0] = RK4 step (Ts / 2: two steps per stage, ocp_utils.py:42-56),
+                                       [1] = n_mass; the steady state x_ss of the cost goes through rlmpc_set_model_vector */
   double zl[RLMPC_MAXD], zu[RLMPC_MAXD]; /* linear penalties of the soft state bounds (cost.zl/zu), per idxsbx row */
   double lg[RLMPC_MAXD], ug[RLMPC_MAXD]; /* bounds of the affine general constraints (constraints.lh/uh) */
 } rlmpc_problem_desc;
@@ -82,6 +85,13 @@ int rlmpc_nrows(const rlmpc_handle* h);
  * shared by the batch; per_sample=1: theta_host is [B, ntheta] (parameter sweeps,
  * scripts/cartpole_mpc_sensitivities.py:79-98). */
 int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, int B);
+/* Stream-ordered variant: theta_dev is a device pointer ([ntheta], or [B, ntheta] with per_sample = 1), copied and
+ * turned into the cost table by kernels on `stream`; no host synchronisation (the learning loop keeps theta on the
+ * device).  The caller orders it against solves by using the same stream. */
+int rlmpc_set_theta_dev(rlmpc_handle* h, const double* theta_dev, int per_sample, int B, void* stream);
+/* Model data too large for model_const.  chain mass: name = "x_ss", the steady state the tracking cost refers to
+ * (compute_parametric_steady_state, ocp_utils.py:150-192: a constant computed once when the OCP is built), n = nx. */
+int rlmpc_set_model_vector(rlmpc_handle* h, const char* name, const double* v_host, int n);
 /* Replaces ocp_nlp_cost_model_set(..., "scaling", ...) (mpc.py:259-285). n = N+1. */
 int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n);
 /* Replaces constraints_set(stage, "lbu"/"ubu"/..) for the nominal bounds. field in

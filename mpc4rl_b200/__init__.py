@@ -8,7 +8,7 @@ Layout
   mpc/        mirror of the reference's rlmpc.mpc package (MPC, AcadosMPC classes)
 """
 __all__ = ["BatchedMPC", "cartpole_spec", "cartpole_original_config", "cartpole_config", "linear_system_spec",
-           "linear_system_param_nominal", "evaporation_spec"]
+           "linear_system_param_nominal", "evaporation_spec", "chain_mass_spec", "get_chain_params"]
 
 
 def __getattr__(name):
@@ -16,7 +16,7 @@ def __getattr__(name):
         from .batched import BatchedMPC
         return BatchedMPC
     if name in ("cartpole_spec", "cartpole_original_config", "cartpole_config", "ProblemSpec", "linear_system_spec",
-                "linear_system_param_nominal", "evaporation_spec"):
+                "linear_system_param_nominal", "evaporation_spec", "chain_mass_spec", "get_chain_params", "chain_define_x0"):
         from . import problems
         return getattr(problems, name)
     raise AttributeError(name)

@@ -12,6 +12,7 @@ MAXN, MAXD = 128, 8
 MODEL_CARTPOLE = 1
 MODEL_LINEAR_SYSTEM = 2
 MODEL_EVAPORATION = 3
+MODEL_CHAIN_MASS = 4
 MODE_V, MODE_Q = 0, 1
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -24,6 +25,7 @@ SYMBOLS = [
     "rlmpc_get_iterate", "rlmpc_store_bytes", "rlmpc_store_copy",
     "rlmpc_put_iterate", "rlmpc_solve", "rlmpc_sens", "rlmpc_solve_sens", "rlmpc_solve_sens_host",
     "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings", "rlmpc_cartpole_env_step",
+    "rlmpc_set_theta_dev", "rlmpc_set_model_vector",
 ]
 
 
@@ -62,6 +64,8 @@ def load():
     lib.rlmpc_dims.argtypes = [H, ip, ip, ip, ip, ip]
     lib.rlmpc_nrows.argtypes = [H]
     lib.rlmpc_set_theta.argtypes = [H, vp, C.c_int, C.c_int]
+    lib.rlmpc_set_theta_dev.argtypes = [H, vp, C.c_int, C.c_int, vp]
+    lib.rlmpc_set_model_vector.argtypes = [H, cp, vp, C.c_int]
     lib.rlmpc_set_cost_scaling.argtypes = [H, vp, C.c_int]
     lib.rlmpc_set_bounds.argtypes = [H, cp, vp, C.c_int]
     lib.rlmpc_set_option.argtypes = [H, cp, C.c_double]

@@ -37,6 +37,9 @@ class BatchedMPC:
         desc = spec.to_desc()
         _cabi.check(self.lib.rlmpc_create(C.byref(desc), self.max_batch, dev.index or 0, C.byref(self._h)))
         self.nx, self.nu, self.ntheta = spec.nx, spec.nu, spec.ntheta
+        for name, vec in getattr(spec, "model_vectors", {}).items():
+            v = np.ascontiguousarray(np.asarray(vec, dtype=np.float64))
+            _cabi.check(self.lib.rlmpc_set_model_vector(self._h, name.encode(), v.ctypes.data_as(C.c_void_p), len(v)))
         # inequality rows per stage: 2*(nu+nbx) + 2*ns, acados order [lbu lbx ubu ubx lsbx usbx]
         self.nrows = int(self.lib.rlmpc_nrows(self._h))
         self.ns = len(spec.idxsbx)
@@ -87,7 +90,17 @@ class BatchedMPC:
 
     # ---- parameters ----
     def set_theta(self, theta) -> None:
-        """theta: [ntheta] shared by the batch, or [B, ntheta] per sample."""
+        """theta: [ntheta] shared by the batch, or [B, ntheta] per sample.  A CUDA tensor is handed over on the
+        current stream without any host synchronisation (rlmpc_set_theta_dev)."""
+        if isinstance(theta, torch.Tensor) and theta.is_cuda:
+            th = theta.detach().to(torch.float64).contiguous()
+            if th.shape[-1] != self.ntheta:
+                raise ValueError(f"theta must have {self.ntheta} entries per sample")
+            per = int(th.dim() == 2)
+            _cabi.check(self.lib.rlmpc_set_theta_dev(self._h, _ptr(th), per, th.shape[0] if per else 0, self._stream()))
+            self._theta_dev = th  # keep the tensor alive until the copy kernel has run
+            self.theta = th
+            return
         th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
         if th.shape[-1] != self.ntheta:
             raise ValueError(f"theta must have {self.ntheta} entries per sample")

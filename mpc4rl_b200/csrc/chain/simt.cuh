@@ -3,7 +3,7 @@
 // The kernel bodies in chain_engine.cuh are written once, as functions of (lane, shared-memory pointer, ...), in
 // terms of the few SIMT primitives below.  Compiled by nvcc they are the product (rlmpc_chain.cu).  The same bodies
 // can be compiled by a host compiler against an emulation of these primitives (cooperative fibers, one per lane;
-// oracle/cpu_port/simt_host.h, TEST INFRASTRUCTURE) to debug the maths on a box without a GPU.  Nothing of the
+// oracle/cpu_port (test infrastructure)) to debug the maths on a box without a GPU.  Nothing of the
 // emulation lives in this tree: a host translation unit must define the CH_* / W* macros before including this.
 #pragma once
 #include "../common.cuh"
@@ -111,6 +111,6 @@ struct StageFeed {
 
 #else  // host emulation: the includer provides CH_DEV, WSYNC, BSYNC, wsum, wmax, wmin, wany, atomic_next, StageFeed
 #ifndef CH_DEV
-#error "host builds must include the SIMT emulation (oracle/cpu_port/simt_host.h) before chain/simt.cuh"
+#error "host builds must include a SIMT emulation header (simt_host.h of the test infrastructure) before chain/simt.cuh"
 #endif
 #endif

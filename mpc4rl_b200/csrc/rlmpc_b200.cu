@@ -18,6 +18,7 @@
 #include "models/cartpole.cuh"
 #include "models/linear_system.cuh"
 #include "models/evaporation.cuh"
+#include "chain/chain_backend.h"
 
 using namespace rlmpc;
 
@@ -662,6 +663,7 @@ constexpr int MAX_SPLIT = 4;
 constexpr int NCNT = 8;  // ints per set of queue counters
 
 struct rlmpc_handle {
+  ChainBackend* chain = nullptr;  // chain-mass problems run on the warp-cooperative engine (rlmpc_chain.cu)
   int model, variant, device, max_batch;
   size_t bs;
   int nx, nu, nth, npm, nr, it_size, ws_size, ct_size;
@@ -975,6 +977,19 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
   CUDA_OK(cudaSetDevice(h->device));
   h->pd.mode = mode;
   h->pd.max_sqp = max_sqp;
+  if (h->chain) {
+    ChainCall c;
+    c.mode = mode; c.max_sqp = max_sqp; c.B = B; c.do_solve = do_solve; c.do_sens = do_sens;
+    const size_t o = (size_t)b0;
+    c.x0 = x0 ? x0 + o * h->nx : nullptr; c.u0 = u0 ? u0 + o * h->nu : nullptr;
+    c.u0_out = u0_out ? u0_out + o * h->nu : nullptr; c.cost_out = cost_out ? cost_out + o : nullptr;
+    c.status_out = status_out ? status_out + o : nullptr; c.dL = dL ? dL + o * h->nth : nullptr;
+    c.dpi = dpi ? dpi + o * h->nth * h->nu : nullptr; c.res_out = res_out ? res_out + o * 4 : nullptr;
+    if (b0 != 0) return fail(RLMPC_EINVAL, "chain mass: split batches are not supported");
+    std::string err;
+    const int rc = chain_run(h->chain, h->pd, c, h->sync_every, s, err);
+    return rc ? fail(rc, err) : 0;
+  }
   KArgs a = base_args(h, B);
   a.x0 = x0; a.u0 = (mode == RLMPC_MODE_Q) ? u0 : nullptr;
   a.u0_out = u0_out; a.cost_out = cost_out; a.status_out = status_out;
@@ -1058,6 +1073,44 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   h->device = device;
   h->max_batch = max_batch;
   h->bs = ((size_t)max_batch + 127) / 128 * 128;
+  if (d->model == RLMPC_MODEL_CHAIN_MASS) {
+    // chain of masses: dense nx = 9 / 21 / 27 stage blocks on the warp-cooperative engine; n_mass = model_const[1]
+    ProblemData& pd = h->pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.N = d->N;
+    pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
+    pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.comp_accept = 0.5;
+    memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
+    memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
+    memcpy(pd.mc, d->model_const, sizeof(pd.mc));
+    h->variant = -1;
+    cudaError_t e = cudaSetDevice(device);
+    std::string err;
+    int rc = 0;
+    if (e != cudaSuccess) { rc = RLMPC_ECUDA; err = cudaGetErrorString(e); }
+    if (!rc) rc = chain_create((int)(d->model_const[1] + 0.5), d->N, max_batch, &h->chain, err);
+    if (!rc) {
+      chain_dims(h->chain, &h->nx, &h->nu, &h->nth, &h->it_size);
+      h->npm = h->nth; h->nr = 2 * h->nu; h->ws_size = 0; h->ct_size = 0;
+      const size_t nio_in = (size_t)max_batch * (h->nx + h->nu);
+      const size_t nio_out = (size_t)max_batch * (h->nu + 1 + 4 + (size_t)h->nth * (1 + h->nu));
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_in, sizeof(double) * nio_in);
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * nio_out);
+      if (e == cudaSuccess) e = cudaMalloc(&h->d_status, sizeof(int) * max_batch);
+      if (e == cudaSuccess) e = cudaMallocHost(&h->h_in, sizeof(double) * nio_in);
+      if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(double) * nio_out);
+      if (e == cudaSuccess) e = cudaMallocHost(&h->h_status, sizeof(int) * max_batch);
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) { rc = (e == cudaErrorMemoryAllocation) ? RLMPC_ENOMEM : RLMPC_ECUDA; err = cudaGetErrorString(e); }
+    }
+    if (rc) {
+      rlmpc_destroy(h);
+      return fail(rc, err);
+    }
+    h->split = 1;
+    *out = h;
+    return 0;
+  }
   switch (d->model) {
     case RLMPC_MODEL_CARTPOLE: {
       // state bounds present?  -> the instantiation that carries the 2*nx extra rows per stage
@@ -1169,6 +1222,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
 void rlmpc_destroy(rlmpc_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->chain) chain_destroy(h->chain);
   cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->itb); cudaFree(h->wsb); cudaFree(h->th); cudaFree(h->ct);
   cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
   cudaFree(h->counters); cudaFree(h->ishard);
@@ -1202,6 +1256,13 @@ int rlmpc_nrows(const rlmpc_handle* h) { return h ? h->nr : RLMPC_EINVAL; }
 int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, int B) {
   if (!h || !theta_host) return fail(RLMPC_EINVAL, "bad arguments");
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->chain) {
+    if (per_sample) return fail(RLMPC_EINVAL, "chain mass: one theta is shared by the batch (per-sample theta is not supported)");
+    std::string err;
+    CUDA_OK(cudaDeviceSynchronize());  // theta is read by kernels that may still be in flight
+    const int rc = chain_set_theta(h->chain, h->pd, theta_host, false, nullptr, err);
+    return rc ? fail(rc, err) : 0;
+  }
   if (!per_sample) {
     CUDA_OK(cudaMemcpy(h->th_stage, theta_host, sizeof(double) * h->nth, cudaMemcpyHostToDevice));
     k_theta_transpose<<<1, TILE>>>(h->th_stage, h->th, TILE, h->nth, 1);
@@ -1217,6 +1278,40 @@ int rlmpc_set_theta(rlmpc_handle* h, const double* theta_host, int per_sample, i
   CUDA_OK(cudaGetLastError());
   h->th_per_sample = 1;
   return refresh_cost_table(h, B);
+}
+
+int rlmpc_set_theta_dev(rlmpc_handle* h, const double* theta_dev, int per_sample, int B, void* stream) {
+  if (!h || !theta_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->chain) {
+    if (per_sample) return fail(RLMPC_EINVAL, "chain mass: one theta is shared by the batch (per-sample theta is not supported)");
+    std::string err;
+    const int rc = chain_set_theta(h->chain, h->pd, theta_dev, true, s, err);
+    return rc ? fail(rc, err) : 0;
+  }
+  if (per_sample) {
+    if (int r = check_batch(h, B)) return r;
+    if (B == 0) return 0;
+  }
+  const int n = per_sample ? B : TILE;
+  k_theta_transpose<<<(n + 127) / 128, 128, 0, s>>>(theta_dev, h->th, n, h->nth, per_sample ? 0 : 1);
+  h->th_per_sample = per_sample ? 1 : 0;
+  DISPATCH_MODEL(h, (k_cost_table<M><<<(n + 127) / 128, 128, 0, s>>>(h->pd, h->th, h->ct, h->th_per_sample, B)));
+  h->launches += 2;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_set_model_vector(rlmpc_handle* h, const char* name, const double* v_host, int n) {
+  if (!h || !name || !v_host || n < 0) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->chain && !strcmp(name, "x_ss")) {
+    std::string err;
+    const int rc = chain_set_xss(h->chain, h->pd, v_host, n, err);
+    return rc ? fail(rc, err) : 0;
+  }
+  return fail(RLMPC_EINVAL, std::string("this model has no vector ") + name);
 }
 
 int rlmpc_set_cost_scaling(rlmpc_handle* h, const double* scale, int n) {
@@ -1239,6 +1334,7 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
   else return fail(RLMPC_EINVAL, std::string("unknown bound field ") + field);
   if (!strcmp(field, "zl")) dst = h->pd.zl;
   if (!strcmp(field, "zu")) dst = h->pd.zu;
+  if (h->chain && strcmp(field, "lbu") && strcmp(field, "ubu")) return fail(RLMPC_EINVAL, "chain mass has input bounds only");
   if (is_x && h->variant == VAR_CARTPOLE) {
     for (int i = 0; i < n; ++i)
       if (v[i] > -BIG && v[i] < BIG)
@@ -1260,7 +1356,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "warm_ipm")) h->pd.warm_ipm = (int)value;
   else if (!strcmp(name, "param_cost")) h->pd.param_cost = (int)value;
   else if (!strcmp(name, "sync_every")) h->sync_every = value < 1 ? 1 : (int)value;
-  else if (!strcmp(name, "timing")) h->timing = (int)value;
+  else if (!strcmp(name, "timing")) { h->timing = (int)value; if (h->chain) chain_set_timing(h->chain, h->timing); }
   else if (!strcmp(name, "overlap")) h->overlap = (int)value;
   else if (!strcmp(name, "ring")) h->ring = (int)value;
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
@@ -1281,6 +1377,11 @@ int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* 
   if (int r = check_batch(h, B)) return r;
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->chain) {
+    std::string err;
+    const int rc = chain_reset(h->chain, h->pd, B, x0_dev, mask_dev, (cudaStream_t)stream, err);
+    return rc ? fail(rc, err) : 0;
+  }
   DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, B, x0_dev, mask_dev)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
@@ -1290,6 +1391,12 @@ int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* 
 int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, double* buf_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
   if (!field || !buf_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  if (h->chain) {
+    std::string err;
+    CUDA_OK(cudaSetDevice(h->device));
+    const int rc = chain_field(h->chain, h->pd, field, stage, B, buf_dev, 0, (cudaStream_t)stream, nullptr, err);
+    return rc ? fail(rc, err) : 0;
+  }
   int off, dim;
   if (int r = field_offset(h, field, stage, &off, &dim)) return r;
   if (B == 0) return 0;
@@ -1303,6 +1410,12 @@ int rlmpc_get_iterate(rlmpc_handle* h, const char* field, int stage, int B, doub
 int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, const double* buf_dev, void* stream) {
   if (int r = check_batch(h, B)) return r;
   if (!field || !buf_dev) return fail(RLMPC_EINVAL, "bad arguments");
+  if (h->chain) {
+    std::string err;
+    CUDA_OK(cudaSetDevice(h->device));
+    const int rc = chain_field(h->chain, h->pd, field, stage, B, const_cast<double*>(buf_dev), 1, (cudaStream_t)stream, nullptr, err);
+    return rc ? fail(rc, err) : 0;
+  }
   int off, dim;
   if (int r = field_offset(h, field, stage, &off, &dim)) return r;
   if (B == 0) return 0;
@@ -1461,6 +1574,7 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 
 size_t rlmpc_store_bytes(const rlmpc_handle* h, int capacity) {
   if (!h || capacity <= 0) return 0;
+  if (h->chain) return chain_store_bytes(h->chain, capacity);
   return sizeof(double) * (size_t)h->it_size * (((size_t)capacity + TILE - 1) / TILE * TILE);
 }
 
@@ -1470,6 +1584,11 @@ int rlmpc_store_copy(rlmpc_handle* h, int B, const int* idx_dev, double* store_d
   if (!idx_dev || !store_dev || capacity <= 0) return fail(RLMPC_EINVAL, "bad arguments");
   if (B == 0) return 0;
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->chain) {
+    std::string err;
+    const int rc = chain_store_copy(h->chain, B, idx_dev, store_dev, capacity, to_store, (cudaStream_t)stream, err);
+    return rc ? fail(rc, err) : 0;
+  }
   const int wpb = 8, chunks = (h->it_size + 63) / 64;
   k_store_copy<<<dim3((B + 31) / 32, (chunks + wpb - 1) / wpb), 32 * wpb, 0, (cudaStream_t)stream>>>(
       h->it, store_dev, h->it_size, B, idx_dev, capacity, to_store);
@@ -1489,12 +1608,17 @@ int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, con
   return 0;
 }
 
-long long rlmpc_launch_count(const rlmpc_handle* h) { return h ? h->launches : 0; }
+long long rlmpc_launch_count(const rlmpc_handle* h) { return h ? h->launches + (h->chain ? chain_launches(h->chain) : 0) : 0; }
 
 int rlmpc_get_timings(rlmpc_handle* h, double* ms_out, int n) {
   if (!h || !ms_out || n < 6) return fail(RLMPC_EINVAL, "bad arguments");
   if (!h->timing) return fail(RLMPC_EINVAL, "option \"timing\" is off");
   CUDA_OK(cudaSetDevice(h->device));
+  if (h->chain) {
+    std::string err;
+    const int rc = chain_timings(h->chain, ms_out, n, err);
+    return rc ? fail(rc, err) : 0;
+  }
   // [lin | qp1 | qp2 (from the end of qp1, possibly on the side stream) | sens_stage | sens_sweep | tail]
   const int from[6] = {0, 1, 2, 2, 4, 5}, to[6] = {1, 2, 3, 4, 5, 6};
   for (int i = 0; i < 6; ++i) {

@@ -194,6 +194,8 @@ class OcpSolverShim:
         if field in ("lam", "t"):
             # acados order within a stage: [lbu, lbx, ubu, ubx, lsbx, usbx] (rlmpc/common/utils.py:4-25); the
             # engine stores [lbu(nu), lbx(nbx), ubu(nu), ubx(nbx), lsbx(ns), usbx(ns)] for every stage 0..N
+            if stage == N and len(self.acados_ocp.constraints.idxbx_e) == 0:
+                return np.zeros(0)
             v = self.engine.get(field, stage, 1)[0].cpu().numpy()
             ng = self.engine.ng
             nv = nu + nbx + ng  # engine order per side: [u, x[bx], h]

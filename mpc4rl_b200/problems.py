@@ -45,6 +45,7 @@ class ProblemSpec:
     state_labels: List[str] = field(default_factory=list)
     input_labels: List[str] = field(default_factory=list)
     parameter_labels: List[str] = field(default_factory=list)  # labels of p["model"]
+    model_vectors: Dict[str, np.ndarray] = field(default_factory=dict)  # model data too large for model_const (chain: x_ss)
 
     @property
     def ntheta(self) -> int:
@@ -241,3 +242,118 @@ def evaporation_spec(model_param: dict | None = None, cost_param: dict | None = 
         lh=np.array([-1e3, -1e3]), uh=np.array([0.0, 0.0]), x_init=x_ss, u_init=u_ss,
         state_labels=["X_2", "P_2"], input_labels=["P_100", "F_200", "s"], parameter_labels=[],
     )
+
+
+# --------------------------------------------------------------------------------------------
+# chain of masses (rlmpc/mpc/chain_mass/ocp_utils.py)
+# --------------------------------------------------------------------------------------------
+def get_chain_params() -> dict:
+    """ocp_utils.py:319-341 (the entries the OCP uses)."""
+    return {"n_mass": 5, "Ts": 0.2, "Tsim": 5, "N": 40, "u_init": np.array([-1, 1, 1]), "with_wall": True, "yPosWall": -0.05,
+            "xPosFirstMass": np.zeros(3), "m": 0.033, "D": 1.0, "L": 0.033, "C": 0.1, "perturb_scale": 1e-2,
+            "nlp_iter": 50, "seed": 50, "nlp_tol": 1e-5}
+
+
+def chain_param_layout(n_mass: int):
+    """define_param_struct_symSX(disturbance=True) (ocp_utils.py:353-371): [m | D | L | C | Q | R | w]; entries with
+    `repeat` are laid out repetition by repetition, matrices column-major.  Returns ({name: slice}, length, labels)."""
+    n_link, M = n_mass - 1, n_mass - 2
+    nx = (2 * M + 1) * 3
+    sizes = [("m", n_link), ("D", 3 * n_link), ("L", 3 * n_link), ("C", 3 * n_link), ("Q", nx * nx), ("R", 9), ("w", 3 * M)]
+    out, o = {}, 0
+    for name, n in sizes:
+        out[name] = slice(o, o + n)
+        o += n
+    labels = [f"m_{i}" for i in range(n_link)]
+    for nm in ("D", "L", "C"):
+        labels += [f"{nm}_{i}_{j}" for i in range(n_link) for j in range(3)]
+    labels += [f"Q_{i}" for i in range(nx * nx)] + [f"R_{i}" for i in range(9)]
+    labels += [f"w_{i}_{j}" for i in range(M) for j in range(3)]
+    return out, o, labels
+
+
+def chain_ode(x: np.ndarray, u: np.ndarray, p: np.ndarray, n_mass: int) -> np.ndarray:
+    """f_expl = [xvel ; u ; f] of ocp_utils.py:59-147 (numpy; used on the host for the steady state only)."""
+    M = n_mass - 2
+    sl, _, _ = chain_param_layout(n_mass)
+    m, D, L, C = p[sl["m"]], p[sl["D"]].reshape(M + 1, 3), p[sl["L"]].reshape(M + 1, 3), p[sl["C"]].reshape(M + 1, 3)
+    w = p[sl["w"]].reshape(M, 3)
+    pos, vel = x[: 3 * (M + 1)].reshape(M + 1, 3), x[3 * (M + 1):].reshape(M, 3)
+    f = np.tile(np.array([0.0, 0.0, -9.81]), (M, 1)) + w
+    for i in range(M + 1):
+        dist = pos[i] - (pos[i - 1] if i > 0 else 0.0)
+        vl = vel[0] if i == 0 else (u - vel[M - 1] if i == M else vel[i] - vel[i - 1])
+        T = D[i] / m[i] * (1.0 - L[i] / np.linalg.norm(dist)) * dist + C[i] * vl
+        if i < M:
+            f[i] -= T
+        if i > 0:
+            f[i - 1] += T
+    return np.concatenate([vel.reshape(-1), u, f.reshape(-1)])
+
+
+def chain_steady_state(n_mass: int, p: np.ndarray, x_end: np.ndarray) -> np.ndarray:
+    """compute_parametric_steady_state (ocp_utils.py:150-192) without IPOPT: xdot = 0 with the last mass held at
+    x_end and u = 0 -- zero velocities and force balance on the intermediate masses; Newton with a central-difference
+    Jacobian on the 3 M unknown positions, started on the straight line like the reference's initial guess."""
+    M = n_mass - 2
+    nx = (2 * M + 1) * 3
+
+    def resid(q):
+        x = np.concatenate([q, x_end, np.zeros(3 * M)])
+        return chain_ode(x, np.zeros(3), p, n_mass)[3 * (M + 1):]
+
+    q = np.zeros(3 * M)
+    q[0::3] = np.linspace(0.0, float(x_end[0]), M + 2)[1:-1]
+    for _ in range(100):
+        r = resid(q)
+        if np.abs(r).max() < 1e-13:
+            break
+        J = np.zeros((3 * M, 3 * M))
+        for j in range(3 * M):
+            e = np.zeros(3 * M)
+            e[j] = 1e-6
+            J[:, j] = (resid(q + e) - resid(q - e)) / 2e-6
+        q = q - np.linalg.solve(J, r)
+    x = np.zeros(nx)
+    x[: 3 * M] = q
+    x[3 * M: 3 * (M + 1)] = x_end
+    return x
+
+
+def chain_define_x0(chain_params: dict) -> np.ndarray:
+    """define_x0 (rlmpc/examples/chain_mass.py:17-25): masses on the straight line to x_end, at rest."""
+    M = chain_params["n_mass"] - 2
+    x0 = np.zeros((2 * M + 1) * 3)
+    x0[: 3 * (M + 1): 3] = np.linspace(chain_params["xPosFirstMass"][0], chain_params["L"] * (M + 1) * 6, M + 2)[1:]
+    return x0
+
+
+def chain_mass_spec(chain_params: dict | None = None, gamma: float = 1.0) -> ProblemSpec:
+    """export_parametric_ocp(chain_params, integrator_type="DISCRETE") as rlmpc/mpc/chain_mass/acados.py:32-45 builds it:
+    disturbance parameters present (w = 0), EXTERNAL cost 1/2 (x - x_ss)'Q(x - x_ss) + 1/2 u'Ru with Q, R part of p
+    (ocp_utils.py:266-277), |u| <= 1, ERK4 with two sub-steps of Ts/2 (:42-56), GAUSS_NEWTON, tol 1e-5, 50 SQP
+    iterations (:298-312).  theta = p has 113 / 499 / 800 entries for n_mass = 3 / 5 / 6."""
+    cp = dict(get_chain_params() if chain_params is None else chain_params)
+    n_mass = int(cp["n_mass"])
+    M = n_mass - 2
+    nx, nu, N, Ts = (2 * M + 1) * 3, 3, int(cp["N"]), float(cp["Ts"])
+    sl, nth, labels = chain_param_layout(n_mass)
+    p = np.zeros(nth)
+    p[sl["m"]] = cp["m"]; p[sl["D"]] = cp["D"]; p[sl["L"]] = cp["L"]; p[sl["C"]] = cp["C"]  # random_scale = 0 (ocp_utils.py:205)
+    q_diag = np.ones(nx)
+    q_diag[3 * M: 3 * M + 3] = M + 1
+    p[sl["Q"]] = (2.0 * np.diag(q_diag)).T.ravel()
+    p[sl["R"]] = (2.0 * 1e-2 * np.eye(nu)).T.ravel()
+    x_end = np.array([cp["L"] * (M + 1) * 6, 0.0, 0.0])
+    x_ss = chain_steady_state(n_mass, p, x_end)
+    spec = ProblemSpec(
+        name=f"chain_mass_ds_{n_mass}", model=_cabi.MODEL_CHAIN_MASS, N=N, nx=nx, nu=nu, tf=N * Ts,
+        p_entries=[("model", (nth,))], p_nominal=p,
+        lbu=-np.ones(nu), ubu=np.ones(nu), lbx=np.zeros(0), ubx=np.zeros(0), lbx_e=np.zeros(0), ubx_e=np.zeros(0),
+        model_const=np.array([Ts / 2.0, float(n_mass)]), gamma=gamma, cost_type="EXTERNAL",
+        state_labels=[f"xpos_{i}" for i in range(3 * (M + 1))] + [f"xvel_{i}" for i in range(3 * M)],
+        input_labels=[f"u_{i}" for i in range(nu)], parameter_labels=labels,
+    )
+    spec.model_vectors = {"x_ss": x_ss}
+    spec.x_ss = x_ss
+    return spec
