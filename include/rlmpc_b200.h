@@ -187,6 +187,11 @@ int rlmpc_td_grad(rlmpc_handle* h, int B, int ncols, const double* td_dev, const
 int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, const double* action_dev,
                             double* reward_dev, int* terminated_dev, int* truncated_dev, int* steps_dev, void* stream);
 
+/* FP64 FMA throughput of the device, measured with a register-resident probe kernel (8 independent chains per thread,
+ * 2048 threads per SM): the compute roofline of this FP64 path.  tflops_out: best of 5 timed launches, counting
+ * FMA = 2 flop.  ("measure first"; MEASURED_PEAKS.json has no FP64 figure.) */
+int rlmpc_fp64_peak(int device, double* tflops_out);
+
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);
 /* With option "timing" = 1 the library records CUDA events on the caller's stream between the phases

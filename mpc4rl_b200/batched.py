@@ -135,12 +135,20 @@ class BatchedMPC:
 
     def get(self, field: str, stage: int, B: int) -> torch.Tensor:
         dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": self.nrows, "t": self.nrows,
-               "rho_x0": self.nx, "rho_u0": self.nu}[field]
+               "rho_x0": self.nx, "rho_u0": self.nu, "meta": 1}[field]
         out = torch.empty(B, dim, dtype=torch.float64, device=self.device)
         _cabi.check(self.lib.rlmpc_get_iterate(self._h, field.encode(), int(stage), int(B), _ptr(out), self._stream()))
         return out
 
     def put(self, field: str, stage: int, value: torch.Tensor) -> None:
+        dim = {"x": self.nx, "u": self.nu, "pi": self.nx, "lam": self.nrows, "t": self.nrows,
+               "rho_x0": self.nx, "rho_u0": self.nu, "meta": 1}.get(field)
+        if dim is None:
+            raise ValueError(f"unknown iterate field {field!r}")
+        if not (value.is_cuda and value.dtype == torch.float64 and value.dim() == 2 and value.shape[1] == dim):
+            raise ValueError(f"{field} rows must be float64 CUDA tensors of shape [B, {dim}], got {tuple(value.shape)} {value.dtype}")
+        if value.shape[0] > self.max_batch:
+            raise ValueError("more rows than max_batch")
         value = value.contiguous()
         _cabi.check(self.lib.rlmpc_put_iterate(self._h, field.encode(), int(stage), value.shape[0], _ptr(value), self._stream()))
 
@@ -228,14 +236,24 @@ class BatchedMPC:
         return acc
 
     PHASES = ("linearize", "qp_fast", "qp_full", "sens_stage", "sens_sweep", "sens_tail")
+    # the chain-mass engine has one QP kernel (no fast path / queue split) and a separate parameter-contraction kernel
+    CHAIN_PHASES = ("linearize", "qp", "unused", "sens_stage", "sens_sweep", "param_contraction")
 
     def timings(self) -> dict:
         """Device milliseconds of the phases of the last call (needs set_option("timing", 1))."""
         ms = np.zeros(8)
         _cabi.check(self.lib.rlmpc_get_timings(self._h, ms.ctypes.data_as(C.c_void_p), 8))
-        d = dict(zip(self.PHASES, ms[:6].tolist()))
+        names = self.CHAIN_PHASES if self.spec.model == _cabi.MODEL_CHAIN_MASS else self.PHASES
+        d = dict(zip(names, ms[:6].tolist()))
+        d.pop("unused", None)
         d["queue_len"], d["queue_ipm_iters"] = int(ms[6]), int(ms[7])
         return d
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured FP64 FMA throughput of this device (rlmpc_fp64_peak)."""
+        v = C.c_double()
+        _cabi.check(self.lib.rlmpc_fp64_peak(self.device.index or 0, C.byref(v)))
+        return float(v.value)
 
     @property
     def launch_count(self) -> int:

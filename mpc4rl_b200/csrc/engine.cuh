@@ -1452,7 +1452,25 @@ struct Engine {
                 acc[r * NPM + j] -= a;
               }
             }
+            if (!M::PARAMS_COST_ONLY && pd.param_cost) {
+              // cost-parameter columns (parameterize_tracking_cost): contracted on the fly into the caller's zero-initialised row
+              double xk[NX], uk[NU], yw[NW];
+              ld<NX>(L.it + (size_t)it_x(N, k) * bs, bs, xk);
+              ld<NU>(L.it + (size_t)it_u(N, k) * bs, bs, uk);
+              MPC_UNROLL for (int i = 0; i < NX; ++i) yw[i] = yx[r * NX + i];
+              MPC_UNROLL for (int i = 0; i < NU; ++i) yw[NX + i] = yu[i];
+              M::cost_param_adj(k == 0 ? 0 : 1, pd.scale[k], L.th, (size_t)TILE, xk, uk, yw, dpidth + (size_t)r * grad_width(pd));
+            }
             MPC_UNROLL for (int i = 0; i < NX; ++i) yx[r * NX + i] = yxn[i];
+          }
+        }
+        if (!M::PARAMS_COST_ONLY && pd.param_cost) {  // terminal stage
+          double xk[NX], yw[NW];
+          ld<NX>(L.it + (size_t)it_x(N, N) * bs, bs, xk);
+          MPC_UNROLL for (int r = 0; r < NU; ++r) {
+            MPC_UNROLL for (int i = 0; i < NX; ++i) yw[i] = yx[r * NX + i];
+            MPC_UNROLL for (int i = 0; i < NU; ++i) yw[NX + i] = 0.0;
+            M::cost_param_adj(2, pd.scale[N], L.th, (size_t)TILE, xk, nullptr, yw, dpidth + (size_t)r * grad_width(pd));
           }
         }
       }

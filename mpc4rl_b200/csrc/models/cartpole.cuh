@@ -86,6 +86,29 @@ struct CartpoleModelT {
     }
   }
 
+  // Cost-parameter columns of dpi/dtheta for one adjoint vector yw = [yx ; yu] of this stage (terminal: yu ignored):
+  //   row[theta] -= yw' d(grad_w s l)/d theta,   d(grad l)/dW_ij = 1/2 (delta_i e_j + delta_j e_i),  d(grad l)/dyref = -W_sym
+  MPC_HD static void cost_param_adj(int kind, double s, const double* th, size_t ths, const double* x, const double* u,
+                                    const double* yw, double* row) {
+    const int n = ny(kind);
+    double e[NW];
+    MPC_UNROLL for (int i = 0; i < NW; ++i) {
+      e[i] = 0.0;
+      if (i < n) e[i] = ((i < NX) ? x[i] : u[i - NX]) - yref(kind, i, th, ths);
+    }
+    const int wo = w_off(kind), yo = yref_off(kind);
+    MPC_UNROLL for (int j = 0; j < NW; ++j) {
+      if (j >= n) continue;
+      double a = 0.0;
+      MPC_UNROLL for (int i = 0; i < NW; ++i) {
+        if (i >= n) continue;
+        a += yw[i] * W(kind, i, j, th, ths);
+        row[wo + j * n + i] -= 0.5 * s * (yw[i] * e[j] + yw[j] * e[i]);
+      }
+      row[yo + j] += s * a;
+    }
+  }
+
   // ---- dynamics -------------------------------------------------------------------------
   // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l);
   // NC = 5 -> columns (x,u) only (SQP linearisation), NC = 8 -> also the parameter columns.

@@ -50,6 +50,7 @@ struct EvaporationModel {
     }
   }
   MPC_HD static void cost_param_grad(int, double, const double*, size_t, const double*, const double*, double*) {}
+  MPC_HD static void cost_param_adj(int, double, const double*, size_t, const double*, const double*, const double*, double*) {}
   // d(s l)/d theta -> gp,  d(grad_w s l)/d theta -> Hwp  for l = 1/2 e'We, e = y - yref:
   //   dl/dW_ij = 1/2 e_i e_j,  dl/dyref = -W_s e,  d(grad l)_a/dW_ij = 1/2 (d_ai e_j + d_aj e_i),  d(grad l)/dyref = -W_s
   MPC_HD static void cost_sens(int kind, double s, const double* y, const double* th, size_t ths, double* gp, double* Hwp) {

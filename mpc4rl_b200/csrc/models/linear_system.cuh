@@ -38,6 +38,7 @@ struct LinearSystemModel {
   }
   // no W / yref entries in p (EXTERNAL cost)
   MPC_HD static void cost_param_grad(int, double, const double*, size_t, const double*, const double*, double*) {}
+  MPC_HD static void cost_param_adj(int, double, const double*, size_t, const double*, const double*, const double*, double*) {}
   // cost terms that depend on model parameters: d(s l)/d theta -> gp, d(grad_w s l)/d theta -> Hwp
   MPC_HD static void cost_sens(int kind, double s, const double* y, const double*, size_t, double* gp, double* Hwp) {
     if (kind == 2) return;

@@ -598,6 +598,24 @@ __global__ void k_cartpole_env_step(const double* __restrict__ par, int B, doubl
   state[4 * b] = x; state[4 * b + 1] = xd; state[4 * b + 2] = th; state[4 * b + 3] = thd;
 }
 
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, enough warps to fill every scheduler.
+// The roofline the path is measured against ("FP64 CUDA-core peaks are not in MEASURED_PEAKS.json --
+// measure them first").
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 1.0 + 1e-3 * (threadIdx.x + j);
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fma(a[j], b, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == 12345.678) out[0] = s;  // keeps the loop alive
+}
+
 // MPC.reset: x_k = x0 for all stages, everything else zero
 template <class M>
 __global__ void k_reset(int N, double* it, int B, const double* x0, const int* mask) {
@@ -702,6 +720,8 @@ struct rlmpc_handle {
   double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
   int *h_status = nullptr, *d_status = nullptr;
   cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_last = nullptr;  // recorded after every stream-ordered call: the host entry point waits for it
+  bool ev_last_set = false;
 };
 
 namespace {
@@ -714,6 +734,15 @@ namespace {
     case VAR_LINEAR: { using M = LinearSystemModel; __VA_ARGS__; } break;     \
     case VAR_EVAPORATION: { using M = EvaporationModel; __VA_ARGS__; } break; \
   }
+
+// stream-ordered entry points leave a marker that rlmpc_solve_sens_host (which runs on the handle's own streams) waits for
+void note_stream(rlmpc_handle* h, cudaStream_t s) {
+  if (!h->ev_last) cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
+  if (h->ev_last && cudaEventRecord(h->ev_last, s) == cudaSuccess) h->ev_last_set = true;
+}
+
+template <class M>
+constexpr bool coop_model() { return CoopSel<M>::value; }
 
 int check_batch(rlmpc_handle* h, int B) {
   if (!h) return fail(RLMPC_EINVAL, "null handle");
@@ -1033,6 +1062,8 @@ int field_offset_t(rlmpc_handle* h, const char* field, int stage, int* off, int*
     *off = E::it_rx0(N); *dim = E::NX;
   } else if (!strcmp(field, "rho_u0")) {
     *off = E::it_ru0(N); *dim = E::NU;
+  } else if (!strcmp(field, "meta")) {  // [0] = 1: (lam, t) hold the result of a QP solve (valid interior-point warm start)
+    *off = E::it_meta(N); *dim = 1;
   } else {
     return fail(RLMPC_EINVAL, std::string("unknown field ") + field);
   }
@@ -1236,6 +1267,7 @@ void rlmpc_destroy(rlmpc_handle* h) {
   cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_status);
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status); cudaFreeHost(h->h_counters);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
   for (int i = 0; i < rlmpc_handle::NEV; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -1288,6 +1320,7 @@ int rlmpc_set_theta_dev(rlmpc_handle* h, const double* theta_dev, int per_sample
     if (per_sample) return fail(RLMPC_EINVAL, "chain mass: one theta is shared by the batch (per-sample theta is not supported)");
     std::string err;
     const int rc = chain_set_theta(h->chain, h->pd, theta_dev, true, s, err);
+    if (!rc) note_stream(h, s);
     return rc ? fail(rc, err) : 0;
   }
   if (per_sample) {
@@ -1300,6 +1333,7 @@ int rlmpc_set_theta_dev(rlmpc_handle* h, const double* theta_dev, int per_sample
   DISPATCH_MODEL(h, (k_cost_table<M><<<(n + 127) / 128, 128, 0, s>>>(h->pd, h->th, h->ct, h->th_per_sample, B)));
   h->launches += 2;
   CUDA_OK(cudaGetLastError());
+  note_stream(h, (cudaStream_t)stream);
   return 0;
 }
 
@@ -1380,11 +1414,13 @@ int rlmpc_reset_masked(rlmpc_handle* h, int B, const double* x0_dev, const int* 
   if (h->chain) {
     std::string err;
     const int rc = chain_reset(h->chain, h->pd, B, x0_dev, mask_dev, (cudaStream_t)stream, err);
+    if (!rc) note_stream(h, (cudaStream_t)stream);
     return rc ? fail(rc, err) : 0;
   }
   DISPATCH_MODEL(h, (k_reset<M><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->pd.N, h->it, B, x0_dev, mask_dev)));
   h->launches++;
   CUDA_OK(cudaGetLastError());
+  note_stream(h, (cudaStream_t)stream);
   return 0;
 }
 
@@ -1414,6 +1450,7 @@ int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, cons
     std::string err;
     CUDA_OK(cudaSetDevice(h->device));
     const int rc = chain_field(h->chain, h->pd, field, stage, B, const_cast<double*>(buf_dev), 1, (cudaStream_t)stream, nullptr, err);
+    if (!rc) note_stream(h, (cudaStream_t)stream);
     return rc ? fail(rc, err) : 0;
   }
   int off, dim;
@@ -1423,26 +1460,33 @@ int rlmpc_put_iterate(rlmpc_handle* h, const char* field, int stage, int B, cons
   k_copy_field<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->it, h->it_size, B, off, dim, const_cast<double*>(buf_dev), 1);
   h->launches++;
   CUDA_OK(cudaGetLastError());
+  note_stream(h, (cudaStream_t)stream);
   return 0;
 }
 
 int rlmpc_solve(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
                 double* u0_out_dev, double* cost_out_dev, int* status_out_dev, void* stream) {
-  return run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, nullptr, nullptr,
-                  nullptr, 1, 0, (cudaStream_t)stream);
+  const int rc = run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, nullptr, nullptr,
+                          nullptr, 1, 0, (cudaStream_t)stream);
+  if (!rc && B > 0) note_stream(h, (cudaStream_t)stream);
+  return rc;
 }
 
 int rlmpc_sens(rlmpc_handle* h, int mode, int B, double* dL_dtheta_dev, double* dpi_dtheta_dev, double* cost_out_dev,
                double* res_out_dev, int* status_out_dev, void* stream) {
-  return run_unit(h, mode, h ? h->pd.max_sqp : 1, B, nullptr, nullptr, nullptr, cost_out_dev, status_out_dev,
-                  dL_dtheta_dev, dpi_dtheta_dev, res_out_dev, 0, 1, (cudaStream_t)stream);
+  const int rc = run_unit(h, mode, h ? h->pd.max_sqp : 1, B, nullptr, nullptr, nullptr, cost_out_dev, status_out_dev,
+                          dL_dtheta_dev, dpi_dtheta_dev, res_out_dev, 0, 1, (cudaStream_t)stream);
+  if (!rc && B > 0) note_stream(h, (cudaStream_t)stream);
+  return rc;
 }
 
 int rlmpc_solve_sens(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_dev, const double* u0_dev,
                      double* u0_out_dev, double* cost_out_dev, int* status_out_dev, double* dL_dtheta_dev,
                      double* dpi_dtheta_dev, double* res_out_dev, void* stream) {
-  return run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, dL_dtheta_dev,
-                  dpi_dtheta_dev, res_out_dev, 1, 1, (cudaStream_t)stream);
+  const int rc = run_unit(h, mode, max_sqp, B, x0_dev, u0_dev, u0_out_dev, cost_out_dev, status_out_dev, dL_dtheta_dev,
+                          dpi_dtheta_dev, res_out_dev, 1, 1, (cudaStream_t)stream);
+  if (!rc && B > 0) note_stream(h, (cudaStream_t)stream);
+  return rc;
 }
 
 int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0_host, const double* u0_host,
@@ -1455,8 +1499,9 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t s = h->own_stream;
   // This entry point runs on the handle's own streams and is synchronous; order it after whatever the caller
-  // has queued for this handle through the stream-ordered entry points (rlmpc_reset, rlmpc_solve, ...).
-  CUDA_OK(cudaDeviceSynchronize());
+  // has queued for this handle through the stream-ordered entry points (rlmpc_reset, rlmpc_solve, ...): those
+  // leave an event behind (note_stream), so no device-wide synchronisation is needed.
+  if (h->ev_last_set) CUDA_OK(cudaStreamWaitEvent(s, h->ev_last, 0));
   const size_t nB = (size_t)B, nx = h->nx, nu = h->nu, nth = h->ng();
   // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are used
   // directly as DMA source / destination; pageable ones go through the handle's pinned staging area.
@@ -1472,7 +1517,12 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
   const bool in_pinned = pinned(x0_host) && pinned(u0_host);
   const bool all_pinned = in_pinned && pinned(u0_out_host) && pinned(cost_out_host) && pinned(res_out_host) &&
                           pinned(dL_dtheta_host) && pinned(dpi_dtheta_host) && pinned(status_out_host);
-  if (all_pinned && max_sqp == 1 && h->split > 1 && B >= 4096 && !h->overlap) {
+  // the per-part pipelines address the queue through per-part counters; only the warp-per-sample queue kernel works in
+  // place on the samples' own records -- the thread-per-sample fallback shares compact buffers by queue slot, so parts
+  // must not run concurrently there (option coop = 0, or a horizon too long for shared memory)
+  bool coop_ok = false;
+  if (!h->chain) DISPATCH_MODEL(h, coop_ok = coop_model<M>() && h->coop && h->coop_grid > 0);
+  if (all_pinned && max_sqp == 1 && h->split > 1 && B >= 4096 && !h->overlap && coop_ok) {
     // Page-locked buffers, RTI: the parts of the batch (option "split") are complete pipelines of their own --
     // copy in, kernel chain, copy out -- on separate streams, so that the copies of one part overlap with the
     // kernels of another.
@@ -1491,6 +1541,7 @@ int rlmpc_solve_sens_host(rlmpc_handle* h, int mode, int max_sqp, int B, const d
       if (b0 >= nB) break;
       const size_t nb = nB - b0 < (size_t)per ? nB - b0 : (size_t)per;
       cudaStream_t sp = (p == 0) ? s : h->part_stream[p - 1];
+      if (p > 0 && h->ev_last_set) CUDA_OK(cudaStreamWaitEvent(sp, h->ev_last, 0));
       CUDA_OK(cudaMemcpyAsync(d_x0 + b0 * nx, x0_host + b0 * nx, sizeof(double) * nb * nx, cudaMemcpyHostToDevice, sp));
       if (u0_host) CUDA_OK(cudaMemcpyAsync(d_u0 + b0 * nu, u0_host + b0 * nu, sizeof(double) * nb * nu, cudaMemcpyHostToDevice, sp));
       CUDA_OK(cudaMemsetAsync(d_dL + b0 * nth, 0, sizeof(double) * nb * nth, sp));
@@ -1587,6 +1638,7 @@ int rlmpc_store_copy(rlmpc_handle* h, int B, const int* idx_dev, double* store_d
   if (h->chain) {
     std::string err;
     const int rc = chain_store_copy(h->chain, B, idx_dev, store_dev, capacity, to_store, (cudaStream_t)stream, err);
+    if (!rc) note_stream(h, (cudaStream_t)stream);
     return rc ? fail(rc, err) : 0;
   }
   const int wpb = 8, chunks = (h->it_size + 63) / 64;
@@ -1594,6 +1646,7 @@ int rlmpc_store_copy(rlmpc_handle* h, int B, const int* idx_dev, double* store_d
       h->it, store_dev, h->it_size, B, idx_dev, capacity, to_store);
   h->launches++;
   CUDA_OK(cudaGetLastError());
+  note_stream(h, (cudaStream_t)stream);
   return 0;
 }
 
@@ -1605,6 +1658,34 @@ int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, con
   k_cartpole_env_step<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(par_dev, B, state_dev, action_dev, reward_dev,
                                                                        terminated_dev, truncated_dev, steps_dev);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_fp64_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+  double best = 0.0;
+  for (int r = 0; r < 6; ++r) {
+    CUDA_OK(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(d, iters);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CUDA_OK(cudaGetLastError());
+  *tflops_out = best;
   return 0;
 }
 

@@ -218,7 +218,34 @@ class OcpSolverShim:
         raise NotImplementedError(field)
 
     # ---- iterate hand-off (examples/chain_mass.py:119-120) ----
+    def _acados_to_engine_rows(self, stage: int, v: np.ndarray) -> np.ndarray:
+        """Inverse of the row map of ``get(stage, "lam" / "t")``: acados stage layout -> the engine's row order.  The
+        stage-0 rows of the x_0 (and Q-mode u_0) equalities have no engine counterpart and are dropped."""
+        nx, nu, N = self.spec.nx, self.spec.nu, self.N
+        nbx, ns, ng = self.engine.nbx, len(self.spec.idxsbx), self.engine.ng
+        nv = nu + nbx + ng
+        out = np.zeros(self.engine.nrows)
+        if stage == N:
+            nbe = len(self.acados_ocp.constraints.idxbx_e)
+            if len(v) != 2 * nbe:
+                raise ValueError(f"stage {stage}: expected {2 * nbe} rows, got {len(v)}")
+            if nbe:
+                out[nu:nu + nbx], out[nv + nu:nv + nu + nbx] = v[:nbe], v[nbe:]
+            return out
+        if stage == 0:
+            if len(v) != 2 * (nu + nx + ng):
+                raise ValueError(f"stage 0: expected {2 * (nu + nx + ng)} rows (lbu, lbx_0, lh, ubu, ubx_0, uh), got {len(v)}")
+            h = nu + nx + ng
+            out[:nu] = v[:nu]; out[nu + nbx:nv] = v[nu + nx:h]
+            out[nv:nv + nu] = v[h:h + nu]; out[nv + nu + nbx:2 * nv] = v[h + nu + nx:2 * h]
+            return out
+        if len(v) != 2 * nv + 2 * ns:
+            raise ValueError(f"stage {stage}: expected {2 * nv + 2 * ns} rows, got {len(v)}")
+        return np.asarray(v, dtype=np.float64).copy()  # same order: [lbu lbx lh ubu ubx uh lsbx usbx]
+
     def store_iterate(self, filename: str = "iterate.json", overwrite: bool = False, verbose: bool = True) -> None:
+        """acados' iterate JSON: x_k, u_k, pi_k and lam_k / t_k in acados' per-stage layout (what get(k, "lam") returns,
+        stage 0 with the rows of the x_0 equalities), so that a real acados install can load_iterate() the file."""
         if os.path.exists(filename) and not overwrite:
             raise FileExistsError(filename)
         d = {}
@@ -228,14 +255,32 @@ class OcpSolverShim:
                 d[f"u_{k}"] = self.get(k, "u").tolist()
                 d[f"pi_{k}"] = self.get(k, "pi").tolist()
             for f in ("lam", "t"):
-                d[f"{f}_{k}"] = self.engine.get(f, k, 1)[0].cpu().numpy().tolist()
+                d[f"{f}_{k}"] = self.get(k, f).tolist()
         with open(filename, "w") as fh:
             json.dump(d, fh, indent=1)
 
     def load_iterate(self, filename: str, verbose: bool = True) -> None:
         with open(filename) as fh:
             d = json.load(fh)
+        dims = {"x": self.spec.nx, "u": self.spec.nu, "pi": self.spec.nx}
         for key, val in d.items():
             f, k = key.rsplit("_", 1)
-            dim = len(val)
-            self.engine.put(f, int(k), torch.tensor([val], dtype=torch.float64, device=self._dev))
+            k = int(k)
+            v = np.asarray(val, dtype=np.float64).reshape(-1)
+            if f in dims:
+                if len(v) != dims[f]:
+                    raise ValueError(f"{key}: expected {dims[f]} values, got {len(v)}")
+            elif f in ("lam", "t"):
+                if self.engine.nrows == 0 or (k == self.N and self.spec.model == 4):
+                    continue
+                if k == self.N and len(v) == 0 and len(self.acados_ocp.constraints.idxbx_e) == 0:
+                    continue
+                v = self._acados_to_engine_rows(k, v)
+            else:
+                continue  # sl / su / z entries of acados files: slack values are rows of t here
+            self.engine.put(f, k, torch.tensor(v.reshape(1, -1), dtype=torch.float64, device=self._dev))
+        one = torch.ones(1, 1, dtype=torch.float64, device=self._dev)
+        try:
+            self.engine.put("meta", 0, one)  # the loaded multipliers are a valid interior-point warm start
+        except RuntimeError:
+            pass

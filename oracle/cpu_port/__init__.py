@@ -112,3 +112,47 @@ def unit(model: int, pd: ProblemData, mode: int, max_sqp: int, theta, x0, u0=Non
     assert r == 0
     out["iterate"] = iterate
     return out
+
+
+# ---- chain of masses: host run of the warp-cooperative engine under the fiber SIMT emulation (chain_port.cpp) ----
+_chain = None
+
+
+def chain_lib():
+    global _chain
+    if _chain is None:
+        so = os.path.join(_DIR, "libchain_port.so")
+        r = subprocess.run(["make", "-C", _DIR, "-s", "libchain_port.so"], capture_output=True, text=True)
+        if r.returncode != 0 and not os.path.exists(so):
+            raise RuntimeError("building oracle/cpu_port/libchain_port.so failed:\n" + r.stdout + r.stderr)
+        _chain = C.CDLL(so)
+        assert _chain.chain_port_sizeof_problem_data() == C.sizeof(ProblemData), "ProblemData layout mismatch"
+    return _chain
+
+
+def chain_unit(n_mass: int, pd: ProblemData, mode: int, max_sqp: int, theta, xss, x0, u0=None, iterate=None,
+               do_solve=True, do_sens=True, threads=0):
+    """solve(+sens) of a batch of chain-mass samples on the host.  iterate: [B, it_size] (contiguous per sample)."""
+    L = chain_lib()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    nx, nth, its = C.c_int(), C.c_int(), C.c_int()
+    assert L.chain_port_dims(n_mass, pd.N, C.byref(nx), C.byref(nth), C.byref(its)) == 0
+    nx, nth, its = nx.value, nth.value, its.value
+    if iterate is None:  # MPC.reset: all stages = x0
+        iterate = np.zeros((B, its))
+        for k in range(pd.N + 1):
+            iterate[:, k * nx:(k + 1) * nx] = x0
+    iterate = np.ascontiguousarray(iterate)
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    xss = np.ascontiguousarray(xss, dtype=np.float64)
+    u0a = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64).reshape(B, 3)
+    out = dict(u0=np.zeros((B, 3)), cost=np.zeros(B), status=np.zeros(B, dtype=np.int32), dL=np.zeros((B, nth)),
+               dpi=np.zeros((B, 3, nth)), res=np.zeros((B, 4)), iters=np.zeros(B, dtype=np.int32))
+    r = L.chain_port_run(C.c_int(n_mass), C.byref(pd), C.c_int(mode), C.c_int(max_sqp), C.c_int(B), _p(theta), _p(xss), _p(x0),
+                         _p(u0a), _p(iterate), C.c_int(int(do_solve)), C.c_int(int(do_sens)), _p(out["u0"]), _p(out["cost"]),
+                         _p(out["status"], C.c_int), _p(out["dL"]), _p(out["dpi"]), _p(out["res"]), _p(out["iters"], C.c_int),
+                         C.c_int(int(threads)))
+    assert r == 0
+    out["iterate"] = iterate
+    return out

@@ -90,3 +90,24 @@ def test_builtin_configs_equal_reference_yaml():
         assert (a.N, a.nx, a.nu, a.tf) == (b.N, b.nx, b.nu, b.tf), name
         for k in ("p_nominal", "lbu", "ubu", "lbx", "ubx", "lbx_e", "ubx_e", "model_const"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), (name, k)
+
+
+def test_integration_md_struct_matches_the_header():
+    """INTEGRATION.md shows the ctypes struct a maintainer would copy: it must have the size and field offsets of the
+    binding the package itself uses (a stale copy under-allocates the struct and rlmpc_create reads past it)."""
+    import ctypes as C  # noqa: F401  (used by the exec'd snippet)
+    import re
+
+    from mpc4rl_b200 import _cabi
+
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class ProblemDesc\(C\.Structure\):.*?\n\n", md, re.S)
+    assert m, "INTEGRATION.md no longer shows the ProblemDesc struct"
+    ns = {"C": C}
+    exec(m.group(0), ns)
+    doc = ns["ProblemDesc"]
+    assert C.sizeof(doc) == C.sizeof(_cabi.ProblemDesc)
+    assert [(n, getattr(doc, n).offset) for n, _ in doc._fields_] == [(n, getattr(_cabi.ProblemDesc, n).offset) for n, _ in _cabi.ProblemDesc._fields_]
+    # and the header declares the same array lengths
+    hdr = open(os.path.join(ROOT, "include", "rlmpc_b200.h")).read()
+    assert "double model_const[24];" in hdr and "double lg[RLMPC_MAXD], ug[RLMPC_MAXD];" in hdr

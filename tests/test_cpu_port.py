@@ -1,0 +1,49 @@
+"""Host builds of the engines (oracle/cpu_port, test infrastructure) against the dense oracle's fixtures: the same
+templates the CUDA kernels instantiate, run without a GPU.  These pin the MATHS of paths whose GPU parity tests need
+a device: the cost-parameter columns of dpi/dtheta (parameterize_tracking_cost) and the warp-cooperative chain-mass
+engine under the fiber emulation of a warp."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cartpole_cost_parameter_columns_match_oracle():
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_paramcost.npz"))
+    spec = cartpole_spec(cartpole_original_config())
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-10, warm_ipm=1, param_cost=1)
+    o = cp.unit(1, pd, 0, 200, g["theta"], g["x0"])
+    ok = (o["status"] == 0) & (g["status"][:, 0] == 0)
+    assert ok.sum() >= 4
+    assert o["dL"].shape[1] == 83 and o["dpi"].shape[2] == 83
+    assert np.abs(o["u0"] - g["u0"])[ok].max() < 1e-8
+    assert np.abs(o["dL"] - g["dV"])[ok].max() < 1e-6 * np.abs(g["dV"][ok]).max()
+    assert np.abs(g["dpi"][ok][:, :, 3:]).max() > 1.0  # the cost columns are live ...
+    assert np.abs(o["dpi"] - g["dpi"])[ok].max() < 1e-5 * np.abs(g["dpi"][ok]).max()  # ... and agree
+
+
+def test_chain_mass_host_run_matches_oracle():
+    from mpc4rl_b200.problems import chain_mass_spec, get_chain_params
+    from oracle import cpu_port as cp
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "chain_mass_3.npz"))
+    cpar = get_chain_params()
+    cpar["n_mass"] = 3
+    spec = chain_mass_spec(cpar)
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-9, warm_ipm=1)
+    n = 4
+    o = cp.chain_unit(3, pd, 0, 60, spec.p_nominal, spec.x_ss, g["x0"][:n])
+    assert np.all(o["status"] == 0)
+    assert np.abs(o["u0"] - g["u0"][:n]).max() < 1e-8
+    assert np.abs(o["cost"] - g["V"][:n]).max() < 1e-9 * np.abs(g["V"]).max()
+    assert np.abs(o["dL"] - g["dV"][:n]).max() < 1e-6 * np.abs(g["dV"]).max()
+    assert np.abs(o["dpi"] - g["dpi"][:n]).max() < 1e-5 * np.abs(g["dpi"]).max()
+    # one RTI step from that iterate at the moved state, sensitivities at the new iterate
+    r = cp.chain_unit(3, pd, 0, 1, spec.p_nominal, spec.x_ss, g["x1"][:n], iterate=o["iterate"])
+    assert np.all(r["status"] == 0)
+    assert np.abs(r["u0"] - g["u1"][:n]).max() < 1e-5
+    assert np.abs(r["dpi"] - g["dpi1"][:n]).max() < 1e-4 * np.abs(g["dpi1"]).max()

@@ -380,3 +380,29 @@ def test_pipelined_host_entry_point_is_bit_identical(spec):
     for a, b in zip(res[0], res[1]):
         for k in ("u0", "cost", "dL", "dpi", "res", "status"):
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_cost_parameter_columns_match_oracle(spec):
+    """parameterize_tracking_cost=True: W_0, W, W_e, yref_0, yref, yref_e carry gradient -- all 83 columns of dL/dp AND
+    of dpi/dp (the latter contracted on the fly in the adjoint sweep) against tests/golden/cartpole_paramcost.npz."""
+    from mpc4rl_b200 import BatchedMPC
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_paramcost.npz"))
+    B = g["x0"].shape[0]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    m.set_option("param_cost", 1)
+    m.set_theta(g["theta"])
+    x0 = _dev(g["x0"])
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=200)
+    ok = (out["status"].cpu().numpy() == 0) & (g["status"][:, 0] == 0)
+    assert ok.sum() >= 4
+    assert out["dL"].shape[1] == 83 and out["dpi"].shape[2] == 83
+    assert np.abs(out["u0"].cpu().numpy() - g["u0"])[ok].max() < 1e-6
+    assert _rel(out["dL"].cpu().numpy()[ok], g["dV"][ok]) < 1e-6
+    assert np.abs(g["dpi"][ok][:, :, 3:]).max() > 1.0
+    assert _rel(out["dpi"].cpu().numpy()[ok], g["dpi"][ok]) < 1e-5
+    # a second call into the same output buffers must not accumulate on top of the first
+    out2 = m.solve_sens(x0, max_sqp=1, out=out)
+    assert _rel(out2["dpi"].cpu().numpy()[ok], g["dpi"][ok]) < 1e-5

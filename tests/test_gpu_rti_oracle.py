@@ -1,0 +1,119 @@
+"""The path bench.py times, checked against the oracle: ONE SQP-RTI step from a stored iterate after the state moved by
+one environment step, and update_nlp's sensitivities at the resulting -- not converged -- iterate.
+
+Fixture: tests/golden/cartpole_original_rti.npz (oracle/make_golden_rti.py, 256 states of the SURVEY.md 8(d) config-2
+distribution; oracle outputs, parity unpinned vs acados): per sample the oracle's converged iterate at x0, the state
+x1 = env.step(x0, u0*), and the result of one dense full SQP step from that iterate with the QP solved to the
+tau-central point, followed by the restated update_nlp (dense dR/dz + SuperLU).
+
+Tolerances (north-star / VERDICT r01): |u0| 1e-5, V 1e-8 rel, dL/dtheta 1e-5 rel, dpi/dtheta 1e-4 rel -- under the
+engine's DEFAULT options, i.e. exactly what bench.py runs (warm interior point, comp_accept = 0.5, warp-per-sample
+queue kernel)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(ROOT, "tests", "golden", "cartpole_original_rti.npz"))
+
+
+def _engine(B):
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    spec = cartpole_spec(cartpole_original_config())
+    return spec, BatchedMPC(spec, max_batch=B, device=0)  # default options = the bench's
+
+
+def _T(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+
+
+def _check(out, g, sel, mpc, keys=("u1", "V1", "dV1", "dpi1")):
+    u = out["u0"].cpu().numpy()[sel]
+    assert np.abs(u - g[keys[0]][sel]).max() < 1e-5
+    V = out["cost"].cpu().numpy()[sel]
+    assert np.abs(V - g[keys[1]][sel]).max() < 1e-8 * np.abs(g[keys[1]][sel]).max()
+    dL = mpc.full_grad(out["dL"]).cpu().numpy()[sel]
+    assert np.abs(dL - g[keys[2]][sel]).max() < 1e-5 * np.abs(g[keys[2]][sel]).max()
+    if keys[3] is not None:
+        dpi = mpc.full_grad(out["dpi"]).cpu().numpy()[sel]
+        assert np.abs(dpi - g[keys[3]][sel]).max() < 1e-4 * np.abs(g[keys[3]][sel]).max()
+
+
+def test_rti_from_own_converged_iterate_fast_path(g):
+    """Warm path: the engine converges at x0 itself (its iterate then agrees with the oracle's to solver accuracy), the
+    state moves by one environment step, one RTI call with sensitivities.  Most samples take the single-Newton-iteration
+    fast path, the rest the warp-per-sample queue -- the mix bench.py times."""
+    B = g["x0"].shape[0]
+    spec, mpc = _engine(B)
+    mpc.set_option("tol", 1e-9)
+    x0 = _T(g["x0"])
+    mpc.reset(x0)
+    u0, _, st = mpc.solve(x0, max_sqp=300)
+    same = (g["status"] == 0) & (st.cpu().numpy() == 0) & (np.abs(u0.cpu().numpy() - g["u0"]).max(1) < 1e-6)
+    assert same.mean() > 0.85, same.mean()  # the rest: full-step SQP 2-cycles in one or both implementations
+    mpc.set_option("tol", 1e-6)
+    mpc.set_option("timing", 1)
+    out = mpc.solve_sens(_T(g["x1"]), max_sqp=1)
+    torch.cuda.synchronize()
+    assert np.all(out["status"].cpu().numpy()[same] == 0)
+    _check(out, g, same, mpc)
+    q = mpc.timings()
+    assert 0 < q["queue_len"] < B  # both the fast path and the queue were exercised
+
+
+def test_rti_from_the_oracles_iterate_queue_path(g):
+    """Same step from EXACTLY the oracle's stored primal iterate (put x, u; no multipliers, so the interior point starts
+    cold and every sample goes through the queue kernel), including the samples on which SQP had not converged."""
+    B = g["x0"].shape[0]
+    spec, mpc = _engine(B)
+    mpc.reset(_T(g["x0"]))
+    for k in range(spec.N + 1):
+        mpc.put("x", k, _T(g["X"][:, k]))
+    for k in range(spec.N):
+        mpc.put("u", k, _T(g["U"][:, k]))
+    out = mpc.solve_sens(_T(g["x1"]), max_sqp=1)
+    torch.cuda.synchronize()
+    ok = out["status"].cpu().numpy() == 0
+    assert ok.mean() > 0.98
+    _check(out, g, ok, mpc)
+    # Q-mode RTI from the same iterate: u_0 clamped to a random action
+    mpc.reset(_T(g["x0"]))
+    for k in range(spec.N + 1):
+        mpc.put("x", k, _T(g["X"][:, k]))
+    for k in range(spec.N):
+        mpc.put("u", k, _T(g["U"][:, k]))
+    outq = mpc.solve_sens(_T(g["x1"]), _T(g["a"]), max_sqp=1)
+    okq = outq["status"].cpu().numpy() == 0
+    assert okq.mean() > 0.98
+    Vq = outq["cost"].cpu().numpy()[okq]
+    assert np.abs(Vq - g["Q1"][okq]).max() < 1e-8 * np.abs(g["Q1"][okq]).max()
+    dQ = mpc.full_grad(outq["dL"]).cpu().numpy()[okq]
+    assert np.abs(dQ - g["dQ1"][okq]).max() < 1e-5 * np.abs(g["dQ1"][okq]).max()
+
+
+def test_strict_acceptance_gives_the_same_step(g):
+    """What comp_accept = 0.5 costs in accuracy: the RTI result with the strict setting (0.05) differs from the default's
+    by far less than the tolerance the test above allows."""
+    B = g["x0"].shape[0]
+    res = []
+    for ca in (0.5, 0.05):
+        spec, mpc = _engine(B)
+        mpc.set_option("comp_accept", ca)
+        x0 = _T(g["x0"])
+        mpc.reset(x0)
+        mpc.solve(x0, max_sqp=300)
+        res.append(mpc.solve_sens(_T(g["x1"]), max_sqp=1))
+    ok = ((res[0]["status"] == 0) & (res[1]["status"] == 0)).cpu().numpy()
+    assert ok.mean() > 0.85
+    du = (res[0]["u0"] - res[1]["u0"]).abs().cpu().numpy()[ok].max()
+    ddpi = (res[0]["dpi"] - res[1]["dpi"]).abs().cpu().numpy()[ok].max() / res[1]["dpi"].abs().cpu().numpy()[ok].max()
+    assert du < 1e-6 and ddpi < 1e-5, (du, ddpi)
