@@ -30,8 +30,6 @@ class _MPCFunction(torch.autograd.Function):
         full = getattr(engine, "_theta_full_dev", None)
         if full is None:
             cur = engine.theta
-            if isinstance(cur, torch.Tensor):
-                cur = cur.detach().cpu().numpy()
             if cur.ndim != 1:
                 raise ValueError("the autograd bridge needs one theta shared by the batch (engine.theta is per-sample)")
             full = torch.as_tensor(cur, dtype=torch.float64).to(engine.device).clone()

@@ -45,8 +45,8 @@ class BatchedMPC:
         self.ns = len(spec.idxsbx)
         self.ng = len(spec.lh)  # affine general constraint rows (lh/uh)
         self.nbx = (self.nrows - 2 * self.ns) // 2 - self.nu - self.ng
-        self.theta = np.array(spec.p_nominal, dtype=np.float64)
-        self.set_theta(self.theta)
+        self._theta_host, self._theta_dev = None, None
+        self.set_theta(np.array(spec.p_nominal, dtype=np.float64))
         # cartpole only: gradient rows over the whole p (incl. W, yref) instead of the model parameters.  The
         # other models have a fixed gradient width (all their parameters).
         self.param_cost = bool(spec.parameterize_tracking_cost) and spec.model == _cabi.MODEL_CARTPOLE
@@ -89,6 +89,13 @@ class BatchedMPC:
         return t.contiguous()
 
     # ---- parameters ----
+    @property
+    def theta(self) -> np.ndarray:
+        """The current parameter vector(s) as a host array (read back once after a device-side set_theta)."""
+        if self._theta_host is None:
+            self._theta_host = self._theta_dev.detach().cpu().numpy()
+        return self._theta_host
+
     def set_theta(self, theta) -> None:
         """theta: [ntheta] shared by the batch, or [B, ntheta] per sample.  A CUDA tensor is handed over on the
         current stream without any host synchronisation (rlmpc_set_theta_dev)."""
@@ -98,15 +105,16 @@ class BatchedMPC:
                 raise ValueError(f"theta must have {self.ntheta} entries per sample")
             per = int(th.dim() == 2)
             _cabi.check(self.lib.rlmpc_set_theta_dev(self._h, _ptr(th), per, th.shape[0] if per else 0, self._stream()))
-            self._theta_dev = th  # keep the tensor alive until the copy kernel has run
-            self.theta = th
+            self._theta_dev = th  # keep the tensor alive until the copy kernel has run; `theta` reads it back lazily
+            self._theta_host = None
             return
         th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64))
         if th.shape[-1] != self.ntheta:
             raise ValueError(f"theta must have {self.ntheta} entries per sample")
         per = int(th.ndim == 2)
         _cabi.check(self.lib.rlmpc_set_theta(self._h, th.ctypes.data_as(C.c_void_p), per, th.shape[0] if per else 0))
-        self.theta = th
+        self._theta_host, self._theta_dev = th, None
+        self._theta_full_dev = None  # (cache of the autograd bridge)
 
     def set_option(self, name: str, value: float) -> None:
         _cabi.check(self.lib.rlmpc_set_option(self._h, name.encode(), float(value)))
