@@ -108,10 +108,13 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * "condense" (1): (thread-per-sample path) queued QPs of input-bounds-only problems are solved in partially condensed form
  * (blocks of 4 stages, like the reference's PARTIAL_CONDENSING_HPIPM) in V-mode when N % 4 == 0,
  * "ring" (1) / "ring_b" (0): cp.async shared-memory ring reader of the stage-form / condensed queue kernel,
- * "comp_accept" (0.5): an interior-point solve (and the single warm Newton iteration of the fast path) ends on
+ * "comp_accept" (0.2): an interior-point solve (and the single warm Newton iteration of the fast path) ends on
  * a full step whose rows all land within lam*t = tau (1 +- comp_accept) -- a neighbourhood of the tau-central
- * point, far inside HPIPM's own complementarity tolerance; at SQP convergence the step vanishes and lam*t = tau
- * holds to rounding whatever the value (0.05 = the strict setting of the first builds),
+ * point, far inside HPIPM's own complementarity tolerance.  Measured against the oracle's exact tau-central RTI step
+ * (tests/golden/cartpole_original_rti.npz, 256 states one environment step away from their iterate; worst sample, warm /
+ * cold start of the interior point): 0.5 -> |du0| 1.5e-6 / 3.3e-5, 0.2 -> 2.3e-7 / 1.1e-6, 0.05 -> 4e-8 / 1.1e-6; the
+ * headline step costs 5.49 / 5.6 / 5.73 ms at 0.5 / 0.2 / 0.05.  0.2 is the largest setting that keeps the north-star
+ * |du0| < 1e-5 with a margin on both paths (tools/comp_accept_study.py),
  * "split" (2): an RTI solve(+sens) call on >= 4096 samples runs the two halves of the batch as two independent
  * chains of kernels on two streams (the caller's and an internal one, joined before the call returns to the
  * stream): kernels bound by different units overlap; 1 = one chain; rlmpc_get_timings then describes the first half,
@@ -191,6 +194,8 @@ int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, con
  * 2048 threads per SM): the compute roofline of this FP64 path.  tflops_out: best of 5 timed launches, counting
  * FMA = 2 flop.  ("measure first"; MEASURED_PEAKS.json has no FP64 figure.) */
 int rlmpc_fp64_peak(int device, double* tflops_out);
+/* Same for the FP64 tensor-core path (mma.sync m8n8k4, DMMA), 512 flop per instruction and warp. */
+int rlmpc_fp64_tensor_peak(int device, double* tflops_out);
 
 /* number of kernels launched through this handle so far (bench.py's gpu_launches) */
 long long rlmpc_launch_count(const rlmpc_handle* h);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "rlmpc_get_iterate", "rlmpc_store_bytes", "rlmpc_store_copy",
     "rlmpc_put_iterate", "rlmpc_solve", "rlmpc_sens", "rlmpc_solve_sens", "rlmpc_solve_sens_host",
     "rlmpc_td_grad", "rlmpc_launch_count", "rlmpc_get_timings", "rlmpc_cartpole_env_step",
-    "rlmpc_set_theta_dev", "rlmpc_set_model_vector", "rlmpc_fp64_peak",
+    "rlmpc_set_theta_dev", "rlmpc_set_model_vector", "rlmpc_fp64_peak", "rlmpc_fp64_tensor_peak",
 ]
 
 
@@ -67,6 +67,7 @@ def load():
     lib.rlmpc_set_theta_dev.argtypes = [H, vp, C.c_int, C.c_int, vp]
     lib.rlmpc_set_model_vector.argtypes = [H, cp, vp, C.c_int]
     lib.rlmpc_fp64_peak.argtypes = [C.c_int, dp]
+    lib.rlmpc_fp64_tensor_peak.argtypes = [C.c_int, dp]
     lib.rlmpc_set_cost_scaling.argtypes = [H, vp, C.c_int]
     lib.rlmpc_set_bounds.argtypes = [H, cp, vp, C.c_int]
     lib.rlmpc_set_option.argtypes = [H, cp, C.c_double]

@@ -24,6 +24,10 @@
 
 namespace rlmpc {
 
+#ifndef CHAIN_USE_DMMA
+#define CHAIN_USE_DMMA 1  // dense block products on the FP64 tensor cores (0: register-tiled DFMA versions, kept for comparison)
+#endif
+
 MPC_HD constexpr int ev2(int n) { return (n + 1) & ~1; }
 MPC_HD double nn(double v) { return (v == v) ? v : 1e300; }  // NaN -> huge, so that maxima keep it
 
@@ -99,13 +103,15 @@ struct ChainEngine {
   // ================================================================================================================
   // (sample, stage) task: linearisation (HESS = false) or exact second-order information (HESS = true) of stage k.
   // ================================================================================================================
-  static constexpr int DELW = ev2(3 * NL);  // per-lane slot of the tangent exchange buffer
+  // per-lane row of the tangent exchange buffers; with DMMA the rows are the K dimension of m8n8k4 tiles (multiple of 4)
+  static constexpr int HKT = (3 * NL + 3) / 4, HMT = (NW + 7) / 8;
+  static constexpr int DELW = CHAIN_USE_DMMA ? 4 * HKT : ev2(3 * NL);
   // shared memory of one warp (doubles)
   static constexpr int SM_X0 = 0, SM_XN = SM_X0 + NX, SM_PI = SM_XN + NX, SM_PIM = SM_PI + NX, SM_KK = SM_PIM + NX,
                        SM_LB = SM_KK + NX, SM_KB = SM_LB + NX, SM_XB = SM_KB + NX, SM_XC = SM_XB + NX, SM_U = SM_XC + NX,
                        SM_GV = SM_U + 4, SM_XS = SM_GV + NW, SM_FL = SM_XS + NSP * NX, SM_NU = SM_FL + 3 * NL,
                        SM_DB = SM_NU + 3 * NL, SM_VB = SM_DB + 3 * NL, SM_SB = ev2(SM_VB + 3 * NL),
-                       SM_GB = SM_SB + NSP * NL * 9, SM_DEL = ev2(SM_GB + NSP * NL * 6), SM_OUT = SM_DEL + 32 * DELW,
+                       SM_GB = SM_SB + NSP * NL * 9, SM_DEL = ev2(SM_GB + NSP * NL * 6), SM_GDL = SM_DEL + 32 * DELW, SM_OUT = SM_GDL + 32 * DELW,
                        SM_STAGE = ev2(SM_OUT + NW * NC);
 
   // cost of a stage at (x, u): gradient into g (NW, shared memory), returns the scaled value.  Lanes over rows.
@@ -139,7 +145,8 @@ struct ChainEngine {
     double* X0 = S + SM_X0; double* XN = S + SM_XN; double* PI = S + SM_PI; double* PIM = S + SM_PIM; double* KK = S + SM_KK;
     double* LB = S + SM_LB; double* KB = S + SM_KB; double* XB = S + SM_XB; double* XC = S + SM_XC; double* U = S + SM_U;
     double* GV = S + SM_GV; double* XS = S + SM_XS; double* FL = S + SM_FL; double* NUv = S + SM_NU; double* DB = S + SM_DB;
-    double* VB = S + SM_VB; double* SB = S + SM_SB; double* GB = S + SM_GB; double* DEL = S + SM_DEL; double* OUT = S + SM_OUT;
+    double* VB = S + SM_VB; double* SB = S + SM_SB; double* GB = S + SM_GB; double* DEL = S + SM_DEL; double* GDL = S + SM_GDL;
+    double* OUT = S + SM_OUT;
     constexpr int C_ = HESS ? Z_C : S_C, E_ = HESS ? Z_E : S_E, R_ = HESS ? Z_S : S_S;
 
     if (lane < NX) {
@@ -261,13 +268,22 @@ struct ChainEngine {
     }
 
     // ---------------- tangent sweep: lane j carries direction e_j of w = [x ; u] ----------------
-    double dx[NX], dacc[NX], dp[NX], dkp[NVEL], dka[NVEL], Hc[HESS ? NW : 1];
+    double dx[NX], dacc[NX], dp[NX], dkp[NVEL], dka[NVEL];
     double du[3];
-    MPC_UNROLL for (int c = 0; c < NX; ++c) dx[c] = (c == lane) ? 1.0 : 0.0;
-    MPC_UNROLL for (int j = 0; j < 3; ++j) du[j] = (lane == NX + j) ? 1.0 : 0.0;
+#if CHAIN_USE_DMMA
+    double hacc[HESS ? HMT : 1][HESS ? HMT : 1][2];  // H tiles of this lane: rows 8 mt + lane / 4, columns 8 nt + 2 (lane % 4) + {0, 1}
+    if constexpr (HESS) {
+      MPC_UNROLL for (int mt = 0; mt < HMT; ++mt) MPC_UNROLL for (int nt = 0; nt < HMT; ++nt) { hacc[mt][nt][0] = 0.0; hacc[mt][nt][1] = 0.0; }
+      for (int e = 3 * NL; e < DELW; ++e) { DEL[lane * DELW + e] = 0.0; GDL[lane * DELW + e] = 0.0; }  // zero padding of the K dimension
+    }
+#else
+    double Hc[HESS ? NW : 1];
     if constexpr (HESS) {
       MPC_UNROLL for (int l = 0; l < NW; ++l) Hc[l] = 0.0;
     }
+#endif
+    MPC_UNROLL for (int c = 0; c < NX; ++c) dx[c] = (c == lane) ? 1.0 : 0.0;
+    MPC_UNROLL for (int j = 0; j < 3; ++j) du[j] = (lane == NX + j) ? 1.0 : 0.0;
     for (int sub = 0; sub < Mo::NSUB; ++sub) {
       MPC_UNROLL for (int c = 0; c < NX; ++c) dacc[c] = 0.0;
       MPC_UNROLL for (int c = 0; c < NVEL; ++c) { dkp[c] = 0.0; dka[c] = 0.0; }
@@ -287,7 +303,12 @@ struct ChainEngine {
             dT[3 * i + j] = Sb[3 * j] * dd[0] + Sb[3 * j + 1] * dd[1] + Sb[3 * j + 2] * dd[2] + th[Mo::TH_C + 3 * i + j] * dvl[j];
           if constexpr (HESS) {
             Mo::sym3_mul(GB + (s * NL + i) * 6, dd, gd + 3 * i);
-            MPC_UNROLL for (int j = 0; j < 3; ++j) DEL[lane * DELW + 3 * i + j] = dd[j];
+            MPC_UNROLL for (int j = 0; j < 3; ++j) {
+              DEL[lane * DELW + 3 * i + j] = dd[j];
+#if CHAIN_USE_DMMA
+              GDL[lane * DELW + 3 * i + j] = gd[3 * i + j];
+#endif
+            }
           }
         }
         // k of this stage: [dp_vel ; du ; -dT_m + dT_{m+1}]
@@ -300,12 +321,25 @@ struct ChainEngine {
         MPC_UNROLL for (int j = 0; j < 3; ++j) dacc[NVEL + j] += bb * du[j];
         if constexpr (HESS) {
           WSYNC();
+#if CHAIN_USE_DMMA
+          // H += D' (G D) over the link geometry of this stage point, D = [tangents of the lanes] (3 NL x NW): a dense
+          // (NW x 3NL) (3NL x NW) contraction on the FP64 tensor cores, HMT^2 HKT mma.sync per stage point
+          MPC_UNROLL for (int kt = 0; kt < HKT; ++kt) {
+            double af[HMT], bf[HMT];
+            MPC_UNROLL for (int mt = 0; mt < HMT; ++mt) {
+              af[mt] = DEL[(8 * mt + (lane >> 2)) * DELW + 4 * kt + (lane & 3)];
+              bf[mt] = GDL[(8 * mt + (lane >> 2)) * DELW + 4 * kt + (lane & 3)];
+            }
+            MPC_UNROLL for (int mt = 0; mt < HMT; ++mt) MPC_UNROLL for (int nt = 0; nt < HMT; ++nt) dmma_8x8x4(af[mt], bf[nt], hacc[mt][nt][0], hacc[mt][nt][1]);
+          }
+#else
           MPC_UNROLL for (int l = 0; l < NW; ++l) {  // H[l][j] += sum_i Delta_i^(l)' G_i Delta_i^(j)
             const double* dl = DEL + l * DELW;
             double acc = 0.0;
             MPC_UNROLL for (int e = 0; e < 3 * NL; ++e) acc += dl[e] * gd[e];
             Hc[l] += acc;
           }
+#endif
           WSYNC();
         }
       }
@@ -351,9 +385,16 @@ struct ChainEngine {
     if (lane == 0) { rec[C_] = cst; rec[E_] = eq; rec[R_] = sres; }
     if constexpr (HESS) {
       WSYNC();
+#if CHAIN_USE_DMMA
+      MPC_UNROLL for (int mt = 0; mt < HMT; ++mt) MPC_UNROLL for (int nt = 0; nt < HMT; ++nt) MPC_UNROLL for (int h_ = 0; h_ < 2; ++h_) {
+        const int m = 8 * mt + (lane >> 2), n = 8 * nt + 2 * (lane & 3) + h_;
+        if (m < NW && n < NW) OUT[m * NW + n] = hacc[mt][nt][h_];
+      }
+#else
       if (lane < NW) {
         MPC_UNROLL for (int l = 0; l < NW; ++l) OUT[l * NW + lane] = Hc[l];
       }
+#endif
       if (lane < 3 * NL) DB[lane] = gth[3];
       WSYNC();
       for (int e = lane; e < NW * NW; e += 32) rec[Z_H + e] = OUT[e];
@@ -417,6 +458,67 @@ struct ChainEngine {
   template <class HF, class GF>
   CH_DEV static bool riccati_step(double* Pm, double* PV, double* Tm, double* HU, double* KK, const double* Mk, bool affine,
                                   bool ufixed, HF hess, GF grad, double* G0I, int lane) {
+#if CHAIN_USE_DMMA
+    // Both products on the FP64 tensor cores (mma.sync m8n8k4): per stage 2 x MT x NT x KT instructions instead of
+    // ~700 DFMA + ~330 LDS per lane -- ncu on the FMA version: shared-memory pipe 37-46 % busy, FP64 pipe 17 %, i.e.
+    // operand delivery, not arithmetic, was the limiter (profiles/r02_summary.md).  Operands are zero-padded by the
+    // guards to multiples of the 8 x 8 x 4 tile.
+    constexpr int MT1 = (NX + 7) / 8, MT2 = (NW + 7) / 8, NT = (NC + 7) / 8, KT = (NX + 3) / 4;
+    const int fr = lane >> 2, fk = lane & 3;
+    {  // T = P [A | B | b] + [0 | 0 | p]
+      double acc[MT1][NT][2];
+      MPC_UNROLL for (int mt = 0; mt < MT1; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+      MPC_UNROLL for (int kt = 0; kt < KT; ++kt) {
+        double af[MT1], bf[NT];
+        const int kk = 4 * kt + fk;
+        MPC_UNROLL for (int mt = 0; mt < MT1; ++mt) {
+          const int i = 8 * mt + fr;
+          af[mt] = (i < NX && kk < NX) ? Pm[i * NX + kk] : 0.0;
+        }
+        MPC_UNROLL for (int nt = 0; nt < NT; ++nt) {
+          const int c = 8 * nt + fr;
+          bf[nt] = (kk < NX && c < NC) ? Mk[kk * NC + c] : 0.0;
+        }
+        MPC_UNROLL for (int mt = 0; mt < MT1; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) dmma_8x8x4(af[mt], bf[nt], acc[mt][nt][0], acc[mt][nt][1]);
+      }
+      WSYNC();  // (every lane has read P and the previous T)
+      MPC_UNROLL for (int mt = 0; mt < MT1; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) MPC_UNROLL for (int h = 0; h < 2; ++h) {
+        const int i = 8 * mt + fr, c = 8 * nt + 2 * fk + h;
+        if (i < NX && c < NC) Tm[i * NC + c] = (c == NW) ? (affine ? acc[mt][nt][h] + PV[i] : 0.0) : acc[mt][nt][h];
+      }
+    }
+    WSYNC();
+    {  // [A B]' T + stage Hessian / gradient  ->  P (x rows, x columns), p (x rows, last column), HU (u rows)
+      double acc[MT2][NT][2];
+      MPC_UNROLL for (int mt = 0; mt < MT2; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+      MPC_UNROLL for (int kt = 0; kt < KT; ++kt) {
+        double af[MT2], bf[NT];
+        const int kk = 4 * kt + fk;
+        MPC_UNROLL for (int mt = 0; mt < MT2; ++mt) {
+          const int i = 8 * mt + fr;
+          af[mt] = (kk < NX && i < NW) ? Mk[kk * NC + i] : 0.0;
+        }
+        MPC_UNROLL for (int nt = 0; nt < NT; ++nt) {
+          const int c = 8 * nt + fr;
+          bf[nt] = (kk < NX && c < NC) ? Tm[kk * NC + c] : 0.0;
+        }
+        MPC_UNROLL for (int mt = 0; mt < MT2; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) dmma_8x8x4(af[mt], bf[nt], acc[mt][nt][0], acc[mt][nt][1]);
+      }
+      MPC_UNROLL for (int mt = 0; mt < MT2; ++mt) MPC_UNROLL for (int nt = 0; nt < NT; ++nt) MPC_UNROLL for (int h = 0; h < 2; ++h) {
+        const int i = 8 * mt + fr, c = 8 * nt + 2 * fk + h;
+        if (i < NW && c < NC) {
+          const double v = acc[mt][nt][h] + (c < NW ? hess(i, c) : grad(i));
+          if (i < NX) {
+            if (c < NX) Pm[i * NX + c] = v;
+            else if (c == NW) PV[i] = v;
+          } else {
+            HU[(i - NX) * NC + c] = v;
+          }
+        }
+      }
+    }
+    WSYNC();
+#else
     {  // T = P [A | B | b] + [0 | 0 | p]
       double acc[3][Tile<NX>::CPL];
       gemm_PM(Pm, Mk, lane, acc);
@@ -451,6 +553,7 @@ struct ChainEngine {
       }
     }
     WSYNC();
+#endif
     bool ok = true;
     if (ufixed) {
       if (lane < NK1) MPC_UNROLL for (int a_ = 0; a_ < NU; ++a_) KK[a_ * NK1 + lane] = 0.0;

@@ -36,6 +36,11 @@ CH_DEV double wmin(double v) {
 CH_DEV bool wany(bool p) { return __any_sync(0xffffffffu, p); }
 CH_DEV int wbcast_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 CH_DEV int atomic_next(int* counter) { return atomicAdd(counter, 1); }
+// FP64 tensor-core tile product (DMMA): C (8 x 8) += A (8 x 4) B (4 x 8), fragments in registers.
+//   lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and C[l / 4][2 (l % 4)], C[l / 4][2 (l % 4) + 1]
+CH_DEV void dmma_8x8x4(double a, double b, double& c0, double& c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 // ---- TMA (bulk asynchronous copy) feed of per-stage records: global -> shared, completion on an mbarrier ----
 // One elected lane arms the barrier with the byte count and issues cp.async.bulk; every lane waits on the

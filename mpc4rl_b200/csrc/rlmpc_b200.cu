@@ -616,6 +616,25 @@ __global__ void k_fp64_peak(double* out, int iters) {
   if (s == 12345.678) out[0] = s;  // keeps the loop alive
 }
 
+// FP64 tensor-core probe: 8 independent m8n8k4 accumulators per warp (DMMA), operands in registers
+__global__ void k_dmma_peak(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
+  const double a = 1.0 + 1e-3 * (threadIdx.x & 31), b = 1.0 - 1e-3 * (threadIdx.x & 7);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                   : "+d"(c[j][0]), "+d"(c[j][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == 12345.678) out[0] = s;
+}
+
 // MPC.reset: x_k = x0 for all stages, everything else zero
 template <class M>
 __global__ void k_reset(int N, double* it, int B, const double* x0, const int* mask) {
@@ -1110,7 +1129,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     memset(&pd, 0, sizeof(pd));
     pd.N = d->N;
     pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-    pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.comp_accept = 0.5;
+    pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.comp_accept = 0.2;
     memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
     memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
     memcpy(pd.mc, d->model_const, sizeof(pd.mc));
@@ -1182,7 +1201,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0; pd.comp_accept = 0.5;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0; pd.comp_accept = 0.2;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -1658,6 +1677,34 @@ int rlmpc_cartpole_env_step(const double* par_dev, int B, double* state_dev, con
   k_cartpole_env_step<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(par_dev, B, state_dev, action_dev, reward_dev,
                                                                        terminated_dev, truncated_dev, steps_dev);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rlmpc_fp64_tensor_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail(RLMPC_EINVAL, "bad arguments");
+  CUDA_OK(cudaSetDevice(device));
+  int sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  const int blocks = sms * 4, threads = 256, iters = 1 << 13;
+  double best = 0.0;
+  for (int r = 0; r < 6; ++r) {
+    CUDA_OK(cudaEventRecord(e0));
+    k_dmma_peak<<<blocks, threads>>>(d, iters);
+    CUDA_OK(cudaEventRecord(e1));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 512.0 * 8.0 * (double)iters * blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CUDA_OK(cudaGetLastError());
+  *tflops_out = best;
   return 0;
 }
 

@@ -58,7 +58,7 @@ def lib():
 
 
 def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0,
-            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20, lg=(), ug=(), condense=0, comp_accept=0.5) -> ProblemData:
+            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20, lg=(), ug=(), condense=0, comp_accept=0.2) -> ProblemData:
     pd = ProblemData()
     pd.sigma_min = sigma_min; pd.sigma0 = sigma0; pd.as_steps = as_steps; pd.condense = condense; pd.comp_accept = comp_accept
     pd.N = N; pd.max_ipm = max_ipm; pd.warm_ipm = warm_ipm; pd.param_cost = param_cost

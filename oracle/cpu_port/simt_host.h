@@ -100,6 +100,20 @@ inline double wmin(double v) {
 }
 inline bool wany(bool p) { return wmax(p ? 1.0 : 0.0) > 0.5; }
 inline int atomic_next(int* counter) { return (*counter)++; }
+// emulation of the m8n8k4 FP64 tensor-core product: fragments are exchanged through the group's scratch
+inline void dmma_8x8x4(double a, double b, double& c0, double& c1) {
+  simt::Group* g = simt::g_grp;
+  const int l = g->cur;
+  g->slot[l] = a;
+  g->slot[32 + l] = b;
+  simt::sync();
+  const int r = l / 4, n0 = 2 * (l % 4);
+  for (int k = 0; k < 4; ++k) {
+    c0 += g->slot[4 * r + k] * g->slot[32 + 4 * n0 + k];
+    c1 += g->slot[4 * r + k] * g->slot[32 + 4 * (n0 + 1) + k];
+  }
+  simt::sync();
+}
 
 struct StageFeed {
   double* buf[2];

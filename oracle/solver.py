@@ -42,64 +42,88 @@ class Solution:
 
 
 def _qp_ipm(H, c, G, g, J, hbar, free, tau, max_iter=200):
-    """min 1/2 d'Hd + c'd  s.t. Gd+g=0, Jd+hbar<=0, d[~free]=0; Mehrotra predictor-corrector.
-    Converges to the tau-central point lam*t = tau."""
+    """min 1/2 d'Hd + c'd  s.t. Gd+g=0, Jd+hbar<=0, d[~free]=0 -- primal-dual interior point, converging to the tau-central
+    point lam*t = tau.  First Mehrotra predictor-corrector; on hard QPs (an RTI step far from the solution: many rows
+    change sides) that heuristic can cycle, so a conservative long-step method (fixed centring, no corrector) takes over.
+    Raises if neither reaches the central point: a fixture must never hold an unconverged QP."""
     n, m, me = len(c), len(hbar), len(g)
     fi = np.where(free)[0]
     nf = len(fi)
     Hf, cf, Gf, Jf = H[np.ix_(fi, fi)], c[fi], G[:, fi], J[:, fi]
-    d = np.zeros(nf)
     if m == 0:
         K = np.block([[Hf, Gf.T], [Gf, np.zeros((me, me))]])
         sol = np.linalg.solve(K, -np.concatenate([cf, g]))
         out = np.zeros(n); out[fi] = sol[:nf]
         return out, sol[nf:], np.zeros(0), np.zeros(0), 0
-    t = np.maximum(-hbar, 1.0)
-    lam = np.ones(m)
-    pi = np.zeros(me)
-    for it in range(max_iter):
-        mu = float(lam @ t) / m
-        C = lam / t
-        Kmat = np.block([[Hf + Jf.T @ (C[:, None] * Jf), Gf.T], [Gf, np.zeros((me, me))]])
 
-        def solve(target):  # target = the vector "sigma*mu - corr" of the complementarity rows
-            rhs = -np.concatenate([cf + Jf.T @ (target / t + C * (t + hbar)), g])
-            sol = np.linalg.solve(Kmat, rhs)
-            dh, pih = sol[:nf], sol[nf:]
-            th = -(Jf @ dh + hbar)
-            lamh = target / t + C * (t - th)
-            return dh, pih, th, lamh
+    def run(mehrotra, iters):
+        d = np.zeros(nf)
+        t = np.maximum(-hbar, 1.0)
+        lam = np.ones(m)
+        pi = np.zeros(me)
+        a_prev = 1.0
+        settled = 0  # consecutive full Newton steps that ended on the central path
+        for it in range(iters):
+            mu = float(lam @ t) / m
+            C = lam / t
+            Kmat = np.block([[Hf + Jf.T @ (C[:, None] * Jf), Gf.T], [Gf, np.zeros((me, me))]])
 
-        def steplen(dt, dl):
-            a = 1.0
-            neg = dt < 0
-            if neg.any():
-                a = min(a, float(np.min(-t[neg] / dt[neg])))
-            neg = dl < 0
-            if neg.any():
-                a = min(a, float(np.min(-lam[neg] / dl[neg])))
-            return a
+            def solve(target):  # target = the vector "sigma*mu - corr" of the complementarity rows
+                rhs = -np.concatenate([cf + Jf.T @ (target / t + C * (t + hbar)), g])
+                sol = np.linalg.solve(Kmat, rhs)
+                dh, pih = sol[:nf], sol[nf:]
+                th = -(Jf @ dh + hbar)
+                lamh = target / t + C * (t - th)
+                return dh, pih, th, lamh
 
-        # predictor (affine scaling towards tau)
-        dh, pih, th, lamh = solve(np.full(m, min(tau, mu)))
-        dta, dla = th - t, lamh - lam
-        a_aff = steplen(dta, dla)
-        mu_aff = float((lam + a_aff * dla) @ (t + a_aff * dta)) / m
-        sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
-        target = np.maximum(sigma * mu, tau) - dta * dla
-        dh, pih, th, lamh = solve(target)
-        dt_, dl_ = th - t, lamh - lam
-        a = min(1.0, 0.995 * steplen(dt_, dl_)) if steplen(dt_, dl_) < 1.0 else 1.0
-        step = np.linalg.norm(a * (dh - d), np.inf)
-        d = d + a * (dh - d)
-        pi = pi + a * (pih - pi)
-        t = t + a * dt_
-        lam = lam + a * dl_
-        comp = np.max(np.abs(lam * t - tau))
-        if a == 1.0 and comp < 1e-3 * tau and step < 1e-13 * (1 + np.linalg.norm(d, np.inf)):
-            break
+            def steplen(dt, dl):
+                a = 1.0
+                neg = dt < 0
+                if neg.any():
+                    a = min(a, float(np.min(-t[neg] / dt[neg])))
+                neg = dl < 0
+                if neg.any():
+                    a = min(a, float(np.min(-lam[neg] / dl[neg])))
+                return a
+
+            if mehrotra:
+                dh, pih, th, lamh = solve(np.full(m, min(tau, mu)))  # predictor (affine scaling towards tau)
+                dta, dla = th - t, lamh - lam
+                a_aff = steplen(dta, dla)
+                mu_aff = float((lam + a_aff * dla) @ (t + a_aff * dta)) / m
+                sigma = (mu_aff / mu) ** 3 if mu > 0 else 0.0
+                target = np.maximum(sigma * mu, tau) - dta * dla
+                frac = 0.995
+            else:
+                sigma = 0.1 if a_prev > 0.9 else 0.5
+                target = np.full(m, max(sigma * mu, tau))
+                frac = 0.9
+            dh, pih, th, lamh = solve(target)
+            dt_, dl_ = th - t, lamh - lam
+            amax = steplen(dt_, dl_)
+            a = min(1.0, frac * amax) if amax < 1.0 else 1.0
+            step = np.linalg.norm(a * (dh - d), np.inf)
+            d = d + a * (dh - d)
+            pi = pi + a * (pih - pi)
+            t = t + a * dt_
+            lam = lam + a * dl_
+            a_prev = a
+            comp = np.max(np.abs(lam * t - tau))
+            settled = settled + 1 if (a == 1.0 and comp < 1e-3 * tau) else 0
+            # a fixed point of the Newton iteration: the step has vanished, or (rounding of lam/t ~ 1e16 keeps it from
+            # vanishing exactly) three full steps in a row stayed on the central path
+            if settled >= 1 and (step < 1e-13 * (1 + np.linalg.norm(d, np.inf)) or settled >= 3):
+                return d, pi, lam, t, it + 1, True
+        return d, pi, lam, t, iters, False
+
+    d, pi, lam, t, it, ok = run(True, min(max_iter, 60))
+    if not ok:
+        d, pi, lam, t, it2, ok = run(False, 400)
+        it += it2
+    if not ok:
+        raise RuntimeError("oracle QP: the interior-point iteration did not reach the tau-central point")
     out = np.zeros(n); out[fi] = d
-    return out, pi, lam, t, it + 1
+    return out, pi, lam, t, it
 
 
 class DenseSolver:
