@@ -99,10 +99,10 @@ FLOPS_SOURCE = "profiles/r02_flops_*.csv (smsp__sass_thread_inst_executed_op_{df
 TRAFFIC_PER_STEP = {"cartpole": None, "cartpole_tiny_pert": None, "chain_mass": None}  # dram read + write bytes of one step
 
 
-def config_dict(B, n_gpus, workload="cartpole", scaling="weak"):
+def config_dict(B, n_gpus, workload="cartpole", scaling="weak", graph=False):
     return {"workload": WORKLOADS[workload]["text"],
             "batch_per_gpu": B, "global_batch": B * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, replicated theta)",
-            "scaling": scaling,
+            "scaling": scaling, "cuda_graph": bool(graph),
             "l2": "working set (iterate + stage scratch, > 1.5 GB per GPU) is larger than L2, no flush needed",
             "seed": 1234}
 
@@ -438,7 +438,8 @@ def run_gpu(args, rank, world, local_rank):
     mpc = BatchedMPC(spec, max_batch=B, device=local_rank)
     chain = args.workload.startswith("chain_mass")
     mpc.set_option("tol", 1e-6)
-    mpc.set_option("timing", 1)
+    if args.graph:
+        mpc.set_option("graph", 1)
     split_opt = 2.0  # library default; "--opt split=n" overrides
     for kv in args.opt:
         k, v = kv.split("=")
@@ -491,6 +492,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- per-kernel device times: replay of the first timed steps with the library's phase events, un-split ----
     phase_ms, queue, n_ph = {}, {}, min(3, args.steps)
+    mpc.set_option("timing", 1)
     mpc.set_option("split", 1)
     W.rewind(mpc)
     for i in range(args.warmup + n_ph):
@@ -504,6 +506,7 @@ def run_gpu(args, rank, world, local_rank):
                     phase_ms[k] = phase_ms.get(k, 0.0) + v / n_ph
     if not chain:
         mpc.set_option("split", split_opt)
+    mpc.set_option("timing", 0)
 
     # ---- e2e: host buffers through the C ABI, every step; the same states, replayed ----
     xs_host = [W.logged(i).cpu().pin_memory().numpy() for i in range(n_steps)]
@@ -555,7 +558,7 @@ def run_gpu(args, rank, world, local_rank):
         line = {
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_dict(B, world, args.workload, args.scaling),
+            "dtype": "f64", "data": "synthetic", "config": config_dict(B, world, args.workload, args.scaling, args.graph),
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
@@ -612,6 +615,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--literal-samples", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the RTI kernel chain as a CUDA graph (engine option graph=1)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -118,6 +118,11 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * "split" (2): an RTI solve(+sens) call on >= 4096 samples runs the two halves of the batch as two independent
  * chains of kernels on two streams (the caller's and an internal one, joined before the call returns to the
  * stream): kernels bound by different units overlap; 1 = one chain; rlmpc_get_timings then describes the first half,
+ * "step_length" (1.0): fixed SQP step length on the primal variables, acados' nlp_solver_step_length.  Full steps
+ * (the reference's setting) 2-cycle on ~8 % of random cart-pole swing-up states; 0.7 converges those at a linear rate,
+ * "graph" (0): 1 = an RTI solve+sens call is captured into a CUDA graph on first use and replayed while its arguments
+ * (mode, batch, every pointer, the options) stay the same; for small batches, where the chain of ~14 launches on two
+ * streams is launch-bound (strong scaling over 8 GPUs: 8 192 samples per rank).  Not combined with "timing",
  * "as_steps" (20): active-set (full Newton step + projection) iterations a warm start may take when
  * its Newton step is infeasible, before it falls back to a cold start,
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */

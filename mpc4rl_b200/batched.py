@@ -287,5 +287,13 @@ class IterateStore:
     def save(self, idx: torch.Tensor) -> None:
         self._copy(idx, 1)
 
+    def load_into(self, other: "BatchedMPC", idx: torch.Tensor) -> None:
+        """Stored iterates -> batch positions of ANOTHER engine of the same problem (e.g. the actor's iterates as the
+        critic's warm start)."""
+        if other.spec.model != self.engine.spec.model or other.spec.N != self.engine.spec.N or other.nrows != self.engine.nrows:
+            raise ValueError("load_into needs an engine of the same problem")
+        i = idx.to(other.device, torch.int32).contiguous()
+        _cabi.check(other.lib.rlmpc_store_copy(other._h, i.numel(), _ptr(i), _ptr(self.buf), self.capacity, 0, other._stream()))
+
     def load(self, idx: torch.Tensor) -> None:
         self._copy(idx, 0)

@@ -881,7 +881,7 @@ struct ChainEngine {
     if (failed || minstep) return R_FAILED;
 
     // ---- the step: w += ap dw, (lam, t) as updated, pi from the costate recursion of the QP ----
-    const double ap = converged ? 1.0 : alpha;
+    const double ap = (converged ? 1.0 : alpha) * pd.step_length;
     for (int e = lane; e < N * NR; e += 32) { it[it_lam(N, 0) + e] = LAM[e]; it[it_t(N, 0) + e] = TT[e]; }
     for (int e = lane; e < N * NU; e += 32) it[it_u(N, 0) + e] = UU[e] + ap * DU[e];
     // pi_{k-1} = q_k + s_k Q dx_k + A_k' pi_k  (k = N: terminal cost), x_k += ap dx_k

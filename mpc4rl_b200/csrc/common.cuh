@@ -57,6 +57,9 @@ struct ProblemData {
   double condense;      // > 0: queued QPs are solved in partially condensed form (condense.cuh) where applicable
   double comp_accept;   // a Newton step / interior-point solve is accepted when it is a full step and every row ends
                         // within lam*t = tau (1 +- comp_accept), i.e. max |dlam dt| <= comp_accept * tau
+  double step_length;   // fixed SQP step length on the primal variables (acados: nlp_solver_step_length, default 1):
+                        // w += step_length * dw; the multipliers are the QP's.  < 1 cures the 2-cycles of full-step
+                        // Gauss-Newton SQP at the price of a linear rate
   double scale[MAXN + 1];  // per-stage cost scaling s_k (dT, gamma^k dT, ...)
   double lbu[MAXD], ubu[MAXD];
   double lbx[MAXD], ubx[MAXD];      // stages 1..N-1, indexed by state component

@@ -464,7 +464,7 @@ struct CoopQP {
     if (failed || minstep) return E::FULL_FAILED;
 
     // ---------------- the step                                      [Engine::apply_step] ----------------
-    const double ap = converged ? 1.0 : alpha;  // iteration limit: damped primal step
+    const double ap = (converged ? 1.0 : alpha) * pd.step_length;  // iteration limit: damped primal step
     for (int k = lane; k < NS; k += 32) {
       const bool act = k >= k_first && k < N;
       const double ll = (act && has_l) ? LL[k] + alpha * (LHL[k] - LL[k]) : 0.0;

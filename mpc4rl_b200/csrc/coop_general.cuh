@@ -429,7 +429,7 @@ struct CoopGen {
     if (failed || minstep) return E::FULL_FAILED;
 
     // ---------------- the step                                      [Engine::apply_step] ----------------
-    const double ap = converged ? 1.0 : alpha;
+    const double ap = (converged ? 1.0 : alpha) * pd.step_length;
     for (int k = lane; k < NS; k += 32) {
       double dw[NW], lam[NR];
 #pragma unroll

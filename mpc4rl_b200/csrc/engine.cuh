@@ -1089,7 +1089,7 @@ struct Engine {
   // damp_primal: the QP was not solved (iteration limit): move the primal variables by alpha * dw
   // only, the interior iterate of the method, instead of the full Newton target.
   MPC_HD static void apply_step(const ProblemData& pd, const Lane& L, double alpha, bool clip, bool damp_primal = false) {
-    const double ap = damp_primal ? alpha : 1.0;
+    const double ap = (damp_primal ? alpha : 1.0) * pd.step_length;
     const int N = pd.N;
     constexpr size_t bs = TILE;
     double pik[NX];  // pi_k (multiplier of x_{k+1} = F(x_k,u_k))

@@ -739,6 +739,12 @@ struct rlmpc_handle {
   double *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
   int *h_status = nullptr, *d_status = nullptr;
   cudaStream_t own_stream = nullptr;
+  // CUDA graph of the RTI solve+sens chain (option "graph"): captured on the first call with a given argument set,
+  // replayed while the arguments (mode, batch, every pointer, options) stay the same -- small batches are launch-bound
+  int use_graph = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  unsigned long long graph_key = 0;
+  long long graph_launches = 0;
   cudaEvent_t ev_last = nullptr;  // recorded after every stream-ordered call: the host entry point waits for it
   bool ev_last_set = false;
 };
@@ -1044,6 +1050,39 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
   a.dL = dL; a.dpi = dpi; a.res_out = res_out;
   int rc = fail(RLMPC_EINVAL, "unknown model");
   if (part < 0) {
+    const bool graphable = h->use_graph && do_solve && do_sens && max_sqp == 1 && !h->timing && !h->overlap;
+    if (graphable) {
+      // FNV-1a over everything the captured kernels bake in
+      unsigned long long key = 1469598103934665603ull;
+      auto mix = [&](const void* p, size_t n) {
+        const unsigned char* c = (const unsigned char*)p;
+        for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
+      };
+      mix(&a, sizeof(a)); mix(&h->pd, sizeof(h->pd)); mix(&h->split, sizeof(int)); mix(&h->coop, sizeof(int));
+      mix(&h->th_per_sample, sizeof(int)); mix(&s, sizeof(s));
+      if (h->graph_exec && key == h->graph_key) {
+        CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
+        h->launches += h->graph_launches;
+        return 0;
+      }
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+      const long long l0 = h->launches;
+      cudaGraph_t g = nullptr;
+      // (the legacy default stream cannot be captured: capture on the handle's own stream, the graph is launched on s)
+      cudaStream_t cs = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) ? h->own_stream : s;
+      CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      DISPATCH_MODEL(h, rc = pipeline<M>(h, a, do_solve, do_sens, cs));
+      cudaError_t ec = cudaStreamEndCapture(cs, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ec != cudaSuccess) return fail(RLMPC_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ec));
+      ec = cudaGraphInstantiate(&h->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (ec != cudaSuccess) { h->graph_exec = nullptr; return fail(RLMPC_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ec)); }
+      h->graph_key = key;
+      h->graph_launches = h->launches - l0;
+      CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
+      return 0;
+    }
     DISPATCH_MODEL(h, rc = pipeline<M>(h, a, do_solve, do_sens, s));
     return rc;
   }
@@ -1129,7 +1168,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
     memset(&pd, 0, sizeof(pd));
     pd.N = d->N;
     pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-    pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.comp_accept = 0.2;
+    pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.comp_accept = 0.2; pd.step_length = 1.0;
     memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
     memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
     memcpy(pd.mc, d->model_const, sizeof(pd.mc));
@@ -1201,7 +1240,7 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   memset(&pd, 0, sizeof(pd));
   pd.N = d->N;
   pd.mode = MODE_V; pd.max_sqp = 1; pd.max_ipm = 50; pd.warm_ipm = 1; pd.param_cost = 0;
-  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0; pd.comp_accept = 0.2;
+  pd.tol = 1e-6; pd.tau = 1e-8; pd.mu0 = 1.0; pd.sigma_min = 0.05; pd.sigma0 = 0.3; pd.as_steps = 20; pd.condense = 0; pd.comp_accept = 0.2; pd.step_length = 1.0;
   memcpy(pd.scale, d->scale, sizeof(double) * (d->N + 1));
   memcpy(pd.lbu, d->lbu, sizeof(pd.lbu)); memcpy(pd.ubu, d->ubu, sizeof(pd.ubu));
   memcpy(pd.lbx, d->lbx, sizeof(pd.lbx)); memcpy(pd.ubx, d->ubx, sizeof(pd.ubx));
@@ -1287,6 +1326,7 @@ void rlmpc_destroy(rlmpc_handle* h) {
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_status); cudaFreeHost(h->h_counters);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_last) cudaEventDestroy(h->ev_last);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   for (int i = 0; i < rlmpc_handle::NEV; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -1415,7 +1455,9 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "ring_b")) h->ring_b = (int)value;
   else if (!strcmp(name, "coop")) h->coop = (int)value;
   else if (!strcmp(name, "comp_accept")) h->pd.comp_accept = value;
+  else if (!strcmp(name, "step_length")) { if (!(value > 0.0 && value <= 1.0)) return fail(RLMPC_EINVAL, "step_length must be in (0, 1]"); h->pd.step_length = value; }
   else if (!strcmp(name, "split")) h->split = (int)value;
+  else if (!strcmp(name, "graph")) h->use_graph = (int)value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);

@@ -21,7 +21,7 @@ class ProblemData(C.Structure):
         ("N", C.c_int), ("mode", C.c_int), ("max_sqp", C.c_int), ("max_ipm", C.c_int),
         ("warm_ipm", C.c_int), ("param_cost", C.c_int), ("fix0", C.c_int),
         ("tol", C.c_double), ("tau", C.c_double), ("mu0", C.c_double),
-        ("sigma_min", C.c_double), ("sigma0", C.c_double), ("as_steps", C.c_double), ("condense", C.c_double), ("comp_accept", C.c_double),
+        ("sigma_min", C.c_double), ("sigma0", C.c_double), ("as_steps", C.c_double), ("condense", C.c_double), ("comp_accept", C.c_double), ("step_length", C.c_double),
         ("scale", C.c_double * (MAXN + 1)),
         ("lbu", C.c_double * MAXD), ("ubu", C.c_double * MAXD),
         ("lbx", C.c_double * MAXD), ("ubx", C.c_double * MAXD),
@@ -58,9 +58,9 @@ def lib():
 
 
 def make_pd(N, scale, lbu, ubu, mc, tol=1e-6, tau=1e-8, mu0=1.0, max_ipm=50, warm_ipm=0, param_cost=0,
-            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20, lg=(), ug=(), condense=0, comp_accept=0.2) -> ProblemData:
+            lbx=(), ubx=(), lbx_e=(), ubx_e=(), sigma_min=0.05, sigma0=0.3, zl=(), zu=(), as_steps=20, lg=(), ug=(), condense=0, comp_accept=0.2, step_length=1.0) -> ProblemData:
     pd = ProblemData()
-    pd.sigma_min = sigma_min; pd.sigma0 = sigma0; pd.as_steps = as_steps; pd.condense = condense; pd.comp_accept = comp_accept
+    pd.sigma_min = sigma_min; pd.sigma0 = sigma0; pd.as_steps = as_steps; pd.condense = condense; pd.comp_accept = comp_accept; pd.step_length = step_length
     pd.N = N; pd.max_ipm = max_ipm; pd.warm_ipm = warm_ipm; pd.param_cost = param_cost
     pd.tol = tol; pd.tau = tau; pd.mu0 = mu0
     for i, v in enumerate(scale):

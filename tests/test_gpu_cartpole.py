@@ -406,3 +406,31 @@ def test_cost_parameter_columns_match_oracle(spec):
     # a second call into the same output buffers must not accumulate on top of the first
     out2 = m.solve_sens(x0, max_sqp=1, out=out)
     assert _rel(out2["dpi"].cpu().numpy()[ok], g["dpi"][ok]) < 1e-5
+
+
+@pytest.mark.parametrize("B", [512, 8192])
+def test_cuda_graph_replay_is_bit_identical(spec, B):
+    """Option "graph": the RTI kernel chain (two streams for B >= 4096) captured once and replayed gives exactly the
+    results of the eagerly launched chain, step after step, also when the inputs change in place."""
+    from mpc4rl_b200 import BatchedMPC
+
+    torch.manual_seed(3)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2.0 * lo) * torch.rand(B, 4, dtype=torch.float64)).cuda()
+    outs = []
+    for graph in (0, 1):
+        m = BatchedMPC(spec, max_batch=B, device=0)
+        m.set_option("graph", graph)
+        m.reset(x0)
+        m.solve(x0, max_sqp=50)
+        x = x0.clone()
+        out = m.alloc_outputs(B)
+        res = []
+        for i in range(4):
+            x.add_(1e-2 * torch.sin(torch.arange(B * 4, device="cuda", dtype=torch.float64).reshape(B, 4) + i))
+            m.solve_sens(x, max_sqp=1, out=out)
+            res.append({k: v.clone() for k, v in out.items()})
+        outs.append(res)
+    for a, b in zip(*outs):
+        for k in ("u0", "cost", "dL", "dpi", "status", "res"):
+            assert torch.equal(a[k], b[k]), k

@@ -105,15 +105,15 @@ def test_strict_acceptance_gives_the_same_step(g):
     """What the default acceptance neighbourhood (comp_accept = 0.2) costs in accuracy: the RTI result with a strict
     setting (0.02) differs from the default's by far less than the tolerance the tests above allow."""
     B = g["x0"].shape[0]
-    res = []
+    res, conv = [], []
     for ca in (0.2, 0.02):
         spec, mpc = _engine(B)
         mpc.set_option("comp_accept", ca)
         x0 = _T(g["x0"])
         mpc.reset(x0)
-        mpc.solve(x0, max_sqp=300)
+        conv.append(mpc.solve(x0, max_sqp=300)[2] == 0)  # (where SQP 2-cycles the two runs stop at different iterates)
         res.append(mpc.solve_sens(_T(g["x1"]), max_sqp=1))
-    ok = ((res[0]["status"] == 0) & (res[1]["status"] == 0)).cpu().numpy()
+    ok = (conv[0] & conv[1] & (res[0]["status"] == 0) & (res[1]["status"] == 0)).cpu().numpy()
     assert ok.mean() > 0.85
     du = (res[0]["u0"] - res[1]["u0"]).abs().cpu().numpy()[ok].max()
     ddpi = (res[0]["dpi"] - res[1]["dpi"]).abs().cpu().numpy()[ok].max() / res[1]["dpi"].abs().cpu().numpy()[ok].max()
