@@ -26,7 +26,7 @@ from ..problems import cartpole_original_config, cartpole_spec
 
 
 def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float = 2e-3, device: int = 0,
-        explore: float = 0.05, seed: int = 0, critic_sqp: int = 40, critic_step_length: float = 0.7, verbose: bool = True):
+        explore: float = 0.05, seed: int = 0, critic_sqp: int = 80, critic_step_length: float = 0.5, verbose: bool = True):
     """``lr`` is a RELATIVE step size: theta moves along mean_i(td_i dQ_i/dtheta) (the reference's semi-gradient
     Q-learning direction, examples/linear_system_mpc_qlearning.py:203) by at most ``lr`` of its own magnitude per
     environment step, and is projected onto physical values (masses and length within [0.2, 5] x nominal).  The
@@ -36,7 +36,7 @@ def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float 
     dev = torch.device("cuda", device)
     actor = BatchedMPC(spec, max_batch=num_envs, device=device)    # owns one warm start per environment
     critic = BatchedMPC(spec, max_batch=num_envs, device=device)   # warm-started from the actor's iterate of the same state
-    critic.set_option("tol", 1e-5)
+    critic.set_option("tol", 1e-4)  # (update_nlp's own acceptance thresholds are 1e-3 / 1e-4, nlp.py:1513-1537)
     # full-step Gauss-Newton SQP 2-cycles on part of the swing-up (all environments pass through it together); a fixed
     # step length < 1 (acados: nlp_solver_step_length) converges there
     critic.set_option("step_length", critic_step_length)
@@ -76,11 +76,14 @@ def run(num_envs: int = 4096, n_steps: int = 50, gamma: float = 0.99, lr: float 
             log.append(dict(step=t, mean_td=float((acc[-2] / n_valid).item()), n_valid=int(acc[-1].item()),
                             mean_cost=float(prev["cost"].mean().item()), theta=theta[:ng].cpu().numpy().copy(),
                             actor_bad=int((out["status"] != 0).sum().item()), critic_bad=int((q["status"] != 0).sum().item()),
-                            critic_res=float(q["res"].max(dim=1).values.median().item())))
+                            critic_res=float(q["res"].max(dim=1).values.median().item()),
+                            critic_codes=torch.bincount(q["status"].long(), minlength=5).tolist(),
+                            actor_codes=torch.bincount(out["status"].long(), minlength=5).tolist()))
             if verbose and rank == 0:
                 print(f"step {t}: mean cost {log[-1]['mean_cost']:.3f} mean TD {log[-1]['mean_td']:.3f} "
                       f"valid {log[-1]['n_valid']} (actor bad {log[-1]['actor_bad']}, critic bad {log[-1]['critic_bad']}, "
-                      f"critic KKT median {log[-1]['critic_res']:.1e}) theta {log[-1]['theta']}", flush=True)
+                      f"critic KKT median {log[-1]['critic_res']:.1e}; status codes actor {log[-1]['actor_codes']} critic "
+                      f"{log[-1]['critic_codes']}) theta {log[-1]['theta']}", flush=True)
         store.save(slots)
         a = 2.0 * (u_t - lo) / (hi - lo) - 1.0
         a = (a + explore * torch.randn(a.shape, generator=g, dtype=torch.float64).to(dev)).clamp(-1.0, 1.0)

@@ -122,10 +122,15 @@ def test_vector_env_matches_reference_dynamics():
 def test_closed_loop_actor_critic_example_runs():
     from mpc4rl_b200.examples.cartpole_mpc_actor_critic import run
 
-    log = run(num_envs=96, n_steps=6, verbose=False)
-    assert len(log) == 5
-    assert all(np.isfinite(l["mean_td"]) and l["n_valid"] > 48 for l in log)
-    assert not np.array_equal(log[0]["theta"], log[-1]["theta"])
+    log = run(num_envs=96, n_steps=24, verbose=False)
+    assert len(log) == 23
+    # every environment contributes (the critic is warm-started from the actor's iterate and uses a damped SQP step)
+    assert all(np.isfinite(l["mean_td"]) and l["n_valid"] >= 0.9 * 96 for l in log), [l["n_valid"] for l in log]
+    th = np.array([l["theta"] for l in log])
+    assert not np.array_equal(th[0], th[-1])
+    assert (th > 0.2 * th[0] - 1e-12).all() and (th < 5.0 * th[0] + 1e-12).all()  # projected onto physical values
+    assert np.abs(th[-1] / th[0] - 1.0).max() < 24 * 2e-3 + 1e-9                      # relative step size bound
+    assert log[-1]["mean_cost"] < log[0]["mean_cost"]                                # the swing-up makes progress
 
 
 def test_iterate_store_keeps_rti_accurate(golden):
