@@ -31,9 +31,18 @@ namespace {
     }                                                                                \
   } while (0)
 
-constexpr int STAGE_WARPS = 4;  // warps per block of the (sample, stage) kernel
-constexpr int QP_WARPS = 2;     // samples in flight per block of the per-sample kernels
-constexpr int SENS_WARPS = 2;
+#ifndef CHAIN_STAGE_WARPS
+#define CHAIN_STAGE_WARPS 4
+#endif
+#ifndef CHAIN_QP_WARPS
+#define CHAIN_QP_WARPS 2
+#endif
+#ifndef CHAIN_SENS_WARPS
+#define CHAIN_SENS_WARPS 1
+#endif
+constexpr int STAGE_WARPS = CHAIN_STAGE_WARPS;  // warps per block of the (sample, stage) kernel
+constexpr int QP_WARPS = CHAIN_QP_WARPS;        // samples in flight per block of the per-sample kernels
+constexpr int SENS_WARPS = CHAIN_SENS_WARPS;
 
 template <int NM>
 __global__ void k_chain_begin(const __grid_constant__ ProblemData pd, const ChainArgs a) {
