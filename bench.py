@@ -91,12 +91,22 @@ WORKLOADS = {
                          text="chain_mass n_mass=6 nx=27 nu=3 N=40 ntheta=800 (all with gradient), V-mode SQP-RTI (K=1) + dL/dtheta + "
                               "dpi/dtheta, warm-started from the previous iterate; x0 = define_x0 + N(0, 1e-2) redrawn every step"),
 }
-# Executed FP64 flops per unit (2 * DFMA + DADD + DMUL thread-level instructions, summed over the kernels of one step,
-# divided by the units of the step): ncu counters of the committed profile runs, see profiles/r02_summary.md.
-# None = not measured for this workload.
-FLOPS_PER_UNIT = {"cartpole": None, "cartpole_tiny_pert": None, "chain_mass": None}
-FLOPS_SOURCE = "profiles/r02_flops_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel)"
-TRAFFIC_PER_STEP = {"cartpole": None, "cartpole_tiny_pert": None, "chain_mass": None}  # dram read + write bytes of one step
+# Executed FP64 flops per unit: 2 * DFMA + DADD + DMUL thread-level instructions summed over the kernels of one step and
+# divided by the units of the step -- ncu counters of the committed step profiles (profiles/r02_step_<workload>.csv,
+# tools/profile_step.py, summarised in profiles/r02_summary.md).  The chain-mass kernels also run FP64 tensor-core
+# instructions (mma.sync m8n8k4 = 512 flop per warp instruction, zero padding of 21 -> 24 included); their count is
+# structural: per sample 40 stages x 144 per Riccati factorisation (one per interior-point iteration of the step + one
+# in the sensitivity sweep) and 40 x 8 x 27 in the Hessian accumulation.  None = not measured for this workload.
+FLOPS_PER_UNIT = {"cartpole": 629630.0, "cartpole_tiny_pert": 291358.0, "chain_mass": 10342403.0}
+FLOPS_SOURCE = "profiles/r02_step_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel) + structural DMMA count"
+# dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step (same profiles)
+TRAFFIC_PER_STEP = {"cartpole": 9.531e9, "cartpole_tiny_pert": 9.289e9, "chain_mass": 31.003e9}
+
+
+def dmma_flops_per_unit(workload, ipm_iters_mean):
+    if workload != "chain_mass":
+        return 0.0
+    return 512.0 * (40 * 144 * (ipm_iters_mean + 1.0) + 40 * 8 * 27)
 
 
 def config_dict(B, n_gpus, workload="cartpole", scaling="weak", graph=False):
@@ -550,6 +560,8 @@ def run_gpu(args, rank, world, local_rank):
         achieved = B * wl["b_alg"] / (kernel_ms * 1e-3) / 1e9
         fp64_peak = mpc.fp64_peak_tflops()
         fpu = FLOPS_PER_UNIT.get(args.workload)
+        if fpu is not None:
+            fpu += dmma_flops_per_unit(args.workload, queue.get("queue_ipm_iters", 0.0) / B)
         fp64 = {"peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in this run: rlmpc_fp64_peak (FMA probe kernel, FMA = 2 flop)"}
         if fpu is not None:
             fa = B * fpu / (kernel_ms * 1e-3) / 1e12
@@ -565,7 +577,7 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": TRAFFIC_PER_STEP.get(args.workload) if B == wl["batch"] else None,
-                         "traffic_source": "profiles/r02_launches_*.csv (dram read + write bytes summed over the kernels of one step)",
+                         "traffic_source": "profiles/r02_step_*.csv (dram read + write bytes summed over the kernels of one step, ncu)",
                          "peak_source": peak_src,
                          "kernel": ("rlmpc_solve_sens = k_chain_stage<lin> + k_chain_qp + k_chain_stage<hess> + k_chain_sens + k_chain_param"
                                     if chain else "rlmpc_solve_sens = k_lin + k_qp1 + k_qp3 + k_sens_stage + k_sens_sweep") + f" (dominant: {dom})",
