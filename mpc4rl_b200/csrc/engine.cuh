@@ -1056,6 +1056,18 @@ struct Engine {
         // infeasible Newton step of a warm start: full step + projection instead of a short step
         ++as_iters;
         mu = ipm_project(pd, L) / m_rows;
+#ifdef AS_TRACE  // host debugging aid: the active set after every active-set step (NU = 1 problems)
+        {
+          char buf[MAXN + 1];
+          int n = 0;
+          for (int k = 0; k < N; ++k) {
+            const double tl = L.it[(size_t)it_t(N, k) * TILE], tu = L.it[(size_t)(it_t(N, k) + NV) * TILE];
+            buf[n++] = tl < 1e-6 ? 'L' : (tu < 1e-6 ? 'U' : '.');
+          }
+          buf[n] = 0;
+          printf("   as %2d amax %.3g  %s\n", as_iters, S.amax, buf);
+        }
+#endif
         alpha = 0.0;
         sigma = pd.sigma_min;
         continue;
