@@ -58,7 +58,8 @@ typedef struct rlmpc_problem_desc {
   double lbu[RLMPC_MAXD], ubu[RLMPC_MAXD]; /* input bounds, all stages (constraints.lbu/ubu) */
   double lbx[RLMPC_MAXD], ubx[RLMPC_MAXD]; /* state bounds stages 1..N-1 (+-1e30 = none) */
   double lbx_e[RLMPC_MAXD], ubx_e[RLMPC_MAXD];
-  double model_const[24];           /* cartpole: [0]=RK4 step h, [1]=g; linear system: [0..2] = P11,P12,P22 of
+  double model_const[24];           /* cartpole: [0]=RK4 step h, [1]=g, [2] != 0: g is a learnable parameter, theta =
+                                       [M, m, l, g | W_0 ...] with 84 entries (scripts/cartpole_mpc_qlearning.py:184-187); linear system: [0..2] = P11,P12,P22 of
                                        the constant terminal cost (linear_system/acados.py:51-57); evaporation:
                                        [0..18] = environment.PARAM in dict order, [19] = RK4 step, [20] = #steps;
                                        chain mass: [0] = RK4 step (Ts / 2: two steps per stage, ocp_utils.py:42-56),

@@ -19,6 +19,7 @@ namespace rlmpc {
 constexpr int MAXN = 128;  // max horizon supported by ProblemData
 constexpr int MAXD = 8;    // max nx / nu held in ProblemData bound arrays (thread-per-sample engine)
 constexpr double BIG = 1e29;  // |bound| >= BIG means "no bound"
+constexpr double AS_RELEASE = 0.5;  // active-set step: slack given to a released row, as a fraction of the row's range
 // Samples are stored in tiles of TILE (one warp): element i of the sample in lane l of tile T lives
 // at base[(T * size + i) * TILE + l].  A warp access to element i is one contiguous 256-byte run
 // (fully coalesced) and, because TILE is a compile-time constant, every element offset inside a

@@ -428,7 +428,7 @@ struct CoopQP {
             double ll = LL[k], tl;
             const double lh = LHL[k], th = THL[k];
             if (!(th > eps_t)) { tl = eps_t; ll = dmax(dmax(lh, ll), 1e-3); }
-            else if (!(lh > 0.0)) { tl = th; ll = pd.tau / th; }
+            else if (!(lh > 0.0)) { tl = dmax(th, AS_RELEASE * range); ll = pd.tau / tl; }
             else { tl = th; ll = lh; }
             LL[k] = ll; TL[k] = tl;
             m2 += ll * tl;
@@ -437,7 +437,7 @@ struct CoopQP {
             double lu = LU[k], tu;
             const double lh = LHU[k], th = THU[k];
             if (!(th > eps_t)) { tu = eps_t; lu = dmax(dmax(lh, lu), 1e-3); }
-            else if (!(lh > 0.0)) { tu = th; lu = pd.tau / th; }
+            else if (!(lh > 0.0)) { tu = dmax(th, AS_RELEASE * range); lu = pd.tau / tu; }
             else { tu = th; lu = lh; }
             LU[k] = lu; TU[k] = tu;
             m2 += lu * tu;

@@ -1,10 +1,11 @@
 // Cart-pole swing-up model of the reference (rlmpc/mpc/cartpole/acados.py:28-108):
-//   x = [s, s_dot, theta, theta_dot], u = [F], model parameters (M, m, l), g fixed.
+//   x = [s, s_dot, theta, theta_dot], u = [F], model parameters (M, m, l) with g fixed (the YAML default), or
+//   (M, m, l, g) when a driver un-fixes g (scripts/cartpole_mpc_qlearning.py:184-187: 84 parameters).
 //   x+ = ONE explicit RK4 step of length h = tf/N/sim_method_num_stages (quirk Q1,
 //   cartpole/acados.py:86-92, rlmpc/common/integrator.py:6-33).
 //   cost y = [x;u], y_e = x (acados.py:104-106), NONLINEAR_LS with W_0/W/W_e, yref_*.
 // theta layout (rlmpc/mpc/nlp.py:970-989, CasADi column-major):
-//   [M, m, l | W_0(25) | W(25) | W_e(16) | yref_0(5) | yref(5) | yref_e(4)]  = 83
+//   [M, m, l (, g) | W_0(25) | W(25) | W_e(16) | yref_0(5) | yref(5) | yref_e(4)]  = 83 (84)
 //
 // First/second derivatives of the RK4 map are built by hand-written forward/adjoint
 // propagation around sympy-generated leaf code (cartpole_gen.cuh) -- this replaces the
@@ -17,14 +18,18 @@ namespace rlmpc {
 #include "cartpole_gen.cuh"
 
 // NBX_ = number of box-constrained states on stages 1..N (0: config/cartpole_original.yaml,
-// 4: config/cartpole.yaml with idxbx = [0,1,2,3]).
-template <int NBX_>
+// 4: config/cartpole.yaml with idxbx = [0,1,2,3]).  NPM_ = 3: (M, m, l) learnable, g = mc[1]; 4: g is theta[3].
+template <int NBX_, int NPM_ = 3>
 struct CartpoleModelT {
-  static constexpr int NX = 4, NU = 1, NPM = 3, NZ = 8;  // NZ = NX+NU+NPM (derivative columns)
+  static_assert(NPM_ == 3 || NPM_ == 4, "model parameters: (M, m, l) or (M, m, l, g)");
+  static constexpr int NX = 4, NU = 1, NPM = NPM_, NZ = 5 + NPM_;  // NZ = NX+NU+NPM (derivative columns)
+  static constexpr int NV = 3 + NPM_;                              // leaf variables (theta, theta_dot, F, parameters)
   static constexpr int NW = NX + NU;
   static constexpr int NBX = NBX_;
-  static constexpr int NTH = 83;
-  static constexpr int TH_W0 = 3, TH_W = 28, TH_WE = 53, TH_YREF0 = 69, TH_YREF = 74, TH_YREFE = 79;
+  static constexpr int NTH = 80 + NPM_;
+  static constexpr int TH_W0 = NPM_, TH_W = TH_W0 + 25, TH_WE = TH_W + 25, TH_YREF0 = TH_WE + 16, TH_YREF = TH_YREF0 + 5,
+                       TH_YREFE = TH_YREF + 5;
+  MPC_HD static double grav(const double* th, size_t ths, const double* mc) { return NPM_ == 4 ? th[3 * ths] : mc[1]; }
   static constexpr int NSX = 0;              // no soft bounds
   static constexpr int NG = 0;               // no general linear rows
   MPC_HD static double gC(int, int) { return 0.0; }
@@ -126,9 +131,10 @@ struct CartpoleModelT {
       }
     }
     MPC_UNROLL for (int st = 0; st < 4; ++st) {
-      double sn, cs, xdd, thdd, jx[6], jt[6];
+      double sn, cs, xdd, thdd, jx[NV], jt[NV];
       sincos(s[2], &sn, &cs);
-      cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
+      if constexpr (NPM_ == 4 && NC > 5) cartpole_f_jac_g(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
+      else cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       if (keep) {  // stage point + the S rows the adjoint pass needs
         double* kp = keep + st * (4 + 2 * NC + 4);
         kp[0] = sn; kp[1] = cs; kp[2] = s[3];
@@ -179,7 +185,7 @@ struct CartpoleModelT {
   MPC_HD static void dyn_lin(const double* x, const double* u, const double* th, size_t ths, const double* mc,
                              double* xn, double* A, double* B) {
     double DF[4 * 5];
-    rk4_fwd<5>(x, u[0], th[0], th[ths], th[2 * ths], mc[1], mc[0], xn, DF, nullptr);
+    rk4_fwd<5>(x, u[0], th[0], th[ths], th[2 * ths], grav(th, ths, mc), mc[0], xn, DF, nullptr);
     MPC_UNROLL for (int i = 0; i < 4; ++i) {
       MPC_UNROLL for (int j = 0; j < 4; ++j) A[i * 4 + j] = DF[i * 5 + j];
       B[i] = DF[i * 5 + 4];
@@ -192,14 +198,14 @@ struct CartpoleModelT {
   MPC_HD static void dyn_sens(const double* x, const double* u, const double* th, size_t ths, const double* mc,
                               const double* pi, double* xn, double* A, double* B, double* Fp, double* Hww,
                               double* Hwp) {
-    constexpr int NC = 8, KS = 4 + 2 * NC + 4;
-    const double F = u[0], M = th[0], m = th[ths], l = th[2 * ths], g = mc[1], h = mc[0];
+    constexpr int NC = NZ, KS = 4 + 2 * NC + 4;
+    const double F = u[0], M = th[0], m = th[ths], l = th[2 * ths], g = grav(th, ths, mc), h = mc[0];
     double DF[4 * NC], keep[4 * KS];
     rk4_fwd<NC>(x, F, M, m, l, g, h, xn, DF, keep);
     MPC_UNROLL for (int i = 0; i < 4; ++i) {
       MPC_UNROLL for (int j = 0; j < 4; ++j) A[i * 4 + j] = DF[i * NC + j];
       B[i] = DF[i * NC + 4];
-      MPC_UNROLL for (int j = 0; j < 3; ++j) Fp[i * 3 + j] = DF[i * NC + 5 + j];
+      MPC_UNROLL for (int j = 0; j < NPM; ++j) Fp[i * NPM + j] = DF[i * NC + 5 + j];
     }
     // adjoint sweep over the RK stages: mu_i = d(pi'F)/dk_i
     double Hacc[NC][NC];
@@ -209,26 +215,27 @@ struct CartpoleModelT {
     MPC_UNROLL for (int st = 3; st >= 0; --st) {
       const double* kp = keep + st * KS;
       const double sn = kp[0], cs = kp[1], thd = kp[2];
-      double xdd, thdd, jx[6], jt[6], hs[36];
-      cartpole_f_hess(sn, cs, thd, F, M, m, l, g, mu[1], mu[3], &xdd, &thdd, jx, jt, hs);
-      // symmetric 6x6 Hessian of mu1*xdd + mu3*thdd wrt v = (theta, theta_dot, F, M, m, l)
-      double Hf[6][6];
-      MPC_UNROLL for (int a = 0; a < 6; ++a) MPC_UNROLL for (int b = a; b < 6; ++b) {
-        Hf[a][b] = hs[a * 6 + b];
-        Hf[b][a] = hs[a * 6 + b];
+      double xdd, thdd, jx[NV], jt[NV], hs[NV * NV];
+      if constexpr (NPM_ == 4) cartpole_f_hess_g(sn, cs, thd, F, M, m, l, g, mu[1], mu[3], &xdd, &thdd, jx, jt, hs);
+      else cartpole_f_hess(sn, cs, thd, F, M, m, l, g, mu[1], mu[3], &xdd, &thdd, jx, jt, hs);
+      // symmetric NV x NV Hessian of mu1*xdd + mu3*thdd wrt v = (theta, theta_dot, F, M, m, l (, g))
+      double Hf[NV][NV];
+      MPC_UNROLL for (int a = 0; a < NV; ++a) MPC_UNROLL for (int b = a; b < NV; ++b) {
+        Hf[a][b] = hs[a * NV + b];
+        Hf[b][a] = hs[a * NV + b];
       }
       const double* Sr0 = kp + 4;       // d s[2] / d zeta
       const double* Sr1 = kp + 4 + NC;  // d s[3] / d zeta
-      double T[6][NC];
+      double T[NV][NC];
       if (st == 0) {  // d s / d zeta = [I 0] at the first stage: rows 2, 3 of S are the unit vectors e_2, e_3
-        MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b)
+        MPC_UNROLL for (int p = 0; p < NV; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b)
           T[p][b] = (b == 2) ? Hf[p][0] : (b == 3) ? Hf[p][1] : (b >= 4) ? Hf[p][b - 2] : 0.0;
         MPC_UNROLL for (int a = 2; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {
           if (b < 2) continue;
           Hacc[a][b] += (a == 2) ? T[0][b] : (a == 3) ? T[1][b] : T[a - 2][b];
         }
       } else {
-        MPC_UNROLL for (int p = 0; p < 6; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+        MPC_UNROLL for (int p = 0; p < NV; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
           double v = Hf[p][0] * Sr0[b] + Hf[p][1] * Sr1[b];
           if (b >= 4) v += Hf[p][b - 2];
           T[p][b] = v;
@@ -258,12 +265,14 @@ struct CartpoleModelT {
     }
     MPC_UNROLL for (int a = 0; a < 5; ++a) {
       MPC_UNROLL for (int b = 0; b < 5; ++b) Hww[a * 5 + b] = (a <= b) ? Hacc[a][b] : Hacc[b][a];
-      MPC_UNROLL for (int b = 0; b < 3; ++b) Hwp[a * 3 + b] = Hacc[a][5 + b];
+      MPC_UNROLL for (int b = 0; b < NPM; ++b) Hwp[a * NPM + b] = Hacc[a][5 + b];
     }
   }
 };
 
-using CartpoleModel = CartpoleModelT<0>;    // input bounds only (config/cartpole_original.yaml)
-using CartpoleModelBX = CartpoleModelT<4>;  // + box bounds on all states (config/cartpole.yaml)
+using CartpoleModel = CartpoleModelT<0>;      // input bounds only (config/cartpole_original.yaml)
+using CartpoleModelBX = CartpoleModelT<4>;    // + box bounds on all states (config/cartpole.yaml)
+using CartpoleModelG = CartpoleModelT<0, 4>;  // input bounds only, g un-fixed: theta = [M, m, l, g | W ...] (84 entries)
+using CartpoleModelBXG = CartpoleModelT<4, 4>;
 
 }  // namespace rlmpc

@@ -694,7 +694,7 @@ __global__ void k_td_grad(int B, int nth, const double* td, const double* dQ, co
 
 }  // namespace
 
-enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2, VAR_EVAPORATION = 3 };
+enum Variant : int { VAR_CARTPOLE = 0, VAR_CARTPOLE_BX = 1, VAR_LINEAR = 2, VAR_EVAPORATION = 3, VAR_CARTPOLE_G = 4, VAR_CARTPOLE_BX_G = 5 };
 
 constexpr int MAX_SPLIT = 4;
 constexpr int NCNT = 8;  // ints per set of queue counters
@@ -756,6 +756,8 @@ namespace {
   switch ((h)->variant) {                                                     \
     case VAR_CARTPOLE: { using M = CartpoleModel; __VA_ARGS__; } break;       \
     case VAR_CARTPOLE_BX: { using M = CartpoleModelBX; __VA_ARGS__; } break;  \
+    case VAR_CARTPOLE_G: { using M = CartpoleModelG; __VA_ARGS__; } break;    \
+    case VAR_CARTPOLE_BX_G: { using M = CartpoleModelBXG; __VA_ARGS__; } break; \
     case VAR_LINEAR: { using M = LinearSystemModel; __VA_ARGS__; } break;     \
     case VAR_EVAPORATION: { using M = EvaporationModel; __VA_ARGS__; } break; \
   }
@@ -1206,7 +1208,9 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
       bool bx = false;
       for (int i = 0; i < 4; ++i)
         bx = bx || d->lbx[i] > -BIG || d->ubx[i] < BIG || d->lbx_e[i] > -BIG || d->ubx_e[i] < BIG;
-      h->variant = bx ? VAR_CARTPOLE_BX : VAR_CARTPOLE;
+      // model_const[2] != 0: g is the fourth model parameter (theta = [M, m, l, g | W ...], 84 entries)
+      const bool gfree = d->model_const[2] > 0.5;
+      h->variant = gfree ? (bx ? VAR_CARTPOLE_BX_G : VAR_CARTPOLE_G) : (bx ? VAR_CARTPOLE_BX : VAR_CARTPOLE);
       break;
     }
     case RLMPC_MODEL_LINEAR_SYSTEM:
@@ -1428,7 +1432,7 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
   if (!strcmp(field, "zl")) dst = h->pd.zl;
   if (!strcmp(field, "zu")) dst = h->pd.zu;
   if (h->chain && strcmp(field, "lbu") && strcmp(field, "ubu")) return fail(RLMPC_EINVAL, "chain mass has input bounds only");
-  if (is_x && h->variant == VAR_CARTPOLE) {
+  if (is_x && (h->variant == VAR_CARTPOLE || h->variant == VAR_CARTPOLE_G)) {
     for (int i = 0; i < n; ++i)
       if (v[i] > -BIG && v[i] < BIG)
         return fail(RLMPC_EINVAL, "this handle was created without state bounds; create it with finite lbx/ubx");

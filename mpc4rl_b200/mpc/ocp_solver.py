@@ -173,6 +173,25 @@ class OcpSolverShim:
     def get_cost(self) -> float:
         return self._cost
 
+    def eval_solution_sensitivity(self, stages, with_respect_to: str = "params_global"):
+        """acados' ``AcadosOcpSolver.eval_solution_sensitivity(stages, with_respect_to)`` as the reference uses it
+        (examples/chain_mass.py:126: ``_, sens_u = sensitivity_solver.eval_solution_sensitivity(0, "params_global")``):
+        returns ``(sens_x, sens_u)`` = d x_stage / d p and d u_stage / d p, shapes (nx, np) and (nu, np), at the current
+        iterate.  Only what the engine computes is available: stage 0, parameters -- d u_0 / d p is the adjoint KKT
+        solve of ``update_nlp``, d x_0 / d p = 0 because x_0 is fixed.  (acados needs a second solver with the EXACT
+        Hessian for this; the engine's sensitivities always use the exact Hessian.)"""
+        if with_respect_to not in ("params_global", "p_global"):
+            raise NotImplementedError(f"eval_solution_sensitivity w.r.t. {with_respect_to!r}: only the parameters are supported")
+        single = np.isscalar(stages)
+        for st in ([stages] if single else list(stages)):
+            if int(st) != 0:
+                raise NotImplementedError("eval_solution_sensitivity: only stage 0 (the policy gradient) is available")
+        _, dpi, _ = self.evaluate()
+        sl = self.spec.p_slices()["model"][0] if "model" in self.spec.p_slices() else slice(0, 0)
+        sens_u = np.array(dpi)[:, sl]  # acados differentiates w.r.t. model.p, the "model" part of the NLP's p
+        sens_x = np.zeros((self.spec.nx, sens_u.shape[1]))
+        return (sens_x, sens_u) if single else (sens_x[None], sens_u[None])
+
     def get_residuals(self):
         """[stat, eq, ineq, comp] of the last evaluation (acados: get_residuals())."""
         _, _, cost, res, _ = self.engine.sens(1, qmode=self.qmode)

@@ -110,8 +110,9 @@ def cartpole_spec(config: dict, gamma: float = 1.0) -> ProblemSpec:
     nstg = int(config["ocp_options"].get("sim_method_num_stages", 4))
     params = config["model"]["params"]
     free = [k for k in ("M", "m", "l", "g") if not params[k]["fixed"]]
-    if free != ["M", "m", "l"]:
-        raise NotImplementedError(f"cartpole device model is generated for free parameters (M, m, l); got {free}")
+    if free not in (["M", "m", "l"], ["M", "m", "l", "g"]):
+        # (the reference's YAML fixes g; scripts/cartpole_mpc_qlearning.py:184-187 un-fixes everything)
+        raise NotImplementedError(f"cartpole device models exist for free parameters (M, m, l) and (M, m, l, g); got {free}")
     cost = config["cost"]
     W_0, W, W_e = (np.array(cost[k], dtype=float) for k in ("W_0", "W", "W_e"))
     yref_0, yref, yref_e = (np.array(cost[k], dtype=float) for k in ("yref_0", "yref", "yref_e"))
@@ -122,7 +123,7 @@ def cartpole_spec(config: dict, gamma: float = 1.0) -> ProblemSpec:
     ubx = full(INF, cons.get("idxbx", []), cons.get("ubx", []))
     lbx_e = full(-INF, cons.get("idxbx_e", []), cons.get("lbx_e", []))
     ubx_e = full(INF, cons.get("idxbx_e", []), cons.get("ubx_e", []))
-    p_entries = [("model", (3,)), ("W_0", W_0.shape), ("W", W.shape), ("W_e", W_e.shape),
+    p_entries = [("model", (len(free),)), ("W_0", W_0.shape), ("W", W.shape), ("W_e", W_e.shape),
                  ("yref_0", yref_0.shape), ("yref", yref.shape), ("yref_e", yref_e.shape)]
     p_nom = np.concatenate([[params[k]["value"] for k in free], W_0.T.ravel(), W.T.ravel(), W_e.T.ravel(),
                             yref_0, yref, yref_e]).astype(float)
@@ -131,7 +132,8 @@ def cartpole_spec(config: dict, gamma: float = 1.0) -> ProblemSpec:
         p_entries=p_entries, p_nominal=p_nom,
         lbu=np.array(cons["lbu"], dtype=float), ubu=np.array(cons["ubu"], dtype=float),
         lbx=lbx, ubx=ubx, lbx_e=lbx_e, ubx_e=ubx_e,
-        model_const=np.array([tf / N / nstg, float(params["g"]["value"])]),  # quirk Q1: one RK4 step of dT/4
+        # quirk Q1: one RK4 step of dT/4; [2] = 1: g is the fourth model parameter
+        model_const=np.array([tf / N / nstg, float(params["g"]["value"]), 1.0 if "g" in free else 0.0]),
         gamma=gamma, cost_type=cost.get("cost_type", "NONLINEAR_LS"),
         state_labels=["x", "x_dot", "theta", "theta_dot"], input_labels=["F"], parameter_labels=free,
     )

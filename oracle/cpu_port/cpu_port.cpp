@@ -142,13 +142,15 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
     for (int i = 0; i < itn_; ++i) iterate[(size_t)i * B + b] = itt[tile_off(b, itn_) + (size_t)i * TILE];
 }
 
-// model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds, 3 = linear system
+// model ids of the host port: 1 = cartpole (input bounds only), 2 = cartpole with state bounds, 3 = linear system,
+// 4 = evaporation, 5 = cartpole with g as fourth model parameter
 #define PORT_DISPATCH(model, expr)                         \
   switch (model) {                                         \
     case 1: { using M = CartpoleModel; expr; } break;      \
     case 2: { using M = CartpoleModelBX; expr; } break;    \
     case 3: { using M = LinearSystemModel; expr; } break;  \
     case 4: { using M = EvaporationModel; expr; } break;   \
+    case 5: { using M = CartpoleModelG; expr; } break;     \
     default: return -1;                                    \
   }
 

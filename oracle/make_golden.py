@@ -167,10 +167,34 @@ def chain_mass_golden(n_mass=3, n=4, seed=50):
     print("wrote", path)
 
 
+def cartpole_free_g_golden(n=6, seed=1234):
+    """cartpole_original with g un-fixed as scripts/cartpole_mpc_qlearning.py:184-187 does: theta = [M, m, l, g | W_0 ...]
+    (84 entries); the states of ``cartpole_golden('original')``'s first samples."""
+    pb = make_cartpole("original", free_g=True)
+    s = DenseSolver(pb)
+    x0s, acts = sample_states(n, seed, "original")
+    x0s[0] = [0.0, 0.0, np.pi / 2, 0.0]
+    out = {k: [] for k in ("V", "u0", "dV", "dpi", "Q", "dQ", "status")}
+    for i in range(n):
+        sol, upd = s.unit(x0s[i], tol=1e-10)
+        solq, updq = s.unit(x0s[i], u0=acts[i], tol=1e-10)
+        print(f"[free g {i}] V={sol.cost:.6f} u0={sol.U[0]} st={sol.status} | Q={solq.cost:.6f} st={solq.status}", flush=True)
+        out["status"].append([sol.status, solq.status])
+        out["V"].append(sol.cost); out["u0"].append(sol.U[0]); out["dV"].append(upd["dL_dp"][0]); out["dpi"].append(upd["dpi_dp"])
+        out["Q"].append(solq.cost); out["dQ"].append(updq["dL_dp"][0])
+    out = {k: np.array(v) for k, v in out.items()}
+    out["x0"] = x0s; out["a"] = acts; out["theta"] = pb.p_nominal
+    path = os.path.join(ROOT, "tests", "golden", "cartpole_free_g.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["original"]
     for v in which:
-        if v == "evaporation":
+        if v == "free_g":
+            cartpole_free_g_golden()
+        elif v == "evaporation":
             evaporation_golden()
         elif v == "evaporation_full":
             evaporation_golden_full()

@@ -162,6 +162,8 @@ def stage_cost_unscaled(pb: Problem, k: int, x, u, p):
 # --------------------------------------------------------------------------------------
 def cartpole_ode(x, u, pm, g: float = 9.8):
     M, m, l = pm[0], pm[1], pm[2]
+    if pm.shape[0] == 4:  # g un-fixed (scripts/cartpole_mpc_qlearning.py:184-187): fourth model parameter
+        g = pm[3]
     s_dot, theta, theta_dot = x[1], x[2], x[3]
     c, sn = torch.cos(theta), torch.sin(theta)
     temp = (u[0] + m * theta_dot**2 * sn) / (m + M)
@@ -169,7 +171,7 @@ def cartpole_ode(x, u, pm, g: float = 9.8):
     return torch.stack([s_dot, temp - m * theta_ddot * c / (m + M), theta_dot, theta_ddot])
 
 
-def make_cartpole(variant: str = "original", gamma: float = 1.0) -> Problem:
+def make_cartpole(variant: str = "original", gamma: float = 1.0, free_g: bool = False) -> Problem:
     """variant 'original' = config/cartpole_original.yaml (N=40, tf=0.8, |u|<=80, no state
     bounds); 'default' = config/cartpole.yaml (N=30, tf=3.0, |u|<=30, state bounds)."""
     if variant == "original":
@@ -185,9 +187,9 @@ def make_cartpole(variant: str = "original", gamma: float = 1.0) -> Problem:
     else:
         raise ValueError(variant)
     h = tf / N / 4  # quirk Q1: ONE RK4 step of dT / sim_method_num_stages (cartpole/acados.py:86-92)
-    p_entries = [("model", (3,)), ("W_0", (5, 5)), ("W", (5, 5)), ("W_e", (4, 4)),
+    p_entries = [("model", (4 if free_g else 3,)), ("W_0", (5, 5)), ("W", (5, 5)), ("W_e", (4, 4)),
                  ("yref_0", (5,)), ("yref", (5,)), ("yref_e", (4,))]
-    p_nom = np.concatenate([[1.0, 0.1, 0.5], W.T.ravel(), W.T.ravel(), W_e.T.ravel(),
+    p_nom = np.concatenate([[1.0, 0.1, 0.5] + ([9.8] if free_g else []), W.T.ravel(), W.T.ravel(), W_e.T.ravel(),
                             np.zeros(5), np.zeros(5), np.zeros(4)])
     pb = Problem(
         name=f"cartpole_{variant}", N=N, nx=4, nu=1, tf=tf, p_entries=p_entries, p_nominal=p_nom,

@@ -26,6 +26,33 @@ def test_cartpole_cost_parameter_columns_match_oracle():
     assert np.abs(o["dpi"] - g["dpi"])[ok].max() < 1e-5 * np.abs(g["dpi"][ok]).max()  # ... and agree
 
 
+def test_cartpole_free_g_matches_oracle():
+    """g un-fixed (scripts/cartpole_mpc_qlearning.py:184-187): theta has 84 entries, 4 of them model parameters."""
+    import copy
+
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_free_g.npz"))
+    cfg = copy.deepcopy(cartpole_original_config())
+    cfg["model"]["params"]["g"]["fixed"] = False
+    spec = cartpole_spec(cfg)
+    assert spec.ntheta == 84 and np.array_equal(spec.p_nominal, g["theta"])
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-10, warm_ipm=1)
+    o = cp.unit(5, pd, 0, 200, g["theta"], g["x0"])
+    ok = (o["status"] == 0) & (g["status"][:, 0] == 0)
+    assert ok.sum() >= 4
+    assert o["dL"].shape[1] == 4 and np.abs(g["dV"][ok][:, 3]).max() > 1e-3  # the g column is live
+    assert np.abs(o["u0"] - g["u0"])[ok].max() < 1e-8
+    assert np.abs(o["dL"] - g["dV"][:, :4])[ok].max() < 1e-6 * np.abs(g["dV"][ok]).max()
+    assert np.abs(o["dpi"] - g["dpi"][:, :, :4])[ok].max() < 1e-5 * np.abs(g["dpi"][ok]).max()
+    q = cp.unit(5, pd, 1, 200, g["theta"], g["x0"], u0=g["a"])
+    okq = (q["status"] == 0) & (g["status"][:, 1] == 0)
+    assert okq.sum() >= 4
+    assert np.abs(q["cost"] - g["Q"])[okq].max() < 1e-9 * np.abs(g["Q"][okq]).max()
+    assert np.abs(q["dL"] - g["dQ"][:, :4])[okq].max() < 1e-6 * np.abs(g["dQ"][okq]).max()
+
+
 def test_chain_mass_host_run_matches_oracle():
     from mpc4rl_b200.problems import chain_mass_spec, get_chain_params
     from oracle import cpu_port as cp

@@ -408,6 +408,46 @@ def test_cost_parameter_columns_match_oracle(spec):
     assert _rel(out2["dpi"].cpu().numpy()[ok], g["dpi"][ok]) < 1e-5
 
 
+def test_free_g_parameter_set_matches_oracle():
+    """g un-fixed as scripts/cartpole_mpc_qlearning.py:184-187 does: 84 parameters, 4 with gradient, against
+    tests/golden/cartpole_free_g.npz (V- and Q-mode)."""
+    import copy
+
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cartpole_free_g.npz"))
+    cfg = copy.deepcopy(cartpole_original_config())
+    cfg["model"]["params"]["g"]["fixed"] = False
+    fspec = cartpole_spec(cfg)
+    assert fspec.ntheta == 84
+    B = g["x0"].shape[0]
+    m = BatchedMPC(fspec, max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    x0 = _dev(g["x0"])
+    m.reset(x0)
+    out = m.solve_sens(x0, max_sqp=200)
+    ok = (out["status"].cpu().numpy() == 0) & (g["status"][:, 0] == 0)
+    assert ok.sum() >= 4
+    assert out["dL"].shape[1] == 4 and np.abs(g["dV"][ok][:, 3]).max() > 1e-3
+    assert np.abs(out["u0"].cpu().numpy() - g["u0"])[ok].max() < 1e-6
+    assert _rel(out["cost"].cpu().numpy()[ok], g["V"][ok]) < 1e-9
+    assert _rel(m.full_grad(out["dL"]).cpu().numpy()[ok], g["dV"][ok]) < 1e-6
+    assert _rel(m.full_grad(out["dpi"]).cpu().numpy()[ok], g["dpi"][ok]) < 1e-5
+    m.reset(x0)
+    q = m.solve_sens(x0, u0=_dev(g["a"]), max_sqp=200)
+    okq = (q["status"].cpu().numpy() == 0) & (g["status"][:, 1] == 0)
+    assert okq.sum() >= 4
+    assert _rel(q["cost"].cpu().numpy()[okq], g["Q"][okq]) < 1e-9
+    assert _rel(m.full_grad(q["dL"]).cpu().numpy()[okq], g["dQ"][okq]) < 1e-6
+    # a changed g moves the solution: the parameter is live in the model, not only in the gradient
+    th = g["theta"].copy()
+    th[3] = 5.0
+    m.set_theta(th)
+    m.reset(x0)
+    o2 = m.solve_sens(x0, max_sqp=200)
+    assert np.abs(o2["cost"].cpu().numpy() - g["V"])[ok].max() > 1e-3
+
+
 @pytest.mark.parametrize("B", [512, 8192])
 def test_cuda_graph_replay_is_bit_identical(spec, B):
     """Option "graph": the RTI kernel chain (two streams for B >= 4096) captured once and replayed gives exactly the

@@ -146,3 +146,49 @@ def test_batch_is_sample_independent_at_size():
         a = out[k].cpu().numpy()
         assert np.array_equal(a[:16], a[16:32]) and np.array_equal(a[:16], a[B - 16:])
     assert np.abs(out["u0"].cpu().numpy()[:16] - g["u0"]).max() < 1e-8
+
+
+def test_reference_acados_cross_check_path(tmp_path):
+    """examples/chain_mass.py:main_acados with both solvers replaced by the shim: set(stage, "p", ..) on every stage,
+    solve_for_x0, store_iterate -> load_iterate into a second solver (acados iterate JSON, lam / t in acados' stage
+    layout), eval_solution_sensitivity(0, "params_global") -- the hand-off a machine with a real acados install would
+    use to pin parity."""
+    from mpc4rl_b200.mpc.chain_mass.ocp_utils import chain_define_x0, define_param_struct_symSX, find_idx_for_labels, get_chain_params
+    from mpc4rl_b200.mpc.ocp_solver import OcpSolverShim
+    from mpc4rl_b200.problems import chain_mass_spec
+
+    cp = get_chain_params()
+    cp["n_mass"] = 3
+    spec = chain_mass_spec(cp)
+    ocp_solver = OcpSolverShim(spec, max_iter=50, tol=1e-9)
+    sens_solver = OcpSolverShim(spec, max_iter=50, tol=1e-9)
+    M, x0 = cp["n_mass"] - 2, chain_define_x0(cp)
+    p_idx = find_idx_for_labels(define_param_struct_symSX(cp["n_mass"], disturbance=True).cat, f"C_{M}_0")[0]
+    p_val = spec.p_nominal.copy()
+    fn = str(tmp_path / "iterate.json")
+    us, ss = [], []
+    for v in np.linspace(0.5, 1.5, 3) * spec.p_nominal[p_idx]:
+        p_val[p_idx] = v
+        for stage in range(spec.N + 1):
+            ocp_solver.set(stage, "p", p_val)
+            sens_solver.set(stage, "p", p_val)
+        us.append(ocp_solver.solve_for_x0(x0))
+        assert ocp_solver.status == 0
+        ocp_solver.store_iterate(filename=fn, overwrite=True, verbose=False)
+        import json
+        d = json.load(open(fn))
+        assert len(d["lam_0"]) == 2 * (3 + spec.nx) and len(d["lam_1"]) == 6 and len(d[f"lam_{spec.N}"]) == 0  # acados layout
+        sens_solver.load_iterate(filename=fn, verbose=False)
+        u2 = sens_solver.solve_for_x0(x0, fail_on_nonzero_status=False, print_stats_on_failure=False)
+        assert sens_solver.status == 0 and np.abs(u2 - us[-1]).max() < 1e-8  # the loaded iterate is already the solution
+        sens_x, sens_u = sens_solver.eval_solution_sensitivity(0, "params_global")
+        assert sens_x.shape == (spec.nx, spec.ntheta) and sens_u.shape == (3, spec.ntheta) and not sens_x.any()
+        ss.append(sens_u[:, p_idx])
+    us, ss = np.array(us), np.array(ss)
+    # secant slopes of the optima bracket the sensitivities (u0 is smooth and monotone in C over this range)
+    h = 0.5 * spec.p_nominal[p_idx]
+    sec = (us[1:] - us[:-1]) / h
+    free = np.abs(ss).max(0) > 1e-8
+    assert free.any()
+    for j in np.where(free)[0]:
+        assert min(ss[0, j], ss[1, j]) - 1e-6 <= sec[0, j] <= max(ss[0, j], ss[1, j]) + 1e-6 or abs(sec[0, j] - 0.5 * (ss[0, j] + ss[1, j])) < 0.2 * abs(sec[0, j])
