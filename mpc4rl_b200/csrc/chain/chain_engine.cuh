@@ -845,7 +845,7 @@ struct ChainEngine {
             double lh, th_;
             row_hat(k, q, side, lh, th_);
             const int r = k * NR + side * NU + q;
-            if (!(th_ > eps_t)) { TT[r] = eps_t; LAM[r] = dmax(dmax(lh, LAM[r]), 1e-3); }
+            if (!(th_ > eps_t)) { LAM[r] = dmax(dmax(lh, LAM[r]), 1e-3); TT[r] = dmin(eps_t, pd.tau / LAM[r]); }
             else if (!(lh > 0.0)) { TT[r] = dmax(th_, AS_RELEASE * (pd.ubu[q] - pd.lbu[q])); LAM[r] = pd.tau / TT[r]; }
             else { TT[r] = th_; LAM[r] = lh; }
             m2 += LAM[r] * TT[r];

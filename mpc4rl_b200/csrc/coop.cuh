@@ -427,7 +427,7 @@ struct CoopQP {
           if (act && has_l) {
             double ll = LL[k], tl;
             const double lh = LHL[k], th = THL[k];
-            if (!(th > eps_t)) { tl = eps_t; ll = dmax(dmax(lh, ll), 1e-3); }
+            if (!(th > eps_t)) { ll = dmax(dmax(lh, ll), 1e-3); tl = dmin(eps_t, pd.tau / ll); }
             else if (!(lh > 0.0)) { tl = dmax(th, AS_RELEASE * range); ll = pd.tau / tl; }
             else { tl = th; ll = lh; }
             LL[k] = ll; TL[k] = tl;
@@ -436,7 +436,7 @@ struct CoopQP {
           if (act && has_u) {
             double lu = LU[k], tu;
             const double lh = LHU[k], th = THU[k];
-            if (!(th > eps_t)) { tu = eps_t; lu = dmax(dmax(lh, lu), 1e-3); }
+            if (!(th > eps_t)) { lu = dmax(dmax(lh, lu), 1e-3); tu = dmin(eps_t, pd.tau / lu); }
             else if (!(lh > 0.0)) { tu = dmax(th, AS_RELEASE * range); lu = pd.tau / tu; }
             else { tu = th; lu = lh; }
             LU[k] = lu; TU[k] = tu;

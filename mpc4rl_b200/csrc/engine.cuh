@@ -903,8 +903,11 @@ struct Engine {
       const double range = row_range(bd, q < 2 * NV ? (q < NV ? q : q - NV) : soft_row(q < R_US ? q - R_LS : q - R_US));
       const double eps_t = 1e-9 * range;
       if (!(th[q] > eps_t)) {          // slack collapses: the row becomes (stays) active
-        t[q] = eps_t;
+        // central for the final target: with t = eps_t a row whose product lam * eps_t exceeds tau asks the next
+        // Newton step for dt ~ -t, i.e. a step length of 1 + O(tau / (lam eps_t)) < 1 / 0.995, which reads as
+        // "infeasible" again -- the evaporation queue spent all of its active-set steps in that loop
         lam[q] = dmax(dmax(lh[q], lam[q]), 1e-3);
+        t[q] = dmin(eps_t, pd.tau / lam[q]);
       } else if (!(lh[q] > 0.0)) {     // multiplier changes sign: the row is released
         // th was computed with the row's barrier weight lam/t still in the Hessian, so it underestimates the free
         // slack by orders of magnitude; keeping it leaves a weight tau/th^2 that only fades over several further
@@ -959,36 +962,68 @@ struct Engine {
     }
   }
 
-  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
-    DirectReader rd(L, pd.N);
-    return qp_ipm(pd, L, alpha_out, rd);
+  // The interior-point loop is written as a resumable state machine: ipm_begin() initialises the rows and the
+  // scalars of the method, every ipm_trip() is one trip of the loop (one Newton iteration: two Riccati sweeps and the
+  // decision what to do with the step).  qp_ipm() runs it to the end inside one thread; the pass kernels of the CUDA
+  // build (k_ipm_pass) run ONE trip per launch over all queued samples and carry IpmState through global memory, so
+  // that samples with different iteration counts do not hold each other up inside a warp.
+  struct IpmState {
+    double mu, alpha, sigma;  // barrier estimate, pending step length of the previous trip (0: none), centring parameter
+    int iters, warm_iters, as_iters;
+    int warm;                 // still on the warm start (active-set steps allowed)
+    int code;                 // 0 running, 1 converged, -1 Riccati failure / NaN, -2 step length collapsed (cold start)
+  };
+  static constexpr int IPM_STATE_WORDS = 8;  // doubles per sample in the pass kernels' state array
+  MPC_HD static void ipm_begin(const ProblemData& pd, const Lane& L, IpmState& s) {
+    const int N = pd.N;
+    // warm = keep the multipliers of the previous QP (clipped away from zero), cold = slacks from the current
+    // point, lam = mu0 / t
+    s.warm = (pd.warm_ipm && L.it[(size_t)it_meta(N) * TILE] > 0.5) ? 1 : 0;
+    s.mu = ipm_init(pd, L, s.warm != 0) / (double)count_rows(pd);
+    s.alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
+    s.sigma = s.warm ? pd.sigma_min : pd.sigma0;
+    s.iters = s.warm_iters = s.as_iters = 0;
+    s.code = 0;
   }
+  // Would the first trip of a warm start repeat exactly the Newton iteration qp_fast() has just done (target tau from
+  // the clipped stored rows)?  Then its lam_hat, t_hat are still in the stage records and the trip can start from them.
+  MPC_HD static bool ipm_first_trip_done(const ProblemData& pd, const IpmState& s) {
+    return s.iters == 0 && s.warm && dmax(s.sigma * s.mu, pd.tau) == pd.tau && pd.max_ipm > 1;
+  }
+  // One trip.  reuse: lam_hat, t_hat of this trip's Newton iteration are already in the stage records (see above):
+  // only the step statistics are recomputed, the two Riccati sweeps are skipped.
   template <class RD>
-  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out, RD& rd) {
+  MPC_HD static void ipm_trip(const ProblemData& pd, const Lane& L, IpmState& s, RD& rd, bool reuse = false) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
     const bool qmode = pd.mode == MODE_Q;
     const double m_rows = (double)count_rows(pd);
-    // ---- initialise (lam,t): warm = keep the multipliers of the previous QP (clipped away from
-    // zero), cold = slacks from the current point, lam = mu0 / t ----
-    bool warm = pd.warm_ipm && L.it[(size_t)it_meta(N) * bs] > 0.5;
-    double mu = ipm_init(pd, L, warm) / m_rows;
-
-    double alpha = 0.0;  // pending step length of the previous iteration (0: nothing pending)
-    double sigma = warm ? pd.sigma_min : pd.sigma0;
-    int iters = 0, warm_iters = 0, as_iters = 0;
-    bool converged = false, failed = false, minstep = false;
-    for (int j = 0; j < pd.max_ipm && !converged; ++j) {
-      ++iters;
-      if (warm && (warm_iters >= WARM_LIMIT + as_iters || (warm_iters > as_iters && alpha > 0.0 && alpha < 0.05))) {
-        // the warm start is jammed (active set changed too much): restart from a cold point
-        warm = false;
-        mu = ipm_init(pd, L, false) / m_rows;
-        alpha = 0.0;
-        sigma = pd.sigma0;
+    bool failed = false;
+    ++s.iters;
+    if (s.warm && (s.warm_iters >= WARM_LIMIT + s.as_iters || (s.warm_iters > s.as_iters && s.alpha > 0.0 && s.alpha < 0.05))) {
+      // the warm start is jammed (active set changed too much): restart from a cold point
+      s.warm = 0;
+      s.mu = ipm_init(pd, L, false) / m_rows;
+      s.alpha = 0.0;
+      s.sigma = pd.sigma0;
+    }
+    if (s.warm) ++s.warm_iters;
+    const double target = dmax(s.sigma * s.mu, pd.tau);
+    StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
+    if (reuse) {
+      for (int k = 0; k <= N; ++k) {
+        if (k == N && NBX == 0) break;
+        const double* w = L.ws + (size_t)k * W_REC * bs;
+        Bnd bd;
+        double lam[NR], t[NR], lh[NR], th[NR];
+        stage_bounds(pd, k, bd);
+        ld<NR>(L.it + (size_t)it_lam(N, k) * bs, bs, lam);
+        ld<NR>(L.it + (size_t)it_t(N, k) * bs, bs, t);
+        ld<NR>(w + (size_t)W_lh * bs, bs, lh);
+        ld<NR>(w + (size_t)W_th * bs, bs, th);
+        rows_stats(bd, lam, t, lh, th, S);
       }
-      if (warm) ++warm_iters;
-      const double target = dmax(sigma * mu, pd.tau);
+    } else {
       // ---------------- backward sweep ----------------
       double P[NX * NX], p[NX];
       rd.begin(N, -1, N + 1);
@@ -1004,7 +1039,7 @@ struct Engine {
           stage_bounds(pd, N, bd);
           rd.rows(N, lam, t, u0, x);
           stage_vars(x, u0, v);
-          rows_update(L, N, N, alpha, wr, lam, t);
+          rows_update(L, N, N, s.alpha, wr, lam, t);
           barrier_add(bd, v, lam, t, target, Hm, g);
         }
         rd.done(N);
@@ -1029,7 +1064,7 @@ struct Engine {
           stage_bounds(pd, k, bd);
           rd.rows(k, lam, t, u, x);
           stage_vars(x, u, v);
-          rows_update(L, N, k, alpha, wr, lam, t);
+          rows_update(L, N, k, s.alpha, wr, lam, t);
           barrier_add(bd, v, lam, t, target, Hm, g);
         }
         rd.done(k);
@@ -1045,73 +1080,88 @@ struct Engine {
         st<NU>(w + (size_t)W_k * bs, bs, kff);
       }
       // ---------------- forward sweep ----------------
-      StepStats S = {1e300, 0.0, 0.0, 0.0, 0.0};
       forward_sweep(pd, L, target, /*clip=*/false, S, rd);
-      if ((failed || !(S.amax == S.amax)) && warm) {
-        // a warm start (or its active-set steps) went wrong numerically: not an error, start over cold
-        warm = false;
-        failed = false;
-        mu = ipm_init(pd, L, false) / m_rows;
-        alpha = 0.0;
-        sigma = pd.sigma0;
-        continue;
-      }
-      if (failed || !(S.amax == S.amax)) break;
-      if (warm && S.amax < 1.0 / 0.995 && as_iters < (int)pd.as_steps) {
-        // infeasible Newton step of a warm start: full step + projection instead of a short step
-        ++as_iters;
-#ifdef AS_TRACE  // which row limits the Newton step (before the projection overwrites lam, t)
-        {
-          double best = 1e300; int bk = -1, bq = -1, kind = 0; double bl = 0, bt = 0, blh = 0, bth = 0;
-          for (int k = 0; k < N; ++k)
-            for (int q = 0; q < NR; ++q) {
-              const double lam = L.it[(size_t)(it_lam(N, k) + q) * TILE], t = L.it[(size_t)(it_t(N, k) + q) * TILE];
-              const double lh = L.ws[((size_t)k * W_REC + W_lh + q) * TILE], th = L.ws[((size_t)k * W_REC + W_th + q) * TILE];
-              if (th - t < 0 && -t / (th - t) < best) { best = -t / (th - t); bk = k; bq = q; kind = 0; bl = lam; bt = t; blh = lh; bth = th; }
-              if (lh - lam < 0 && -lam / (lh - lam) < best) { best = -lam / (lh - lam); bk = k; bq = q; kind = 1; bl = lam; bt = t; blh = lh; bth = th; }
-            }
-          printf("      limiting row: stage %d row %d %s lam %.3e t %.3e -> lh %.3e th %.3e (target %.2e)\n", bk, bq, kind ? "dl<0" : "dt<0", bl, bt, blh, bth, target);
-        }
-#endif
-        mu = ipm_project(pd, L) / m_rows;
-#ifdef AS_TRACE  // host debugging aid: the active set after every active-set step (NU = 1 problems)
-        {
-          char buf[MAXN + 1];
-          int n = 0;
-          for (int k = 0; k < N; ++k) {
-            const double tl = L.it[(size_t)it_t(N, k) * TILE], tu = L.it[(size_t)(it_t(N, k) + NV) * TILE];
-            buf[n++] = tl < 1e-6 ? 'L' : (tu < 1e-6 ? 'U' : '.');
-          }
-          buf[n] = 0;
-          printf("   as %2d amax %.3g  %s\n", as_iters, S.amax, buf);
-        }
-#endif
-        alpha = 0.0;
-        sigma = pd.sigma_min;
-        continue;
-      }
-      alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
-      if (!warm && alpha < 1e-9) {  // a cold-started iteration has collapsed onto the boundary (HPIPM: MIN_STEP),
-        minstep = true;             // e.g. infeasible QP.  (A jammed WARM start restarts cold instead, above.)
-        break;
-      }
-      const double mu_new = (S.s0 + alpha * S.s1 + alpha * alpha * S.s2) / m_rows;
-#ifdef IPM_TRACE
-      printf("  ipm it %2d warm %d sigma %.3f mu %.3e target %.3e amax %.4g alpha %.4g cmax %.3e mu_new %.3e\n", iters, (int)warm,
-             sigma, mu, target, S.amax, alpha, S.cmax, mu_new);
-#endif
-      if (target <= pd.tau && alpha == 1.0 && S.cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) converged = true;
-      // centring heuristic: aggressive after long steps, conservative after short ones
-      const double r = 1.0 - alpha;
-      sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
-      mu = mu_new;
     }
-    *alpha_out = alpha;
-    if (failed) return -1;
-    if (minstep) return -2;
-    return converged ? iters : -(iters + 1000);
+    if ((failed || !(S.amax == S.amax)) && s.warm) {
+      // a warm start (or its active-set steps) went wrong numerically: not an error, start over cold
+      s.warm = 0;
+      s.mu = ipm_init(pd, L, false) / m_rows;
+      s.alpha = 0.0;
+      s.sigma = pd.sigma0;
+      return;
+    }
+    if (failed || !(S.amax == S.amax)) {
+      s.code = -1;
+      return;
+    }
+    if (s.warm && S.amax < 1.0 / 0.995 && s.as_iters < (int)pd.as_steps) {
+      // infeasible Newton step of a warm start: full step + projection instead of a short step
+      ++s.as_iters;
+#ifdef AS_TRACE  // host debugging aid: which row limits the Newton step (before the projection overwrites lam, t)
+      {
+        double best = 1e300; int bk = -1, bq = -1, kind = 0; double bl = 0, bt = 0, blh = 0, bth = 0;
+        for (int k = 0; k < N; ++k)
+          for (int q = 0; q < NR; ++q) {
+            const double lam = L.it[(size_t)(it_lam(N, k) + q) * TILE], t = L.it[(size_t)(it_t(N, k) + q) * TILE];
+            const double lh = L.ws[((size_t)k * W_REC + W_lh + q) * TILE], th = L.ws[((size_t)k * W_REC + W_th + q) * TILE];
+            if (th - t < 0 && -t / (th - t) < best) { best = -t / (th - t); bk = k; bq = q; kind = 0; bl = lam; bt = t; blh = lh; bth = th; }
+            if (lh - lam < 0 && -lam / (lh - lam) < best) { best = -lam / (lh - lam); bk = k; bq = q; kind = 1; bl = lam; bt = t; blh = lh; bth = th; }
+          }
+        printf("      limiting row: stage %d row %d %s lam %.3e t %.3e -> lh %.3e th %.3e (target %.2e)\n", bk, bq, kind ? "dl<0" : "dt<0", bl, bt, blh, bth, target);
+      }
+#endif
+      s.mu = ipm_project(pd, L) / m_rows;
+#ifdef AS_TRACE  // ... and the active set after the step (NU = 1 problems)
+      {
+        char buf[MAXN + 1];
+        int n = 0;
+        for (int k = 0; k < N; ++k) {
+          const double tl = L.it[(size_t)it_t(N, k) * TILE], tu = L.it[(size_t)(it_t(N, k) + NV) * TILE];
+          buf[n++] = tl < 1e-6 ? 'L' : (tu < 1e-6 ? 'U' : '.');
+        }
+        buf[n] = 0;
+        printf("   as %2d amax %.3g  %s\n", s.as_iters, S.amax, buf);
+      }
+#endif
+      s.alpha = 0.0;
+      s.sigma = pd.sigma_min;
+      return;
+    }
+    s.alpha = (S.amax >= 1.0 / 0.995) ? 1.0 : 0.995 * S.amax;
+    if (!s.warm && s.alpha < 1e-9) {  // a cold-started iteration has collapsed onto the boundary (HPIPM: MIN_STEP),
+      s.code = -2;                    // e.g. infeasible QP.  (A jammed WARM start restarts cold instead, above.)
+      return;
+    }
+    const double mu_new = (S.s0 + s.alpha * S.s1 + s.alpha * s.alpha * S.s2) / m_rows;
+#ifdef IPM_TRACE
+    printf("  ipm it %2d warm %d sigma %.3f mu %.3e target %.3e amax %.4g alpha %.4g cmax %.3e mu_new %.3e\n", s.iters, s.warm,
+           s.sigma, s.mu, target, S.amax, s.alpha, S.cmax, mu_new);
+#endif
+    if (target <= pd.tau && s.alpha == 1.0 && S.cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) s.code = 1;
+    // centring heuristic: aggressive after long steps, conservative after short ones
+    const double r = 1.0 - s.alpha;
+    s.sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
+    s.mu = mu_new;
+  }
+  // return value of qp_ipm for a finished (or abandoned: iteration limit) state
+  MPC_HD static int ipm_result(const IpmState& s) {
+    if (s.code == -1) return -1;
+    if (s.code == -2) return -2;
+    return s.code == 1 ? s.iters : -(s.iters + 1000);
   }
 
+  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out) {
+    DirectReader rd(L, pd.N);
+    return qp_ipm(pd, L, alpha_out, rd);
+  }
+  template <class RD>
+  MPC_HD static int qp_ipm(const ProblemData& pd, const Lane& L, double* alpha_out, RD& rd) {
+    IpmState s;
+    ipm_begin(pd, L, s);
+    for (int j = 0; j < pd.max_ipm && s.code == 0; ++j) ipm_trip(pd, L, s, rd);
+    *alpha_out = s.alpha;
+    return ipm_result(s);
+  }
   // ---------------------------------------------------------------------------------------
   // Apply the QP step: w += dw, (lam,t) <- last IPM update, pi <- QP multipliers (backward
   // recursion of the x-stationarity rows).
@@ -1213,10 +1263,35 @@ struct Engine {
   MPC_HD static int qp_full(const ProblemData& pd, const Lane& L, int* ipm_iters, RD& rd) {
     double alpha = 0.0;
     const int r = qp_ipm(pd, L, &alpha, rd);
+    return full_result(pd, L, r, alpha, ipm_iters);
+  }
+  // r: return value of qp_ipm
+  MPC_HD static int full_result(const ProblemData& pd, const Lane& L, int r, double alpha, int* ipm_iters) {
     if (ipm_iters) *ipm_iters += (r > 0) ? r : ((r >= -2) ? 0 : -(r + 1000));
     if (r == -1 || r == -2) return FULL_FAILED;
     apply_step(pd, L, alpha, /*clip=*/false, /*damp_primal=*/r < 0);
     return (r < 0) ? FULL_MAXITER : FULL_OK;
+  }
+
+  // One launch of the pass kernel for one queued sample: (first pass: start the method; if qp_fast() has already done
+  // the first Newton iteration, pick its result up) + ONE full trip.  st: this sample's IPM_STATE_WORDS state words,
+  // stride ss.  Returns the Full code when the sample finished in this pass (the step is applied), -1 when it goes on.
+  MPC_HD static int ipm_pass(const ProblemData& pd, const Lane& L, double* st, size_t ss, bool first, bool swept, int* ipm_iters) {
+    IpmState s;
+    DirectReader rd(L, pd.N);
+    if (first) {
+      ipm_begin(pd, L, s);
+      if (swept && ipm_first_trip_done(pd, s)) ipm_trip(pd, L, s, rd, /*reuse=*/true);
+    } else {
+      s.mu = st[0]; s.alpha = st[ss]; s.sigma = st[2 * ss];
+      s.iters = (int)st[3 * ss]; s.warm_iters = (int)st[4 * ss]; s.as_iters = (int)st[5 * ss]; s.warm = (int)st[6 * ss];
+      s.code = 0;
+    }
+    if (s.code == 0 && s.iters < pd.max_ipm) ipm_trip(pd, L, s, rd, false);
+    if (s.code != 0 || s.iters >= pd.max_ipm) return full_result(pd, L, ipm_result(s), s.alpha, ipm_iters);
+    st[0] = s.mu; st[ss] = s.alpha; st[2 * ss] = s.sigma;
+    st[3 * ss] = (double)s.iters; st[4 * ss] = (double)s.warm_iters; st[5 * ss] = (double)s.as_iters; st[6 * ss] = (double)s.warm;
+    return -1;
   }
 
   MPC_HD static void set_initial(const ProblemData& pd, const Lane& L, const double* x0, size_t x0s, const double* u0,

@@ -91,6 +91,8 @@ struct KArgs {
   int last_round;    // this SQP round only evaluates the convergence test
   int have_solve;    // sens: a solve preceded in this call (keep its status)
   int two_ended;     // k_qp1 files samples that probably need one more iteration at the END of the queue array (see k_qp3)
+  double* ipm_state;  // [Engine::IPM_STATE_WORDS][state_stride]: interior-point state of the queued samples between pass kernels
+  int state_stride;
   int b0;            // first sample of the range [b0, b0 + B) this launch works on (0 unless the batch is split over two streams)
 };
 
@@ -117,6 +119,7 @@ __device__ __forceinline__ bool queue_lane(const KArgs& a, int j, int& b, int& s
   }
   if (j >= a.counters[0]) return false;
   b = a.hard[j];
+  if (a.work[b] != WK_HARD) return false;  // finished in a pass kernel
   slot = j;
   L = make_lane<M>(a, b);
   L.it = a.it2 + tile_off(j, a.it_size);
@@ -181,6 +184,37 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
       a.hard[a.B - 1 - atomicAdd(&a.counters[4], 1)] = b;
     else
       a.hard[atomicAdd(&a.counters[0], 1)] = b;
+  }
+}
+
+// sample kernel, one interior-point iteration ("trip") of every queued sample, in place: thread b owns sample b like
+// in k_qp1, so every access of a warp is a contiguous run of the tiled arrays, whichever of its samples are queued.
+// A queued QP needs 3-4 iterations on the closed-loop workload (1-8 over the batch): running the loop to the end
+// inside one thread (k_qp2) makes a warp as slow as its slowest sample, the warp-per-sample kernel (k_qp3) spends ~150
+// instructions per sample and stage where a thread spends ~11.  Here the loop is cut into launches instead: pass p
+// does iteration p + 1 of every sample that still needs one (Engine::ipm_pass), carries the scalars of the method in
+// ipm_state, applies the step of the samples that finish, and the few samples left after the last pass go to k_qp3 /
+// k_qp2 as before.
+#ifndef RLMPC_PASS_MINB
+#define RLMPC_PASS_MINB 4
+#endif
+template <class M>
+__global__ void __launch_bounds__(TPB, RLMPC_PASS_MINB) k_ipm_pass(const __grid_constant__ ProblemData pd, const KArgs a, const int first) {
+  using E = Engine<M>;
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = a.b0 + bi;
+  if (bi >= a.B || a.work[b] != WK_HARD) return;
+  const Lane L = make_lane<M>(a, b);
+  int iters = 0;
+  const int st = E::ipm_pass(pd, L, a.ipm_state + b, (size_t)a.state_stride, first != 0, a.ishard[b] == 2, &iters);
+  if (first) a.ishard[b] = 1;  // the stage records no longer hold the Newton iteration of k_qp1
+  if (st < 0) return;
+  atomicAdd(&a.counters[3], iters);
+  if (pd.max_sqp == 1 || st == E::FULL_FAILED) {
+    a.status[b] = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL;
+    a.work[b] = WK_DONE;
+  } else {
+    a.work[b] = WK_ACTIVE;
   }
 }
 
@@ -399,6 +433,9 @@ __global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData
 #ifndef RLMPC_COOP_WARPS
 #define RLMPC_COOP_WARPS 4
 #endif
+#ifndef RLMPC_COOP_MINB
+#define RLMPC_COOP_MINB 3
+#endif
 constexpr int COOP_WARPS = RLMPC_COOP_WARPS;  // samples in flight per block
 
 // Which cooperative solver, and how many samples per block: the lean one (coop.cuh) where it applies, else the
@@ -407,24 +444,27 @@ template <class M, bool LEAN = CoopOK<M>::value, bool GEN = CoopGenOK<M>::value>
 struct CoopSel {
   static constexpr bool value = false;
   static constexpr int WARPS = 1;
+  static constexpr int MINB = 1;
 };
 template <class M, bool GEN>
 struct CoopSel<M, true, GEN> {
   static constexpr bool value = true;
   static constexpr int WARPS = COOP_WARPS;
+  static constexpr int MINB = RLMPC_COOP_MINB;  // 15 KB of shared memory per sample: 3 blocks of 4 samples per SM, 168 registers each
   using Solver = CoopQP<M>;
 };
 template <class M>
 struct CoopSel<M, false, true> {
   static constexpr bool value = true;
   static constexpr int WARPS = 1;
+  static constexpr int MINB = 1;
   using Solver = CoopGen<M>;
 };
 
 // persistent grid; warps fetch queue positions from counters[2].  Works on the samples' own iterate and
 // stage records (no compact copies: the QP lives in shared memory for the whole solve).
 template <class M>
-__global__ void __launch_bounds__(CoopSel<M>::WARPS * 32) k_qp3(const __grid_constant__ ProblemData pd, const KArgs a) {
+__global__ void __launch_bounds__(CoopSel<M>::WARPS * 32, CoopSel<M>::MINB) k_qp3(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   using Cq = typename CoopSel<M>::Solver;
   extern __shared__ double coop_smem[];
@@ -437,6 +477,7 @@ __global__ void __launch_bounds__(CoopSel<M>::WARPS * 32) k_qp3(const __grid_con
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= n) break;
     const int b = a.hard[j < nf ? j : a.B - 1 - (j - nf)];
+    if (a.work[b] != WK_HARD) continue;  // finished in a pass kernel (warp-uniform: one sample per warp)
     const Lane L = make_lane<M>(a, b);
     int iters = 0;
     const int st = Cq::solve(pd, L, S, lane, a.ishard[b] == 2, &iters);
@@ -722,6 +763,11 @@ struct rlmpc_handle {
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
   int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
   int inplace_queue = 0;
+  int ipm_passes = 0;  // pass kernels (one interior-point iteration of every queued sample each) before the queue kernel.
+                       // Measured slower on every workload (headline: queue 2.48 -> 3.76 ms with 5 passes, evaporation
+                       // 4.05 -> 6.56 ms): a pass costs its full ~0.45 ms as long as most WARPS still hold one queued
+                       // sample, whatever the fraction of active lanes (profiles/r02_summary.md), so it is off by default
+  double* ipm_state = nullptr;
   int overlap = 0;  // 1: RTI + sens runs the full interior-point pass of the queued samples on a side stream,
                     // concurrently with the sensitivity kernels of all other samples.  Measured slower
                     // (the few latency-bound warps of the queue lose issue slots to the bulk kernels).
@@ -794,6 +840,7 @@ KArgs base_args(rlmpc_handle* h, int B) {
   a.th = h->th; a.ct = h->ct; a.th_per_sample = h->th_per_sample; a.B = B;
   a.work = h->work; a.status = h->status; a.cost = h->cost; a.hard = h->hard; a.counters = h->counters;
   a.ishard = h->ishard;
+  a.ipm_state = h->ipm_state; a.state_stride = (int)h->bs;
   return a;
 }
 
@@ -905,6 +952,10 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
         CUDA_OK(cudaEventRecord(h->ev_fork, s));
         CUDA_OK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         sq = h->side_stream;
+      }
+      for (int p = 0; p < h->ipm_passes; ++p) {
+        k_ipm_pass<M><<<gs, TPB, 0, sq>>>(h->pd, a, p == 0 ? 1 : 0);
+        h->launches++;
       }
       bool coop_done = false;
       if constexpr (CoopSel<M>::value) {
@@ -1060,7 +1111,7 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
         const unsigned char* c = (const unsigned char*)p;
         for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
       };
-      mix(&a, sizeof(a)); mix(&h->pd, sizeof(h->pd)); mix(&h->split, sizeof(int)); mix(&h->coop, sizeof(int));
+      mix(&a, sizeof(a)); mix(&h->pd, sizeof(h->pd)); mix(&h->split, sizeof(int)); mix(&h->coop, sizeof(int)); mix(&h->ipm_passes, sizeof(int));
       mix(&h->th_per_sample, sizeof(int)); mix(&s, sizeof(s));
       if (h->graph_exec && key == h->graph_key) {
         CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
@@ -1271,6 +1322,8 @@ int rlmpc_create(const rlmpc_problem_desc* d, int max_batch, int device, rlmpc_h
   if (e == cudaSuccess) e = cudaMalloc(&h->hard, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMalloc(&h->ishard, sizeof(int) * h->bs);
   if (e == cudaSuccess) e = cudaMemset(h->ishard, 0, sizeof(int) * h->bs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->ipm_state, sizeof(double) * 8 * h->bs);
+  if (e == cudaSuccess) e = cudaMemset(h->ipm_state, 0, sizeof(double) * 8 * h->bs);
   if (e == cudaSuccess) {  // side stream of the "overlap" option: highest priority, so that the few queue blocks are placed first
     int prio_lo = 0, prio_hi = 0;
     e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -1318,7 +1371,7 @@ void rlmpc_destroy(rlmpc_handle* h) {
   if (h->chain) chain_destroy(h->chain);
   cudaFree(h->it); cudaFree(h->ws); cudaFree(h->it2); cudaFree(h->ws2); cudaFree(h->itb); cudaFree(h->wsb); cudaFree(h->th); cudaFree(h->ct);
   cudaFree(h->th_stage); cudaFree(h->cost); cudaFree(h->work); cudaFree(h->status); cudaFree(h->hard);
-  cudaFree(h->counters); cudaFree(h->ishard);
+  cudaFree(h->counters); cudaFree(h->ishard); cudaFree(h->ipm_state);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   for (int i = 0; i < MAX_SPLIT - 1; ++i) {
     if (h->part_stream[i]) cudaStreamDestroy(h->part_stream[i]);
@@ -1464,6 +1517,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "graph")) h->use_graph = (int)value;
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
+  else if (!strcmp(name, "ipm_passes")) h->ipm_passes = value < 0 ? 0 : (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }

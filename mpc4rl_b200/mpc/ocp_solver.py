@@ -70,6 +70,9 @@ class OcpSolverShim:
         self._cost = float("nan")
         self._res = np.full(4, np.nan)
         self._dev = self.engine.device
+        # acados starts a fresh solver from x_k = constraints.x0 on every stage; here x_0 arrives with the first solve, so
+        # an iterate nobody has written yet (set / load_iterate / reset) is initialised there (MPC.reset semantics)
+        self._iterate_written = False
 
     # ---- helpers ----
     def _t(self, v, n):
@@ -96,6 +99,7 @@ class OcpSolverShim:
         elif field in ("x", "u", "pi"):
             dim = {"x": self.spec.nx, "u": self.spec.nu, "pi": self.spec.nx}[field]
             self.engine.put(field, stage, self._t(value, dim))
+            self._iterate_written = True
         elif field == "p":
             sl = self.spec.p_slices()["model"][0]
             self._theta[sl] = np.asarray(value, dtype=np.float64).reshape(-1)
@@ -140,11 +144,15 @@ class OcpSolverShim:
 
     def reset(self) -> None:
         self.engine.reset(B=1)
+        self._iterate_written = True
 
     def solve(self) -> int:
         if not np.array_equal(self._lbx0, self._ubx0):
             raise NotImplementedError("the engine fixes x_0: set(0,'lbx',x0) and set(0,'ubx',x0) must agree")
         x0 = self._t(self._lbx0, self.spec.nx)
+        if not self._iterate_written:
+            self.engine.reset(x0)
+            self._iterate_written = True
         u0 = None
         if self.qmode:
             u0 = self._t(self._lbu0, self.spec.nu)
@@ -298,6 +306,7 @@ class OcpSolverShim:
             else:
                 continue  # sl / su / z entries of acados files: slack values are rows of t here
             self.engine.put(f, k, torch.tensor(v.reshape(1, -1), dtype=torch.float64, device=self._dev))
+        self._iterate_written = True
         one = torch.ones(1, 1, dtype=torch.float64, device=self._dev)
         try:
             self.engine.put("meta", 0, one)  # the loaded multipliers are a valid interior-point warm start

@@ -17,6 +17,8 @@
 using namespace rlmpc;
 
 static int g_threads = 0;  // 0 = all hardware threads
+static int g_passes = 0;   // > 0: queued QPs go through that many single-trip passes (Engine::ipm_pass, what k_ipm_pass does)
+                           // before the one-thread loop takes over
 
 // queued QP: partially condensed (blocks of 4 stages) where the product does that too
 template <class M>
@@ -78,7 +80,8 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
         const bool last = (K > 1 && r == K);
         for (int k = 0; k <= pd.N; ++k) E::lin_stage(pd, L, k);
         typename E::Residuals R;
-        const int code = E::qp_fast(pd, L, R, nullptr, /*polish=*/!last);
+        int swept = 0;
+        const int code = E::qp_fast(pd, L, R, &swept, /*polish=*/!last);
         cost = R.cost;
         if (code == E::FAST_NAN) { status = ST_NAN; break; }
         if (code == E::FAST_CONVERGED) { status = ST_OK; break; }
@@ -88,7 +91,12 @@ static void run(const ProblemData& pd0, int mode, int max_sqp, int B, const doub
           if (K == 1) { status = ST_OK; break; }
           continue;
         }
-        const int st = qp_full_maybe_condensed<M>(pd, L, &ipm_iter);
+        int st = -1;
+        if (g_passes > 0) {
+          double state[E::IPM_STATE_WORDS];
+          for (int p = 0; p < g_passes && st < 0; ++p) st = E::ipm_pass(pd, L, state, 1, p == 0, swept != 0, &ipm_iter);
+        }
+        if (st < 0) st = qp_full_maybe_condensed<M>(pd, L, &ipm_iter);
         ++sqp_iter;
         if (K == 1 || st == E::FULL_FAILED) { status = (st == E::FULL_OK) ? ST_OK : ST_QPFAIL; break; }
       }
@@ -158,6 +166,8 @@ extern "C" {
 
 void cpu_port_set_threads(int n) { g_threads = n; }
 int cpu_port_get_threads() { return g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency(); }
+
+void cpu_port_set_passes(int n) { g_passes = n; }
 
 int cpu_port_sizeof_problem_data() { return (int)sizeof(ProblemData); }
 

@@ -1,0 +1,126 @@
+"""The large golden sets (oracle/make_golden_large.py: 256 converged samples of cartpole_original and of the linear system,
+64 of cartpole.yaml) against the host build of the engine (CPU suite) and against the CUDA path through the C ABI
+(-m gpu).  Tolerances as in the small sets: |u0| 1e-6 abs, V/Q 1e-9 rel, dV/dtheta 1e-6 rel,
+dpi/dtheta 1e-5 rel; samples on which the ORACLE's full-step SQP did not converge are skipped (and counted)."""
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz not generated")
+    return np.load(path)
+
+
+def _rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
+
+
+def _check(g, v, q, min_ok, dpi_mask=None):
+    """v / q: dicts with status, u0, cost, dL, dpi (engine gradient width) of the V- and the Q-mode run."""
+    cols = g["cols"]
+    okv = (g["status"][:, 0] == 0) & (v["status"] == 0)
+    okq = (g["status"][:, 1] == 0) & (q["status"] == 0)
+    assert okv.mean() >= min_ok and okq.mean() >= min_ok, (okv.mean(), okq.mean())
+    # the engine may converge where the oracle's undamped SQP cycles, never the other way round on more than a handful
+    assert ((g["status"][:, 0] == 0) & (v["status"] != 0)).sum() <= 2
+    w = v["dL"].shape[1]
+    assert np.array_equal(cols, np.arange(len(cols))) and w >= len(cols)  # live columns = the engine's gradient prefix
+    assert np.abs(v["u0"] - g["u0"])[okv].max() < 1e-6
+    assert _rel(v["cost"][okv], g["V"][okv]) < 1e-9
+    assert _rel(v["dL"][okv][:, :len(cols)], g["dV"][okv]) < 1e-6
+    m = okv if dpi_mask is None else okv & dpi_mask
+    assert _rel(v["dpi"][m][:, :, :len(cols)], g["dpi"][m]) < 1e-5
+    assert _rel(q["cost"][okq], g["Q"][okq]) < 1e-9
+    assert _rel(q["dL"][okq][:, :len(cols)], g["dQ"][okq]) < 1e-6
+    return int(okv.sum()), int(okq.sum())
+
+
+# ---------------------------------------------------------------- host build (CPU suite)
+def test_host_port_cartpole_original_256():
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    g = _load("cartpole_original_256")
+    spec = cartpole_spec(cartpole_original_config())
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-10, warm_ipm=1)
+    v = cp.unit(1, pd, 0, 300, g["theta"], g["x0"])
+    q = cp.unit(1, pd, 1, 300, g["theta"], g["x0"], u0=g["a"])
+    nv, nq = _check(g, v, q, 0.85)
+    assert nv >= 220 and nq >= 220
+
+
+def test_host_port_linear_system_256():
+    from scipy.linalg import solve_discrete_are
+
+    from oracle import cpu_port as cp
+    from oracle.problems import linear_system_param_nominal, make_linear_system
+
+    g = _load("linear_system_256")
+    par = linear_system_param_nominal()
+    P = solve_discrete_are(par["A"], par["B"], par["Q"], par["R"])
+    pb = make_linear_system(gamma=0.9)
+    scale = np.array([pb.stage_scale(k) for k in range(pb.N + 1)])
+    pd = cp.make_pd(pb.N, scale, pb.lbu, pb.ubu, [P[0, 0], P[0, 1], P[1, 1]], tol=1e-10, warm_ipm=1, lbx=pb.lbx, ubx=pb.ubx,
+                    zl=pb.zl, zu=pb.zu)
+    v = cp.unit(3, pd, 0, 100, g["theta"], g["x0"], nx=2, nu=1)
+    q = cp.unit(3, pd, 1, 100, g["theta"], g["x0"], u0=g["a"], nx=2, nu=1)
+    # dpi/dtheta with an active slack: the reference formula is a ratio of interior-point stiffnesses (quirks Q4 / Q7),
+    # compared only where no softened bound is active
+    soft = g["slmax"] > 1e-6 if "slmax" in g.files else None
+    nv, nq = _check(g, v, q, 0.95, None if soft is None else ~soft)
+    assert nv >= 250
+
+
+# ---------------------------------------------------------------- CUDA path
+def _gpu_run(spec, g, max_sqp):
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC
+
+    dev = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda:0")
+    B = g["x0"].shape[0]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    x0 = dev(g["x0"])
+    res = []
+    for u0 in (None, dev(g["a"])):
+        m.reset(x0)
+        o = m.solve_sens(x0, u0=u0, max_sqp=max_sqp)
+        res.append({k: t.cpu().numpy() for k, t in o.items()})
+    return res
+
+
+@pytest.mark.gpu
+def test_gpu_cartpole_original_256():
+    from mpc4rl_b200 import cartpole_original_config, cartpole_spec
+
+    g = _load("cartpole_original_256")
+    v, q = _gpu_run(cartpole_spec(cartpole_original_config()), g, 300)
+    nv, nq = _check(g, v, q, 0.85)
+    assert nv >= 220 and nq >= 220
+
+
+@pytest.mark.gpu
+def test_gpu_cartpole_default_64():
+    from mpc4rl_b200 import cartpole_config, cartpole_spec
+
+    g = _load("cartpole_default_64")
+    v, q = _gpu_run(cartpole_spec(cartpole_config()), g, 300)
+    _check(g, v, q, 0.7)
+
+
+@pytest.mark.gpu
+def test_gpu_linear_system_256():
+    from mpc4rl_b200 import linear_system_spec
+
+    g = _load("linear_system_256")
+    v, q = _gpu_run(linear_system_spec(gamma=0.9), g, 100)
+    soft = g["slmax"] > 1e-6 if "slmax" in g.files else None
+    nv, nq = _check(g, v, q, 0.95, None if soft is None else ~soft)
+    assert nv >= 250
