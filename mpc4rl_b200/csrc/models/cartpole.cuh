@@ -115,19 +115,23 @@ struct CartpoleModelT {
   }
 
   // ---- dynamics -------------------------------------------------------------------------
-  // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l);
-  // NC = 5 -> columns (x,u) only (SQP linearisation), NC = 8 -> also the parameter columns.
+  // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l (, g));
+  // NC = 5 -> columns (x,u) only (SQP linearisation), NC = NZ -> also the parameter columns.
+  // The accelerations depend on v = (theta, theta_dot, F, M, m, l (, g)) = zeta[2..] only -- neither on the cart position
+  // nor on its velocity -- so the columns of s and s_dot are known in closed form (dF/ds = e_0, dF/ds_dot = (h, 1, 0, 0)')
+  // and carry no curvature: only the NE = NC - 2 columns of v are propagated (column e <-> zeta[e + 2]).
   template <int NC>
   MPC_HD static void rk4_fwd(const double* x, double F, double M, double m, double l, double g, double h,
                              double* xn, double* DF /* 4 x NC row-major */,
                              double* keep /* optional per-stage data for the adjoint pass, or nullptr */) {
-    double S[4][NC], acc[4][NC], s[4], xa[4];
+    constexpr int NE = NC - 2;
+    double S[4][NE], acc[4][NE], s[4], xa[4];
     MPC_UNROLL for (int i = 0; i < 4; ++i) {
       s[i] = x[i];
       xa[i] = 0.0;
-      MPC_UNROLL for (int c = 0; c < NC; ++c) {
-        S[i][c] = (i == c) ? 1.0 : 0.0;
-        acc[i][c] = 0.0;
+      MPC_UNROLL for (int e = 0; e < NE; ++e) {
+        S[i][e] = (i == e + 2) ? 1.0 : 0.0;
+        acc[i][e] = 0.0;
       }
     }
     MPC_UNROLL for (int st = 0; st < 4; ++st) {
@@ -136,48 +140,50 @@ struct CartpoleModelT {
       if constexpr (NPM_ == 4 && NC > 5) cartpole_f_jac_g(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       else cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       if (keep) {  // stage point + the S rows the adjoint pass needs
-        double* kp = keep + st * (4 + 2 * NC + 4);
+        double* kp = keep + st * (4 + 2 * NE + 4);
         kp[0] = sn; kp[1] = cs; kp[2] = s[3];
         kp[3] = 0.0;
-        MPC_UNROLL for (int c = 0; c < NC; ++c) { kp[4 + c] = S[2][c]; kp[4 + NC + c] = S[3][c]; }
-        kp[4 + 2 * NC + 0] = jx[0]; kp[4 + 2 * NC + 1] = jx[1];
-        kp[4 + 2 * NC + 2] = jt[0]; kp[4 + 2 * NC + 3] = jt[1];
+        MPC_UNROLL for (int e = 0; e < NE; ++e) { kp[4 + e] = S[2][e]; kp[4 + NE + e] = S[3][e]; }
+        kp[4 + 2 * NE + 0] = jx[0]; kp[4 + 2 * NE + 1] = jx[1];
+        kp[4 + 2 * NE + 2] = jt[0]; kp[4 + 2 * NE + 3] = jt[1];
       }
       const double k[4] = {s[1], xdd, s[3], thdd};
-      double Dk[4][NC];
-      MPC_UNROLL for (int c = 0; c < NC; ++c) {
-        if (st == 0) {  // S = I at the first stage: written out, a product with an exact zero is not folded away in IEEE arithmetic
-          Dk[0][c] = (c == 1) ? 1.0 : 0.0;
-          Dk[2][c] = (c == 3) ? 1.0 : 0.0;
-          Dk[1][c] = (c == 2) ? jx[0] : (c == 3) ? jx[1] : (c >= 4) ? jx[2 + (c - 4)] : 0.0;
-          Dk[3][c] = (c == 2) ? jt[0] : (c == 3) ? jt[1] : (c >= 4) ? jt[2 + (c - 4)] : 0.0;
+      double Dk[4][NE];
+      MPC_UNROLL for (int e = 0; e < NE; ++e) {
+        if (st == 0) {  // S = [0 ; 0 ; e_0 ; e_1] at the first stage: written out, a product with an exact zero is not folded away in IEEE arithmetic
+          Dk[0][e] = 0.0;
+          Dk[2][e] = (e == 1) ? 1.0 : 0.0;
+          Dk[1][e] = jx[e];  // v = zeta[2..]: the Jacobian row itself
+          Dk[3][e] = jt[e];
           continue;
         }
-        Dk[0][c] = S[1][c];
-        Dk[2][c] = S[3][c];
-        double a = jx[0] * S[2][c] + jx[1] * S[3][c];
-        double b = jt[0] * S[2][c] + jt[1] * S[3][c];
-        if (c >= 4) { a += jx[2 + (c - 4)]; b += jt[2 + (c - 4)]; }
-        Dk[1][c] = a;
-        Dk[3][c] = b;
+        Dk[0][e] = S[1][e];
+        Dk[2][e] = S[3][e];
+        double a = jx[0] * S[2][e] + jx[1] * S[3][e];
+        double b = jt[0] * S[2][e] + jt[1] * S[3][e];
+        if (e >= 2) { a += jx[e]; b += jt[e]; }
+        Dk[1][e] = a;
+        Dk[3][e] = b;
       }
       const double wgt = (st == 0 || st == 3) ? 1.0 : 2.0;
       MPC_UNROLL for (int i = 0; i < 4; ++i) {
         xa[i] += wgt * k[i];
-        MPC_UNROLL for (int c = 0; c < NC; ++c) acc[i][c] += wgt * Dk[i][c];
+        MPC_UNROLL for (int e = 0; e < NE; ++e) acc[i][e] += wgt * Dk[i][e];
       }
       if (st < 3) {
         const double a = (st < 2) ? 0.5 * h : h;
         MPC_UNROLL for (int i = 0; i < 4; ++i) {
           s[i] = x[i] + a * k[i];
-          MPC_UNROLL for (int c = 0; c < NC; ++c) S[i][c] = ((i == c) ? 1.0 : 0.0) + a * Dk[i][c];
+          MPC_UNROLL for (int e = 0; e < NE; ++e) S[i][e] = ((i == e + 2) ? 1.0 : 0.0) + a * Dk[i][e];
         }
       }
     }
     const double h6 = h / 6.0;
     MPC_UNROLL for (int i = 0; i < 4; ++i) {
       xn[i] = x[i] + h6 * xa[i];
-      MPC_UNROLL for (int c = 0; c < NC; ++c) DF[i * NC + c] = ((i == c) ? 1.0 : 0.0) + h6 * acc[i][c];
+      DF[i * NC + 0] = (i == 0) ? 1.0 : 0.0;
+      DF[i * NC + 1] = (i == 0) ? h6 * 6.0 : (i == 1) ? 1.0 : 0.0;  // sum of the RK weights of ds_dot/ds_dot = 1
+      MPC_UNROLL for (int e = 0; e < NE; ++e) DF[i * NC + 2 + e] = ((i == e + 2) ? 1.0 : 0.0) + h6 * acc[i][e];
     }
   }
 
@@ -198,7 +204,8 @@ struct CartpoleModelT {
   MPC_HD static void dyn_sens(const double* x, const double* u, const double* th, size_t ths, const double* mc,
                               const double* pi, double* xn, double* A, double* B, double* Fp, double* Hww,
                               double* Hwp) {
-    constexpr int NC = NZ, KS = 4 + 2 * NC + 4;
+    constexpr int NC = NZ, NE = NC - 2, KS = 4 + 2 * NE + 4;
+    static_assert(NE == NV, "the propagated columns are the leaf variables v = zeta[2..]");
     const double F = u[0], M = th[0], m = th[ths], l = th[2 * ths], g = grav(th, ths, mc), h = mc[0];
     double DF[4 * NC], keep[4 * KS];
     rk4_fwd<NC>(x, F, M, m, l, g, h, xn, DF, keep);
@@ -207,9 +214,10 @@ struct CartpoleModelT {
       B[i] = DF[i * NC + 4];
       MPC_UNROLL for (int j = 0; j < NPM; ++j) Fp[i * NPM + j] = DF[i * NC + 5 + j];
     }
-    // adjoint sweep over the RK stages: mu_i = d(pi'F)/dk_i
-    double Hacc[NC][NC];
-    MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = 0; b < NC; ++b) Hacc[a][b] = 0.0;
+    // adjoint sweep over the RK stages: mu_i = d(pi'F)/dk_i.  Curvature lives in the v-columns only (see rk4_fwd):
+    // Hacc is the NE x NE block of the Hessian over zeta[2..], its rows / columns of s and s_dot are zero.
+    double Hacc[NE][NE];
+    MPC_UNROLL for (int a = 0; a < NE; ++a) MPC_UNROLL for (int b = 0; b < NE; ++b) Hacc[a][b] = 0.0;
     double mu[4];
     MPC_UNROLL for (int i = 0; i < 4; ++i) mu[i] = (h / 6.0) * pi[i];
     MPC_UNROLL for (int st = 3; st >= 0; --st) {
@@ -224,25 +232,20 @@ struct CartpoleModelT {
         Hf[a][b] = hs[a * NV + b];
         Hf[b][a] = hs[a * NV + b];
       }
-      const double* Sr0 = kp + 4;       // d s[2] / d zeta
-      const double* Sr1 = kp + 4 + NC;  // d s[3] / d zeta
-      double T[NV][NC];
-      if (st == 0) {  // d s / d zeta = [I 0] at the first stage: rows 2, 3 of S are the unit vectors e_2, e_3
-        MPC_UNROLL for (int p = 0; p < NV; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b)
-          T[p][b] = (b == 2) ? Hf[p][0] : (b == 3) ? Hf[p][1] : (b >= 4) ? Hf[p][b - 2] : 0.0;
-        MPC_UNROLL for (int a = 2; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {
-          if (b < 2) continue;
-          Hacc[a][b] += (a == 2) ? T[0][b] : (a == 3) ? T[1][b] : T[a - 2][b];
-        }
+      const double* Sr0 = kp + 4;       // d s[2] / d v
+      const double* Sr1 = kp + 4 + NE;  // d s[3] / d v
+      if (st == 0) {  // d (theta, theta_dot) / d v = [e_0 ; e_1] at the first stage: D = I
+        MPC_UNROLL for (int a = 0; a < NE; ++a) MPC_UNROLL for (int b = a; b < NE; ++b) Hacc[a][b] += Hf[a][b];
       } else {
-        MPC_UNROLL for (int p = 0; p < NV; ++p) MPC_UNROLL for (int b = 0; b < NC; ++b) {
+        double T[NV][NE];
+        MPC_UNROLL for (int p = 0; p < NV; ++p) MPC_UNROLL for (int b = 0; b < NE; ++b) {
           double v = Hf[p][0] * Sr0[b] + Hf[p][1] * Sr1[b];
-          if (b >= 4) v += Hf[p][b - 2];
+          if (b >= 2) v += Hf[p][b];
           T[p][b] = v;
         }
-        MPC_UNROLL for (int a = 0; a < NC; ++a) MPC_UNROLL for (int b = a; b < NC; ++b) {  // symmetric: upper triangle
+        MPC_UNROLL for (int a = 0; a < NE; ++a) MPC_UNROLL for (int b = a; b < NE; ++b) {  // symmetric: upper triangle
           double v = Sr0[a] * T[0][b] + Sr1[a] * T[1][b];
-          if (a >= 4) v += T[a - 2][b];
+          if (a >= 2) v += T[a][b];
           Hacc[a][b] += v;
         }
       }
@@ -250,8 +253,8 @@ struct CartpoleModelT {
         // adjoint of the stage point s_st = x + a*k_{st-1}:  mu_{st-1} = w*h/6*pi + a * (df/ds)' mu_st
         const double a = (st == 3) ? h : 0.5 * h;
         const double wgt = (st - 1 == 0) ? 1.0 : 2.0;
-        const double jx0 = kp[4 + 2 * NC + 0], jx1 = kp[4 + 2 * NC + 1];
-        const double jt0 = kp[4 + 2 * NC + 2], jt1 = kp[4 + 2 * NC + 3];
+        const double jx0 = kp[4 + 2 * NE + 0], jx1 = kp[4 + 2 * NE + 1];
+        const double jt0 = kp[4 + 2 * NE + 2], jt1 = kp[4 + 2 * NE + 3];
         const double a0 = 0.0;
         const double a1 = mu[0];
         const double a2 = jx0 * mu[1] + jt0 * mu[3];
@@ -264,8 +267,9 @@ struct CartpoleModelT {
       }
     }
     MPC_UNROLL for (int a = 0; a < 5; ++a) {
-      MPC_UNROLL for (int b = 0; b < 5; ++b) Hww[a * 5 + b] = (a <= b) ? Hacc[a][b] : Hacc[b][a];
-      MPC_UNROLL for (int b = 0; b < NPM; ++b) Hwp[a * NPM + b] = Hacc[a][5 + b];
+      MPC_UNROLL for (int b = 0; b < 5; ++b)
+        Hww[a * 5 + b] = (a < 2 || b < 2) ? 0.0 : ((a <= b) ? Hacc[a - 2][b - 2] : Hacc[b - 2][a - 2]);
+      MPC_UNROLL for (int b = 0; b < NPM; ++b) Hwp[a * NPM + b] = (a < 2) ? 0.0 : Hacc[a - 2][3 + b];
     }
   }
 };
