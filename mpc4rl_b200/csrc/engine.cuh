@@ -107,11 +107,15 @@ struct Engine {
     MPC_UNROLL for (int i = 0; i < n; ++i) p[(size_t)i * bs] = in[i];
   }
 
-  // in-place LDL'-based solve of a small SPD system G X = R (G: n x n, R: n x m); returns false if not PD
-  template <int n, int m>
+  // in-place LDL'-based solve of a small symmetric system G X = R (G: n x n, R: n x m).  PD = true: returns false if
+  // G is not positive definite (the QP solves: an indefinite reduced Hessian is a failed QP).  PD = false: pivots of
+  // either sign are accepted, false only for a zero / NaN pivot (the sensitivities: the reference solves the KKT
+  // system of update_nlp with a general sparse LU, nlp.py:1413-1424, which needs it nonsingular, not definite --
+  // at an unconverged RTI iterate the exact Hessian of the Lagrangian often is indefinite).
+  template <int n, int m, bool PD = true>
   MPC_HD static bool spd_solve(double* G, double* R) {
     if (n == 1) {
-      if (!(G[0] > 0.0)) return false;
+      if (PD ? !(G[0] > 0.0) : !(G[0] > 0.0 || G[0] < 0.0)) return false;
       const double inv = 1.0 / G[0];
       MPC_UNROLL for (int j = 0; j < m; ++j) R[j] *= inv;
       return true;
@@ -120,7 +124,7 @@ struct Engine {
     MPC_UNROLL for (int j = 0; j < n; ++j) {
       double d = G[j * n + j];
       MPC_UNROLL for (int p = 0; p < j; ++p) d -= G[j * n + p] * G[j * n + p] * G[p * n + p];
-      if (!(d > 0.0)) ok = false;
+      if (PD ? !(d > 0.0) : !(d > 0.0 || d < 0.0)) ok = false;
       G[j * n + j] = d;
       const double inv = 1.0 / d;
       MPC_UNROLL for (int i = j + 1; i < n; ++i) {
@@ -476,7 +480,8 @@ struct Engine {
   }
 
   // One backward Riccati step.  In: P (NX x NX full), p; stage data.  Out: P, p (overwritten), K, kff.
-  // Returns false if the reduced Hessian block G is not positive definite.
+  // Returns false if the reduced Hessian block G is not positive definite (PD = false: not invertible, see spd_solve).
+  template <bool PD = true>
   MPC_HD static bool riccati_step(double* P, double* p, const double* A, const double* B, const double* b,
                                   const double* Hm /* NW x NW: [Q S'; S R] incl. barrier */,
                                   const double* g /* NW: [gq ; gr] */, double* K, double* kff,
@@ -524,7 +529,7 @@ struct Engine {
       R[i * (NX + 1 + NU) + NX] = -gv[i];
       MPC_UNROLL for (int j = 0; j < NU; ++j) R[i * (NX + 1 + NU) + NX + 1 + j] = (i == j) ? 1.0 : 0.0;
     }
-    const bool ok = spd_solve<NU, NX + 1 + NU>(G, R);
+    const bool ok = spd_solve<NU, NX + 1 + NU, PD>(G, R);
     MPC_UNROLL for (int i = 0; i < NU; ++i) {
       MPC_UNROLL for (int j = 0; j < NX; ++j) K[i * NX + j] = R[i * (NX + 1 + NU) + j];
       kff[i] = R[i * (NX + 1 + NU) + NX];
@@ -1481,7 +1486,11 @@ struct Engine {
         MPC_UNROLL for (int i = 0; i < NW; ++i) zg[i] = 0.0;
         MPC_UNROLL for (int i = 0; i < NX; ++i) zb[i] = 0.0;
         if (!ufixed) {
-          if (!riccati_step(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
+#ifdef RLMPC_SENS_REQUIRE_PD  // (round-1 behaviour, kept to label fixtures: oracle/make_golden_indefinite.py)
+          if (!riccati_step<true>(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
+#else
+          if (!riccati_step<false>(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
+#endif
         } else {
           MPC_UNROLL for (int i = 0; i < NU * NX; ++i) K[i] = 0.0;
           MPC_UNROLL for (int i = 0; i < NU * NU; ++i) Ginv[i] = 0.0;

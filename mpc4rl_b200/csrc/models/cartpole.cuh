@@ -139,13 +139,12 @@ struct CartpoleModelT {
       sincos(s[2], &sn, &cs);
       if constexpr (NPM_ == 4 && NC > 5) cartpole_f_jac_g(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       else cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
-      if (keep) {  // stage point + the S rows the adjoint pass needs
-        double* kp = keep + st * (4 + 2 * NE + 4);
+      if (keep) {  // stage point + the S rows the adjoint pass needs (first stage: unit vectors, not stored)
+        double* kp = keep + st * (3 + 2 * NE);
         kp[0] = sn; kp[1] = cs; kp[2] = s[3];
-        kp[3] = 0.0;
-        MPC_UNROLL for (int e = 0; e < NE; ++e) { kp[4 + e] = S[2][e]; kp[4 + NE + e] = S[3][e]; }
-        kp[4 + 2 * NE + 0] = jx[0]; kp[4 + 2 * NE + 1] = jx[1];
-        kp[4 + 2 * NE + 2] = jt[0]; kp[4 + 2 * NE + 3] = jt[1];
+        if (st > 0) {
+          MPC_UNROLL for (int e = 0; e < NE; ++e) { kp[3 + e] = S[2][e]; kp[3 + NE + e] = S[3][e]; }
+        }
       }
       const double k[4] = {s[1], xdd, s[3], thdd};
       double Dk[4][NE];
@@ -204,7 +203,7 @@ struct CartpoleModelT {
   MPC_HD static void dyn_sens(const double* x, const double* u, const double* th, size_t ths, const double* mc,
                               const double* pi, double* xn, double* A, double* B, double* Fp, double* Hww,
                               double* Hwp) {
-    constexpr int NC = NZ, NE = NC - 2, KS = 4 + 2 * NE + 4;
+    constexpr int NC = NZ, NE = NC - 2, KS = 3 + 2 * NE;
     static_assert(NE == NV, "the propagated columns are the leaf variables v = zeta[2..]");
     const double F = u[0], M = th[0], m = th[ths], l = th[2 * ths], g = grav(th, ths, mc), h = mc[0];
     double DF[4 * NC], keep[4 * KS];
@@ -232,8 +231,8 @@ struct CartpoleModelT {
         Hf[a][b] = hs[a * NV + b];
         Hf[b][a] = hs[a * NV + b];
       }
-      const double* Sr0 = kp + 4;       // d s[2] / d v
-      const double* Sr1 = kp + 4 + NE;  // d s[3] / d v
+      const double* Sr0 = kp + 3;       // d s[2] / d v
+      const double* Sr1 = kp + 3 + NE;  // d s[3] / d v
       if (st == 0) {  // d (theta, theta_dot) / d v = [e_0 ; e_1] at the first stage: D = I
         MPC_UNROLL for (int a = 0; a < NE; ++a) MPC_UNROLL for (int b = a; b < NE; ++b) Hacc[a][b] += Hf[a][b];
       } else {
@@ -253,8 +252,7 @@ struct CartpoleModelT {
         // adjoint of the stage point s_st = x + a*k_{st-1}:  mu_{st-1} = w*h/6*pi + a * (df/ds)' mu_st
         const double a = (st == 3) ? h : 0.5 * h;
         const double wgt = (st - 1 == 0) ? 1.0 : 2.0;
-        const double jx0 = kp[4 + 2 * NE + 0], jx1 = kp[4 + 2 * NE + 1];
-        const double jt0 = kp[4 + 2 * NE + 2], jt1 = kp[4 + 2 * NE + 3];
+        const double jx0 = jx[0], jx1 = jx[1], jt0 = jt[0], jt1 = jt[1];  // Jacobian at this stage point (just re-evaluated)
         const double a0 = 0.0;
         const double a1 = mu[0];
         const double a2 = jx0 * mu[1] + jt0 * mu[3];

@@ -49,7 +49,7 @@ int fail(int code, const std::string& msg) {
 #define RLMPC_STAGE_TPB 128  // threads per block of the (sample, stage) kernels
 #endif
 #ifndef RLMPC_LIN_MINB
-#define RLMPC_LIN_MINB 1
+#define RLMPC_LIN_MINB 4  // cart-pole: 136 -> 128 registers, 0.201 -> 0.169 ms per 65 536 x 41 (profiles/r02_summary.md)
 #endif
 #ifndef RLMPC_SS_MINB
 #define RLMPC_SS_MINB 1

@@ -124,3 +124,78 @@ def test_gpu_linear_system_256():
     soft = g["slmax"] > 1e-6 if "slmax" in g.files else None
     nv, nq = _check(g, v, q, 0.95, None if soft is None else ~soft)
     assert nv >= 250
+
+
+# ---------------------------------------------------------------- indefinite exact Hessian (closed-loop RTI iterates)
+def _check_indefinite(g, status, u0, cost, dL, dpi):
+    assert g["indefinite"].sum() >= 8 and (~g["indefinite"]).sum() >= 8  # the fixture covers both kinds
+    assert np.all(status == 0), status  # the reference's sparse LU does not need a definite reduced Hessian
+    assert np.abs(u0 - g["u1"]).max() < 1e-5
+    assert np.abs(cost - g["V1"]).max() < 1e-8 * np.abs(g["V1"]).max()
+    for sel in (g["indefinite"], ~g["indefinite"]):
+        assert np.abs(dL - g["dV1"])[sel].max() < 1e-5 * np.abs(g["dV1"][sel]).max()
+        rel = np.abs(dpi - g["dpi1"])[sel].max(axis=(1, 2)) / np.abs(g["dpi1"][sel]).max(axis=(1, 2))
+        assert rel.max() < 1e-4, rel  # per sample: dpi/dtheta spans 1e-5 .. 1e5 over these iterates
+
+
+def test_host_port_sensitivities_with_indefinite_exact_hessian():
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    g = _load("cartpole_original_indefinite")
+    spec = cartpole_spec(cartpole_original_config())
+    N, B = spec.N, g["x1"].shape[0]
+    pd = cp.make_pd(N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-6, warm_ipm=1)
+    it = np.zeros((cp.lib().cpu_port_iterate_size(1, N), B))
+    it[:(N + 1) * 4] = g["X"].reshape(B, -1).T
+    it[(N + 1) * 4:(N + 1) * 4 + N] = g["U"].reshape(B, -1).T
+    o = cp.unit(1, pd, 0, 1, g["theta"], g["x1"], iterate=it)
+    _check_indefinite(g, o["status"], o["u0"], o["cost"], o["dL"], o["dpi"])
+
+
+@pytest.mark.gpu
+def test_gpu_sensitivities_with_indefinite_exact_hessian():
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    g = _load("cartpole_original_indefinite")
+    spec = cartpole_spec(cartpole_original_config())
+    B = g["x1"].shape[0]
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+    m = BatchedMPC(spec, max_batch=B, device=0)  # default options = the bench's
+    m.reset(dev(g["x1"]))
+    for k in range(spec.N + 1):
+        m.put("x", k, dev(g["X"][:, k]))
+    for k in range(spec.N):
+        m.put("u", k, dev(g["U"][:, k]))
+    o = m.solve_sens(dev(g["x1"]), max_sqp=1)
+    _check_indefinite(g, o["status"].cpu().numpy(), o["u0"].cpu().numpy(), o["cost"].cpu().numpy(), o["dL"].cpu().numpy(),
+                      o["dpi"].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_gpu_evaporation_32():
+    """32 states of the SURVEY.md 8(d) config-4 distribution at the oracle's affordable horizon N = 40 (gamma 0.95), V- and
+    Q-mode, all 60 tracking-cost parameter columns."""
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC, evaporation_spec
+
+    g = _load("evaporation_32")
+    spec = evaporation_spec(gamma=0.95, N=40)
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+    B = g["x0"].shape[0]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-9)
+    x0 = dev(g["x0"])
+    res = []
+    for u0 in (None, dev(g["a"])):
+        m.reset(B=B)  # every stage on the steady state (evaporation_process/acados.py:104-109)
+        for k in range(spec.N + 1):
+            m.put("x", k, dev(np.tile(spec.x_init, (B, 1))))
+        for k in range(spec.N):
+            m.put("u", k, dev(np.tile(spec.u_init, (B, 1))))
+        o = m.solve_sens(x0, u0=u0, max_sqp=100)
+        res.append({k: t.cpu().numpy() for k, t in o.items()})
+    _check(g, res[0], res[1], 0.9)
