@@ -21,7 +21,7 @@ def _rel(a, b):
     return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300)
 
 
-def _check(g, v, q, min_ok, dpi_mask=None):
+def _check(g, v, q, min_ok, dpi_mask=None, dpi_tol=1e-5):
     """v / q: dicts with status, u0, cost, dL, dpi (engine gradient width) of the V- and the Q-mode run."""
     cols = g["cols"]
     okv = (g["status"][:, 0] == 0) & (v["status"] == 0)
@@ -35,7 +35,7 @@ def _check(g, v, q, min_ok, dpi_mask=None):
     assert _rel(v["cost"][okv], g["V"][okv]) < 1e-9
     assert _rel(v["dL"][okv][:, :len(cols)], g["dV"][okv]) < 1e-6
     m = okv if dpi_mask is None else okv & dpi_mask
-    assert _rel(v["dpi"][m][:, :, :len(cols)], g["dpi"][m]) < 1e-5
+    assert _rel(v["dpi"][m][:, :, :len(cols)], g["dpi"][m]) < dpi_tol
     assert _rel(q["cost"][okq], g["Q"][okq]) < 1e-9
     assert _rel(q["dL"][okq][:, :len(cols)], g["dQ"][okq]) < 1e-6
     return int(okv.sum()), int(okq.sum())
@@ -122,7 +122,9 @@ def test_gpu_linear_system_256():
     g = _load("linear_system_256")
     v, q = _gpu_run(linear_system_spec(gamma=0.9), g, 100)
     soft = g["slmax"] > 1e-6 if "slmax" in g.files else None
-    nv, nq = _check(g, v, q, 0.95, None if soft is None else ~soft)
+    # 2e-5: x_0 is eliminated here while the reference's formula carries it as two barrier rows of finite stiffness (quirk
+    # Q7), an O(tau / stiffness) difference that shows on a few of the 188 slack-free samples (worst: 1.2e-5)
+    nv, nq = _check(g, v, q, 0.95, None if soft is None else ~soft, dpi_tol=2e-5)
     assert nv >= 250
 
 
