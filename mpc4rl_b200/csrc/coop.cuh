@@ -60,7 +60,7 @@ template <class M>
 struct CoopQP {
   using E = Engine<M>;
   static constexpr int NX = M::NX, NU = M::NU, NW = NX + NU, NC = NW + 1, NWS = E::NWS;
-  static constexpr int PER_STAGE = NX * NC + NW + NW + 9;  // Mk, g, K|kff (later dx, du), 9 row/scalar fields
+  static constexpr int PER_STAGE = NX * NC + NW + NW + 7;  // Mk, g, K|kff (later dx, du), 7 row/scalar fields
   static constexpr int SCRATCH = 2 * NX + NX * NC + NW * NC + 3 * NWS + 1;
   __host__ __device__ static constexpr int smem_doubles(int N) { return PER_STAGE * (N + 1) + SCRATCH; }
 
@@ -107,13 +107,12 @@ struct CoopQP {
     double* TU = TL + NS;
     double* LHL = TU + NS;  // lam_hat, t_hat of the last Newton step
     double* LHU = LHL + NS;
-    double* THL = LHU + NS;
-    double* THU = THL + NS;
+    // (t_hat is not stored: it is the distance to the bound after the step, th_l / th_u below, from u_k and du_k)
     // (u,u) Hessian entry and u-gradient of the stage incl. barrier terms: live from the row phase to the end
     // of the backward sweep, when lam_hat of the previous step is dead, so they share its storage
     double* HB = LHL;
     double* GB = LHU;
-    double* pv = THU + NS;  // scratch
+    double* pv = LHU + NS;  // scratch
     double* pv2 = pv + NX;
     double* PM = pv2 + NX;
     double* T = PM + NX * NC;
@@ -130,6 +129,9 @@ struct CoopQP {
     const double range = (has_l && has_u) ? ub - lb : 1.0;
     const int k_first = qmode ? 1 : 0;  // stages [k_first, N) carry the input rows
     const double m_rows = (double)((N - k_first) * ((has_l ? 1 : 0) + (has_u ? 1 : 0)));
+    // t_hat of the last Newton step is not stored: it is the slack of the bound at u_k + du_k, (u_k - lb) + du_k resp.
+    // (ub - u_k) - du_k, and du_k sits in the feedback-law slot of stage k from the forward sweep until the next
+    // backward sweep (rows that do not exist: 0)
 
     // ---------------- stage the QP ----------------
     constexpr int NAB = NX * NX + NX * NU + NX;  // record elements [W_A, W_q): A, B, b
@@ -156,7 +158,7 @@ struct CoopQP {
       LU[k] = L.it[(size_t)(E::it_lam(N, k) + 1) * bs];
       TL[k] = L.it[(size_t)E::it_t(N, k) * bs];
       TU[k] = L.it[(size_t)(E::it_t(N, k) + 1) * bs];
-      LHL[k] = LHU[k] = THL[k] = THU[k] = 0.0;
+      LHL[k] = LHU[k] = 0.0;
     }
     for (int idx = lane; idx < 3 * NWS; idx += 32) {
       const int kind = idx / NWS, e = idx - kind * NWS;
@@ -237,8 +239,11 @@ struct CoopQP {
       for (int k = lane; k < NS; k += 32) {
         double ll = LL[k], lu = LU[k], tl = TL[k], tu = TU[k];
         if (alpha > 0.0) {
-          ll += alpha * (LHL[k] - ll); tl += alpha * (THL[k] - tl);
-          lu += alpha * (LHU[k] - lu); tu += alpha * (THU[k] - tu);
+          const bool row = k >= k_first && k < N;
+          const double duk = row ? Kk[k * NW + NX] : 0.0, uk = U[k];
+          const double thl = (row && has_l) ? (uk - lb) + duk : 0.0, thu = (row && has_u) ? (ub - uk) - duk : 0.0;
+          ll += alpha * (LHL[k] - ll); tl += alpha * (thl - tl);
+          lu += alpha * (LHU[k] - lu); tu += alpha * (thu - tu);
           LL[k] = ll; LU[k] = lu; TL[k] = tl; TU[k] = tu;
         }
         const bool act = k >= k_first && k < N;
@@ -361,18 +366,17 @@ struct CoopQP {
       double amax = 1e300, s0 = 0.0, s1 = 0.0, s2 = 0.0, cmax = 0.0;
       for (int k = lane; k < NS; k += 32) {
         const bool act = k >= k_first && k < N;
+        if (reuse && k < N) Kk[k * NW + NX] = L.ws[((size_t)k * E::W_REC + E::W_du) * bs];  // du_k of k_qp1's Newton iteration
         const double dv = (k < N) ? Kk[k * NW + NX] : 0.0, u = U[k];
         double lhl = 0.0, thl = 0.0, lhu = 0.0, thu = 0.0;
         if (act && has_l) {
           const double ll = LL[k], tl = TL[k];
+          thl = (u - lb) + dv;
           if (reuse) {
             lhl = L.ws[((size_t)k * E::W_REC + E::W_lh) * bs];
-            thl = L.ws[((size_t)k * E::W_REC + E::W_th) * bs];
           } else {
-            const double d = (u - lb) + dv;
             const double itb = 1.0 / tl, cb = ll * itb, ab = target * itb + ll;
-            thl = d;
-            lhl = ab - cb * d;
+            lhl = ab - cb * thl;
           }
           const double dt = thl - tl, dl = lhl - ll;
           if (dt < 0.0) amax = dmin(amax, -tl / dt);
@@ -382,14 +386,12 @@ struct CoopQP {
         }
         if (act && has_u) {
           const double lu = LU[k], tu = TU[k];
+          thu = (ub - u) - dv;
           if (reuse) {
             lhu = L.ws[((size_t)k * E::W_REC + E::W_lh + 1) * bs];
-            thu = L.ws[((size_t)k * E::W_REC + E::W_th + 1) * bs];
           } else {
-            const double d = (ub - u) - dv;
             const double itb = 1.0 / tu, cb = lu * itb, ab = target * itb + lu;
-            thu = d;
-            lhu = ab - cb * d;
+            lhu = ab - cb * thu;
           }
           const double dt = thu - tu, dl = lhu - lu;
           if (dt < 0.0) amax = dmin(amax, -tu / dt);
@@ -397,7 +399,7 @@ struct CoopQP {
           s0 += lu * tu; s1 += lu * dt + tu * dl; s2 += dl * dt;
           cmax = dmax(cmax, dabs(dl * dt));
         }
-        LHL[k] = lhl; THL[k] = thl; LHU[k] = lhu; THU[k] = thu;
+        LHL[k] = lhl; LHU[k] = lhu;
       }
       __syncwarp();
       {  // NaN anywhere in the step must reach amax like in the scalar code (a NaN slack fails "dt < 0")
@@ -426,7 +428,7 @@ struct CoopQP {
           const bool act = k >= k_first && k < N;
           if (act && has_l) {
             double ll = LL[k], tl;
-            const double lh = LHL[k], th = THL[k];
+            const double lh = LHL[k], th = (U[k] - lb) + Kk[k * NW + NX];
             if (!(th > eps_t)) { ll = dmax(dmax(lh, ll), 1e-3); tl = dmin(eps_t, pd.tau / ll); }
             else if (!(lh > 0.0)) { tl = dmax(th, AS_RELEASE * range); ll = pd.tau / tl; }
             else { tl = th; ll = lh; }
@@ -435,7 +437,7 @@ struct CoopQP {
           }
           if (act && has_u) {
             double lu = LU[k], tu;
-            const double lh = LHU[k], th = THU[k];
+            const double lh = LHU[k], th = (ub - U[k]) - Kk[k * NW + NX];
             if (!(th > eps_t)) { lu = dmax(dmax(lh, lu), 1e-3); tu = dmin(eps_t, pd.tau / lu); }
             else if (!(lh > 0.0)) { tu = dmax(th, AS_RELEASE * range); lu = pd.tau / tu; }
             else { tu = th; lu = lh; }
@@ -455,7 +457,8 @@ struct CoopQP {
         break;
       }
       const double mu_new = (s0 + alpha * s1 + alpha * alpha * s2) / m_rows;
-      if (target <= pd.tau && alpha == 1.0 && cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) converged = true;
+      // (not on the picked-up iteration: k_qp1 has declined exactly this step, and its dx is not in shared memory)
+      if (!reuse && target <= pd.tau && alpha == 1.0 && cmax <= dmin(pd.comp_accept * pd.tau, 0.1 * pd.tol)) converged = true;
       const double r = 1.0 - alpha;
       sigma = dmin(0.8, dmax(pd.sigma_min, r * r * 4.0 + pd.sigma_min));
       mu = mu_new;
@@ -468,9 +471,10 @@ struct CoopQP {
     for (int k = lane; k < NS; k += 32) {
       const bool act = k >= k_first && k < N;
       const double ll = (act && has_l) ? LL[k] + alpha * (LHL[k] - LL[k]) : 0.0;
-      const double tl = (act && has_l) ? TL[k] + alpha * (THL[k] - TL[k]) : 0.0;
+      const double duk = act ? Kk[k * NW + NX] : 0.0;
+      const double tl = (act && has_l) ? TL[k] + alpha * (((U[k] - lb) + duk) - TL[k]) : 0.0;
       const double lu = (act && has_u) ? LU[k] + alpha * (LHU[k] - LU[k]) : 0.0;
-      const double tu = (act && has_u) ? TU[k] + alpha * (THU[k] - TU[k]) : 0.0;
+      const double tu = (act && has_u) ? TU[k] + alpha * (((ub - U[k]) - duk) - TU[k]) : 0.0;
       if (k < N) {
         L.it[(size_t)E::it_lam(N, k) * bs] = ll;
         L.it[(size_t)(E::it_lam(N, k) + 1) * bs] = lu;

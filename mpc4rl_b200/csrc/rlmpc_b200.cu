@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(32) k_qp2c(const __grid_constant__ ProblemData
 #define RLMPC_COOP_WARPS 4
 #endif
 #ifndef RLMPC_COOP_MINB
-#define RLMPC_COOP_MINB 3
+#define RLMPC_COOP_MINB 4
 #endif
 constexpr int COOP_WARPS = RLMPC_COOP_WARPS;  // samples in flight per block
 
@@ -450,7 +450,7 @@ template <class M, bool GEN>
 struct CoopSel<M, true, GEN> {
   static constexpr bool value = true;
   static constexpr int WARPS = COOP_WARPS;
-  static constexpr int MINB = RLMPC_COOP_MINB;  // 15 KB of shared memory per sample: 3 blocks of 4 samples per SM, 168 registers each
+  static constexpr int MINB = RLMPC_COOP_MINB;  // 14.0 KB of shared memory per sample: 4 blocks of 4 samples per SM (16 warps), 128 registers each
   using Solver = CoopQP<M>;
 };
 template <class M>
@@ -890,6 +890,10 @@ cudaError_t setup_coop(rlmpc_handle* h, int N, cudaError_t e) {
     // with different horizons can coexist (the launch passes the size this handle needs)
     e = cudaFuncSetAttribute(k_qp3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qp3<M>, CoopSel<M>::WARPS * 32, smem);
+    if (const char* cap = getenv("RLMPC_COOP_BLOCKS_PER_SM")) {  // tuning / debugging aid
+      const int c = atoi(cap);
+      if (c > 0 && c < per_sm) per_sm = c;
+    }
     if (e == cudaSuccess) h->coop_grid = sms * per_sm;
   }
   return e;
