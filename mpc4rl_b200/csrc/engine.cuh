@@ -1385,6 +1385,17 @@ struct Engine {
     double gp[NPM];
     MPC_UNROLL for (int i = 0; i < NPM; ++i) gp[i] = 0.0;
     double P[NX * NX], pdummy[NX], carry[NX];
+    // dpi/dtheta for a handful of model parameters (cart-pole: 3 or 4): DIRECT sensitivities -- the KKT system of
+    // update_nlp with right-hand side -dR/dtheta_j is a Riccati solve with gradient Hwp[:, j] and affine term Fp[:, j],
+    // i.e. one more vector recursion p_j per parameter riding on the factorisation of the backward sweep, and
+    // dpi/dtheta_j = du_0 = -G_0^{-1} gv_0 (x_0 is fixed).  No forward pass, no P / K records, every stage record is
+    // read once.  With many parameters (cost parameters, linear system) the adjoint solves below are cheaper.
+    constexpr bool FWD_OK = !M::PARAMS_COST_ONLY && NPM > 0 && NPM <= 4;
+    constexpr int NPF = FWD_OK ? NPM : 1;
+    const bool fwd = FWD_OK && !pd.param_cost && dpidth != nullptr;
+    double pv[NPF * NX], dpi_f[NU * NPF];
+    MPC_UNROLL for (int i = 0; i < NPF * NX; ++i) pv[i] = 0.0;
+    MPC_UNROLL for (int i = 0; i < NU * NPF; ++i) dpi_f[i] = 0.0;
     {  // terminal stage
       const double* w = L.ws + (size_t)N * W_REC * bs;
       double g[NW], Hm[NW * NW];
@@ -1476,12 +1487,24 @@ struct Engine {
           if (j != i) Hm[j * NW + i] = Hm[i * NW + j];
         }
         barrier_hess(bd, lam, t, Hm);
-        double Pp[NPS];
-        {
+        double Hwp[NW * NPF], vj[NPF * NX];
+        if (fwd) {  // v_j = p_j + P_{k+1} Fp[:, j]  (before P is overwritten)
+          if constexpr (FWD_OK) {
+            double Fp[NX * NPM];
+            ld<NW * NPM>(w + (size_t)S_Hwp * bs, bs, Hwp);
+            ld<NX * NPM>(w + (size_t)S_Fp * bs, bs, Fp);
+            MPC_UNROLL for (int j = 0; j < NPM; ++j) MPC_UNROLL for (int i = 0; i < NX; ++i) {
+              double a = pv[j * NX + i];
+              MPC_UNROLL for (int l = 0; l < NX; ++l) a += P[i * NX + l] * Fp[l * NPM + j];
+              vj[j * NX + i] = a;
+            }
+          }
+        } else {
+          double Pp[NPS];
           int c_ = 0;
           MPC_UNROLL for (int i = 0; i < NX; ++i) MPC_UNROLL for (int j = i; j < NX; ++j) Pp[c_++] = P[i * NX + j];
+          st<NPS>(w + (size_t)S_P * bs, bs, Pp);
         }
-        st<NPS>(w + (size_t)S_P * bs, bs, Pp);
         double K[NU * NX], kff[NU], Ginv[NU * NU], zg[NW], zb[NX];
         MPC_UNROLL for (int i = 0; i < NW; ++i) zg[i] = 0.0;
         MPC_UNROLL for (int i = 0; i < NX; ++i) zb[i] = 0.0;
@@ -1495,16 +1518,50 @@ struct Engine {
           MPC_UNROLL for (int i = 0; i < NU * NX; ++i) K[i] = 0.0;
           MPC_UNROLL for (int i = 0; i < NU * NU; ++i) Ginv[i] = 0.0;
         }
-        st<NU * NX>(w + (size_t)S_K * bs, bs, K);
-        if (k == 0) st<NU * NU>(w + (size_t)S_Gi * bs, bs, Ginv);
+        if (fwd) {
+          if constexpr (FWD_OK) {
+            if (!ufixed) {
+              MPC_UNROLL for (int j = 0; j < NPM; ++j) {
+                double gv[NU];
+                MPC_UNROLL for (int a = 0; a < NU; ++a) {
+                  double v = Hwp[(NX + a) * NPM + j];
+                  MPC_UNROLL for (int l = 0; l < NX; ++l) v += B[l * NU + a] * vj[j * NX + l];
+                  gv[a] = v;
+                }
+                if (k == 0) {
+                  MPC_UNROLL for (int a = 0; a < NU; ++a) {
+                    double v = 0.0;
+                    MPC_UNROLL for (int b = 0; b < NU; ++b) v -= Ginv[a * NU + b] * gv[b];
+                    dpi_f[a * NPM + j] = v;
+                  }
+                }
+                MPC_UNROLL for (int i = 0; i < NX; ++i) {  // p_j <- q_j + A'v_j + H'kff_j,  H'kff_j = K'gv_j
+                  double v = Hwp[i * NPM + j];
+                  MPC_UNROLL for (int l = 0; l < NX; ++l) v += A[l * NX + i] * vj[j * NX + l];
+                  MPC_UNROLL for (int a = 0; a < NU; ++a) v += K[a * NX + i] * gv[a];
+                  pv[j * NX + i] = v;
+                }
+              }
+            }
+          }
+        } else {
+          st<NU * NX>(w + (size_t)S_K * bs, bs, K);
+          if (k == 0) st<NU * NU>(w + (size_t)S_Gi * bs, bs, Ginv);
+        }
       }
     }
     MPC_UNROLL for (int i = 0; i < NX; ++i) (void)pdummy[i];
     if (dLdth) {
       MPC_UNROLL for (int j = 0; j < NPM; ++j) dLdth[j] = gp[j];
     }
+    if (fwd) {
+      if constexpr (FWD_OK) {
+        MPC_UNROLL for (int r = 0; r < NU; ++r) MPC_UNROLL for (int j = 0; j < NPM; ++j)
+          dpidth[(size_t)r * grad_width(pd) + j] = qmode ? 0.0 : dpi_f[r * NPM + j];
+      }
+    }
     // ---- forward pass: NU adjoint solves  K y_i = e_{u0,i},  dpi_i/dtheta = -y_i' dR/dtheta ----
-    if (dpidth) {
+    if (dpidth && !fwd) {
       double acc[NU * NPM];
       MPC_UNROLL for (int i = 0; i < NU * NPM; ++i) acc[i] = 0.0;
       if (!qmode) {
