@@ -1509,7 +1509,7 @@ struct Engine {
         MPC_UNROLL for (int i = 0; i < NW; ++i) zg[i] = 0.0;
         MPC_UNROLL for (int i = 0; i < NX; ++i) zb[i] = 0.0;
         if (!ufixed) {
-#ifdef RLMPC_SENS_REQUIRE_PD  // (round-1 behaviour, kept to label fixtures: oracle/make_golden_indefinite.py)
+#ifdef RLMPC_SENS_REQUIRE_PD  // (round-1 behaviour; a test-side build uses it to label the samples of the indefinite-Hessian fixture)
           if (!riccati_step<true>(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
 #else
           if (!riccati_step<false>(P, pdummy, A, B, zb, Hm, zg, K, kff, Ginv)) ok = false;
