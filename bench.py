@@ -92,15 +92,15 @@ WORKLOADS = {
                               "dpi/dtheta, warm-started from the previous iterate; x0 = define_x0 + N(0, 1e-2) redrawn every step"),
 }
 # Executed FP64 flops per unit: 2 * DFMA + DADD + DMUL thread-level instructions summed over the kernels of one step and
-# divided by the units of the step -- ncu counters of the committed step profiles (profiles/r02_step_<workload>.csv,
+# divided by the units of the step -- ncu counters of the committed step profiles (profiles/r02z_step_<workload>.csv (final build of round 2),
 # tools/profile_step.py, summarised in profiles/r02_summary.md).  The chain-mass kernels also run FP64 tensor-core
 # instructions (mma.sync m8n8k4 = 512 flop per warp instruction, zero padding of 21 -> 24 included); their count is
 # structural: per sample 40 stages x 144 per Riccati factorisation (one per interior-point iteration of the step + one
 # in the sensitivity sweep) and 40 x 8 x 27 in the Hessian accumulation.  None = not measured for this workload.
-FLOPS_PER_UNIT = {"cartpole": 629630.0, "cartpole_tiny_pert": 291358.0, "chain_mass": 10342403.0}
-FLOPS_SOURCE = "profiles/r02_step_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel) + structural DMMA count"
+FLOPS_PER_UNIT = {"cartpole": 409179.0, "cartpole_tiny_pert": 272861.0, "evaporation": 1266374.0, "chain_mass": 10111474.0}
+FLOPS_SOURCE = "profiles/r02z_step_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel) + structural DMMA count"
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step (same profiles)
-TRAFFIC_PER_STEP = {"cartpole": 9.531e9, "cartpole_tiny_pert": 9.289e9, "chain_mass": 31.003e9}
+TRAFFIC_PER_STEP = {"cartpole": 8.441e9, "cartpole_tiny_pert": 8.238e9, "evaporation": 11.254e9, "chain_mass": 29.108e9}
 
 
 def dmma_flops_per_unit(workload, ipm_iters_mean):
@@ -577,7 +577,7 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
                          "traffic": TRAFFIC_PER_STEP.get(args.workload) if B == wl["batch"] else None,
-                         "traffic_source": "profiles/r02_step_*.csv (dram read + write bytes summed over the kernels of one step, ncu)",
+                         "traffic_source": "profiles/r02z_step_*.csv (dram read + write bytes summed over the kernels of one step, ncu)",
                          "peak_source": peak_src,
                          "kernel": ("rlmpc_solve_sens = k_chain_stage<lin> + k_chain_qp + k_chain_stage<hess> + k_chain_sens + k_chain_param"
                                     if chain else "rlmpc_solve_sens = k_lin + k_qp1 + k_qp3 + k_sens_stage + k_sens_sweep") + f" (dominant: {dom})",

@@ -126,6 +126,8 @@ int rlmpc_set_bounds(rlmpc_handle* h, const char* field, const double* v, int n)
  * streams is launch-bound (strong scaling over 8 GPUs: 8 192 samples per rank).  Not combined with "timing",
  * "as_steps" (20): active-set (full Newton step + projection) iterations a warm start may take when
  * its Newton step is infeasible, before it falls back to a cold start,
+ * "fuse_lin" (0): 1 = the convergence-test / fast-path kernel linearises every stage itself instead of reading the
+ * records of a separate (sample, stage) launch (measured equal at best, see profiles/r02_summary.md),
  * "ipm_passes" (0): n > 0 = n thread-per-sample pass kernels, each ONE interior-point iteration of every queued
  * sample in place, ahead of the queue kernel (measured slower on every workload, see profiles/r02_summary.md),
  * "param_cost" (0: dL/dtheta only for model parameters = parameterize_tracking_cost False) */

@@ -622,6 +622,10 @@ struct Engine {
   // the accuracy update_nlp's R = 0 assumes for the sensitivities), not merely within the acceptance
   // neighbourhood comp_accept of the steps on the way; otherwise one more (cheap, warm) Newton iteration
   // follows.  Off for the final test-only round of an SQP solve, where the plain acados criterion decides.
+  // LIN: linearise every stage right before the backward sweep reads it (the sample's own thread does lin_stage();
+  // the record still goes to memory for the forward sweep and the queue kernel, but is read back from cache here, and
+  // the separate (sample, stage) launch disappears).
+  template <bool LIN = false>
   MPC_HD static int qp_fast(const ProblemData& pd, const Lane& L, Residuals& R, int* swept = nullptr, bool polish = true) {
     const int N = pd.N;
     constexpr size_t bs = TILE;
@@ -632,6 +636,7 @@ struct Engine {
     double P[NX * NX], p[NX];
     double carry[NX];  // x-stationarity of stage k+1 without the -pi_k term
     {                  // terminal stage
+      if (LIN) lin_stage(pd, L, N);
       const double* w = L.ws + (size_t)N * W_REC * bs;
       double g[NW], Hm[NW * NW];
       ld<NX>(w + (size_t)W_q * bs, bs, g);
@@ -662,6 +667,7 @@ struct Engine {
       }
     }
     for (int k = N - 1; k >= 0; --k) {
+      if (LIN) lin_stage(pd, L, k);
       double* w = L.ws + (size_t)k * W_REC * bs;
       double A[NX * NX], B[NX * NU], bb[NX], g[NW], x[NX], u[NU], pik[NX], lam[NR], t[NR], v[NV];
       ld<NX * NX>(w + (size_t)W_A * bs, bs, A);

@@ -150,8 +150,12 @@ __global__ void __launch_bounds__(STPB, RLMPC_LIN_MINB) k_lin(const __grid_const
 }
 
 // sample kernel: convergence test + one warm interior-point Newton iteration (fast path)
-template <class M>
-__global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
+#ifndef RLMPC_QP1L_MINB
+#define RLMPC_QP1L_MINB 8
+#endif
+// LIN: the linearisation of every stage is done by the sample's own thread inside the sweep (option "fuse_lin")
+template <class M, bool LIN>
+__global__ void __launch_bounds__(TPB, LIN ? RLMPC_QP1L_MINB : RLMPC_QP1_MINB) k_qp1(const __grid_constant__ ProblemData pd, const KArgs a) {
   using E = Engine<M>;
   const int bi = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = a.b0 + bi;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(TPB, RLMPC_QP1_MINB) k_qp1(const __grid_consta
   const Lane L = make_lane<M>(a, b);
   typename E::Residuals R;
   int swept = 0;
-  const int code = E::qp_fast(pd, L, R, &swept, /*polish=*/!a.last_round);
+  const int code = E::template qp_fast<LIN>(pd, L, R, &swept, /*polish=*/!a.last_round);
   a.cost[b] = R.cost;
   a.ishard[b] = (code == E::FAST_HARD && !a.last_round) ? (swept ? 2 : 1) : 0;
   if (code == E::FAST_NAN) {
@@ -763,6 +767,9 @@ struct rlmpc_handle {
   int *work = nullptr, *status = nullptr, *hard = nullptr, *ishard = nullptr, *counters = nullptr;
   int ring = 1;     // queued interior-point pass reads through the cp.async shared-memory ring (0: direct loads)
   int inplace_queue = 0;
+  int fuse_lin = 0;    // 1: k_qp1 linearises the stages itself (no k_lin launch).  Measured equal at best: the fused kernel
+                       // takes 0.66 ms (128 registers) against 0.17 + 0.50 ms of the two launches, the step 2.42 vs 2.40 ms --
+                       // the FP64 work of the linearisation does not hide under the sweep's memory time at 65 536 threads
   int ipm_passes = 0;  // pass kernels (one interior-point iteration of every queued sample each) before the queue kernel.
                        // Measured slower on every workload (headline: queue 2.48 -> 3.76 ms with 5 passes, evaporation
                        // 4.05 -> 6.56 ms): a pass costs its full ~0.45 ms as long as most WARPS still hold one queued
@@ -945,11 +952,17 @@ int pipeline_solve(rlmpc_handle* h, KArgs a, cudaStream_t s, bool fork_qp2) {
     CUDA_OK(cudaMemsetAsync(a.counters, 0, NCNT * sizeof(int), s));
     mark(h, 0, s);
     if constexpr (CoopSel<M>::value) a.two_ended = (h->coop && h->coop_grid > 0 && !a.inplace && !fork_qp2) ? 1 : 0;
-    k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
-    mark(h, 1, s);
-    k_qp1<M><<<gs, TPB, 0, s>>>(h->pd, a);
+    if (h->fuse_lin) {
+      mark(h, 1, s);
+      k_qp1<M, true><<<gs, TPB, 0, s>>>(h->pd, a);
+      h->launches += 1;
+    } else {
+      k_lin<M><<<gstage, STPB, 0, s>>>(h->pd, a);
+      mark(h, 1, s);
+      k_qp1<M, false><<<gs, TPB, 0, s>>>(h->pd, a);
+      h->launches += 2;
+    }
     mark(h, 2, s);
-    h->launches += 2;
     if (!a.last_round) {
       cudaStream_t sq = s;
       if (fork_qp2) {  // queued samples continue on the side stream; the caller joins on ev_join
@@ -1115,7 +1128,7 @@ int run_unit(rlmpc_handle* h, int mode, int max_sqp, int B, const double* x0, co
         const unsigned char* c = (const unsigned char*)p;
         for (size_t i = 0; i < n; ++i) { key ^= c[i]; key *= 1099511628211ull; }
       };
-      mix(&a, sizeof(a)); mix(&h->pd, sizeof(h->pd)); mix(&h->split, sizeof(int)); mix(&h->coop, sizeof(int)); mix(&h->ipm_passes, sizeof(int));
+      mix(&a, sizeof(a)); mix(&h->pd, sizeof(h->pd)); mix(&h->split, sizeof(int)); mix(&h->coop, sizeof(int)); mix(&h->ipm_passes, sizeof(int)); mix(&h->fuse_lin, sizeof(int));
       mix(&h->th_per_sample, sizeof(int)); mix(&s, sizeof(s));
       if (h->graph_exec && key == h->graph_key) {
         CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
@@ -1522,6 +1535,7 @@ int rlmpc_set_option(rlmpc_handle* h, const char* name, double value) {
   else if (!strcmp(name, "condense")) h->condense = (int)value;
   else if (!strcmp(name, "inplace_queue")) h->inplace_queue = (int)value;
   else if (!strcmp(name, "ipm_passes")) h->ipm_passes = value < 0 ? 0 : (int)value;
+  else if (!strcmp(name, "fuse_lin")) h->fuse_lin = (int)value;
   else return fail(RLMPC_EINVAL, std::string("unknown option ") + name);
   return 0;
 }
