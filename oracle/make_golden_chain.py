@@ -6,7 +6,7 @@ rlmpc/mpc/chain_mass/ocp_utils.py:42-56, 59-147, 195-316, 353-371 as restated in
   * one SQP-RTI step from the converged V iterate after the state moved by one closed-loop step of the nominal
     model plus a small disturbance, x0' = f_disc(x0, u0*) + N(0, 1e-3), and update_nlp at the resulting iterate.
 
-    python -m oracle.make_golden_chain <n_mass> <n_samples> [n_procs]    # tests/golden/chain_mass_<n_mass>.npz
+    python -m oracle.make_golden_chain <n_mass> <n_samples> [n_procs] [tag]   # tests/golden/chain_mass_<n_mass><tag>.npz
 """
 from __future__ import annotations
 
@@ -41,7 +41,7 @@ def _one(args):
                 x1=x1, V1=r.cost, u1=r.U[0], dV1=ru["dL_dp"][0], dpi1=ru["dpi_dp"], kkt1=r.kkt)
 
 
-def main(n_mass=3, n=4, procs=4, seed=50):
+def main(n_mass=3, n=4, procs=4, seed=50, tag=""):
     from .problems import make_chain_mass
 
     pb = make_chain_mass(n_mass)
@@ -53,10 +53,11 @@ def main(n_mass=3, n=4, procs=4, seed=50):
         res = pool.map(_one, [(n_mass, i, x0s[i], acts[i], noise[i]) for i in range(n)], chunksize=1)
     out = {k: np.array([r[k] for r in res]) for k in res[0]}
     out["theta"] = pb.p_nominal; out["x_ss"] = pb.x_ss; out["n_mass"] = n_mass
-    path = os.path.join(ROOT, "tests", "golden", f"chain_mass_{n_mass}.npz")
+    path = os.path.join(ROOT, "tests", "golden", f"chain_mass_{n_mass}{tag}.npz")
     np.savez_compressed(path, **out)
     print("wrote", path)
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 4)
+    # optional 4th argument: file-name tag of an additional (larger) set, e.g. "_64" -> chain_mass_3_64.npz
+    main(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 4, tag=sys.argv[4] if len(sys.argv) > 4 else "")
