@@ -135,6 +135,7 @@ struct CoopQP {
 
     // ---------------- stage the QP ----------------
     constexpr int NAB = NX * NX + NX * NU + NX;  // record elements [W_A, W_q): A, B, b
+#pragma unroll 4  // several of the scattered global loads in flight per lane
     for (int idx = lane; idx < N * NAB; idx += 32) {
       const int k = idx / NAB, e = idx - k * NAB;
       const double v = L.ws[((size_t)k * E::W_REC + e) * bs];
@@ -148,6 +149,7 @@ struct CoopQP {
       }
       Mk[k * NX * NC + row * NC + col] = v;
     }
+#pragma unroll 4  // several of the scattered global loads in flight per lane
     for (int idx = lane; idx < NS * NW; idx += 32) {
       const int k = idx / NW, e = idx - k * NW;
       Gk[idx] = (k < N || e < NX) ? L.ws[((size_t)k * E::W_REC + E::W_q + e) * bs] : 0.0;

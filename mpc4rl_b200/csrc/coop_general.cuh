@@ -64,6 +64,7 @@ struct CoopGen {
 
     // ---------------- stage the QP ----------------
     constexpr int NAB = NX * NX + NX * NU + NX;  // record elements [W_A, W_q): A, B, b
+#pragma unroll 4  // several of the scattered global loads in flight per lane
     for (int idx = lane; idx < N * NAB; idx += 32) {
       const int k = idx / NAB, e = idx - k * NAB;
       const double v = L.ws[((size_t)k * E::W_REC + e) * bs];
@@ -77,11 +78,13 @@ struct CoopGen {
       }
       Mk[k * NX * NC + row * NC + col] = v;
     }
+#pragma unroll 4  // several of the scattered global loads in flight per lane
     for (int idx = lane; idx < NS * NW; idx += 32) {
       const int k = idx / NW, e = idx - k * NW;
       Gk[idx] = (k < N || e < NX) ? L.ws[((size_t)k * E::W_REC + E::W_q + e) * bs] : 0.0;
       XU[idx] = (e < NX) ? L.it[(size_t)(E::it_x(N, k) + e) * bs] : (k < N ? L.it[(size_t)(E::it_u(N, k) + e - NX) * bs] : 0.0);
     }
+#pragma unroll 4  // several of the scattered global loads in flight per lane
     for (int idx = lane; idx < NS * NR; idx += 32) {
       const int k = idx / NR, q = idx - k * NR;
       LAM[q * NS + k] = L.it[(size_t)(E::it_lam(N, k) + q) * bs];

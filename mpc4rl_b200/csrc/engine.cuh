@@ -121,12 +121,14 @@ struct Engine {
       return true;
     }
     bool ok = true;
+    double dinv[n];  // reciprocal pivots: one division per pivot, the n x m diagonal scalings below multiply
     MPC_UNROLL for (int j = 0; j < n; ++j) {
       double d = G[j * n + j];
       MPC_UNROLL for (int p = 0; p < j; ++p) d -= G[j * n + p] * G[j * n + p] * G[p * n + p];
       if (PD ? !(d > 0.0) : !(d > 0.0 || d < 0.0)) ok = false;
       G[j * n + j] = d;
       const double inv = 1.0 / d;
+      dinv[j] = inv;
       MPC_UNROLL for (int i = j + 1; i < n; ++i) {
         double v = G[i * n + j];
         MPC_UNROLL for (int p = 0; p < j; ++p) v -= G[i * n + p] * G[j * n + p] * G[p * n + p];
@@ -139,7 +141,7 @@ struct Engine {
         MPC_UNROLL for (int p = 0; p < i; ++p) v -= G[i * n + p] * R[p * m + c];
         R[i * m + c] = v;
       }
-      MPC_UNROLL for (int i = 0; i < n; ++i) R[i * m + c] /= G[i * n + i];
+      MPC_UNROLL for (int i = 0; i < n; ++i) R[i * m + c] *= dinv[i];
       MPC_UNROLL for (int i = n - 1; i >= 0; --i) {
         double v = R[i * m + c];
         MPC_UNROLL for (int p = i + 1; p < n; ++p) v -= G[p * n + i] * R[p * m + c];
