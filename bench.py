@@ -97,10 +97,10 @@ WORKLOADS = {
 # instructions (mma.sync m8n8k4 = 512 flop per warp instruction, zero padding of 21 -> 24 included); their count is
 # structural: per sample 40 stages x 144 per Riccati factorisation (one per interior-point iteration of the step + one
 # in the sensitivity sweep) and 40 x 8 x 27 in the Hessian accumulation.  None = not measured for this workload.
-FLOPS_PER_UNIT = {"cartpole": 409179.0, "cartpole_tiny_pert": 272861.0, "evaporation": 1266374.0, "chain_mass": 10111474.0}
+FLOPS_PER_UNIT = {"cartpole": 409203.0, "cartpole_tiny_pert": 272867.0, "evaporation": 1161237.0, "chain_mass": 10111470.0}
 FLOPS_SOURCE = "profiles/r02z_step_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel) + structural DMMA count"
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step (same profiles)
-TRAFFIC_PER_STEP = {"cartpole": 8.441e9, "cartpole_tiny_pert": 8.238e9, "evaporation": 11.254e9, "chain_mass": 29.108e9}
+TRAFFIC_PER_STEP = {"cartpole": 8.449e9, "cartpole_tiny_pert": 8.245e9, "evaporation": 11.264e9, "chain_mass": 29.106e9}
 
 
 def dmma_flops_per_unit(workload, ipm_iters_mean):
