@@ -114,6 +114,21 @@ struct CartpoleModelT {
     }
   }
 
+  // sin / cos of the pole angle at the later RK stage points: theta_0 + d with |d| = O(h theta_dot) small, so the angle
+  // addition formulas with degree-13 / degree-12 Taylor polynomials of sin d / cos d (error < 3e-18 for |d| <= 0.25)
+  // replace three of the four FP64 sincos calls of a step (ncu: sincos was 24 % of the instructions of k_lin).
+  MPC_HD static void stage_sincos(double d, double angle, double sn0, double cs0, double* sn, double* cs) {
+    if (!(dabs(d) <= 0.25)) {
+      sincos(angle, sn, cs);
+      return;
+    }
+    const double q = d * d;
+    const double sd = d * (1.0 - q * (1.0 / 6.0) * (1.0 - q * (1.0 / 20.0) * (1.0 - q * (1.0 / 42.0) * (1.0 - q * (1.0 / 72.0) * (1.0 - q * (1.0 / 110.0) * (1.0 - q * (1.0 / 156.0)))))));
+    const double cd = 1.0 - q * 0.5 * (1.0 - q * (1.0 / 12.0) * (1.0 - q * (1.0 / 30.0) * (1.0 - q * (1.0 / 56.0) * (1.0 - q * (1.0 / 90.0) * (1.0 - q * (1.0 / 132.0))))));
+    *sn = sn0 * cd + cs0 * sd;
+    *cs = cs0 * cd - sn0 * sd;
+  }
+
   // ---- dynamics -------------------------------------------------------------------------
   // One RK4 step with forward propagation of d(.)/d zeta, zeta = (x0..x3, F, M, m, l (, g));
   // NC = 5 -> columns (x,u) only (SQP linearisation), NC = NZ -> also the parameter columns.
@@ -125,7 +140,7 @@ struct CartpoleModelT {
                              double* xn, double* DF /* 4 x NC row-major */,
                              double* keep /* optional per-stage data for the adjoint pass, or nullptr */) {
     constexpr int NE = NC - 2;
-    double S[4][NE], acc[4][NE], s[4], xa[4];
+    double S[4][NE], acc[4][NE], s[4], xa[4], sn0 = 0.0, cs0 = 1.0;
     MPC_UNROLL for (int i = 0; i < 4; ++i) {
       s[i] = x[i];
       xa[i] = 0.0;
@@ -136,7 +151,12 @@ struct CartpoleModelT {
     }
     MPC_UNROLL for (int st = 0; st < 4; ++st) {
       double sn, cs, xdd, thdd, jx[NV], jt[NV];
-      sincos(s[2], &sn, &cs);
+      if (st == 0) {
+        sincos(s[2], &sn, &cs);
+        sn0 = sn; cs0 = cs;
+      } else {
+        stage_sincos(s[2] - x[2], s[2], sn0, cs0, &sn, &cs);
+      }
       if constexpr (NPM_ == 4 && NC > 5) cartpole_f_jac_g(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       else cartpole_f_jac(sn, cs, s[3], F, M, m, l, g, &xdd, &thdd, jx, jt);
       if (keep) {  // stage point + the S rows the adjoint pass needs (first stage: unit vectors, not stored)
