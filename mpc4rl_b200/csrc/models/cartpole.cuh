@@ -122,9 +122,11 @@ struct CartpoleModelT {
       sincos(angle, sn, cs);
       return;
     }
-    const double q = d * d;
-    const double sd = d * (1.0 - q * (1.0 / 6.0) * (1.0 - q * (1.0 / 20.0) * (1.0 - q * (1.0 / 42.0) * (1.0 - q * (1.0 / 72.0) * (1.0 - q * (1.0 / 110.0) * (1.0 - q * (1.0 / 156.0)))))));
-    const double cd = 1.0 - q * 0.5 * (1.0 - q * (1.0 / 12.0) * (1.0 - q * (1.0 / 30.0) * (1.0 - q * (1.0 / 56.0) * (1.0 - q * (1.0 / 90.0) * (1.0 - q * (1.0 / 132.0))))));
+    const double q = d * d;  // Horner, coefficients (-1)^k / (2k+1)!  and  (-1)^k / (2k)!
+    const double ps = -1.0 / 6.0 + q * (1.0 / 120.0 + q * (-1.0 / 5040.0 + q * (1.0 / 362880.0 + q * (-1.0 / 39916800.0 + q * (1.0 / 6227020800.0)))));
+    const double pc = -0.5 + q * (1.0 / 24.0 + q * (-1.0 / 720.0 + q * (1.0 / 40320.0 + q * (-1.0 / 3628800.0 + q * (1.0 / 479001600.0)))));
+    const double sd = d + (d * q) * ps;
+    const double cd = 1.0 + q * pc;
     *sn = sn0 * cd + cs0 * sd;
     *cs = cs0 * cd - sn0 * sd;
   }
