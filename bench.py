@@ -97,10 +97,10 @@ WORKLOADS = {
 # instructions (mma.sync m8n8k4 = 512 flop per warp instruction, zero padding of 21 -> 24 included); their count is
 # structural: per sample 40 stages x 144 per Riccati factorisation (one per interior-point iteration of the step + one
 # in the sensitivity sweep) and 40 x 8 x 27 in the Hessian accumulation.  None = not measured for this workload.
-FLOPS_PER_UNIT = {"cartpole": 409203.0, "cartpole_tiny_pert": 272867.0, "evaporation": 1161237.0, "chain_mass": 10111470.0}
+FLOPS_PER_UNIT = {"cartpole": 373203.0, "cartpole_tiny_pert": 236867.0, "evaporation": 1161236.0, "chain_mass": 10111475.0}
 FLOPS_SOURCE = "profiles/r02z_step_*.csv (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on.sum per kernel) + structural DMMA count"
 # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step (same profiles)
-TRAFFIC_PER_STEP = {"cartpole": 8.449e9, "cartpole_tiny_pert": 8.245e9, "evaporation": 11.264e9, "chain_mass": 29.106e9}
+TRAFFIC_PER_STEP = {"cartpole": 8.430e9, "cartpole_tiny_pert": 8.230e9, "evaporation": 11.260e9, "chain_mass": 29.114e9}
 
 
 def dmma_flops_per_unit(workload, ipm_iters_mean):
@@ -220,6 +220,8 @@ class Workload:
                 self.env(x1, (u0[:, 0] / ENV["force_mag"]).clamp(-1.0, 1.0))
                 self.store_x1[c * B:(c + 1) * B] = x1
             self.idx = [torch.randperm(cap, generator=g)[:B].to(dev, torch.int32) for _ in range(n_steps)]
+            self.idx_long = [i.long() for i in self.idx]
+            self.xbuf = torch.empty(B, self.spec.nx, dtype=torch.float64, device=dev)
             self.install_guess(mpc)
             mpc.solve(self.x0, max_sqp=60)
         if self.name in ("cartpole_tiny_pert", "cartpole_bx", "evaporation"):
@@ -260,6 +262,8 @@ class Workload:
             self.xcur = self.x0.clone()
 
     def advance(self, i, out, mpc, record=True):
+        import torch
+
         if self.name == "cartpole":
             if i > 0:  # the state moves under the policy of the previous step
                 self.env(self.xcur, (out["u0"][:, 0] / ENV["force_mag"]).clamp(-1.0, 1.0))
@@ -268,7 +272,8 @@ class Workload:
             return self.xcur
         if self.name == "cartpole_replay":
             self.store.load(self.idx[i])
-            x = self.store_x1[self.idx[i].long()]
+            # (no allocation inside the timed region: preallocated index / state buffers)
+            x = torch.index_select(self.store_x1, 0, self.idx_long[i], out=self.xbuf)
             if record:
                 self.log[i].copy_(x)
             return x
