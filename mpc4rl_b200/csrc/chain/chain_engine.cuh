@@ -185,7 +185,7 @@ struct ChainEngine {
         WSYNC();
         if (lane < NL) {  // one lane per link: force and Jacobian block
           typename Mo::Link lk;
-          Mo::link_at(xs, U, lane, lk);
+          Mo::link_at(xs, U, th, lane, lk);
           Mo::link_force(th, lane, lk, FL + 3 * lane);
           Mo::link_S(th, lane, lk, SB + (s * NL + lane) * 9);
         }
@@ -225,7 +225,7 @@ struct ChainEngine {
           if (lane < NL) {
             typename Mo::Link lk;
             double nu[3];
-            Mo::link_at(xs, U, lane, lk);
+            Mo::link_at(xs, U, th, lane, lk);
             Mo::link_nu(KB, lane, nu);
             const double* Sb = SB + (s * NL + lane) * 9;
             for (int l = 0; l < 3; ++l) {
@@ -239,8 +239,8 @@ struct ChainEngine {
           if (lane < 3 * NL) {  // parameter gradient of this stage point, lane = (link i, component j)
             const int i = lane / 3, j = lane - 3 * i;
             typename Mo::Link lk;
-            Mo::link_at(xs, U, i, lk);
-            const double im = 1.0 / th[Mo::TH_M + i], Dj = th[Mo::TH_D + 3 * i + j], Lj = th[Mo::TH_L + 3 * i + j];
+            Mo::link_at(xs, U, th, i, lk);
+            const double im = lk.im, Dj = th[Mo::TH_D + 3 * i + j], Lj = th[Mo::TH_L + 3 * i + j];
             const double nuj = NUv[lane];
             const double e = (1.0 - Lj * lk.ir) * lk.d[j] * im;
             gth[0] += nuj * e;

@@ -34,27 +34,37 @@ struct ChainModel {
 
   // geometry of link i at state x (u only for the last link's velocity)
   struct Link {
-    double d[3], vl[3], r, ir;  // dist, link velocity, |dist|, 1/|dist|
+    double d[3], vl[3], r, ir, im;  // dist, link velocity, |dist|, 1/|dist|, 1/mass of the link (one division per link
+                                    // evaluation instead of one per derivative routine)
   };
-  MPC_HD static void link_at(const double* x, const double* u, int i, Link& k) {
+  MPC_HD static double inv_sqrt(double v) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(v);  // one MUFU.RSQ64H + refinement instead of sqrt followed by a division
+#else
+    return 1.0 / sqrt(v);
+#endif
+  }
+  MPC_HD static void link_at(const double* x, const double* u, const double* th, int i, Link& k) {
     MPC_UNROLL for (int j = 0; j < 3; ++j) {
       k.d[j] = x[3 * i + j] - (i > 0 ? x[3 * (i - 1) + j] : 0.0);
       if (i == 0) k.vl[j] = x[NPOS + j];
       else if (i == M) k.vl[j] = u[j] - x[NPOS + 3 * (M - 1) + j];
       else k.vl[j] = x[NPOS + 3 * i + j] - x[NPOS + 3 * (i - 1) + j];
     }
-    k.r = sqrt(k.d[0] * k.d[0] + k.d[1] * k.d[1] + k.d[2] * k.d[2]);
-    k.ir = 1.0 / k.r;
+    const double dd = k.d[0] * k.d[0] + k.d[1] * k.d[1] + k.d[2] * k.d[2];
+    k.ir = inv_sqrt(dd);
+    k.r = dd * k.ir;
+    k.im = 1.0 / th[TH_M + i];
   }
   // total link force T_i
   MPC_HD static void link_force(const double* th, int i, const Link& k, double* T) {
-    const double im = 1.0 / th[TH_M + i];
+    const double im = k.im;
     MPC_UNROLL for (int j = 0; j < 3; ++j)
       T[j] = th[TH_D + 3 * i + j] * im * (1.0 - th[TH_L + 3 * i + j] * k.ir) * k.d[j] + th[TH_C + 3 * i + j] * k.vl[j];
   }
   // S = dT/d(dist) (3 x 3, row-major): S[j][l] = c_j ((1 - L_j / r) delta_jl + L_j d_j d_l / r^3)
   MPC_HD static void link_S(const double* th, int i, const Link& k, double* S) {
-    const double im = 1.0 / th[TH_M + i], ir3 = k.ir * k.ir * k.ir;
+    const double im = k.im, ir3 = k.ir * k.ir * k.ir;
     MPC_UNROLL for (int j = 0; j < 3; ++j) {
       const double c = th[TH_D + 3 * i + j] * im, Lj = th[TH_L + 3 * i + j];
       MPC_UNROLL for (int l = 0; l < 3; ++l) S[3 * j + l] = c * ((j == l ? 1.0 - Lj * k.ir : 0.0) + Lj * k.d[j] * k.d[l] * ir3);
@@ -63,7 +73,7 @@ struct ChainModel {
   // G = Hessian of nu'T wrt dist, packed [00 01 02 11 12 22]:  a_j = nu_j c_j L_j, s = a'd,
   //   G = (a d' + d a' + s I) / r^3 - 3 s d d' / r^5
   MPC_HD static void link_G(const double* th, int i, const Link& k, const double* nu, double* G) {
-    const double im = 1.0 / th[TH_M + i], ir2 = k.ir * k.ir, ir3 = ir2 * k.ir;
+    const double im = k.im, ir2 = k.ir * k.ir, ir3 = ir2 * k.ir;
     double a[3], s = 0.0;
     MPC_UNROLL for (int j = 0; j < 3; ++j) {
       a[j] = nu[j] * th[TH_D + 3 * i + j] * im * th[TH_L + 3 * i + j];
@@ -88,7 +98,7 @@ struct ChainModel {
   // gradient of nu'T_i wrt the link's own parameters, added to g (compact numbering).  With tangents (dd, dvl of the
   // geometry, dnu of the weight; all may be null = zero) it adds the directional derivative of that gradient instead.
   MPC_HD static void link_theta_grad(const double* th, int i, const Link& k, const double* nu, double* g) {
-    const double im = 1.0 / th[TH_M + i];
+    const double im = k.im;
     double gm = 0.0;
     MPC_UNROLL for (int j = 0; j < 3; ++j) {
       const double Dj = th[TH_D + 3 * i + j], Lj = th[TH_L + 3 * i + j];
@@ -102,7 +112,7 @@ struct ChainModel {
   }
   MPC_HD static void link_theta_grad_tan(const double* th, int i, const Link& k, const double* nu, const double* dnu,
                                          const double* dd, const double* dvl, double* g) {
-    const double im = 1.0 / th[TH_M + i], ir3 = k.ir * k.ir * k.ir;
+    const double im = k.im, ir3 = k.ir * k.ir * k.ir;
     const double ddot = k.d[0] * dd[0] + k.d[1] * dd[1] + k.d[2] * dd[2];
     double gm = 0.0;
     MPC_UNROLL for (int j = 0; j < 3; ++j) {
@@ -127,7 +137,7 @@ struct ChainModel {
     for (int i = 0; i <= M; ++i) {
       Link k;
       double T[3];
-      link_at(x, u, i, k);
+      link_at(x, u, th, i, k);
       link_force(th, i, k, T);
       MPC_UNROLL for (int j = 0; j < 3; ++j) {
         if (i < M) f[NPOS + 3 * i + j] -= T[j];
@@ -151,7 +161,7 @@ struct ChainModel {
     for (int i = 0; i <= M; ++i) {
       Link k;
       double S[9], dd[3], dvl[3];
-      link_at(x, u, i, k);
+      link_at(x, u, th, i, k);
       link_S(th, i, k, S);
       link_tan(dx, du, i, dd, dvl);
       MPC_UNROLL for (int j = 0; j < 3; ++j) {
@@ -180,7 +190,7 @@ struct ChainModel {
     for (int i = 0; i <= M; ++i) {
       Link k;
       double S[9], nu[3], dbar[3], vbar[3];
-      link_at(x, u, i, k);
+      link_at(x, u, th, i, k);
       link_S(th, i, k, S);
       link_nu(mu, i, nu);
       MPC_UNROLL for (int l = 0; l < 3; ++l) {
@@ -201,7 +211,7 @@ struct ChainModel {
     for (int i = 0; i <= M; ++i) {
       Link k;
       double S[9], G[6], nu[3], dnu[3], dd[3], dvl[3], gd[3], dbar[3], vbar[3];
-      link_at(x, u, i, k);
+      link_at(x, u, th, i, k);
       link_S(th, i, k, S);
       link_nu(mu, i, nu);
       link_nu(dmu, i, dnu);
