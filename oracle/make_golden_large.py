@@ -7,6 +7,7 @@ outputs of the restatement, not of the reference ("parity unpinned").  Only what
     python -m oracle.make_golden_large cartpole_default 64
     python -m oracle.make_golden_large linear_system 256
     python -m oracle.make_golden_large evaporation 32
+    python -m oracle.make_golden_large evaporation_n100 8        # full horizon, about 40 minutes with 4 workers
 """
 from __future__ import annotations
 
@@ -30,6 +31,8 @@ def _problem(name):
         return make_linear_system(gamma=0.9)
     if name == "evaporation":
         return make_evaporation(gamma=0.95, N=40)
+    if name == "evaporation_n100":  # the reference's full horizon: ~10 minutes of dense oracle per solve
+        return make_evaporation(gamma=0.95, N=100)
     raise ValueError(name)
 
 
@@ -43,6 +46,8 @@ def _states(name, n, seed=4321):
         return sample_states(n, seed, "default")
     if name == "linear_system":
         return rng.uniform([0.0, -1.0], [1.0, 1.0], size=(n, 2)), rng.uniform(-1.0, 1.0, size=(n, 1))
+    if name == "evaporation_n100":
+        rng = np.random.default_rng(seed + 1)
     x = rng.uniform([25.0, 49.7], [40.0, 70.0], size=(n, 2))
     return x, np.column_stack([rng.uniform(150.0, 350.0, size=(n, 2)), np.full(n, 0.5)])
 
@@ -62,7 +67,7 @@ def _one(args):
     res = []
     for u0 in (None, a):
         try:  # a failed oracle solve is recorded (status -1), never repaired
-            sol, upd = s.unit(x0, u0=u0, tol=1e-10 if name != "evaporation" else 1e-9)
+            sol, upd = s.unit(x0, u0=u0, tol=1e-10 if not name.startswith("evaporation") else 1e-9)
             sl = max(float(np.max(sol.slbx, initial=0.0)), float(np.max(sol.subx, initial=0.0))) if hasattr(sol, "slbx") else 0.0
             res.append((sol.status, sol.cost, np.array(sol.U[0]), upd["dL_dp"][0], upd["dpi_dp"], sl))
         except Exception as e:  # noqa: BLE001

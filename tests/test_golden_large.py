@@ -77,6 +77,27 @@ def test_host_port_linear_system_256():
     assert nv >= 250
 
 
+@pytest.mark.parametrize("fixture,N", [("evaporation_32", 40), ("evaporation_n100_8", 100)])
+def test_host_port_evaporation_sets(fixture, N):
+    from oracle import cpu_port as cp
+    from oracle.problems import EVAPORATION_PARAM, make_evaporation
+
+    g = _load(fixture)
+    pb = make_evaporation(gamma=0.95, N=N)
+    scale = np.array([pb.stage_scale(k) for k in range(N + 1)])
+    pd = cp.make_pd(N, scale, pb.lbu, pb.ubu, list(EVAPORATION_PARAM.values()) + [0.25, 4], tol=1e-9, warm_ipm=1, lg=pb.lh, ug=pb.uh)
+    B, nx, nu = g["x0"].shape[0], 2, 3
+    res = []
+    for mode, u0 in ((0, None), (1, g["a"])):
+        it = np.zeros((cp.lib().cpu_port_iterate_size(4, N), B))  # every stage on the steady state, like the reference
+        for k in range(N + 1):
+            it[k * nx:(k + 1) * nx, :] = pb.x_init[:, None]
+        for k in range(N):
+            it[(N + 1) * nx + k * nu:(N + 1) * nx + (k + 1) * nu, :] = pb.u_init[:, None]
+        res.append(cp.unit(4, pd, mode, 100, g["theta"], g["x0"], u0=u0, iterate=it, nx=nx, nu=nu))
+    _check(g, res[0], res[1], 0.9)
+
+
 # ---------------------------------------------------------------- CUDA path
 def _gpu_run(spec, g, max_sqp):
     import torch
@@ -177,15 +198,16 @@ def test_gpu_sensitivities_with_indefinite_exact_hessian():
 
 
 @pytest.mark.gpu
-def test_gpu_evaporation_32():
-    """32 states of the SURVEY.md 8(d) config-4 distribution at the oracle's affordable horizon N = 40 (gamma 0.95), V- and
-    Q-mode, all 60 tracking-cost parameter columns."""
+@pytest.mark.parametrize("fixture,N", [("evaporation_32", 40), ("evaporation_n100_8", 100)])
+def test_gpu_evaporation_sets(fixture, N):
+    """32 states of the SURVEY.md 8(d) config-4 distribution at the oracle's affordable horizon N = 40 and 8 at the
+    reference's full horizon N = 100 (gamma 0.95), V- and Q-mode, all 60 tracking-cost parameter columns."""
     import torch
 
     from mpc4rl_b200 import BatchedMPC, evaporation_spec
 
-    g = _load("evaporation_32")
-    spec = evaporation_spec(gamma=0.95, N=40)
+    g = _load(fixture)
+    spec = evaporation_spec(gamma=0.95, N=N)
     dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
     B = g["x0"].shape[0]
     m = BatchedMPC(spec, max_batch=B, device=0)
