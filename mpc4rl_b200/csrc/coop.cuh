@@ -338,11 +338,14 @@ struct CoopQP {
       __syncwarp();
       {
         double kr[NW], ar[NC];
+        // (shared-window loads with immediate offsets, like the backward sweep; lanes >= NX read row 0 and never store)
+        const unsigned sMrow = sMk + 8 * ((lane < NX ? lane : 0) * NC);
         auto fetch_f = [&](int k) {
+          const unsigned kk = sKk + (unsigned)k * (8 * NW), mm = sMrow + (unsigned)k * (8 * NX * NC);
 #pragma unroll
-          for (int l = 0; l < NW; ++l) kr[l] = Kk[k * NW + l];
+          for (int l = 0; l < NW; ++l) kr[l] = lds(kk + 8 * l);
 #pragma unroll
-          for (int l = 0; l < NC; ++l) ar[l] = (lane < NX) ? Mk[k * NX * NC + lane * NC + l] : 0.0;
+          for (int l = 0; l < NC; ++l) ar[l] = lds(mm + 8 * l);
         };
         fetch_f(0);
         __syncwarp();  // every lane holds stage 0's feedback law before its slot is overwritten
