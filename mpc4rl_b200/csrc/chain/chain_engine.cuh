@@ -453,11 +453,13 @@ struct ChainEngine {
   // One backward Riccati step in shared memory.
   //   in : Pm (NX x NX, symmetric), PV (p, NX), Mk = [A | B | b] (b ignored when `affine` is false)
   //        hess(i, c): Hessian entry of the stage incl. barrier terms (i, c < NW), grad(i): gradient entry
-  //   out: Pm, PV of this stage; KK = [K | kff] (NU x NK1); returns false if the reduced Hessian is not positive definite
+  //   out: Pm, PV of this stage; KK = [K | kff] (NU x NK1); returns false if the reduced Hessian is not positive definite (need_pd;
+  //        the QP solves) resp. not invertible (the sensitivities: update_nlp solves its KKT system with a general sparse LU,
+  //        nlp.py:1413-1424, which needs it nonsingular, not definite)
   // Tm (NX x NC), HU (NU x NC) are scratch.  G0I (optional, 9): inverse of the reduced Hessian G.
   template <class HF, class GF>
   CH_DEV static bool riccati_step(double* Pm, double* PV, double* Tm, double* HU, double* KK, const double* Mk, bool affine,
-                                  bool ufixed, HF hess, GF grad, double* G0I, int lane) {
+                                  bool ufixed, bool need_pd, HF hess, GF grad, double* G0I, int lane) {
 #if CHAIN_USE_DMMA
     // Both products on the FP64 tensor cores (mma.sync m8n8k4): per stage 2 x MT x NT x KT instructions instead of
     // ~700 DFMA + ~330 LDS per lane -- ncu on the FMA version: shared-memory pipe 37-46 % busy, FP64 pipe 17 %, i.e.
@@ -563,15 +565,16 @@ struct ChainEngine {
       return true;
     }
     {  // K = -G^{-1} H, kff = -G^{-1} gv : every lane factorises the NU x NU block, lane c solves column c
-      double G[NU * NU], rhs[NU];
+      double G[NU * NU], rhs[NU], dinv[NU];
       MPC_UNROLL for (int a_ = 0; a_ < NU; ++a_) MPC_UNROLL for (int b_ = 0; b_ < NU; ++b_) G[a_ * NU + b_] = HU[a_ * NC + NX + b_];
-      // LDL'
+      // LDL' (reciprocal pivots: the diagonal scalings of the solves multiply)
       MPC_UNROLL for (int j = 0; j < NU; ++j) {
         double d = G[j * NU + j];
         MPC_UNROLL for (int p = 0; p < j; ++p) d -= G[j * NU + p] * G[j * NU + p] * G[p * NU + p];
-        if (!(d > 0.0)) ok = false;
+        if (need_pd ? !(d > 0.0) : !(d > 0.0 || d < 0.0)) ok = false;
         G[j * NU + j] = d;
         const double inv = 1.0 / d;
+        dinv[j] = inv;
         MPC_UNROLL for (int i = j + 1; i < NU; ++i) {
           double v = G[i * NU + j];
           MPC_UNROLL for (int p = 0; p < j; ++p) v -= G[i * NU + p] * G[j * NU + p] * G[p * NU + p];
@@ -580,7 +583,7 @@ struct ChainEngine {
       }
       auto solve = [&](double* r) {
         MPC_UNROLL for (int i = 0; i < NU; ++i) MPC_UNROLL for (int p = 0; p < i; ++p) r[i] -= G[i * NU + p] * r[p];
-        MPC_UNROLL for (int i = 0; i < NU; ++i) r[i] /= G[i * NU + i];
+        MPC_UNROLL for (int i = 0; i < NU; ++i) r[i] *= dinv[i];
         MPC_UNROLL for (int i = NU - 1; i >= 0; --i) MPC_UNROLL for (int p = i + 1; p < NU; ++p) r[i] -= G[p * NU + i] * r[p];
       };
       if (lane < NK1) {
@@ -744,7 +747,7 @@ struct ChainEngine {
           return s * tab[TB_R + (i - NX) * NU + (c - NX)] + (i == c ? rd[i - NX] : 0.0);
         };
         auto grad = [&](int i) -> double { return gk[i] + (i >= NX ? rg[i - NX] : 0.0); };
-        const bool ok = riccati_step(Pm, PV, Tm, HU, KK, Mk, true, false, hess, grad, nullptr, lane);
+        const bool ok = riccati_step(Pm, PV, Tm, HU, KK, Mk, true, false, /*need_pd=*/true, hess, grad, nullptr, lane);
         ok_all = ok_all && ok;
         for (int e = lane; e < NU * NK1; e += 32) ws[(size_t)k * REC + S_K + e] = KK[e];
         WSYNC();  // slot k&1 is free again
@@ -1009,7 +1012,7 @@ struct ChainEngine {
           return v;
         };
         auto grad = [&](int) -> double { return 0.0; };
-        const bool ok = riccati_step(Pm, PV, Tm, HU, KK, Mk, false, false, hess, grad, k == 0 ? G0I : nullptr, lane);
+        const bool ok = riccati_step(Pm, PV, Tm, HU, KK, Mk, false, false, /*need_pd=*/false, hess, grad, k == 0 ? G0I : nullptr, lane);
         ok_all = ok_all && ok;
         for (int e = lane; e < NU * NX; e += 32) ws[(size_t)k * REC + Z_K + e] = KK[(e / NX) * NK1 + (e % NX)];
         WSYNC();
