@@ -53,6 +53,44 @@ def test_cartpole_free_g_matches_oracle():
     assert np.abs(q["dL"] - g["dQ"][:, :4])[okq].max() < 1e-6 * np.abs(g["dQ"][okq]).max()
 
 
+def test_interior_point_pass_state_machine_equals_the_monolithic_loop():
+    """Engine::ipm_pass (one interior-point iteration per call, state carried outside: what the pass kernels of option
+    ipm_passes run, and what k_qp3's pick-up of k_qp1's first iteration mirrors) against Engine::qp_ipm run to the end in
+    one call: same iterates, statuses and outputs over closed-loop RTI steps -- also when the passes run out and the
+    monolithic loop takes the sample over."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from bench import env_step_np, synth_states
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    spec = cartpole_spec(cartpole_original_config())
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-6, warm_ipm=1)
+    x0 = synth_states(256, 1234).numpy()
+    runs = {}
+    try:
+        for passes in (0, 6, 2):
+            cp.lib().cpu_port_set_passes(passes)
+            o = cp.unit(1, pd, 0, 30, spec.p_nominal, x0)
+            it, x1, outs = o["iterate"], x0, []
+            for _ in range(3):
+                x1 = env_step_np(x1, o["u0"][:, 0])
+                o = cp.unit(1, pd, 0, 1, spec.p_nominal, x1, iterate=it)
+                it = o["iterate"]
+                outs.append(o)
+            runs[passes] = outs
+    finally:
+        cp.lib().cpu_port_set_passes(0)
+    assert (runs[0][0]["iters"][:, 1] > 1).mean() > 0.5  # most samples need more than the one Newton iteration of qp_fast
+    for passes in (6, 2):
+        for a, b in zip(runs[0], runs[passes]):
+            assert np.array_equal(a["status"], b["status"])
+            assert np.abs(a["u0"] - b["u0"]).max() < 1e-9
+            assert np.abs(a["cost"] - b["cost"]).max() < 1e-9 * np.abs(a["cost"]).max()
+            assert np.abs(a["dpi"] - b["dpi"]).max() < 1e-6 * np.abs(a["dpi"]).max()
+
+
 def test_chain_mass_host_run_matches_oracle():
     from mpc4rl_b200.problems import chain_mass_spec, get_chain_params
     from oracle import cpu_port as cp
