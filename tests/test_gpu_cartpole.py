@@ -474,3 +474,35 @@ def test_cuda_graph_replay_is_bit_identical(spec, B):
     for a, b in zip(*outs):
         for k in ("u0", "cost", "dL", "dpi", "status", "res"):
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("opt", [("ipm_passes", 3), ("fuse_lin", 1)])
+def test_opt_in_kernel_variants_give_the_same_results(spec, opt):
+    """The measured-and-rejected variants stay selectable (profiles/r02_summary.md): pass kernels ahead of the queue kernel
+    (option ipm_passes) and the linearisation inside the fast-path kernel (option fuse_lin).  Same statuses, outputs equal
+    to rounding, over a cold SQP solve and closed-loop-sized RTI steps."""
+    B = 4096
+    g = torch.Generator(device="cpu").manual_seed(21)
+    lo = torch.tensor([-1.0, -2.0, -np.pi, -4.0], dtype=torch.float64)
+    x0 = (lo + (-2 * lo) * torch.rand(B, 4, generator=g, dtype=torch.float64)).cuda()
+    dx = 2e-2 * torch.randn(2, B, 4, generator=g, dtype=torch.float64).cuda()
+    runs = []
+    for on in (False, True):
+        m = _mpc(spec, B)
+        m.set_option("tol", 1e-8)
+        if on:
+            m.set_option(opt[0], opt[1])
+        m.reset(x0)
+        outs = [m.solve_sens(x0, max_sqp=60)] + [m.solve_sens(x0 + dx[i], max_sqp=1) for i in range(2)]
+        runs.append([{k: v.cpu().numpy() for k, v in o.items()} for o in outs])
+    conv = None
+    for step, (a, b) in enumerate(zip(*runs)):
+        same = a["status"] == b["status"]
+        assert same.mean() > 0.995, (step, same.mean())
+        ok = same & (a["status"] == 0)
+        conv = ok if conv is None else conv
+        ok = ok & conv
+        assert ok.mean() > 0.8, (step, ok.mean())
+        assert np.abs(a["u0"] - b["u0"])[ok].max() < 1e-7, step
+        assert _rel(a["cost"][ok], b["cost"][ok]) < 1e-9, step
+        assert _rel(a["dpi"][ok], b["dpi"][ok]) < 1e-5, step
