@@ -199,6 +199,8 @@ class DenseSolver:
 
         m = len(gi)
         pi = np.zeros(N * nx); lam = np.full(m, 0.0); t = np.full(m, 1.0)
+        if init is not None and len(init) > 2:  # stored multipliers (pi, lam over ALL rows): the exact Hessian of the first step
+            pi = np.array(init[2], float).ravel().copy(); lam = np.array(init[3], float)[gi].copy()
         status, kkt, it = 2, np.inf, 0
         for it in range(max_iter + 1):
             c = grad(cost_v)(v).numpy()

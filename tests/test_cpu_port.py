@@ -5,6 +5,7 @@ engine under the fiber emulation of a warp."""
 import os
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -91,24 +92,25 @@ def test_interior_point_pass_state_machine_equals_the_monolithic_loop():
             assert np.abs(a["dpi"] - b["dpi"]).max() < 1e-6 * np.abs(a["dpi"]).max()
 
 
-def test_chain_mass_host_run_matches_oracle():
+@pytest.mark.parametrize("n_mass,n", [(3, 4), (6, 2)])  # nx = 9 / 113 parameters; nx = 27 / 800 parameters (BASELINE configs[2])
+def test_chain_mass_host_run_matches_oracle(n_mass, n):
     from mpc4rl_b200.problems import chain_mass_spec, get_chain_params
     from oracle import cpu_port as cp
 
-    g = np.load(os.path.join(ROOT, "tests", "golden", "chain_mass_3.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"chain_mass_{n_mass}.npz"))
     cpar = get_chain_params()
-    cpar["n_mass"] = 3
+    cpar["n_mass"] = n_mass
     spec = chain_mass_spec(cpar)
+    assert spec.ntheta == g["theta"].shape[0]
     pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-9, warm_ipm=1)
-    n = 4
-    o = cp.chain_unit(3, pd, 0, 60, spec.p_nominal, spec.x_ss, g["x0"][:n])
+    o = cp.chain_unit(n_mass, pd, 0, 60, spec.p_nominal, spec.x_ss, g["x0"][:n])
     assert np.all(o["status"] == 0)
     assert np.abs(o["u0"] - g["u0"][:n]).max() < 1e-8
     assert np.abs(o["cost"] - g["V"][:n]).max() < 1e-9 * np.abs(g["V"]).max()
     assert np.abs(o["dL"] - g["dV"][:n]).max() < 1e-6 * np.abs(g["dV"]).max()
     assert np.abs(o["dpi"] - g["dpi"][:n]).max() < 1e-5 * np.abs(g["dpi"]).max()
     # one RTI step from that iterate at the moved state, sensitivities at the new iterate
-    r = cp.chain_unit(3, pd, 0, 1, spec.p_nominal, spec.x_ss, g["x1"][:n], iterate=o["iterate"])
+    r = cp.chain_unit(n_mass, pd, 0, 1, spec.p_nominal, spec.x_ss, g["x1"][:n], iterate=o["iterate"])
     assert np.all(r["status"] == 0)
     assert np.abs(r["u0"] - g["u1"][:n]).max() < 1e-5
     assert np.abs(r["dpi"] - g["dpi1"][:n]).max() < 1e-4 * np.abs(g["dpi1"]).max()
