@@ -10,7 +10,8 @@ what oracle/make_golden_rti.py does for cartpole_original, for config/cartpole.y
      with x_0 := x1, QP at the tau-central point, V-mode and Q-mode
   4. restated update_nlp at the new, not converged, iterate.
 
-    python -m oracle.make_golden_rti_more <cartpole_default|linear_system|evaporation> <n_samples> [n_procs]
+    python -m oracle.make_golden_rti_more <cartpole_default|linear_system|evaporation|evaporation_n100> <n_samples> [n_procs]
+(evaporation_n100: the reference's full horizon, about 25 minutes for 8 samples on 8 processes)
 """
 from __future__ import annotations
 
@@ -55,7 +56,7 @@ def _one(args):
     pb = s.pb
     nth, nu = len(pb.p_nominal), pb.nu
     rng = np.random.default_rng(seed)
-    tol = 1e-9 if name == "evaporation" else 1e-10
+    tol = 1e-9 if name.startswith("evaporation") else 1e-10
     nan = dict(x1=np.full(pb.nx, np.nan), V1=np.nan, u1=np.full(nu, np.nan), dV1=np.full(nth, np.nan), dpi1=np.full((nu, nth), np.nan),
                kkt1=np.nan, sl1=0.0, Q1=np.nan, dQ1=np.full(nth, np.nan))
     try:

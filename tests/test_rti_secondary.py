@@ -1,7 +1,7 @@
 """The SQP-RTI step + sensitivities that bench.py times, on the SECONDARY configurations, against the dense oracle:
 config/cartpole.yaml (state bounds, one environment step), the linear system (softened bound, one step of
 LinearSystemEnv) and the evaporation process (general rows, exact Hessian; N = 40, the oracle's affordable horizon).
-Fixtures: tests/golden/{cartpole_default,linear_system,evaporation}_rti.npz (oracle/make_golden_rti_more.py: ONE dense
+Fixtures: tests/golden/{cartpole_default,linear_system,evaporation,evaporation_n100}_rti.npz (oracle/make_golden_rti_more.py: ONE dense
 SQP step from the stored converged iterate incl. multipliers, QP at the tau-central point, restated update_nlp at the
 new iterate; oracle outputs, parity unpinned vs acados).  Host build of the engine in the CPU suite, CUDA path through
 the C ABI under -m gpu.  Tolerances of the timed path (tests/test_gpu_rti_oracle.py): |du0| 1e-5, V 1e-8 rel,
@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = ["cartpole_default", "linear_system", "evaporation"]
+NAMES = ["cartpole_default", "linear_system", "evaporation", "evaporation_n100"]  # the last: full horizon N = 100, 8 states
 
 
 def _load(name):
@@ -79,7 +79,7 @@ def test_host_port_rti_step_matches_oracle(name):
     pb, pd, model, nx, nu = _host_problem(name)
     B, N = g["x0"].shape[0], pb.N
     it = None
-    if name == "evaporation":  # every stage on the steady state, like the reference
+    if name.startswith("evaporation"):  # every stage on the steady state, like the reference
         it = np.zeros((cp.lib().cpu_port_iterate_size(model, N), B))
         for k in range(N + 1):
             it[k * nx:(k + 1) * nx, :] = pb.x_init[:, None]
@@ -103,15 +103,16 @@ def test_gpu_rti_step_matches_oracle(name):
 
     g = _load(name)
     spec = {"cartpole_default": lambda: cartpole_spec(cartpole_config()), "linear_system": lambda: linear_system_spec(gamma=0.9),
-            "evaporation": lambda: evaporation_spec(gamma=0.95, N=40)}[name]()
+            "evaporation": lambda: evaporation_spec(gamma=0.95, N=40),
+            "evaporation_n100": lambda: evaporation_spec(gamma=0.95, N=100)}[name]()
     dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
     B = g["x0"].shape[0]
     x0, x1 = dev(g["x0"]), dev(np.where(np.isfinite(g["x1"]), g["x1"], g["x0"]))
     res = []
     for u0 in (None, dev(g["a"])):
         m = BatchedMPC(spec, max_batch=B, device=0)  # default options = the bench's, except the tolerance of the setup solve
-        m.set_option("tol", 1e-9 if name == "evaporation" else 1e-10)
-        if name == "evaporation":
+        m.set_option("tol", 1e-9 if name.startswith("evaporation") else 1e-10)
+        if name.startswith("evaporation"):
             m.reset(B=B)
             for k in range(spec.N + 1):
                 m.put("x", k, dev(np.tile(spec.x_init, (B, 1))))
