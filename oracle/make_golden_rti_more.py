@@ -11,7 +11,7 @@ what oracle/make_golden_rti.py does for cartpole_original, for config/cartpole.y
   4. restated update_nlp at the new, not converged, iterate.
 
     python -m oracle.make_golden_rti_more <cartpole_default|linear_system|evaporation|evaporation_n100> <n_samples> [n_procs]
-(evaporation_n100: the reference's full horizon, about 25 minutes for 8 samples on 8 processes)
+(evaporation_n100: the reference's full horizon, about 3 minutes per 8 samples on 8 processes)
 """
 from __future__ import annotations
 

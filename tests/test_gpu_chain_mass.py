@@ -1,6 +1,6 @@
 """Chain-of-masses MPC on the warp-cooperative CUDA engine against the dense oracle.
 
-Fixtures: tests/golden/chain_mass_{3,5,6,3_64}.npz (oracle/make_golden_chain.py; oracle outputs, parity unpinned vs acados).
+Fixtures: tests/golden/chain_mass_{3,5,6,3_64,5_64}.npz (oracle/make_golden_chain.py; oracle outputs, parity unpinned vs acados).
 Tolerances vs the restated oracle: |u0| 1e-8, V/Q 1e-9 rel, dL/dtheta 1e-6 rel, dpi/dtheta 1e-5 rel.
 """
 import os
@@ -38,7 +38,7 @@ def _fixture(name):
     return g, int(g["n_mass"])
 
 
-FIXTURES = ["chain_mass_3", "chain_mass_5", "chain_mass_6", "chain_mass_3_64"]  # 16, 16, 16 and 64 samples (n_mass 6: nx = 27, 800 parameters)
+FIXTURES = ["chain_mass_3", "chain_mass_5", "chain_mass_6", "chain_mass_3_64", "chain_mass_5_64"]  # 16, 16, 16, 64 and 64 samples (n_mass 6: nx = 27, 800 parameters)
 
 
 @pytest.mark.parametrize("fixture", FIXTURES)
