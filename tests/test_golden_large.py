@@ -223,3 +223,54 @@ def test_gpu_evaporation_sets(fixture, N):
         o = m.solve_sens(x0, u0=u0, max_sqp=100)
         res.append({k: t.cpu().numpy() for k, t in o.items()})
     _check(g, res[0], res[1], 0.9)
+
+
+# ---------------------------------------------------------------- away from the nominal parameters: one theta per sample
+def _check_theta(g, v, q):
+    okv = (g["status"][:, 0] == 0) & (v["status"] == 0)
+    okq = (g["status"][:, 1] == 0) & (q["status"] == 0)
+    assert okv.sum() >= 24 and okq.sum() >= 24, (okv.sum(), okq.sum())
+    assert np.ptp(g["theta"][:, :3], axis=0).min() > 0.02  # every model parameter really differs between samples
+    assert np.abs(v["u0"] - g["u0"])[okv].max() < 1e-6
+    assert _rel(v["cost"][okv], g["V"][okv]) < 1e-9
+    assert _rel(v["dL"][okv][:, :3], g["dV"][okv]) < 1e-6
+    rel = np.abs(v["dpi"][:, :, :3] - g["dpi"])[okv].max(axis=(1, 2)) / np.abs(g["dpi"][okv]).max(axis=(1, 2))
+    assert rel.max() < 1e-5, rel  # per sample: the scale of dpi/dtheta changes with theta
+    assert _rel(q["cost"][okq], g["Q"][okq]) < 1e-9
+    assert _rel(q["dL"][okq][:, :3], g["dQ"][okq]) < 1e-6
+
+
+def test_host_port_per_sample_parameters_match_oracle():
+    """32 cart-pole states, each with its own (M, m, l) = nominal x U(0.6, 1.4) (oracle/make_golden_theta.py): what
+    MPC.set_p does between learning steps, and the [B, ntheta] form of rlmpc_set_theta."""
+    from mpc4rl_b200.problems import cartpole_original_config, cartpole_spec
+    from oracle import cpu_port as cp
+
+    g = _load("cartpole_original_theta")
+    spec = cartpole_spec(cartpole_original_config())
+    pd = cp.make_pd(spec.N, spec.cost_scaling(), spec.lbu, spec.ubu, spec.model_const, tol=1e-10, warm_ipm=1)
+    v = cp.unit(1, pd, 0, 300, g["theta"], g["x0"])
+    q = cp.unit(1, pd, 1, 300, g["theta"], g["x0"], u0=g["a"])
+    _check_theta(g, v, q)
+
+
+@pytest.mark.gpu
+def test_gpu_per_sample_parameters_match_oracle():
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC, cartpole_original_config, cartpole_spec
+
+    g = _load("cartpole_original_theta")
+    spec = cartpole_spec(cartpole_original_config())
+    dev = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda:0")
+    B = g["x0"].shape[0]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-10)
+    m.set_theta(g["theta"])  # [B, ntheta]: one parameter vector per sample
+    x0 = dev(g["x0"])
+    res = []
+    for u0 in (None, dev(g["a"])):
+        m.reset(x0)
+        o = m.solve_sens(x0, u0=u0, max_sqp=300)
+        res.append({k: t.cpu().numpy() for k, t in o.items()})
+    _check_theta(g, res[0], res[1])
