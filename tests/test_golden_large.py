@@ -274,3 +274,77 @@ def test_gpu_per_sample_parameters_match_oracle():
         o = m.solve_sens(x0, u0=u0, max_sqp=300)
         res.append({k: t.cpu().numpy() for k, t in o.items()})
     _check_theta(g, res[0], res[1])
+
+
+def _check_theta_full(g, v, q, min_ok, dpi_tol=1e-5):
+    """Linear system / evaporation away from nominal: all parameter columns, per-sample scale for dpi/dtheta."""
+    okv = (g["status"][:, 0] == 0) & (v["status"] == 0)
+    okq = (g["status"][:, 1] == 0) & (q["status"] == 0)
+    assert okv.sum() >= min_ok and okq.sum() >= min_ok, (okv.sum(), okq.sum())
+    nc = g["dV"].shape[1]
+    assert np.abs(v["u0"] - g["u0"])[okv].max() < 1e-6
+    assert _rel(v["cost"][okv], g["V"][okv]) < 1e-9
+    assert _rel(v["dL"][okv][:, :nc], g["dV"][okv]) < 1e-6
+    m = okv & (g["slmax"] <= 1e-6)  # dpi/dtheta with an active slack: quirks Q4 / Q7 (see _check above)
+    assert m.sum() >= min_ok // 2
+    rel = np.abs(v["dpi"][:, :, :nc] - g["dpi"])[m].max(axis=(1, 2)) / np.abs(g["dpi"][m]).max(axis=(1, 2))
+    assert rel.max() < dpi_tol, rel
+    assert _rel(q["cost"][okq], g["Q"][okq]) < 1e-9
+    assert _rel(q["dL"][okq][:, :nc], g["dQ"][okq]) < 1e-6
+
+
+def test_host_port_linear_system_and_evaporation_away_from_nominal():
+    """Per-sample theta for the two problems whose learning loops move it: the linear system's 12 model parameters
+    (N(0, 0.03^2) around nominal) and the evaporation process' tracking weights / references (N = 40)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_rti_secondary import _host_problem
+
+    from oracle import cpu_port as cp
+
+    for name, min_ok in (("linear_system", 28), ("evaporation", 14)):
+        g = _load(name + "_theta")
+        pb, pd, model, nx, nu = _host_problem(name)
+        B, N = g["x0"].shape[0], pb.N
+        res = []
+        for mode, u0 in ((0, None), (1, g["a"])):
+            it = None
+            if name == "evaporation":
+                it = np.zeros((cp.lib().cpu_port_iterate_size(model, N), B))
+                for k in range(N + 1):
+                    it[k * nx:(k + 1) * nx, :] = pb.x_init[:, None]
+                for k in range(N):
+                    it[(N + 1) * nx + k * nu:(N + 1) * nx + (k + 1) * nu, :] = pb.u_init[:, None]
+            res.append(cp.unit(model, pd, mode, 300, g["theta"], g["x0"], u0=u0, iterate=it, nx=nx, nu=nu))
+        _check_theta_full(g, res[0], res[1], min_ok, dpi_tol=2e-5 if name == "linear_system" else 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,min_ok", [("linear_system", 28), ("evaporation", 14)])
+def test_gpu_linear_system_and_evaporation_away_from_nominal(name, min_ok):
+    import torch
+
+    from mpc4rl_b200 import BatchedMPC, evaporation_spec, linear_system_spec
+
+    g = _load(name + "_theta")
+    spec = linear_system_spec(gamma=0.9) if name == "linear_system" else evaporation_spec(gamma=0.95, N=40)
+    dev = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+    B = g["x0"].shape[0]
+    m = BatchedMPC(spec, max_batch=B, device=0)
+    m.set_option("tol", 1e-9 if name == "evaporation" else 1e-10)
+    m.set_theta(g["theta"])  # [B, ntheta]
+    x0 = dev(g["x0"])
+    res = []
+    for u0 in (None, dev(g["a"])):
+        if name == "evaporation":
+            m.reset(B=B)
+            for k in range(spec.N + 1):
+                m.put("x", k, dev(np.tile(spec.x_init, (B, 1))))
+            for k in range(spec.N):
+                m.put("u", k, dev(np.tile(spec.u_init, (B, 1))))
+        else:
+            m.reset(x0)
+        o = m.solve_sens(x0, u0=u0, max_sqp=300)
+        res.append({k: t.cpu().numpy() for k, t in o.items()})
+    _check_theta_full(g, res[0], res[1], min_ok, dpi_tol=2e-5 if name == "linear_system" else 1e-5)
